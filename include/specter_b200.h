@@ -1,0 +1,129 @@
+/* specter_b200 -- C ABI of the B200-native backend for SPECTER's per-RK-substep hot path.
+ *
+ * This header is the drop-in boundary.  Each entry point replaces one Fortran procedure of
+ * the reference's fftp / pseudo / boundary modules (cited "ref:" below, paths relative to
+ * /root/reference/src).  A thin ISO_C_BINDING module binds these names.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; sx_last_error() gives the
+ *    message (the reference prints "[ERROR] ..." and STOPs instead, e.g. vboundary.f90:102).
+ *  - one plan per process / GPU (the reference: one MPI rank per GPU, specter.fpp:263-268);
+ *    calls on a plan are ordered on the plan's CUDA stream and are not re-entrant.
+ *  - array arguments are DEVICE pointers unless the name ends in _host.  Layouts are the
+ *    reference's, byte for byte:
+ *       spectral / mixed  COMPLEX(GP) a(nz,ny,ista:iend)  -> interleaved (re,im) doubles, z fastest
+ *       real              REAL(GP)    r(nx,ny,ksta:kend)  -> doubles, x fastest
+ *  - transforms are unnormalised in both directions, as in the reference (fftp.fpp).
+ *  - there is no CPU fallback: sx_plan_create fails if no CUDA device is usable.
+ */
+#ifndef SPECTER_B200_H
+#define SPECTER_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sx_plan sx_plan;
+
+typedef struct sx_config {
+  int nx, ny, nz;      /* ref: NX,NY,NZ  (Makefile.in:6-8, pseudospec_mod.fpp:18-35) */
+  int Cz, oz;          /* continuation points / matching order in z (Makefile.in:16,21) */
+  int ord;             /* RK order ORD (Makefile.in:24, module order) */
+  double Lx, Ly, Lz;   /* &boxparams (specter.fpp:201-239) */
+  const char* tdir;    /* FC-Gram table directory (parameter.inp tdir) */
+  int nprocs, myrank;  /* slab decomposition (specter.fpp:288-289); 1,0 for a single GPU */
+  int device;          /* CUDA device ordinal; -1 = myrank % device_count (specter.fpp:263-284) */
+} sx_config;
+
+const char* sx_last_error(void);
+const char* sx_version(void);
+
+/* ref: fcgram_create_plan (fcgram_mod.f90:49-144) + fftp3d_create_plan (fftp.fpp:61-162)
+ *      + grid / wavenumber set-up (specter.fpp:683-800) */
+int sx_plan_create(const sx_config* cfg, sx_plan** plan);
+int sx_plan_destroy(sx_plan* plan);
+/* local slab extents, 1-based inclusive as `range` returns them (fftp.fpp:1154-1184) */
+int sx_plan_info(const sx_plan* plan, int* ista, int* iend, int* ksta, int* kend, int* pkend);
+int sx_range(int n1, int n2, int nprocs, int irank, int* sta, int* end);
+/* kernels launched by this plan so far */
+unsigned long long sx_plan_launch_count(const sx_plan* plan);
+int sx_plan_synchronize(sx_plan* plan);
+/* multi-GPU: 128-byte NCCL unique id created on rank 0 and shared by the caller
+ * (MPI_BCAST in the Fortran driver, torch.distributed in the Python harness) */
+int sx_nccl_unique_id(void* id128);
+int sx_plan_set_comm(sx_plan* plan, const void* id128);
+
+/* device memory helpers so a host language needs no CUDA runtime of its own */
+int sx_malloc(sx_plan* plan, size_t bytes, void** dptr);
+int sx_free(sx_plan* plan, void* dptr);
+int sx_malloc_host(size_t bytes, void** hptr); /* pinned */
+int sx_free_host(void* hptr);
+int sx_memcpy_h2d(sx_plan* plan, void* dptr, const void* hptr, size_t bytes);
+int sx_memcpy_d2h(sx_plan* plan, void* hptr, const void* dptr, size_t bytes);
+size_t sx_spectral_bytes(const sx_plan* plan); /* 16*nz*ny*(iend-ista+1) */
+size_t sx_real_bytes(const sx_plan* plan);     /* 8*nx*ny*(kend-ksta+1) */
+
+/* ---- fftp module ------------------------------------------------------------ */
+/* ref: fftp3d_real_to_complex (fftp.fpp:388-425) */
+int sx_fftp3d_real_to_complex(sx_plan* plan, const double* in_real, double* out_spec);
+/* ref: fftp3d_complex_to_real (fftp.fpp:789-821); unlike the reference `in` is preserved */
+int sx_fftp3d_complex_to_real(sx_plan* plan, const double* in_spec, double* out_real);
+/* ref: fftp2d_real_to_complex_xy (fftp.fpp:428-524) */
+int sx_fftp2d_real_to_complex_xy(sx_plan* plan, const double* in_real, double* out_mixed);
+/* ref: fftp2d_complex_to_real_xy (fftp.fpp:824-919) */
+int sx_fftp2d_complex_to_real_xy(sx_plan* plan, const double* in_mixed, double* out_real);
+/* ref: fftp1d_real_to_complex_z (fftp.fpp:720-786): FC-Gram continuation + forward z FFT, in place */
+int sx_fftp1d_real_to_complex_z(sx_plan* plan, double* inout);
+/* ref: fftp1d_complex_to_real_z (fftp.fpp:1060-1094): backward z FFT, in place */
+int sx_fftp1d_complex_to_real_z(sx_plan* plan, double* inout);
+
+/* ---- pseudo module ---------------------------------------------------------- */
+int sx_derivk(sx_plan* plan, const double* a, double* b, int dir);               /* ref: pseudospec_hd.f90:28-94 */
+int sx_laplak(sx_plan* plan, const double* a, double* b);                        /* ref: :97-127 */
+int sx_curlk(sx_plan* plan, const double* a, const double* b, double* c, int dir); /* ref: :130-206 */
+int sx_fc_filter(sx_plan* plan, double* a);                                      /* ref: :1082-1115 */
+/* ref: gradre (pseudospec_hd.f90:209-319): (A.grad)A */
+int sx_gradre(sx_plan* plan, const double* a, const double* b, const double* c, double* d, double* e, double* f);
+/* ref: prodre (pseudospec_hd.f90:322-402): curl(A) x A */
+int sx_prodre(sx_plan* plan, const double* a, const double* b, const double* c, double* d, double* e, double* f);
+/* diagnostics; results valid on rank 0 after the caller's reduction (single rank: final) */
+int sx_energy(sx_plan* plan, const double* a, const double* b, const double* c, int kin, double* out);   /* ref: :405-635 */
+int sx_divergence(sx_plan* plan, const double* a, const double* b, const double* c, double* out);        /* ref: :1118-1235 */
+int sx_cross(sx_plan* plan, const double* a, const double* b, const double* c, const double* d,
+             const double* e, const double* f, int kin, double* out);                                     /* ref: :778-940 */
+int sx_hdcheck(sx_plan* plan, const double* a, const double* b, const double* c, const double* d,
+               const double* e, const double* f, double* eng, double* ens, double* pot);                  /* ref: :943-1005 */
+
+/* ---- boundary module -------------------------------------------------------- */
+/* ref: sol_project (boundary_mod.fpp:197-402); d returns the potential in the mixed domain */
+int sx_sol_project(sx_plan* plan, double* a, double* b, double* c, double* d, int bctarget, int bczsta, int bczend);
+/* ref: v_imposebc_and_project (vboundary.f90:67-151); no-slip walls, v_zsta/v_zend = wall (vx,vy) */
+int sx_v_imposebc_and_project(sx_plan* plan, double* vx, double* vy, double* vz, double* pr, int rki,
+                              const double v_zsta[2], const double v_zend[2]);
+/* ref: bouncheck_z (boundary_mod.fpp:681-801); b may be NULL */
+int sx_bouncheck_z(sx_plan* plan, double* bot, double* top, const double* a, const double* b);
+/* ref: vdiagnostic (vboundary.f90:214-269): out[5] = div, vt0, vtL, vn0, vnL */
+int sx_vdiagnostic(sx_plan* plan, const double* a, const double* b, const double* c, double out[5]);
+
+/* ---- the RK substep (include/hd/hd_rkstep{1,2}.f90) --------------------------------- */
+/* Device-resident HD state owned by the plan.  put/get move whole fields in the reference
+ * layout; NULL pointers are skipped. */
+int sx_hd_put_state(sx_plan* plan, const double* vx_host, const double* vy_host, const double* vz_host,
+                    const double* pr_host, const double* fx_host, const double* fy_host, const double* fz_host);
+int sx_hd_get_state(sx_plan* plan, double* vx_host, double* vy_host, double* vz_host, double* pr_host);
+/* device pointers of the plan-owned state: which = 0..2 v, 3 pr, 4..6 f, 7..9 RK base C1..C3 */
+int sx_hd_state_ptr(sx_plan* plan, int which, double** dptr);
+/* ref: hd_rkstep1.f90:4-6 (C1..C3 <- v) */
+int sx_hd_rkstep1(sx_plan* plan);
+/* ref: hd_rkstep2.f90:3-36, one substep `o` of `ord`.  impl = 0: fused B200 path (default);
+ * impl = 1: the same substep composed from the per-operator entry points above. */
+int sx_hd_rkstep2(sx_plan* plan, int o, double dt, double nu, const double v_zsta[2], const double v_zend[2], int impl);
+/* one full time step (rkstep1 + ord substeps) on host arrays: H2D of v,pr,f, compute, D2H of v,pr */
+int sx_hd_step_host(sx_plan* plan, double* vx_host, double* vy_host, double* vz_host, double* pr_host,
+                    const double* fx_host, const double* fy_host, const double* fz_host, double dt, double nu,
+                    const double v_zsta[2], const double v_zend[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

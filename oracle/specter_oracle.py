@@ -1,0 +1,746 @@
+"""CPU oracle for the SPECTER per-RK-substep hot path (numpy / scipy.fft, FP64).
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it, and only as the checker / reported baseline.
+The product path (``specter_b200``) never imports anything from ``oracle/``.
+
+It is a literal restatement -- same pass structure, same (non)normalisation,
+same quirks -- of the reference's Fortran for this path.  Every function cites
+the reference ``file:line`` (relative to /root/reference/src) it follows.
+
+PARITY PINNING.  The reference (Fortran + MPI + FFTW) cannot be compiled in
+this image (no gfortran / MPI / FFTW) and ships no golden
+vectors: its own tests (src/tests/*.f90) only *print* error norms of analytic
+identities.  The oracle is therefore pinned against (i) those analytic
+known-answer identities re-stated as assertions (tests/test_oracle_*.py),
+(ii) the reference's FC-Gram table fixtures, (iii) mpmath spot checks.  Bitwise
+parity with an FFTW build is "unpinned" beyond FFT rounding (FFTW is a
+third-party dependency absent from /root/reference; the DFT is mathematically
+fixed: forward sign -1, backward +1, both unnormalised).
+
+Array conventions (memory-identical to the Fortran arrays):
+  spectral / mixed  Fortran ``a(nz,ny,ista:iend)``  <->  numpy ``a[i,j,k]`` shape (nxl,ny,nz), C order
+  real              Fortran ``r(nx,ny,ksta:kend)``  <->  numpy ``r[k,j,i]`` shape (nzl,ny,nx), C order
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.fft as sfft
+
+IM = 1j
+_WORKERS = int(os.environ.get("SPECTER_ORACLE_WORKERS", "0")) or (os.cpu_count() or 1)
+
+
+def set_workers(n: int) -> None:
+    global _WORKERS
+    _WORKERS = max(1, int(n))
+
+
+# ----------------------------------------------------------------------------
+# slab partition                                             fftp/fftp.fpp:1154-1184
+# ----------------------------------------------------------------------------
+def range_(n1: int, n2: int, nprocs: int, irank: int):
+    """``range`` (fftp.fpp:1177-1181): 1-based inclusive [sta,end] of rank irank."""
+    iwork1 = (n2 - n1 + 1) // nprocs
+    iwork2 = (n2 - n1 + 1) % nprocs
+    ista = irank * iwork1 + n1 + min(irank, iwork2)
+    iend = ista + iwork1 - 1
+    if iwork2 > irank:
+        iend += 1
+    return ista, iend
+
+
+# ----------------------------------------------------------------------------
+# FC-Gram tables                                     fftp/fcgram_mod.f90:180-365
+# ----------------------------------------------------------------------------
+def load_dirichlet_tables(tdir: str, C: int, d: int) -> np.ndarray:
+    """``load_dirichlet_tables`` (fcgram_mod.f90:228-252): dir = A . Q^T, shape (C,d).
+
+    Files are raw little-endian f64 streams in Fortran (column-major) order.
+    """
+    A = np.fromfile(os.path.join(tdir, f"A{C}-{d}.dat"), dtype="<f8")
+    Q = np.fromfile(os.path.join(tdir, f"Q{d}.dat"), dtype="<f8")
+    if A.size != C * d or Q.size != d * d:
+        raise ValueError("FC-Gram table size mismatch")
+    A = A.reshape(d, C).T  # A(C,d) column-major
+    Q = Q.reshape(d, d).T
+    return np.ascontiguousarray(A @ Q.T)
+
+
+def load_neumann_tables(tdir: str, d: int, dz: float, order: int) -> np.ndarray:
+    """``load_neumann_tables`` (fcgram_mod.f90:261-365): neu = Q(d,:) . Qn^T,
+    last entry scaled by (dz/dxp)^order.  order=1 -> Q1n, order=2 -> Q2n."""
+    Q = np.fromfile(os.path.join(tdir, f"Q{d}.dat"), dtype="<f8").reshape(d, d).T
+    raw = np.fromfile(os.path.join(tdir, f"Q{order}n{d}.dat"), dtype="<f8")
+    dxp = raw[0]
+    Qn = raw[1:].reshape(d, d).T
+    neu = Qn @ Q[d - 1, :]  # neu(k) = sum_j Q(d,j) Qn(k,j)   (fcgram_mod.f90:355-358)
+    neu = np.array(neu, dtype=np.float64)
+    neu[d - 1] *= (dz / dxp) ** order
+    return neu
+
+
+# ----------------------------------------------------------------------------
+# grids, wavenumbers                                      specter.fpp:683-800
+# ----------------------------------------------------------------------------
+@dataclass
+class Grid:
+    nx: int
+    ny: int
+    nz: int
+    Cz: int
+    oz: int
+    Lx: float = 1.0
+    Ly: float = 1.0
+    Lz: float = 1.0
+    tdir: str = ""
+    nprocs: int = 1
+    myrank: int = 0
+    ord: int = 2
+    x: np.ndarray = field(init=False, repr=False)
+    y: np.ndarray = field(init=False, repr=False)
+    z: np.ndarray = field(init=False, repr=False)
+
+    def __post_init__(self):
+        nx, ny, nz, Cz = self.nx, self.ny, self.nz, self.Cz
+        pi = np.pi
+        # periodic x,y (specter.fpp:683-724); non-periodic z (:742-749)
+        self.dx = self.Lx * 2.0 * pi / nx
+        self.Dkx = 1.0 / self.Lx
+        self.dy = self.Ly * 2.0 * pi / ny
+        self.Dky = 1.0 / self.Ly
+        if Cz == 0:
+            self.dz = self.Lz * 2.0 * pi / nz
+            self.Dkz = 1.0 / self.Lz
+        else:
+            self.dz = self.Lz / (nz - Cz - 1)
+            self.Dkz = 2.0 * pi / (self.dz * nz)
+        self.x = self.dx * np.arange(nx, dtype=np.float64)
+        self.y = self.dy * np.arange(ny, dtype=np.float64)
+        self.z = self.dz * np.arange(nz, dtype=np.float64)
+        # wavenumbers (specter.fpp:772-789): index n/2+1 holds -n/2
+        self.kx_full = self._kvec(nx) * self.Dkx
+        self.ky = self._kvec(ny) * self.Dky
+        self.kz = self._kvec(nz) * self.Dkz
+        self.nxh = nx // 2 + 1
+        self.ista, self.iend = range_(1, self.nxh, self.nprocs, self.myrank)
+        self.ksta, self.kend = range_(1, nz, self.nprocs, self.myrank)
+        self.pkend = min(nz - Cz, self.kend)  # specter.fpp:750
+        self.nxl = self.iend - self.ista + 1
+        self.nzl = self.kend - self.ksta + 1
+        self.kx = self.kx_full[self.ista - 1 : self.iend]  # local kx(ista:iend)
+        # kk2, khom (specter.fpp:791-800)
+        self.kk2 = (
+            self.kx[:, None, None] ** 2 + self.ky[None, :, None] ** 2 + self.kz[None, None, :] ** 2
+        )
+        self.khom = np.sqrt(self.kk2[:, :, 0])
+        self.N = float(nx) * float(ny) * float(nz)
+        if self.tdir and Cz > 0:
+            self.dir = load_dirichlet_tables(self.tdir, Cz, self.oz)
+        else:
+            self.dir = None
+        self.neu = None
+        self.neu2 = None
+
+    @staticmethod
+    def _kvec(n: int) -> np.ndarray:
+        k = np.empty(n, dtype=np.float64)
+        if n == 1:
+            k[0] = 0.0
+            return k
+        for i in range(1, n // 2 + 1):
+            k[i - 1] = float(i - 1)
+            k[i + n // 2 - 1] = float(i - n // 2 - 1)
+        return k
+
+    def load_neumann(self):
+        self.neu = load_neumann_tables(self.tdir, self.oz, self.dz, 1)
+        self.neu2 = load_neumann_tables(self.tdir, self.oz, self.dz, 2)
+
+    # shapes
+    def cshape(self):
+        return (self.nxl, self.ny, self.nz)
+
+    def rshape(self):
+        return (self.nzl, self.ny, self.nx)
+
+
+# ----------------------------------------------------------------------------
+# transforms                                                   fftp/fftp.fpp
+# ----------------------------------------------------------------------------
+def fc_continue_z(g: Grid, a: np.ndarray) -> None:
+    """FC-Gram continuation, in place on the last axis (fftp.fpp:757-772).
+
+    f(n-C+ii) = sum_jj dir(ii,jj) f(n-C-d+jj) + dir(C-ii+1,jj) f(d-jj+1), summed
+    in the reference's order jj=1..d.
+    """
+    n, C, d = g.nz, g.Cz, g.oz
+    if C <= 0:
+        return
+    dirm = g.dir  # (C,d)
+    dflip = dirm[::-1, :]  # dir(C-ii+1, jj)
+    # jj = 1
+    acc = dirm[:, 0] * a[..., n - C - d : n - C - d + 1] + dflip[:, 0] * a[..., d - 1 : d]
+    for jj in range(2, d + 1):
+        acc = acc + dirm[:, jj - 1] * a[..., n - C - d + jj - 1 : n - C - d + jj] \
+                  + dflip[:, jj - 1] * a[..., d - jj : d - jj + 1]
+    a[..., n - C :] = acc
+
+
+def fftp1d_real_to_complex_z(g: Grid, a: np.ndarray) -> np.ndarray:
+    """fftp.fpp:720-786: continuation + unnormalised forward c2c along z, in place."""
+    fc_continue_z(g, a)
+    a[...] = sfft.fft(a, axis=-1, norm="backward", workers=_WORKERS)
+    return a
+
+
+def fftp1d_complex_to_real_z(g: Grid, a: np.ndarray) -> np.ndarray:
+    """fftp.fpp:1060-1094: unnormalised backward c2c along z, in place."""
+    a[...] = sfft.ifft(a, axis=-1, norm="forward", workers=_WORKERS)
+    return a
+
+
+def fftp2d_real_to_complex_xy(g: Grid, r: np.ndarray) -> np.ndarray:
+    """fftp.fpp:428-524 (single rank): 2-D r2c over (x,y) per z-plane, then the
+    transpose (x,y,z)->(z,y,x).  r[k,j,i] -> out[i,j,k]."""
+    c = sfft.rfft(r, axis=2, norm="backward", workers=_WORKERS)
+    c = sfft.fft(c, axis=1, norm="backward", workers=_WORKERS)
+    return np.ascontiguousarray(c.transpose(2, 1, 0))
+
+
+def fftp2d_complex_to_real_xy(g: Grid, a: np.ndarray) -> np.ndarray:
+    """fftp.fpp:824-919 (single rank): transpose, then 2-D c2r (FFTW semantics:
+    complex backward along y, then Hermitian c2r along x which ignores the
+    imaginary parts of the kx=0 and kx=nx/2 entries).  a[i,j,k] -> r[k,j,i]."""
+    c = a.transpose(2, 1, 0)
+    c = sfft.ifft(c, axis=1, norm="forward", workers=_WORKERS)
+    return sfft.irfft(c, n=g.nx, axis=2, norm="forward", workers=_WORKERS)
+
+
+def fftp3d_real_to_complex(g: Grid, r: np.ndarray) -> np.ndarray:
+    """fftp.fpp:388-425 (y periodic branch)."""
+    out = fftp2d_real_to_complex_xy(g, r)
+    return fftp1d_real_to_complex_z(g, out)
+
+
+def fftp3d_complex_to_real(g: Grid, a: np.ndarray) -> np.ndarray:
+    """fftp.fpp:789-821.  (The reference destroys its input; this does not.)"""
+    c = a.copy()
+    fftp1d_complex_to_real_z(g, c)
+    return fftp2d_complex_to_real_xy(g, c)
+
+
+# ----------------------------------------------------------------------------
+# spectral operators                               pseudo/pseudospec_hd.f90
+# ----------------------------------------------------------------------------
+def derivk(g: Grid, a: np.ndarray, dir: int) -> np.ndarray:
+    """pseudospec_hd.f90:28-94: b = im*k_dir*a."""
+    if dir == 1:
+        return (IM * g.kx)[:, None, None] * a
+    if dir == 2:
+        return (IM * g.ky)[None, :, None] * a
+    return (IM * g.kz)[None, None, :] * a
+
+
+def laplak(g: Grid, a: np.ndarray) -> np.ndarray:
+    """pseudospec_hd.f90:97-127: b = -kk2*a."""
+    return -g.kk2 * a
+
+
+def curlk(g: Grid, a: np.ndarray, b: np.ndarray, dir: int) -> np.ndarray:
+    """pseudospec_hd.f90:130-206."""
+    if dir == 1:
+        c1 = derivk(g, a, 3)
+        c2 = derivk(g, b, 2)
+        return c2 - c1
+    if dir == 2:
+        c1 = derivk(g, a, 3)
+        c2 = derivk(g, b, 1)
+        return c1 - c2
+    c1 = derivk(g, a, 2)
+    c2 = derivk(g, b, 1)
+    return c2 - c1
+
+
+def fc_filter_factors(g: Grid):
+    """The three separable factors of ``fc_filter`` (pseudospec_hd.f90:1099-1109)."""
+    alpha = 16.0 * np.log(10.0)
+    p2 = 100.0  # 2*p, p=50d0
+    fx = np.exp(-alpha * (2 * g.kx / g.nx / g.Dkx) ** p2)
+    fy = np.exp(-alpha * (2 * g.ky / g.ny / g.Dky) ** p2)
+    fz = np.exp(-alpha * (2 * g.kz / g.nz / g.Dkz) ** p2)
+    return fx, fy, fz
+
+
+def fc_filter(g: Grid, a: np.ndarray) -> np.ndarray:
+    """pseudospec_hd.f90:1082-1115: a*fx*fy*fz (left-to-right), in place."""
+    fx, fy, fz = fc_filter_factors(g)
+    a *= fx[:, None, None]
+    a *= fy[None, :, None]
+    a *= fz[None, None, :]
+    return a
+
+
+def _phys(g: Grid):
+    """Local physical z-planes ksta..pkend as a slice of the local real array."""
+    return slice(0, g.pkend - g.ksta + 1)
+
+
+def gradre(g: Grid, a, b, c):
+    """(A.grad)A, pseudospec_hd.f90:209-319.  Products only on k<=pkend; the other
+    planes of rx,ry,rz are uninitialised in the reference (we use 0) and are
+    overwritten by the continuation in the forward transform."""
+    ph = _phys(g)
+    rx = np.zeros(g.rshape())
+    ry = np.zeros(g.rshape())
+    rz = np.zeros(g.rshape())
+    comps = (a, b, c)
+    for d_ in (1, 2, 3):
+        r1 = fftp3d_complex_to_real(g, comps[d_ - 1])
+        r2 = fftp3d_complex_to_real(g, derivk(g, a, d_))
+        r3 = fftp3d_complex_to_real(g, derivk(g, b, d_))
+        r4 = fftp3d_complex_to_real(g, derivk(g, c, d_))
+        rx[ph] += r1[ph] * r2[ph]
+        ry[ph] += r1[ph] * r3[ph]
+        rz[ph] += r1[ph] * r4[ph]
+    tmp = 1.0 / g.N ** 2
+    rx[ph] *= tmp
+    ry[ph] *= tmp
+    rz[ph] *= tmp
+    return (fftp3d_real_to_complex(g, rx), fftp3d_real_to_complex(g, ry),
+            fftp3d_real_to_complex(g, rz))
+
+
+def prodre(g: Grid, a, b, c):
+    """curl(A) x A, pseudospec_hd.f90:322-402."""
+    ph = _phys(g)
+    r1 = fftp3d_complex_to_real(g, curlk(g, b, c, 1))
+    r2 = fftp3d_complex_to_real(g, curlk(g, a, c, 2))
+    r3 = fftp3d_complex_to_real(g, curlk(g, a, b, 3))
+    r4 = fftp3d_complex_to_real(g, a)
+    r5 = fftp3d_complex_to_real(g, b)
+    r6 = fftp3d_complex_to_real(g, c)
+    tmp = 1.0 / g.N ** 2
+    rx = np.zeros(g.rshape()); ry = np.zeros(g.rshape()); rz = np.zeros(g.rshape())
+    rx[ph] = (r2[ph] * r6[ph] - r5[ph] * r3[ph]) * tmp
+    ry[ph] = (r3[ph] * r4[ph] - r6[ph] * r1[ph]) * tmp
+    rz[ph] = (r1[ph] * r5[ph] - r4[ph] * r2[ph]) * tmp
+    return (fftp3d_real_to_complex(g, rx), fftp3d_real_to_complex(g, ry),
+            fftp3d_real_to_complex(g, rz))
+
+
+# ----------------------------------------------------------------------------
+# diagnostics                      pseudospec_hd.f90:405-635, 778-940, 1118-1235
+# ----------------------------------------------------------------------------
+def _weights(g: Grid) -> np.ndarray:
+    w = np.full(g.nxl, 2.0)
+    if g.ista == 1:
+        w[0] = 1.0
+    return w
+
+
+def _mean_phys(g: Grid, R1: np.ndarray, tmp: float) -> float:
+    """Weighted sum over kx (1 for kx=0 else 2), ky and physical z rows."""
+    nph = g.nz - g.Cz
+    return float(np.sum(_weights(g)[:, None, None] * R1[:, :, :nph] * tmp))
+
+
+def _abs2_iz(g: Grid, c: np.ndarray) -> np.ndarray:
+    c1 = c.copy()
+    fftp1d_complex_to_real_z(g, c1)
+    return c1.real ** 2 + c1.imag ** 2
+
+
+def energy(g: Grid, a, b, c, kin: int) -> float:
+    """pseudospec_hd.f90:405-635.  kin=0 reproduces the reference's quirk: the
+    y-component of the curl is added twice and the z-component never (:527,:540)."""
+    tmp = 1.0 / g.N ** 2 / float(g.nz - g.Cz)
+    if kin == 1:
+        R1 = _abs2_iz(g, a) + _abs2_iz(g, b) + _abs2_iz(g, c)
+    elif kin == 0:
+        R1 = _abs2_iz(g, curlk(g, b, c, 1))
+        R1 = R1 + _abs2_iz(g, curlk(g, a, c, 2))
+        R1 = R1 + _abs2_iz(g, curlk(g, a, c, 2))
+    else:
+        C1 = curlk(g, b, c, 1)
+        C2 = curlk(g, a, c, 2)
+        C3 = curlk(g, a, b, 3)
+        C4 = curlk(g, C2, C3, 1)
+        C3n = curlk(g, C1, C3, 2)
+        C1n = curlk(g, C1, C2, 3)
+        R1 = _abs2_iz(g, C4) + _abs2_iz(g, C3n) + _abs2_iz(g, C1n)
+    return _mean_phys(g, R1, tmp)
+
+
+def cross(g: Grid, a, b, c, d, e, f, kin: int) -> float:
+    """pseudospec_hd.f90:778-940 (kin=1: <A.B>; kin=0: <curl A . curl B>)."""
+    tmp = 1.0 / g.N ** 2 / float(g.nz - g.Cz)
+
+    def prod(p, q):
+        c1 = p.copy(); c2 = q.copy()
+        fftp1d_complex_to_real_z(g, c1); fftp1d_complex_to_real_z(g, c2)
+        return (c1 * np.conj(c2)).real
+
+    if kin == 1:
+        r1 = prod(a, d) + prod(b, e) + prod(c, f)
+    else:
+        r1 = prod(curlk(g, b, c, 1), curlk(g, e, f, 1))
+        r1 = r1 + prod(curlk(g, a, c, 2), curlk(g, d, f, 2))
+        r1 = r1 + prod(curlk(g, a, b, 3), curlk(g, d, e, 3))
+    return _mean_phys(g, r1, tmp)
+
+
+def divergence(g: Grid, a, b, c) -> float:
+    """pseudospec_hd.f90:1118-1235."""
+    tmp = 1.0 / g.N ** 2 / float(g.nz - g.Cz)
+    C2 = derivk(g, a, 1)
+    C2 = C2 + derivk(g, b, 2)
+    C2 = C2 + derivk(g, c, 3)
+    return _mean_phys(g, _abs2_iz(g, C2), tmp)
+
+
+def bouncheck_z(g: Grid, a, b=None):
+    """boundary_mod.fpp:681-801: mean |a|^2 (+|b|^2) on rows z=0 and z=Lz."""
+    tmp = (1.0 / g.N) ** 2
+    top_row = g.nz - g.Cz - 1
+    A2 = _abs2_iz(g, a)
+    R1 = A2[:, :, 0]
+    R2 = A2[:, :, top_row]
+    if b is not None:
+        B2 = _abs2_iz(g, b)
+        R1 = R1 + B2[:, :, 0]
+        R2 = R2 + B2[:, :, top_row]
+    w = _weights(g)[:, None]
+    return float(np.sum(w * R1 * tmp)), float(np.sum(w * R2 * tmp))
+
+
+def hdcheck(g: Grid, a, b, c, d, e, f):
+    """pseudospec_hd.f90:943-1005 -> the balance.txt columns (eng, ens, pot)."""
+    eng = energy(g, a, b, c, 1)
+    ens = energy(g, a, b, c, 0)
+    pot = cross(g, a, b, c, d, e, f, 1)
+    return eng, ens, pot
+
+
+def vdiagnostic(g: Grid, a, b, c):
+    """vboundary.f90:214-269 -> noslip_diagnostic.txt columns."""
+    tm1 = divergence(g, a, b, c)
+    tmp, tmq = bouncheck_z(g, a, b)
+    tmr, tms = bouncheck_z(g, c)
+    return tm1, tmp, tmq, tmr, tms
+
+
+def normvec(g: Grid, a, b, c, d: float, kin: int):
+    """pseudospec_hd.f90:1238-1286."""
+    rmp = np.sqrt(d / energy(g, a, b, c, kin))
+    a *= rmp; b *= rmp; c *= rmp
+
+
+# ----------------------------------------------------------------------------
+# boundary module                                    boundary/boundary_mod.fpp
+# ----------------------------------------------------------------------------
+def goto_domain_w_boundaries(g: Grid, *fields):
+    """boundary_mod.fpp:72-150: z-IFFT, then x 1/nz on physical rows only."""
+    tmp = 1.0 / float(g.nz)
+    nph = g.nz - g.Cz
+    for a in fields:
+        fftp1d_complex_to_real_z(g, a)
+        a[:, :, :nph] *= tmp
+
+
+def goto_3d_fourier(g: Grid, *fields):
+    """boundary_mod.fpp:153-194."""
+    for a in fields:
+        fftp1d_real_to_complex_z(g, a)
+
+
+def poisson_inhomogeneous(g: Grid, a, b, c) -> np.ndarray:
+    """boundary_mod.fpp:405-448.  The 0/0 at mode (1,1,1) is overwritten by 0."""
+    num = (g.kx[:, None, None] * a + g.ky[None, :, None] * b + g.kz[None, None, :] * c)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = -IM * num / g.kk2
+    if g.ista == 1:
+        d[0, 0, 0] = 0.0
+    return d
+
+
+def laplace_z(g: Grid, bc: np.ndarray, bczsta: int, bczend: int):
+    """boundary_mod.fpp:451-678.  bc[i,j,0:2] -> a[i,j,k], b[i,j,k] for all nz rows."""
+    Lz = g.Lz
+    kh = g.khom
+    bc1 = bc[:, :, 0]
+    bc2 = bc[:, :, 1]
+    coef1 = np.empty_like(bc1)
+    coef2 = np.empty_like(bc1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e1 = np.exp(-kh * Lz)
+        if bczsta == bczend and bczsta == 0:  # pure Dirichlet  (:499-528)
+            tmp = 1.0 / (1 - np.exp(-2 * kh * Lz))
+            coef1[...] = (bc2 - bc1 * e1) * tmp
+            coef2[...] = (bc1 - bc2 * e1) * tmp
+            if g.ista == 1:
+                coef1[0, 0] = (bc2[0, 0] - bc1[0, 0]) / Lz
+                coef2[0, 0] = bc1[0, 0]
+        elif bczsta == bczend and bczsta == 1:  # pure Neumann   (:531-560)
+            tmp = 1.0 / (kh * (1 - np.exp(-2 * kh * Lz)))
+            coef1[...] = (bc2 - bc1 * e1) * tmp
+            coef2[...] = (-bc1 + bc2 * e1) * tmp
+            if g.ista == 1:
+                coef1[0, 0] = bc1[0, 0]
+                coef2[0, 0] = 0.0
+        elif bczsta == bczend and bczsta == 2:  # pure Robin     (:563-592)
+            tmp = 1.0 / (2 * kh)
+            coef1[...] = bc2 * tmp
+            coef2[...] = bc1 * tmp
+            if g.ista == 1:
+                coef1[0, 0] = bc1[0, 0]
+                coef2[0, 0] = 0.0
+        elif bczsta == 0 and bczend == 2:  # Dirichlet bottom / Robin top (:595-624)
+            tmp = 1.0 / (2 * kh)
+            coef1[...] = bc2 * tmp
+            coef2[...] = (bc1 * 2 * kh - bc2 * e1) * tmp
+            if g.ista == 1:
+                coef1[0, 0] = bc2[0, 0]
+                coef2[0, 0] = bc1[0, 0]
+        else:
+            raise ValueError("[ERROR] Unsupported BC combination in call to laplace_z.")
+    z = g.z
+    ep = np.exp(kh[:, :, None] * (z[None, None, :] - Lz))
+    em = np.exp(-kh[:, :, None] * z[None, None, :])
+    a = coef1[:, :, None] * ep + coef2[:, :, None] * em
+    b = kh[:, :, None] * (coef1[:, :, None] * ep - coef2[:, :, None] * em)
+    if g.ista == 1:  # (0,0) mode: linear profile using real(coef)  (:635-639)
+        a[0, 0, :] = coef1[0, 0].real * z + coef2[0, 0].real
+        b[0, 0, :] = coef1[0, 0].real
+    return a, b
+
+
+def sol_project(g: Grid, a, b, c, bctarget: int, bczsta: int, bczend: int):
+    """boundary_mod.fpp:197-402.  a,b,c updated in place; returns d (mixed domain)."""
+    d = poisson_inhomogeneous(g, a, b, c)
+    a -= IM * g.kx[:, None, None] * d
+    b -= IM * g.ky[None, :, None] * d
+    c -= IM * g.kz[None, None, :] * d
+    tmp = 1.0 / float(g.nz)
+    top = g.nz - g.Cz - 1
+    if bctarget == 0:
+        C1 = d * tmp
+    elif bctarget == 1:
+        C1 = c * tmp
+    else:
+        raise ValueError("bctarget")
+    C2 = None
+    if bczsta == 2 or bczend == 2:
+        C2 = derivk(g, C1, 3)
+        fftp1d_complex_to_real_z(g, C2)
+    fftp1d_complex_to_real_z(g, C1)
+    bc = np.empty((g.nxl, g.ny, 2), dtype=np.complex128)
+    if bczsta == 0:
+        bc[:, :, 0] = -C1[:, :, 0] if bctarget == 0 else C1[:, :, 0]
+    elif bczsta == 2:
+        bc[:, :, 0] = C2[:, :, 0] - g.khom * C1[:, :, 0]
+    else:
+        raise ValueError("[ERROR] Unsupported BC kind in call to sol_project.")
+    if bczend == 0:
+        bc[:, :, 1] = -C1[:, :, top] if bctarget == 0 else C1[:, :, top]
+    elif bczend == 2:
+        bc[:, :, 1] = -(C2[:, :, top] + g.khom * C1[:, :, top])
+    else:
+        raise ValueError("[ERROR] Unsupported BC kind in call to sol_project.")
+    C2, C3 = laplace_z(g, bc, bczsta + bctarget, bczend + bctarget)
+    if bctarget == 0:
+        d = C1 + C2
+    else:
+        fftp1d_complex_to_real_z(g, d)
+        d = d * tmp + C2
+    fftp1d_real_to_complex_z(g, C2)
+    fftp1d_real_to_complex_z(g, C3)
+    a -= IM * g.kx[:, None, None] * C2
+    b -= IM * g.ky[None, :, None] * C2
+    c -= C3
+    return d
+
+
+def noslip_z(g: Grid, o: int, vx, vy, pr, vbound, pos: int):
+    """vboundary.f90:154-211 (vx,vy in the mixed domain)."""
+    ind = 0 if pos == 0 else g.nz - g.Cz - 1
+    tmp = 1.0 / float(o)
+    if o != g.ord:
+        tmp = float(o + 1) * tmp
+    vx[:, :, ind] = IM * g.kx[:, None] * pr[:, :, ind] * tmp
+    vy[:, :, ind] = IM * g.ky[None, :] * pr[:, :, ind] * tmp
+    if g.ista == 1:
+        vx[0, 0, ind] = g.nx * g.ny * vbound[0]
+        vy[0, 0, ind] = g.nx * g.ny * vbound[1]
+
+
+def v_imposebc_and_project(g: Grid, vx, vy, vz, pr, rki: int,
+                           v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0)):
+    """vboundary.f90:67-151.  vx,vy,vz in place; returns the new pr."""
+    goto_domain_w_boundaries(g, vx, vy)
+    noslip_z(g, rki, vx, vy, pr, v_zsta, 0)
+    noslip_z(g, rki, vx, vy, pr, v_zend, 1)
+    goto_3d_fourier(g, vx, vy)
+    return sol_project(g, vx, vy, vz, 1, 0, 0)
+
+
+# ----------------------------------------------------------------------------
+# the HD substep                 include/hd/hd_rkstep{1,2}.f90, specter.fpp:1142-1161
+# ----------------------------------------------------------------------------
+@dataclass
+class HDState:
+    vx: np.ndarray
+    vy: np.ndarray
+    vz: np.ndarray
+    pr: np.ndarray
+    fx: np.ndarray
+    fy: np.ndarray
+    fz: np.ndarray
+
+
+def hd_rkstep2(g: Grid, s: HDState, C1, C2, C3, o: int, dt: float, nu: float,
+               v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0)):
+    """One RK substep, include/hd/hd_rkstep2.f90:3-36."""
+    rmp = 1.0 / float(o)
+    C4, C5, C6 = gradre(g, s.vx, s.vy, s.vz)
+    fc_filter(g, C4); fc_filter(g, C5); fc_filter(g, C6)
+    s.vx = laplak(g, s.vx); s.vy = laplak(g, s.vy); s.vz = laplak(g, s.vz)
+    s.vx = C1 + dt * (nu * s.vx - C4 + s.fx) * rmp
+    s.vy = C2 + dt * (nu * s.vy - C5 + s.fy) * rmp
+    s.vz = C3 + dt * (nu * s.vz - C6 + s.fz) * rmp
+    s.pr = v_imposebc_and_project(g, s.vx, s.vy, s.vz, s.pr, o, v_zsta, v_zend)
+
+
+def hd_step(g: Grid, s: HDState, dt: float, nu: float, on_substep=None, **kw):
+    """One full time step: rkstep1 copy + ``ord`` substeps (specter.fpp:1142-1161)."""
+    C1 = s.vx.copy(); C2 = s.vy.copy(); C3 = s.vz.copy()
+    for o in range(g.ord, 0, -1):
+        hd_rkstep2(g, s, C1, C2, C3, o, dt, nu, **kw)
+        if on_substep is not None:
+            on_substep(o, s)
+
+
+# ----------------------------------------------------------------------------
+# synthetic inputs               pseudospec_mod.fpp:101-119, initialv.f90, initialfv.f90
+# ----------------------------------------------------------------------------
+class Randu:
+    """Park-Miller ``randu`` (pseudospec_mod.fpp:101-119); ``am=1./im`` is
+    evaluated in single precision before widening."""
+    IQ, IR, MASK, IA, IMOD = 127773, 2836, 123459876, 16807, 2147483647
+
+    def __init__(self, seed: int):
+        self.idum = int(seed)
+        self.am = float(np.float32(1.0) / np.float32(self.IMOD))
+
+    def __call__(self) -> float:
+        idum = self.idum ^ self.MASK
+        k = idum // self.IQ
+        idum = self.IA * (idum - k * self.IQ) - self.IR * k
+        if idum < 0:
+            idum += self.IMOD
+        r = self.am * idum
+        r = (r - 0.5) * 2
+        self.idum = idum ^ self.MASK
+        return r
+
+
+_CR_ROOTS = [np.float64(np.float32(v)) for v in (
+    4.73004074, 7.85320462, 10.99560784, 14.13716549,
+    17.27875966, 20.42035225, 23.56194490, 26.70353756)]
+
+
+def initialv(g: Grid, seed=1000, kdn=2.0, kup=4.0, vparam0=1.0, vparam1=2.0, u0=1.0):
+    """Chandrasekhar-Reid no-slip solenoidal noise, initialv.f90:25-203 (1 rank,
+    single-stream randu order).  Returns vx,vy,vz in (kz,ky,kx)."""
+    assert g.nprocs == 1
+    rnd = Randu(seed)
+    nph = g.nz - g.Cz
+    z = g.z[:nph]
+    Lz = g.Lz
+    pi = np.pi
+    C1 = np.zeros(g.cshape(), dtype=np.complex128)
+    C2 = np.zeros_like(C1)
+    C3 = np.zeros_like(C1)
+    ny = g.ny
+    for kk in range(int(vparam0), int(vparam1) + 1):
+        if kk <= 8:
+            rm1 = float(_CR_ROOTS[kk - 1])
+        elif kk % 2 == 1:
+            rm1 = (2 * kk - 0.5) * pi
+        else:
+            rm1 = (2 * kk + 0.5) * pi
+        s = rm1 * (z / Lz - 0.5)
+        if kk % 2 == 1:
+            dphi = rm1 / Lz * (np.sinh(s) / np.cosh(0.5 * rm1) + np.sin(s) / np.cos(0.5 * rm1))
+            phi = np.cosh(s) / np.cosh(0.5 * rm1) - np.cos(s) / np.cos(0.5 * rm1)
+        else:
+            dphi = rm1 / Lz * (np.cosh(s) / np.sinh(0.5 * rm1) - np.cos(s) / np.sin(0.5 * rm1))
+            phi = np.sinh(s) / np.sinh(0.5 * rm1) - np.sin(s) / np.sin(0.5 * rm1)
+        psi = np.sin(kk * pi * z / Lz)
+
+        def add(i, j, mirror):
+            k2 = g.kk2[i, j, 0]
+            if not (k2 <= kup ** 2 and k2 >= kdn ** 2):
+                return
+            rmp = 2 * pi * rnd()
+            rmq = rnd() / np.sqrt(k2 + rm1 ** 2) ** 3
+            ph = np.cos(rmp) + IM * np.sin(rmp)
+            C1[i, j, :nph] += rmq * ph * dphi
+            C2[i, j, :nph] += rmq * ph * phi
+            if mirror:
+                jm = (ny - j) % ny  # Fortran index ny-j+2
+                C1[i, jm, :nph] = np.conj(C1[i, j, :nph])
+                C2[i, jm, :nph] = np.conj(C2[i, j, :nph])
+            if kk % 2 == 0:
+                rmp = pi / 2 + rmp
+            rmq = rnd() / np.sqrt(k2 + kk ** 2 * pi ** 2 / Lz ** 2) ** 2
+            ph = np.cos(rmp) + IM * np.sin(rmp)
+            C3[i, j, :nph] += rmq * ph * psi
+            if mirror:
+                C3[i, jm, :nph] = np.conj(C3[i, j, :nph])
+
+        for j in range(0, ny // 2 + 1):
+            add(0, j, True)
+        for i in range(1, g.nxl):
+            for j in range(ny):
+                add(i, j, False)
+    vz = -(derivk(g, derivk(g, C2, 1), 1) + derivk(g, derivk(g, C2, 2), 2))
+    vx = derivk(g, C1, 1) + derivk(g, C3, 2)
+    vy = derivk(g, C1, 2) - derivk(g, C3, 1)
+    fftp1d_real_to_complex_z(g, vx)
+    fftp1d_real_to_complex_z(g, vy)
+    fftp1d_real_to_complex_z(g, vz)
+    normvec(g, vx, vy, vz, u0, 1)
+    return vx, vy, vz
+
+
+def initialfv(g: Grid, f0=1.0):
+    """initialfv.f90:25-31: uniform body force in x, mode (1,1,1) scaled by N."""
+    fx = np.zeros(g.cshape(), dtype=np.complex128)
+    fy = np.zeros_like(fx)
+    fz = np.zeros_like(fx)
+    if g.ista == 1:
+        fx[0, 0, 0] = f0 * g.N
+    return fx, fy, fz
+
+
+def make_hd_state(g: Grid, **ic) -> HDState:
+    vx, vy, vz = initialv(g, **ic)
+    fx, fy, fz = initialfv(g)
+    pr = np.zeros(g.cshape(), dtype=np.complex128)
+    return HDState(vx, vy, vz, pr, fx, fy, fz)
+
+
+def analytic_field(g: Grid, kind="sin"):
+    """The src/tests fields: sin4x cos8y sin6z (fc_dirichlet.f90:14, energy.f90:13)
+    or sin4x cos8y exp(.4 z/Lz) (poisson.f90:21) on the local real slab."""
+    z = g.z[g.ksta - 1 : g.kend][:, None, None]
+    y = g.y[None, :, None]
+    x = g.x[None, None, :]
+    if kind == "sin":
+        return np.sin(4 * x) * np.cos(8 * y) * np.sin(6 * z)
+    return np.sin(4 * x) * np.cos(8 * y) * np.exp(0.4 * z / g.Lz)

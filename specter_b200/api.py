@@ -1,0 +1,333 @@
+"""Host-side mirror of the reference's fftp / pseudo / boundary interface over the C ABI.
+
+The method names and argument meaning follow the Fortran procedures they replace
+(``fftp3d_real_to_complex``, ``derivk``, ``gradre``, ``sol_project``,
+``v_imposebc_and_project`` ... see include/specter_b200.h for the file:line of each), so
+the parity tests read like the reference's own src/tests/*.f90.
+
+There is NO CPU path here: :func:`load_library` only ever opens the nvcc-built
+``csrc/libspecter_b200.so`` and raises if it is missing; plan creation fails if no CUDA
+device is present.  (tests/ may hand an explicit path of the kernel-emulation build to
+:class:`Library` to check kernel logic on CPU -- that build is test infrastructure.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libspecter_b200.so")
+
+
+class SpecterError(RuntimeError):
+    pass
+
+
+class sx_config(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("Cz", C.c_int), ("oz", C.c_int),
+                ("ord", C.c_int), ("Lx", C.c_double), ("Ly", C.c_double), ("Lz", C.c_double),
+                ("tdir", C.c_char_p), ("nprocs", C.c_int), ("myrank", C.c_int), ("device", C.c_int)]
+
+
+_P = C.c_void_p
+_D = C.c_void_p  # device/host data pointers travel as void*
+_I = C.c_int
+_F = C.c_double
+_PD = C.POINTER(C.c_double)
+_PI = C.POINTER(C.c_int)
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); this table is also what
+# tests/test_abi.py checks against include/specter_b200.h
+SIGNATURES = {
+    "sx_last_error": [],
+    "sx_version": [],
+    "sx_plan_create": [C.POINTER(sx_config), C.POINTER(_P)],
+    "sx_plan_destroy": [_P],
+    "sx_plan_info": [_P, _PI, _PI, _PI, _PI, _PI],
+    "sx_range": [_I, _I, _I, _I, _PI, _PI],
+    "sx_plan_launch_count": [_P],
+    "sx_plan_synchronize": [_P],
+    "sx_nccl_unique_id": [_D],
+    "sx_plan_set_comm": [_P, _D],
+    "sx_malloc": [_P, C.c_size_t, C.POINTER(_D)],
+    "sx_free": [_P, _D],
+    "sx_malloc_host": [C.c_size_t, C.POINTER(_D)],
+    "sx_free_host": [_D],
+    "sx_memcpy_h2d": [_P, _D, _D, C.c_size_t],
+    "sx_memcpy_d2h": [_P, _D, _D, C.c_size_t],
+    "sx_spectral_bytes": [_P],
+    "sx_real_bytes": [_P],
+    "sx_fftp3d_real_to_complex": [_P, _D, _D],
+    "sx_fftp3d_complex_to_real": [_P, _D, _D],
+    "sx_fftp2d_real_to_complex_xy": [_P, _D, _D],
+    "sx_fftp2d_complex_to_real_xy": [_P, _D, _D],
+    "sx_fftp1d_real_to_complex_z": [_P, _D],
+    "sx_fftp1d_complex_to_real_z": [_P, _D],
+    "sx_derivk": [_P, _D, _D, _I],
+    "sx_laplak": [_P, _D, _D],
+    "sx_curlk": [_P, _D, _D, _D, _I],
+    "sx_fc_filter": [_P, _D],
+    "sx_gradre": [_P, _D, _D, _D, _D, _D, _D],
+    "sx_prodre": [_P, _D, _D, _D, _D, _D, _D],
+    "sx_energy": [_P, _D, _D, _D, _I, _PD],
+    "sx_divergence": [_P, _D, _D, _D, _PD],
+    "sx_cross": [_P, _D, _D, _D, _D, _D, _D, _I, _PD],
+    "sx_hdcheck": [_P, _D, _D, _D, _D, _D, _D, _PD, _PD, _PD],
+    "sx_sol_project": [_P, _D, _D, _D, _D, _I, _I, _I],
+    "sx_v_imposebc_and_project": [_P, _D, _D, _D, _D, _I, _PD, _PD],
+    "sx_bouncheck_z": [_P, _PD, _PD, _D, _D],
+    "sx_vdiagnostic": [_P, _D, _D, _D, _PD],
+    "sx_hd_put_state": [_P, _D, _D, _D, _D, _D, _D, _D],
+    "sx_hd_get_state": [_P, _D, _D, _D, _D],
+    "sx_hd_state_ptr": [_P, _I, C.POINTER(_D)],
+    "sx_hd_rkstep1": [_P],
+    "sx_hd_rkstep2": [_P, _I, _F, _F, _PD, _PD, _I],
+    "sx_hd_step_host": [_P, _D, _D, _D, _D, _D, _D, _D, _F, _F, _PD, _PD],
+}
+_RESTYPES = {"sx_last_error": C.c_char_p, "sx_version": C.c_char_p,
+             "sx_plan_launch_count": C.c_ulonglong, "sx_spectral_bytes": C.c_size_t,
+             "sx_real_bytes": C.c_size_t}
+
+
+class Library:
+    """ctypes binding of one build of the C ABI."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise SpecterError(
+                f"{path} not found: build the CUDA extension first (python -m specter_b200.build); "
+                "specter_b200 has no CPU fallback")
+        self.path = path
+        self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        for name, args in SIGNATURES.items():
+            fn = getattr(self.dll, name)  # AttributeError if the ABI is incomplete
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, C.c_int)
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise SpecterError(self.dll.sx_last_error().decode())
+
+    def version(self) -> str:
+        return self.dll.sx_version().decode()
+
+
+_LIB: Optional[Library] = None
+
+
+def load_library() -> Library:
+    """The product library (CUDA, sm_100a).  Never falls back to anything else."""
+    global _LIB
+    if _LIB is None:
+        _LIB = Library(LIB_PATH)
+    return _LIB
+
+
+def sx_range(n1, n2, nprocs, irank, lib: Optional[Library] = None):
+    """``range`` (fftp.fpp:1154-1184)."""
+    lib = lib or load_library()
+    a, b = C.c_int(), C.c_int()
+    lib.check(lib.dll.sx_range(n1, n2, nprocs, irank, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+class DeviceArray:
+    """A device buffer in one of the two reference layouts."""
+
+    def __init__(self, plan: "Plan", kind: str):
+        self.plan = plan
+        self.kind = kind  # "spectral" (complex128 (nxl,ny,nz) C-order == Fortran (nz,ny,ista:iend)) | "real"
+        self.shape = plan.cshape if kind == "spectral" else plan.rshape
+        self.dtype = np.complex128 if kind == "spectral" else np.float64
+        self.nbytes = int(np.prod(self.shape)) * np.dtype(self.dtype).itemsize
+        ptr = C.c_void_p()
+        plan.lib.check(plan.lib.dll.sx_malloc(plan.handle, max(self.nbytes, 16), C.byref(ptr)))
+        self.ptr = ptr
+
+    def put(self, host: np.ndarray) -> "DeviceArray":
+        h = np.ascontiguousarray(host, dtype=self.dtype)
+        if h.shape != tuple(self.shape):
+            raise SpecterError(f"shape mismatch: got {h.shape}, expected {tuple(self.shape)}")
+        self.plan.lib.check(self.plan.lib.dll.sx_memcpy_h2d(self.plan.handle, self.ptr, h.ctypes.data, self.nbytes))
+        return self
+
+    def get(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=self.dtype)
+        self.plan.lib.check(self.plan.lib.dll.sx_memcpy_d2h(self.plan.handle, out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.plan.lib.dll.sx_free(self.plan.handle, self.ptr)
+            self.ptr = None
+
+
+def _vec2(v):
+    return (C.c_double * 2)(float(v[0]), float(v[1]))
+
+
+class Plan:
+    """FCPLAN + BCPLAN + grid of the reference, bound to one GPU (fcgram_create_plan, setup_bc)."""
+
+    def __init__(self, nx, ny, nz, Cz, oz, ord=2, Lx=1.0, Ly=1.0, Lz=1.0, tdir="", nprocs=1, myrank=0,
+                 device=-1, lib: Optional[Library] = None):
+        self.lib = lib or load_library()
+        self.cfg = sx_config(nx, ny, nz, Cz, oz, ord, Lx, Ly, Lz, tdir.encode(), nprocs, myrank, device)
+        self.handle = C.c_void_p()
+        self.lib.check(self.lib.dll.sx_plan_create(C.byref(self.cfg), C.byref(self.handle)))
+        v = [C.c_int() for _ in range(5)]
+        self.lib.check(self.lib.dll.sx_plan_info(self.handle, *[C.byref(x) for x in v]))
+        self.ista, self.iend, self.ksta, self.kend, self.pkend = [x.value for x in v]
+        self.nx, self.ny, self.nz, self.Cz, self.oz, self.ord = nx, ny, nz, Cz, oz, ord
+        self.nxl = self.iend - self.ista + 1
+        self.nzl = self.kend - self.ksta + 1
+        self.cshape = (self.nxl, ny, nz)
+        self.rshape = (self.nzl, ny, nx)
+        self._arrays = []
+
+    # ---- memory ----
+    def spectral(self, host: Optional[np.ndarray] = None) -> DeviceArray:
+        a = DeviceArray(self, "spectral")
+        self._arrays.append(a)
+        return a.put(host) if host is not None else a
+
+    def real(self, host: Optional[np.ndarray] = None) -> DeviceArray:
+        a = DeviceArray(self, "real")
+        self._arrays.append(a)
+        return a.put(host) if host is not None else a
+
+    def close(self):
+        if self.handle:
+            for a in self._arrays:
+                a.free()
+            self._arrays = []
+            self.lib.dll.sx_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self.lib.check(self.lib.dll.sx_plan_synchronize(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.dll.sx_plan_launch_count(self.handle))
+
+    def _call(self, name, *args):
+        self.lib.check(getattr(self.lib.dll, name)(self.handle, *args))
+
+    # ---- fftp ----
+    def fftp3d_real_to_complex(self, r: DeviceArray, out: DeviceArray):
+        self._call("sx_fftp3d_real_to_complex", r.ptr, out.ptr)
+
+    def fftp3d_complex_to_real(self, a: DeviceArray, out: DeviceArray):
+        self._call("sx_fftp3d_complex_to_real", a.ptr, out.ptr)
+
+    def fftp2d_real_to_complex_xy(self, r: DeviceArray, out: DeviceArray):
+        self._call("sx_fftp2d_real_to_complex_xy", r.ptr, out.ptr)
+
+    def fftp2d_complex_to_real_xy(self, a: DeviceArray, out: DeviceArray):
+        self._call("sx_fftp2d_complex_to_real_xy", a.ptr, out.ptr)
+
+    def fftp1d_real_to_complex_z(self, a: DeviceArray):
+        self._call("sx_fftp1d_real_to_complex_z", a.ptr)
+
+    def fftp1d_complex_to_real_z(self, a: DeviceArray):
+        self._call("sx_fftp1d_complex_to_real_z", a.ptr)
+
+    # ---- pseudo ----
+    def derivk(self, a, b, dir):
+        self._call("sx_derivk", a.ptr, b.ptr, dir)
+
+    def laplak(self, a, b):
+        self._call("sx_laplak", a.ptr, b.ptr)
+
+    def curlk(self, a, b, c, dir):
+        self._call("sx_curlk", a.ptr, b.ptr, c.ptr, dir)
+
+    def fc_filter(self, a):
+        self._call("sx_fc_filter", a.ptr)
+
+    def gradre(self, a, b, c, d, e, f):
+        self._call("sx_gradre", a.ptr, b.ptr, c.ptr, d.ptr, e.ptr, f.ptr)
+
+    def prodre(self, a, b, c, d, e, f):
+        self._call("sx_prodre", a.ptr, b.ptr, c.ptr, d.ptr, e.ptr, f.ptr)
+
+    def energy(self, a, b, c, kin) -> float:
+        out = C.c_double()
+        self._call("sx_energy", a.ptr, b.ptr, c.ptr, kin, C.byref(out))
+        return out.value
+
+    def divergence(self, a, b, c) -> float:
+        out = C.c_double()
+        self._call("sx_divergence", a.ptr, b.ptr, c.ptr, C.byref(out))
+        return out.value
+
+    def cross(self, a, b, c, d, e, f, kin) -> float:
+        out = C.c_double()
+        self._call("sx_cross", a.ptr, b.ptr, c.ptr, d.ptr, e.ptr, f.ptr, kin, C.byref(out))
+        return out.value
+
+    def hdcheck(self, a, b, c, d, e, f):
+        o = [C.c_double() for _ in range(3)]
+        self._call("sx_hdcheck", a.ptr, b.ptr, c.ptr, d.ptr, e.ptr, f.ptr, *[C.byref(x) for x in o])
+        return tuple(x.value for x in o)
+
+    # ---- boundary ----
+    def sol_project(self, a, b, c, d, bctarget, bczsta, bczend):
+        self._call("sx_sol_project", a.ptr, b.ptr, c.ptr, d.ptr, bctarget, bczsta, bczend)
+
+    def v_imposebc_and_project(self, vx, vy, vz, pr, rki, v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0)):
+        self._call("sx_v_imposebc_and_project", vx.ptr, vy.ptr, vz.ptr, pr.ptr, rki, _vec2(v_zsta), _vec2(v_zend))
+
+    def bouncheck_z(self, a, b=None):
+        bot, top = C.c_double(), C.c_double()
+        self._call("sx_bouncheck_z", C.byref(bot), C.byref(top), a.ptr, b.ptr if b is not None else None)
+        return bot.value, top.value
+
+    def vdiagnostic(self, a, b, c):
+        out = (C.c_double * 5)()
+        self._call("sx_vdiagnostic", a.ptr, b.ptr, c.ptr, out)
+        return tuple(out)
+
+    # ---- HD substep on plan-owned state ----
+    def hd_put_state(self, vx=None, vy=None, vz=None, pr=None, fx=None, fy=None, fz=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.complex128)
+                for a in (vx, vy, vz, pr, fx, fy, fz)]
+        for a in arrs:
+            if a is not None and a.shape != tuple(self.cshape):
+                raise SpecterError("hd_put_state: shape mismatch")
+        self._call("sx_hd_put_state", *[None if a is None else a.ctypes.data for a in arrs])
+
+    def hd_get_state(self):
+        out = [np.empty(self.cshape, dtype=np.complex128) for _ in range(4)]
+        self._call("sx_hd_get_state", *[a.ctypes.data for a in out])
+        return out
+
+    def hd_rkstep1(self):
+        self._call("sx_hd_rkstep1")
+
+    def hd_rkstep2(self, o, dt, nu, v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0), impl=0):
+        self._call("sx_hd_rkstep2", o, dt, nu, _vec2(v_zsta), _vec2(v_zend), impl)
+
+    def hd_step(self, dt, nu, v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0), impl=0):
+        """rkstep1 + ord substeps on the device-resident state (specter.fpp:1142-1161)."""
+        self.hd_rkstep1()
+        for o in range(self.ord, 0, -1):
+            self.hd_rkstep2(o, dt, nu, v_zsta, v_zend, impl)
+
+    def hd_step_host(self, vx, vy, vz, pr, fx, fy, fz, dt, nu, v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0)):
+        """One full step on HOST arrays (in place): H2D, rkstep1 + ord substeps, D2H."""
+        for a in (vx, vy, vz, pr, fx, fy, fz):
+            if not (a.flags["C_CONTIGUOUS"] and a.dtype == np.complex128 and a.shape == tuple(self.cshape)):
+                raise SpecterError("hd_step_host needs C-contiguous complex128 arrays of the plan's spectral shape")
+        self._call("sx_hd_step_host", vx.ctypes.data, vy.ctypes.data, vz.ctypes.data, pr.ctypes.data,
+                   fx.ctypes.data, fy.ctypes.data, fz.ctypes.data, dt, nu, _vec2(v_zsta), _vec2(v_zend))

@@ -1,0 +1,487 @@
+// C ABI (include/specter_b200.h): plan construction and the per-operator entry points that
+// mirror the reference's fftp / pseudo / boundary modules, composed from the kernels in
+// sx_kernels_fft.cu and sx_kernels_ops.cu.
+#include <cstring>
+#include <fstream>
+#include <mutex>
+
+#include "../../include/specter_b200.h"
+#include "sx_fft.cuh"
+#include "sx_plan.h"
+
+namespace sx {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+
+// `range` (fftp.fpp:1177-1181)
+static void range_(int n1, int n2, int nprocs, int irank, int* ista, int* iend) {
+  const int iwork1 = (n2 - n1 + 1) / nprocs;
+  const int iwork2 = (n2 - n1 + 1) % nprocs;
+  *ista = irank * iwork1 + n1 + (irank < iwork2 ? irank : iwork2);
+  *iend = *ista + iwork1 - 1;
+  if (iwork2 > irank) *iend += 1;
+}
+
+static void kvec(int n, double Dk, std::vector<double>& k) {  // specter.fpp:772-789
+  k.assign(n, 0.0);
+  for (int i = 1; i <= n / 2; ++i) {
+    k[i - 1] = (double)(i - 1);
+    k[i + n / 2 - 1] = (double)(i - n / 2 - 1);
+  }
+  for (auto& v : k) v *= Dk;
+}
+
+static int read_f64(const std::string& path, size_t count, std::vector<double>& out) {
+  std::ifstream f(path, std::ios::binary);
+  SX_REQUIRE(f.good(), "Could not find table " + path);
+  out.resize(count);
+  f.read(reinterpret_cast<char*>(out.data()), (std::streamsize)(count * sizeof(double)));
+  SX_REQUIRE((size_t)f.gcount() == count * sizeof(double), "FC-Gram table too short: " + path);
+  return 0;
+}
+
+// load_dirichlet_tables (fcgram_mod.f90:180-257): dir = A . Q^T, stored row-major [C][d]
+static int load_dirichlet(Plan& p, const std::string& tdir) {
+  const int C = p.Cz, d = p.oz;
+  std::vector<double> A, Q;
+  if (read_f64(tdir + "/A" + std::to_string(C) + "-" + std::to_string(d) + ".dat", (size_t)C * d, A)) return 1;
+  if (read_f64(tdir + "/Q" + std::to_string(d) + ".dat", (size_t)d * d, Q)) return 1;
+  p.h_dir.assign((size_t)C * d, 0.0);
+  for (int ii = 0; ii < C; ++ii)
+    for (int jj = 0; jj < d; ++jj) {
+      double s = 0.0;
+      for (int m = 0; m < d; ++m) s += A[(size_t)m * C + ii] * Q[(size_t)m * d + jj];  // A(ii,m)*Q(jj,m)
+      p.h_dir[(size_t)ii * d + jj] = s;
+    }
+  return 0;
+}
+
+template <class T> static int upload(T** dptr, const T* h, size_t n) {
+  SX_CUDA_CHECK(cudaMalloc((void**)dptr, n * sizeof(T)));
+  SX_CUDA_CHECK(cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int upload_twiddles(int n, cplx** d) {
+  std::vector<cplx> h((size_t)twiddle_count(n) + 1);
+  int cnt = 0;
+  build_twiddles(n, h.data(), &cnt);
+  return upload(d, h.data(), (size_t)cnt + 1);
+}
+
+int plan_cwork(Plan& p, int idx, cplx** out) {
+  if ((int)p.cwork.size() <= idx) p.cwork.resize(idx + 1, nullptr);
+  if (!p.cwork[idx]) SX_CUDA_CHECK(cudaMalloc((void**)&p.cwork[idx], p.csize() * sizeof(cplx)));
+  *out = p.cwork[idx];
+  return 0;
+}
+int plan_rwork(Plan& p, int idx, double** out) {
+  if ((int)p.rwork.size() <= idx) p.rwork.resize(idx + 1, nullptr);
+  if (!p.rwork[idx]) SX_CUDA_CHECK(cudaMalloc((void**)&p.rwork[idx], p.rsize() * sizeof(double)));
+  *out = p.rwork[idx];
+  return 0;
+}
+
+static int plan_init(Plan& p, const sx_config& c) {
+  SX_REQUIRE(c.nx > 0 && c.ny > 0 && c.nz > 0, "invalid grid size");
+  SX_REQUIRE(fft_size_supported(c.nx, false) && fft_size_supported(c.ny, false) && fft_size_supported(c.nz, true),
+             "nx, ny must be powers of two in [16,2048] and nz in [16,4096]");
+  SX_REQUIRE((c.Cz == 0 && c.oz == 0) || (c.Cz > 0 && c.oz > 0),
+             "Mismatch in continuation or matching points in z direction. Aborting...");
+  SX_REQUIRE(c.Cz == 0 || (c.oz <= 10 && c.Cz + 2 * c.oz < c.nz), "invalid Cz/oz for this nz");
+  SX_REQUIRE(c.nprocs >= 1 && c.myrank >= 0 && c.myrank < c.nprocs, "invalid nprocs/myrank");
+  SX_REQUIRE(c.nprocs == 1, "nprocs > 1 needs sx_plan_set_comm (multi-GPU path not built in this version)");
+  SX_REQUIRE(c.ord >= 1, "ord must be >= 1");
+  p.nx = c.nx; p.ny = c.ny; p.nz = c.nz; p.Cz = c.Cz; p.oz = c.oz; p.ord = c.ord;
+  p.Lx = c.Lx; p.Ly = c.Ly; p.Lz = c.Lz;
+  p.nprocs = c.nprocs; p.myrank = c.myrank;
+  int ndev = 0;
+  SX_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  SX_REQUIRE(ndev > 0, "no CUDA device: specter_b200 has no CPU fallback");
+  p.device = c.device >= 0 ? c.device : c.myrank % ndev;
+  SX_CUDA_CHECK(cudaSetDevice(p.device));
+  p.nxh = p.nx / 2 + 1;
+  range_(1, p.nxh, p.nprocs, p.myrank, &p.ista, &p.iend);
+  range_(1, p.nz, p.nprocs, p.myrank, &p.ksta, &p.kend);
+  p.pkend = (p.nz - p.Cz) < p.kend ? (p.nz - p.Cz) : p.kend;
+  p.nxl = p.iend - p.ista + 1;
+  p.nzl = p.kend - p.ksta + 1;
+  const double pi = 3.14159265358979323846;
+  // specter.fpp:683-749
+  p.dx = p.Lx * 2.0 * pi / p.nx; p.Dkx = 1.0 / p.Lx;
+  p.dy = p.Ly * 2.0 * pi / p.ny; p.Dky = 1.0 / p.Ly;
+  if (p.Cz == 0) { p.dz = p.Lz * 2.0 * pi / p.nz; p.Dkz = 1.0 / p.Lz; }
+  else { p.dz = p.Lz / (p.nz - p.Cz - 1); p.Dkz = 2.0 * pi / (p.dz * p.nz); }
+  std::vector<double> kxf;
+  kvec(p.nx, p.Dkx, kxf);
+  kvec(p.ny, p.Dky, p.h_ky);
+  kvec(p.nz, p.Dkz, p.h_kz);
+  p.h_kx.assign(kxf.begin() + (p.ista - 1), kxf.begin() + p.iend);
+  p.h_z.resize(p.nz);
+  for (int k = 0; k < p.nz; ++k) p.h_z[k] = p.dz * k;
+  // fc_filter factors (pseudospec_hd.f90:1099-1109)
+  const double alpha = 16 * std::log(10.0), p2 = 100.0;
+  std::vector<double> fx(p.nxl), fy(p.ny), fz(p.nz);
+  for (int i = 0; i < p.nxl; ++i) fx[i] = std::exp(-alpha * std::pow(2 * p.h_kx[i] / p.nx / p.Dkx, p2));
+  for (int j = 0; j < p.ny; ++j) fy[j] = std::exp(-alpha * std::pow(2 * p.h_ky[j] / p.ny / p.Dky, p2));
+  for (int k = 0; k < p.nz; ++k) fz[k] = std::exp(-alpha * std::pow(2 * p.h_kz[k] / p.nz / p.Dkz, p2));
+  if (p.Cz > 0) {
+    SX_REQUIRE(c.tdir != nullptr, "tdir is required when Cz > 0");
+    if (load_dirichlet(p, c.tdir)) return 1;
+  } else {
+    p.h_dir.assign(1, 0.0);
+  }
+  SX_CUDA_CHECK(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+  if (upload(&p.d_kx, p.h_kx.data(), p.h_kx.size())) return 1;
+  if (upload(&p.d_ky, p.h_ky.data(), p.h_ky.size())) return 1;
+  if (upload(&p.d_kz, p.h_kz.data(), p.h_kz.size())) return 1;
+  if (upload(&p.d_fx, fx.data(), fx.size())) return 1;
+  if (upload(&p.d_fy, fy.data(), fy.size())) return 1;
+  if (upload(&p.d_fz, fz.data(), fz.size())) return 1;
+  if (upload(&p.d_z, p.h_z.data(), p.h_z.size())) return 1;
+  if (upload(&p.d_dir, p.h_dir.data(), p.h_dir.size())) return 1;
+  if (upload_twiddles(p.nx, &p.tw_x)) return 1;
+  if (upload_twiddles(p.ny, &p.tw_y)) return 1;
+  if (upload_twiddles(p.nz, &p.tw_z)) return 1;
+  p.red_blocks = 148 * 4;
+  SX_CUDA_CHECK(cudaMalloc((void**)&p.d_red, p.red_blocks * sizeof(double)));
+  SX_CUDA_CHECK(cudaMallocHost((void**)&p.h_red, p.red_blocks * sizeof(double)));
+  return 0;
+}
+
+static void plan_release(Plan& p) {
+  hd_state_free(p);
+  for (auto* q : p.cwork) if (q) cudaFree(q);
+  for (auto* q : p.rwork) if (q) cudaFree(q);
+  void* tabs[] = {p.d_kx, p.d_ky, p.d_kz, p.d_fx, p.d_fy, p.d_fz, p.d_z, p.d_dir, p.tw_x, p.tw_y, p.tw_z, p.d_red};
+  for (void* q : tabs) if (q) cudaFree(q);
+  if (p.h_red) cudaFreeHost(p.h_red);
+  if (p.stream) cudaStreamDestroy(p.stream);
+}
+
+// ---- composite transforms -------------------------------------------------------------
+static inline cplx* C(double* a) { return reinterpret_cast<cplx*>(a); }
+static inline const cplx* C(const double* a) { return reinterpret_cast<const cplx*>(a); }
+
+int fft1d_z_fwd(Plan& p, cplx* a) {  // fftp1d_real_to_complex_z
+  return launch_zfft(p, a, a, (long)p.ny * p.nxl, -1, p.Cz > 0, 1.0, 1.0);
+}
+int fft1d_z_bwd(Plan& p, const cplx* in, cplx* out, double scale_phys) {  // fftp1d_complex_to_real_z
+  return launch_zfft(p, in, out, (long)p.ny * p.nxl, +1, false, scale_phys, 1.0);
+}
+int fft2d_xy_r2c(Plan& p, const double* r, cplx* out, int nz_active) {
+  if (launch_x_r2c(p, r, out, p.nz, nz_active, 1.0)) return 1;
+  return launch_yfft(p, out, out, p.nz, p.nxh, nz_active, -1, 1.0);
+}
+int fft2d_xy_c2r(Plan& p, cplx* mixed_destroyed, double* r, int nz_active) {
+  if (launch_yfft(p, mixed_destroyed, mixed_destroyed, p.nz, p.nxh, nz_active, +1, 1.0)) return 1;
+  return launch_x_c2r(p, mixed_destroyed, r, p.nz, nz_active, 1.0);
+}
+int fft3d_r2c(Plan& p, const double* r, cplx* out) {
+  // planes above the physical region are overwritten by the continuation (fftp.fpp:761)
+  if (fft2d_xy_r2c(p, r, out, p.Cz > 0 ? p.nphys() : p.nz)) return 1;
+  return fft1d_z_fwd(p, out);
+}
+int fft3d_c2r(Plan& p, const cplx* in, double* r) {
+  cplx* w;
+  if (plan_cwork(p, 0, &w)) return 1;
+  if (fft1d_z_bwd(p, in, w, 1.0)) return 1;
+  return fft2d_xy_c2r(p, w, r, p.nz);
+}
+
+// ---- pseudo: gradre / prodre -----------------------------------------------------------
+int gradre(Plan& p, const cplx* a, const cplx* b, const cplx* c, cplx* d, cplx* e, cplx* f) {
+  double* r[12];
+  double *rx, *ry, *rz;
+  for (int i = 0; i < 12; ++i) if (plan_rwork(p, i, &r[i])) return 1;
+  if (plan_rwork(p, 12, &rx) || plan_rwork(p, 13, &ry) || plan_rwork(p, 14, &rz)) return 1;
+  cplx* t;
+  if (plan_cwork(p, 1, &t)) return 1;
+  const cplx* comp[3] = {a, b, c};
+  for (int dir = 1; dir <= 3; ++dir) {
+    if (fft3d_c2r(p, comp[dir - 1], r[4 * (dir - 1)])) return 1;
+    for (int q = 0; q < 3; ++q) {
+      if (op_derivk(p, comp[q], t, dir)) return 1;
+      if (fft3d_c2r(p, t, r[4 * (dir - 1) + 1 + q])) return 1;
+    }
+  }
+  if (op_gradre_products(p, r, rx, ry, rz)) return 1;
+  if (fft3d_r2c(p, rx, d) || fft3d_r2c(p, ry, e) || fft3d_r2c(p, rz, f)) return 1;
+  return 0;
+}
+
+int prodre(Plan& p, const cplx* a, const cplx* b, const cplx* c, cplx* d, cplx* e, cplx* f) {
+  double* r[9];
+  for (int i = 0; i < 9; ++i) if (plan_rwork(p, i, &r[i])) return 1;
+  cplx* t;
+  if (plan_cwork(p, 1, &t)) return 1;
+  if (op_curlk(p, b, c, t, 1) || fft3d_c2r(p, t, r[0])) return 1;
+  if (op_curlk(p, a, c, t, 2) || fft3d_c2r(p, t, r[1])) return 1;
+  if (op_curlk(p, a, b, t, 3) || fft3d_c2r(p, t, r[2])) return 1;
+  if (fft3d_c2r(p, a, r[3]) || fft3d_c2r(p, b, r[4]) || fft3d_c2r(p, c, r[5])) return 1;
+  if (op_cross_products(p, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8])) return 1;
+  if (fft3d_r2c(p, r[6], d) || fft3d_r2c(p, r[7], e) || fft3d_r2c(p, r[8], f)) return 1;
+  return 0;
+}
+
+// ---- boundary: sol_project / v_imposebc_and_project -------------------------------------
+int sol_project(Plan& p, cplx* a, cplx* b, cplx* c, cplx* d, int bctarget, int bczsta, int bczend) {
+  SX_REQUIRE(bctarget == 0 || bctarget == 1, "sol_project: bctarget must be 0 or 1");
+  SX_REQUIRE((bczsta == 0 || bczsta == 2) && (bczend == 0 || bczend == 2),
+             "Unsupported BC kind in call to sol_project. Aborting...");
+  cplx *C1, *C2, *C3, *C2in = nullptr;
+  if (plan_cwork(p, 2, &C1) || plan_cwork(p, 3, &C2) || plan_cwork(p, 4, &C3)) return 1;
+  if (op_proj_inhomogeneous(p, a, b, c, d, C1, bctarget)) return 1;
+  if (bczsta == 2 || bczend == 2) {
+    if (plan_cwork(p, 5, &C2in)) return 1;
+    if (op_derivk(p, C1, C2in, 3) || fft1d_z_bwd(p, C2in, C2in, 1.0)) return 1;
+  }
+  if (fft1d_z_bwd(p, C1, C1, 1.0)) return 1;
+  if (op_laplace_z(p, C1, C2in, C2, C3, bctarget, bczsta, bczend)) return 1;
+  if (bctarget == 1 && fft1d_z_bwd(p, d, d, 1.0)) return 1;
+  if (op_pr_combine(p, d, C1, C2, bctarget)) return 1;
+  if (fft1d_z_fwd(p, C2) || fft1d_z_fwd(p, C3)) return 1;
+  return op_apply_hom(p, a, b, c, C2, C3);
+}
+
+int v_imposebc_and_project(Plan& p, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int rki, const double* zs,
+                           const double* ze) {
+  SX_REQUIRE(rki >= 1, "Non-slip BC require `rki` keyword argument in call to imposebc_and_project. Aborting...");
+  const double inv_nz = 1.0 / (double)p.nz;
+  // goto_domain_w_boundaries (boundary_mod.fpp:72-150)
+  if (fft1d_z_bwd(p, vx, vx, inv_nz) || fft1d_z_bwd(p, vy, vy, inv_nz)) return 1;
+  if (op_noslip(p, vx, vy, pr, rki, zs ? zs[0] : 0.0, zs ? zs[1] : 0.0, ze ? ze[0] : 0.0, ze ? ze[1] : 0.0)) return 1;
+  // goto_3d_fourier (boundary_mod.fpp:153-194)
+  if (fft1d_z_fwd(p, vx) || fft1d_z_fwd(p, vy)) return 1;
+  return sol_project(p, vx, vy, vz, pr, 1, 0, 0);
+}
+
+// ---- diagnostics -------------------------------------------------------------------------
+static double norm_tmp(const Plan& p) {
+  const double N = (double)p.nx * (double)p.ny * (double)p.nz;
+  return 1.0 / (N * N) / (double)(p.nz - p.Cz);
+}
+static int abs2_iz_sum(Plan& p, const cplx* a, double scale, int row, double* out) {
+  cplx* w;
+  if (plan_cwork(p, 2, &w)) return 1;
+  if (fft1d_z_bwd(p, a, w, 1.0)) return 1;
+  return op_reduce_phys(p, w, nullptr, 0, row, scale, out);
+}
+
+int energy(Plan& p, const cplx* a, const cplx* b, const cplx* c, int kin, double* out) {
+  const double tmp = norm_tmp(p);
+  double s = 0.0, t = 0.0;
+  if (kin == 1) {
+    const cplx* f[3] = {a, b, c};
+    for (int i = 0; i < 3; ++i) { if (abs2_iz_sum(p, f[i], tmp, -1, &t)) return 1; s += t; }
+  } else if (kin == 0) {
+    // the reference adds the y component of the curl twice and never the z component
+    // (pseudospec_hd.f90:527,540); reproduced on purpose.
+    cplx* w;
+    if (plan_cwork(p, 3, &w)) return 1;
+    if (op_curlk(p, b, c, w, 1) || abs2_iz_sum(p, w, tmp, -1, &t)) return 1; s += t;
+    if (op_curlk(p, a, c, w, 2) || abs2_iz_sum(p, w, tmp, -1, &t)) return 1; s += t;
+    if (op_curlk(p, a, c, w, 2) || abs2_iz_sum(p, w, tmp, -1, &t)) return 1; s += t;
+  } else if (kin == 2) {
+    cplx *c1, *c2, *c3, *c4;
+    if (plan_cwork(p, 3, &c1) || plan_cwork(p, 4, &c2) || plan_cwork(p, 5, &c3) || plan_cwork(p, 6, &c4)) return 1;
+    if (op_curlk(p, b, c, c1, 1) || op_curlk(p, a, c, c2, 2) || op_curlk(p, a, b, c3, 3)) return 1;
+    if (op_curlk(p, c2, c3, c4, 1) || abs2_iz_sum(p, c4, tmp, -1, &t)) return 1; s += t;
+    if (op_curlk(p, c1, c3, c4, 2) || abs2_iz_sum(p, c4, tmp, -1, &t)) return 1; s += t;
+    if (op_curlk(p, c1, c2, c4, 3) || abs2_iz_sum(p, c4, tmp, -1, &t)) return 1; s += t;
+  } else {
+    SX_REQUIRE(false, "energy: kin must be 0, 1 or 2");
+  }
+  *out = s;
+  return 0;
+}
+
+int divergence(Plan& p, const cplx* a, const cplx* b, const cplx* c, double* out) {
+  // div = i(kx a + ky b + kz c): reuse curl-style kernels via derivk + accumulate
+  cplx *w, *t;
+  if (plan_cwork(p, 3, &w) || plan_cwork(p, 4, &t)) return 1;
+  // w = i kx a + i ky b  == -(curlk(a,b,.,3) with b->-b)... keep it literal instead:
+  if (op_derivk(p, a, w, 1)) return 1;
+  if (op_derivk(p, b, t, 2)) return 1;
+  // w += t ; then t = i kz c ; w += t   (pseudospec_hd.f90:1160-1193)
+  if (op_add(p, w, t)) return 1;
+  if (op_derivk(p, c, t, 3)) return 1;
+  if (op_add(p, w, t)) return 1;
+  return abs2_iz_sum(p, w, norm_tmp(p), -1, out);
+}
+
+int cross(Plan& p, const cplx* a, const cplx* b, const cplx* c, const cplx* d, const cplx* e, const cplx* f,
+          int kin, double* out) {
+  SX_REQUIRE(kin == 0 || kin == 1, "cross: kin must be 0 or 1");
+  const double tmp = norm_tmp(p);
+  cplx *w1, *w2;
+  if (plan_cwork(p, 2, &w1) || plan_cwork(p, 3, &w2)) return 1;
+  double s = 0.0, t = 0.0;
+  const cplx* A[3] = {a, b, c};
+  const cplx* B[3] = {d, e, f};
+  for (int q = 0; q < 3; ++q) {
+    if (kin == 1) {
+      if (fft1d_z_bwd(p, A[q], w1, 1.0) || fft1d_z_bwd(p, B[q], w2, 1.0)) return 1;
+    } else {
+      const int i1 = q == 0 ? 1 : 0, i2 = q == 2 ? 1 : 2;  // (b,c), (a,c), (a,b)
+      if (op_curlk(p, A[i1], A[i2], w1, q + 1) || op_curlk(p, B[i1], B[i2], w2, q + 1)) return 1;
+      if (fft1d_z_bwd(p, w1, w1, 1.0) || fft1d_z_bwd(p, w2, w2, 1.0)) return 1;
+    }
+    if (op_reduce_phys(p, w1, w2, 1, -1, tmp, &t)) return 1;
+    s += t;
+  }
+  *out = s;
+  return 0;
+}
+
+int bouncheck_z(Plan& p, double* bot, double* top, const cplx* a, const cplx* b) {
+  const double N = (double)p.nx * (double)p.ny * (double)p.nz;
+  const double tmp = (1.0 / N) * (1.0 / N);
+  const int rt = p.nz - p.Cz - 1;
+  cplx* w;
+  if (plan_cwork(p, 2, &w)) return 1;
+  double s0 = 0, s1 = 0, t = 0;
+  const cplx* f[2] = {a, b};
+  for (int q = 0; q < 2; ++q) {
+    if (!f[q]) continue;
+    if (fft1d_z_bwd(p, f[q], w, 1.0)) return 1;
+    if (op_reduce_phys(p, w, nullptr, 0, 0, tmp, &t)) return 1; s0 += t;
+    if (op_reduce_phys(p, w, nullptr, 0, rt, tmp, &t)) return 1; s1 += t;
+  }
+  *bot = s0; *top = s1;
+  return 0;
+}
+
+}  // namespace sx
+
+// ===========================================================================================
+using namespace sx;
+#define SX_PLAN(pl) \
+  if (!(pl)) { sx::set_error("[ERROR] null plan"); return 1; } \
+  sx::Plan& p = (pl)->p
+
+extern "C" {
+
+const char* sx_last_error(void) { return sx::g_last_error.c_str(); }
+const char* sx_version(void) {
+#ifdef SX_EMU
+  return "specter_b200 0.1 (CPU emulation build: tests only)";
+#else
+  return "specter_b200 0.1 (sm_100a)";
+#endif
+}
+
+int sx_plan_create(const sx_config* cfg, sx_plan** plan) {
+  if (!cfg || !plan) { sx::set_error("[ERROR] null argument to sx_plan_create"); return 1; }
+  sx_plan* pl = new sx_plan();
+  if (plan_init(pl->p, *cfg)) { plan_release(pl->p); delete pl; *plan = nullptr; return 1; }
+  *plan = pl;
+  return 0;
+}
+int sx_plan_destroy(sx_plan* plan) {
+  if (!plan) return 0;
+  cudaSetDevice(plan->p.device);
+  cudaStreamSynchronize(plan->p.stream);
+  plan_release(plan->p);
+  delete plan;
+  return 0;
+}
+int sx_plan_info(const sx_plan* plan, int* ista, int* iend, int* ksta, int* kend, int* pkend) {
+  if (!plan) { sx::set_error("[ERROR] null plan"); return 1; }
+  const Plan& p = plan->p;
+  if (ista) *ista = p.ista;
+  if (iend) *iend = p.iend;
+  if (ksta) *ksta = p.ksta;
+  if (kend) *kend = p.kend;
+  if (pkend) *pkend = p.pkend;
+  return 0;
+}
+int sx_range(int n1, int n2, int nprocs, int irank, int* sta, int* end) {
+  if (nprocs < 1 || irank < 0 || irank >= nprocs || !sta || !end) { sx::set_error("[ERROR] bad arguments to sx_range"); return 1; }
+  range_(n1, n2, nprocs, irank, sta, end);
+  return 0;
+}
+unsigned long long sx_plan_launch_count(const sx_plan* plan) { return plan ? plan->p.launches : 0ULL; }
+int sx_plan_synchronize(sx_plan* plan) { SX_PLAN(plan); SX_CUDA_CHECK(cudaStreamSynchronize(p.stream)); return 0; }
+
+int sx_nccl_unique_id(void*) { sx::set_error("[ERROR] multi-GPU path not built in this version"); return 1; }
+int sx_plan_set_comm(sx_plan*, const void*) { sx::set_error("[ERROR] multi-GPU path not built in this version"); return 1; }
+
+int sx_malloc(sx_plan* plan, size_t bytes, void** dptr) { SX_PLAN(plan); SX_CUDA_CHECK(cudaSetDevice(p.device)); SX_CUDA_CHECK(cudaMalloc(dptr, bytes)); return 0; }
+int sx_free(sx_plan* plan, void* dptr) { SX_PLAN(plan); SX_CUDA_CHECK(cudaStreamSynchronize(p.stream)); SX_CUDA_CHECK(cudaFree(dptr)); return 0; }
+int sx_malloc_host(size_t bytes, void** hptr) { SX_CUDA_CHECK(cudaMallocHost(hptr, bytes)); return 0; }
+int sx_free_host(void* hptr) { SX_CUDA_CHECK(cudaFreeHost(hptr)); return 0; }
+int sx_memcpy_h2d(sx_plan* plan, void* dptr, const void* hptr, size_t bytes) {
+  SX_PLAN(plan);
+  SX_CUDA_CHECK(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, p.stream));
+  SX_CUDA_CHECK(cudaStreamSynchronize(p.stream));
+  return 0;
+}
+int sx_memcpy_d2h(sx_plan* plan, void* hptr, const void* dptr, size_t bytes) {
+  SX_PLAN(plan);
+  SX_CUDA_CHECK(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, p.stream));
+  SX_CUDA_CHECK(cudaStreamSynchronize(p.stream));
+  return 0;
+}
+size_t sx_spectral_bytes(const sx_plan* plan) { return plan ? plan->p.csize() * sizeof(cplx) : 0; }
+size_t sx_real_bytes(const sx_plan* plan) { return plan ? plan->p.rsize() * sizeof(double) : 0; }
+
+int sx_fftp3d_real_to_complex(sx_plan* plan, const double* in, double* out) { SX_PLAN(plan); return fft3d_r2c(p, in, C(out)); }
+int sx_fftp3d_complex_to_real(sx_plan* plan, const double* in, double* out) { SX_PLAN(plan); return fft3d_c2r(p, C(in), out); }
+int sx_fftp2d_real_to_complex_xy(sx_plan* plan, const double* in, double* out) { SX_PLAN(plan); return fft2d_xy_r2c(p, in, C(out), p.nz); }
+int sx_fftp2d_complex_to_real_xy(sx_plan* plan, const double* in, double* out) {
+  SX_PLAN(plan);
+  cplx* w;
+  if (plan_cwork(p, 0, &w) || op_copy(p, C(in), w)) return 1;
+  return fft2d_xy_c2r(p, w, out, p.nz);
+}
+int sx_fftp1d_real_to_complex_z(sx_plan* plan, double* a) { SX_PLAN(plan); return fft1d_z_fwd(p, C(a)); }
+int sx_fftp1d_complex_to_real_z(sx_plan* plan, double* a) { SX_PLAN(plan); return fft1d_z_bwd(p, C(a), C(a), 1.0); }
+
+int sx_derivk(sx_plan* plan, const double* a, double* b, int dir) { SX_PLAN(plan); return op_derivk(p, C(a), C(b), dir); }
+int sx_laplak(sx_plan* plan, const double* a, double* b) { SX_PLAN(plan); return op_laplak(p, C(a), C(b)); }
+int sx_curlk(sx_plan* plan, const double* a, const double* b, double* c, int dir) { SX_PLAN(plan); return op_curlk(p, C(a), C(b), C(c), dir); }
+int sx_fc_filter(sx_plan* plan, double* a) { SX_PLAN(plan); return op_fc_filter(p, C(a)); }
+int sx_gradre(sx_plan* plan, const double* a, const double* b, const double* c, double* d, double* e, double* f) {
+  SX_PLAN(plan); return gradre(p, C(a), C(b), C(c), C(d), C(e), C(f));
+}
+int sx_prodre(sx_plan* plan, const double* a, const double* b, const double* c, double* d, double* e, double* f) {
+  SX_PLAN(plan); return prodre(p, C(a), C(b), C(c), C(d), C(e), C(f));
+}
+int sx_energy(sx_plan* plan, const double* a, const double* b, const double* c, int kin, double* out) {
+  SX_PLAN(plan); return energy(p, C(a), C(b), C(c), kin, out);
+}
+int sx_divergence(sx_plan* plan, const double* a, const double* b, const double* c, double* out) {
+  SX_PLAN(plan); return divergence(p, C(a), C(b), C(c), out);
+}
+int sx_cross(sx_plan* plan, const double* a, const double* b, const double* c, const double* d, const double* e,
+             const double* f, int kin, double* out) {
+  SX_PLAN(plan); return cross(p, C(a), C(b), C(c), C(d), C(e), C(f), kin, out);
+}
+int sx_hdcheck(sx_plan* plan, const double* a, const double* b, const double* c, const double* d, const double* e,
+               const double* f, double* eng, double* ens, double* pot) {
+  SX_PLAN(plan);
+  if (energy(p, C(a), C(b), C(c), 1, eng)) return 1;
+  if (energy(p, C(a), C(b), C(c), 0, ens)) return 1;
+  return cross(p, C(a), C(b), C(c), C(d), C(e), C(f), 1, pot);
+}
+int sx_sol_project(sx_plan* plan, double* a, double* b, double* c, double* d, int bctarget, int bczsta, int bczend) {
+  SX_PLAN(plan); return sol_project(p, C(a), C(b), C(c), C(d), bctarget, bczsta, bczend);
+}
+int sx_v_imposebc_and_project(sx_plan* plan, double* vx, double* vy, double* vz, double* pr, int rki,
+                              const double v_zsta[2], const double v_zend[2]) {
+  SX_PLAN(plan); return v_imposebc_and_project(p, C(vx), C(vy), C(vz), C(pr), rki, v_zsta, v_zend);
+}
+int sx_bouncheck_z(sx_plan* plan, double* bot, double* top, const double* a, const double* b) {
+  SX_PLAN(plan); return bouncheck_z(p, bot, top, C(a), b ? C(b) : nullptr);
+}
+int sx_vdiagnostic(sx_plan* plan, const double* a, const double* b, const double* c, double out[5]) {
+  SX_PLAN(plan);
+  if (divergence(p, C(a), C(b), C(c), &out[0])) return 1;
+  if (bouncheck_z(p, &out[1], &out[2], C(a), C(b))) return 1;
+  return bouncheck_z(p, &out[3], &out[4], C(c), nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// specter_b200 -- common device/host helpers.
+//
+// All kernels are hand-written for sm_100a (B200).  The SX_EMU switch exists only
+// so that tests/emu can run the *same kernel source* on CPU threads in a
+// container without a GPU; the shipped library is always built by nvcc.
+#pragma once
+#ifndef SX_EMU
+#include <cuda_runtime.h>
+#define SX_DYN_SMEM(type, name) \
+  extern __shared__ __align__(16) unsigned char sx_dyn_smem_raw[]; \
+  type* name = reinterpret_cast<type*>(sx_dyn_smem_raw)
+#define SX_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace sx {
+
+typedef double2 cplx;
+
+__host__ __device__ __forceinline__ cplx cmake(double x, double y) { return make_double2(x, y); }
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+  return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return cmake(a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cscale(cplx a, double s) { return cmake(a.x * s, a.y * s); }
+// i*a and -i*a
+__host__ __device__ __forceinline__ cplx cmuli(cplx a) { return cmake(-a.y, a.x); }
+__host__ __device__ __forceinline__ cplx cmulmi(cplx a) { return cmake(a.y, -a.x); }
+// a + s*b (real s)
+__host__ __device__ __forceinline__ cplx caxpy(double s, cplx b, cplx a) {
+  return cmake(fma(s, b.x, a.x), fma(s, b.y, a.y));
+}
+
+__host__ __device__ __forceinline__ int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- error plumbing (host) -------------------------------------------------
+void set_error(const std::string& msg);
+#define SX_CUDA_CHECK(expr)                                                          \
+  do {                                                                               \
+    cudaError_t sx_e_ = (expr);                                                      \
+    if (sx_e_ != cudaSuccess) {                                                      \
+      sx::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(sx_e_) +   \
+                    " at " + __FILE__ + ":" + std::to_string(__LINE__));             \
+      return 1;                                                                      \
+    }                                                                                \
+  } while (0)
+#define SX_KERNEL_CHECK() SX_CUDA_CHECK(cudaGetLastError())
+#define SX_REQUIRE(cond, msg)                        \
+  do {                                               \
+    if (!(cond)) {                                   \
+      sx::set_error(std::string("[ERROR] ") + msg);  \
+      return 1;                                      \
+    }                                                \
+  } while (0)
+
+}  // namespace sx

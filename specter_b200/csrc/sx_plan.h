@@ -1,0 +1,93 @@
+// Internal plan object behind the C ABI (include/specter_b200.h).
+#pragma once
+#include <string>
+#include <vector>
+#include "sx_common.cuh"
+
+namespace sx {
+
+struct HdState;  // fused-path device state (sx_rkstep.cu)
+
+struct Plan {
+  // configuration (mirrors FCPLAN + grid/kes modules of the reference)
+  int nx = 0, ny = 0, nz = 0, Cz = 0, oz = 0, ord = 2;
+  double Lx = 1, Ly = 1, Lz = 1;
+  int nprocs = 1, myrank = 0, device = 0;
+  // slab partition, 1-based inclusive like the reference (fftp.fpp:1154-1184)
+  int nxh = 0, ista = 1, iend = 0, ksta = 1, kend = 0, pkend = 0, nxl = 0, nzl = 0;
+  double dx = 0, dy = 0, dz = 0, Dkx = 0, Dky = 0, Dkz = 0;
+  // host copies
+  std::vector<double> h_kx, h_ky, h_kz, h_z, h_dir, h_neu, h_neu2;
+  // device tables
+  double *d_kx = nullptr, *d_ky = nullptr, *d_kz = nullptr;  // kx is the LOCAL slab kx(ista:iend)
+  double *d_fx = nullptr, *d_fy = nullptr, *d_fz = nullptr;  // fc_filter separable factors
+  double *d_z = nullptr, *d_dir = nullptr;
+  cplx *tw_x = nullptr, *tw_y = nullptr, *tw_z = nullptr;
+  cudaStream_t stream = nullptr;
+  // scratch pool (lazily grown): complex spectral-sized and real-sized work arrays
+  std::vector<cplx*> cwork;
+  std::vector<double*> rwork;
+  double* d_red = nullptr;   // reduction partials
+  double* h_red = nullptr;   // pinned host landing zone
+  int red_blocks = 0;
+  HdState* hd = nullptr;
+  unsigned long long launches = 0;  // kernels launched by this plan (bench "gpu_launches")
+
+  size_t csize() const { return (size_t)nz * ny * nxl; }   // complex elements per spectral field
+  size_t rsize() const { return (size_t)nx * ny * nzl; }   // doubles per real field
+  int nphys() const { return nz - Cz; }
+};
+
+// scratch management
+int plan_cwork(Plan& p, int idx, cplx** out);
+int plan_rwork(Plan& p, int idx, double** out);
+
+// ---- FFT stage launchers (sx_kernels_fft.cu) ----------------------------------
+int launch_zfft(Plan& p, const cplx* in, cplx* out, long npencils, int dir, bool cont,
+                double scale_phys, double scale_cont);
+int launch_yfft(Plan& p, const cplx* in, cplx* out, int nzc, int nxc, int nz_active, int dir,
+                double scale);
+int launch_x_c2r(Plan& p, const cplx* spec, double* real, int nzc, int nz_active, double scale);
+int launch_x_r2c(Plan& p, const double* real, cplx* spec, int nzc, int nz_active, double scale);
+bool fft_size_supported(int n, bool zdir);
+
+// ---- operator launchers (sx_kernels_ops.cu) -------------------------------------
+int op_derivk(Plan& p, const cplx* a, cplx* b, int dir);
+int op_laplak(Plan& p, const cplx* a, cplx* b);
+int op_curlk(Plan& p, const cplx* a, const cplx* b, cplx* c, int dir);
+int op_fc_filter(Plan& p, cplx* a);
+int op_copy(Plan& p, const cplx* a, cplx* b);
+int op_add(Plan& p, cplx* a, const cplx* b);
+int op_scale_phys(Plan& p, cplx* a, double s);
+int op_rk_axpy(Plan& p, cplx* v, const cplx* v0, const cplx* nl, const cplx* f, double dt,
+               double nu, double rmp);
+int op_gradre_products(Plan& p, double* const r[12], double* rx, double* ry, double* rz);
+int op_cross_products(Plan& p, const double* a1, const double* a2, const double* a3,
+                      const double* b1, const double* b2, const double* b3, double* rx,
+                      double* ry, double* rz);
+int op_proj_inhomogeneous(Plan& p, cplx* a, cplx* b, cplx* c, cplx* d, cplx* C1, int bctarget);
+int op_laplace_z(Plan& p, const cplx* C1, const cplx* C2in, cplx* C2, cplx* C3, int bctarget,
+                 int bczsta, int bczend);
+int op_pr_combine(Plan& p, cplx* d, const cplx* C1, const cplx* C2, int bctarget);
+int op_apply_hom(Plan& p, cplx* a, cplx* b, cplx* c, const cplx* C2, const cplx* C3);
+int op_noslip(Plan& p, cplx* vx, cplx* vy, const cplx* pr, int o, double vbx0, double vby0,
+              double vbx1, double vby1);
+int op_reduce_phys(Plan& p, const cplx* a, const cplx* b, int mode, int row, double scale,
+                   double* result);
+
+// ---- composite operators (sx_api.cu) ------------------------------------------------
+int fft1d_z_fwd(Plan& p, cplx* a);
+int fft1d_z_bwd(Plan& p, const cplx* in, cplx* out, double scale_phys);
+int fft3d_r2c(Plan& p, const double* r, cplx* out);
+int fft3d_c2r(Plan& p, const cplx* in, double* r);
+int gradre(Plan& p, const cplx* a, const cplx* b, const cplx* c, cplx* d, cplx* e, cplx* f);
+int v_imposebc_and_project(Plan& p, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int rki, const double* zs,
+                           const double* ze);
+int hd_state_free(Plan& p);
+
+}  // namespace sx
+
+// the opaque handle of include/specter_b200.h
+struct sx_plan {
+  sx::Plan p;
+};

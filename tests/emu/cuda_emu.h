@@ -1,0 +1,172 @@
+// Minimal CUDA-on-CPU shim.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiling specter_b200/csrc/*.cu with g++ -DSX_EMU -include tests/emu/cuda_emu.h
+// produces tests/emu/_build/libspecter_emu.so: the *same kernel source* executed by
+// OS threads (one per CUDA thread, std::barrier for __syncthreads).  The non-GPU
+// test-suite uses it to check kernel index math / barrier structure in a
+// container that has no GPU.  The product package never loads it (specter_b200
+// only ever dlopens libspecter_b200.so and fails loudly without a CUDA device).
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__ __restrict
+#define __launch_bounds__(...)
+#define __constant__ static
+
+struct double2 { double x, y; };
+struct double4 { double x, y, z, w; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+struct emu_event { std::chrono::steady_clock::time_point t; };
+typedef emu_event* cudaEvent_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaStreamNonBlocking = 1 };
+
+namespace emu {
+struct BlockCtx {
+  std::barrier<>* bar;
+  char* smem;
+  double* shfl;  // scratch for warp shuffles (one slot per thread)
+};
+inline thread_local uint3 t_threadIdx, t_blockIdx;
+inline thread_local dim3 t_blockDim, t_gridDim;
+inline thread_local BlockCtx t_ctx;
+
+template <class F>
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
+  const unsigned nthr = block.x * block.y * block.z;
+  const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+  if (nthr == 0 || nblocks == 0) return;
+  unsigned ngroups = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 8u));
+  if (nthr >= 512) ngroups = std::min(ngroups, 4u);
+  if ((unsigned long long)ngroups > nblocks) ngroups = (unsigned)nblocks;
+  std::vector<std::thread> pool;
+  pool.reserve((size_t)ngroups * nthr);
+  std::vector<std::unique_ptr<std::barrier<>>> bars;
+  std::vector<std::vector<char>> smems(ngroups);
+  std::vector<std::vector<double>> shfls(ngroups);
+  for (unsigned g = 0; g < ngroups; ++g) {
+    bars.emplace_back(new std::barrier<>(nthr));
+    smems[g].assign(smem_bytes + 64, 0);
+    shfls[g].assign(nthr * 2, 0.0);
+  }
+  for (unsigned g = 0; g < ngroups; ++g) {
+    for (unsigned t = 0; t < nthr; ++t) {
+      pool.emplace_back([&, g, t]() {
+        t_blockDim = block;
+        t_gridDim = grid;
+        t_threadIdx.x = t % block.x;
+        t_threadIdx.y = (t / block.x) % block.y;
+        t_threadIdx.z = t / (block.x * block.y);
+        t_ctx.bar = bars[g].get();
+        t_ctx.smem = smems[g].data();
+        t_ctx.shfl = shfls[g].data();
+        for (unsigned long long b = g; b < nblocks; b += ngroups) {
+          t_blockIdx.x = (unsigned)(b % grid.x);
+          t_blockIdx.y = (unsigned)((b / grid.x) % grid.y);
+          t_blockIdx.z = (unsigned)(b / ((unsigned long long)grid.x * grid.y));
+          body();
+          t_ctx.bar->arrive_and_wait();
+        }
+      });
+    }
+  }
+  for (auto& th : pool) th.join();
+}
+}  // namespace emu
+
+#define threadIdx (emu::t_threadIdx)
+#define blockIdx (emu::t_blockIdx)
+#define blockDim (emu::t_blockDim)
+#define gridDim (emu::t_gridDim)
+static inline void __syncthreads() { emu::t_ctx.bar->arrive_and_wait(); }
+#define SX_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::t_ctx.smem)
+
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline double atomicAdd(double* addr, double v) {
+  std::atomic_ref<double> r(*addr);
+  double old = r.load();
+  while (!r.compare_exchange_weak(old, old + v)) {}
+  return old;
+}
+// Warp shuffles emulated through block-wide scratch: valid only when every thread
+// of the block executes the call (which is how the kernels use them).
+static inline double __shfl_xor_sync(unsigned, double v, int lanemask) {
+  unsigned tid = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
+  emu::t_ctx.shfl[tid] = v;
+  __syncthreads();
+  unsigned nthr = blockDim.x * blockDim.y * blockDim.z;
+  unsigned src = tid ^ (unsigned)lanemask;
+  double r = (src < nthr) ? emu::t_ctx.shfl[src] : v;
+  __syncthreads();
+  return r;
+}
+static inline double __shfl_down_sync(unsigned, double v, int delta) {
+  unsigned tid = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
+  emu::t_ctx.shfl[tid] = v;
+  __syncthreads();
+  unsigned nthr = blockDim.x * blockDim.y * blockDim.z;
+  unsigned src = tid + (unsigned)delta;
+  double r = (src < nthr && (src / 32) == (tid / 32)) ? emu::t_ctx.shfl[src] : v;
+  __syncthreads();
+  return r;
+}
+
+// ---- runtime subset -------------------------------------------------------
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(1, n ? n : 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
+static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { std::memmove(d, s, n); return 0; }
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { std::memset(d, v, n); return 0; }
+static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaDeviceSynchronize() { return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event(); return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0) { e->t = std::chrono::steady_clock::now(); return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+  return 0;
+}
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+
+#define SX_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
