@@ -2,13 +2,12 @@
 //
 // Compiling specter_b200/csrc/*.cu with g++ -DSX_EMU -include tests/emu/cuda_emu.h
 // produces tests/emu/_build/libspecter_emu.so: the *same kernel source* executed by
-// OS threads (one per CUDA thread, std::barrier for __syncthreads).  The non-GPU
+// user-level fibers (one per CUDA thread; __syncthreads is a yield).  The non-GPU
 // test-suite uses it to check kernel index math / barrier structure in a
 // container that has no GPU.  The product package never loads it (specter_b200
 // only ever dlopens libspecter_b200.so and fails loudly without a CUDA device).
 #pragma once
 #include <atomic>
-#include <barrier>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -19,6 +18,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <ucontext.h>
 #include <vector>
 
 #define __global__
@@ -49,53 +49,99 @@ enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum { cudaStreamNonBlocking = 1 };
 
 namespace emu {
-struct BlockCtx {
-  std::barrier<>* bar;
-  char* smem;
-  double* shfl;  // scratch for warp shuffles (one slot per thread)
+// One OS worker per block group; the CUDA threads of a block are user-level fibers (ucontext)
+// scheduled round-robin, so __syncthreads() is a yield: every fiber runs up to its next barrier
+// before any fiber passes it.
+struct Fiber {
+  ucontext_t ctx;
+  bool done;
+};
+struct Worker {
+  ucontext_t main;
+  std::vector<Fiber> fibers;
+  std::vector<char> stacks;
+  size_t stack_bytes = 0;
+  int current = 0;
+  const std::function<void()>* body = nullptr;
+  dim3 block;
+  char* smem = nullptr;
+  std::vector<double> shfl;
 };
 inline thread_local uint3 t_threadIdx, t_blockIdx;
 inline thread_local dim3 t_blockDim, t_gridDim;
-inline thread_local BlockCtx t_ctx;
+inline thread_local Worker* t_worker = nullptr;
+
+inline void set_tid(Worker* w, unsigned t) {
+  t_threadIdx.x = t % w->block.x;
+  t_threadIdx.y = (t / w->block.x) % w->block.y;
+  t_threadIdx.z = t / (w->block.x * w->block.y);
+}
+inline void fiber_entry() {
+  Worker* w = t_worker;
+  (*w->body)();
+  Fiber& f = w->fibers[w->current];
+  f.done = true;
+  swapcontext(&f.ctx, &w->main);
+}
+inline void yield() {
+  Worker* w = t_worker;
+  swapcontext(&w->fibers[w->current].ctx, &w->main);
+}
+inline void run_block(Worker* w, unsigned nthr) {
+  for (unsigned t = 0; t < nthr; ++t) {
+    Fiber& f = w->fibers[t];
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = w->stacks.data() + (size_t)t * w->stack_bytes;
+    f.ctx.uc_stack.ss_size = w->stack_bytes;
+    f.ctx.uc_link = nullptr;
+    f.done = false;
+    makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+  }
+  unsigned remaining = nthr;
+  while (remaining) {
+    for (unsigned t = 0; t < nthr; ++t) {
+      Fiber& f = w->fibers[t];
+      if (f.done) continue;
+      w->current = (int)t;
+      set_tid(w, t);
+      swapcontext(&w->main, &f.ctx);
+      if (f.done) --remaining;
+    }
+  }
+}
 
 template <class F>
-void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body_in) {
   const unsigned nthr = block.x * block.y * block.z;
   const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
   if (nthr == 0 || nblocks == 0) return;
   unsigned ngroups = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 8u));
-  if (nthr >= 512) ngroups = std::min(ngroups, 4u);
   if ((unsigned long long)ngroups > nblocks) ngroups = (unsigned)nblocks;
+  const std::function<void()> body = body_in;
   std::vector<std::thread> pool;
-  pool.reserve((size_t)ngroups * nthr);
-  std::vector<std::unique_ptr<std::barrier<>>> bars;
-  std::vector<std::vector<char>> smems(ngroups);
-  std::vector<std::vector<double>> shfls(ngroups);
+  pool.reserve(ngroups);
   for (unsigned g = 0; g < ngroups; ++g) {
-    bars.emplace_back(new std::barrier<>(nthr));
-    smems[g].assign(smem_bytes + 64, 0);
-    shfls[g].assign(nthr * 2, 0.0);
-  }
-  for (unsigned g = 0; g < ngroups; ++g) {
-    for (unsigned t = 0; t < nthr; ++t) {
-      pool.emplace_back([&, g, t]() {
-        t_blockDim = block;
-        t_gridDim = grid;
-        t_threadIdx.x = t % block.x;
-        t_threadIdx.y = (t / block.x) % block.y;
-        t_threadIdx.z = t / (block.x * block.y);
-        t_ctx.bar = bars[g].get();
-        t_ctx.smem = smems[g].data();
-        t_ctx.shfl = shfls[g].data();
-        for (unsigned long long b = g; b < nblocks; b += ngroups) {
-          t_blockIdx.x = (unsigned)(b % grid.x);
-          t_blockIdx.y = (unsigned)((b / grid.x) % grid.y);
-          t_blockIdx.z = (unsigned)(b / ((unsigned long long)grid.x * grid.y));
-          body();
-          t_ctx.bar->arrive_and_wait();
-        }
-      });
-    }
+    pool.emplace_back([&, g]() {
+      Worker w;
+      w.block = block;
+      w.body = &body;
+      w.stack_bytes = 64 * 1024;
+      w.stacks.resize((size_t)nthr * w.stack_bytes);
+      w.fibers.resize(nthr);
+      std::vector<char> smem(smem_bytes + 64, 0);
+      w.smem = smem.data();
+      w.shfl.assign((size_t)nthr * 2, 0.0);
+      t_worker = &w;
+      t_blockDim = block;
+      t_gridDim = grid;
+      for (unsigned long long b = g; b < nblocks; b += ngroups) {
+        t_blockIdx.x = (unsigned)(b % grid.x);
+        t_blockIdx.y = (unsigned)((b / grid.x) % grid.y);
+        t_blockIdx.z = (unsigned)(b / ((unsigned long long)grid.x * grid.y));
+        run_block(&w, nthr);
+      }
+      t_worker = nullptr;
+    });
   }
   for (auto& th : pool) th.join();
 }
@@ -105,8 +151,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
 #define blockIdx (emu::t_blockIdx)
 #define blockDim (emu::t_blockDim)
 #define gridDim (emu::t_gridDim)
-static inline void __syncthreads() { emu::t_ctx.bar->arrive_and_wait(); }
-#define SX_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::t_ctx.smem)
+static inline void __syncthreads() { emu::yield(); }
+#define SX_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::t_worker->smem)
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline double atomicAdd(double* addr, double v) {
@@ -119,21 +165,21 @@ static inline double atomicAdd(double* addr, double v) {
 // of the block executes the call (which is how the kernels use them).
 static inline double __shfl_xor_sync(unsigned, double v, int lanemask) {
   unsigned tid = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
-  emu::t_ctx.shfl[tid] = v;
+  emu::t_worker->shfl[tid] = v;
   __syncthreads();
   unsigned nthr = blockDim.x * blockDim.y * blockDim.z;
   unsigned src = tid ^ (unsigned)lanemask;
-  double r = (src < nthr) ? emu::t_ctx.shfl[src] : v;
+  double r = (src < nthr) ? emu::t_worker->shfl[src] : v;
   __syncthreads();
   return r;
 }
 static inline double __shfl_down_sync(unsigned, double v, int delta) {
   unsigned tid = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
-  emu::t_ctx.shfl[tid] = v;
+  emu::t_worker->shfl[tid] = v;
   __syncthreads();
   unsigned nthr = blockDim.x * blockDim.y * blockDim.z;
   unsigned src = tid + (unsigned)delta;
-  double r = (src < nthr && (src / 32) == (tid / 32)) ? emu::t_ctx.shfl[src] : v;
+  double r = (src < nthr && (src / 32) == (tid / 32)) ? emu::t_worker->shfl[src] : v;
   __syncthreads();
   return r;
 }
