@@ -48,6 +48,19 @@ int sx_range(int n1, int n2, int nprocs, int irank, int* sta, int* end);
 /* kernels launched by this plan so far */
 unsigned long long sx_plan_launch_count(const sx_plan* plan);
 int sx_plan_synchronize(sx_plan* plan);
+/* CUDA-event timing on the plan's own stream (replaces the GTStart/GTStop wall timers around the
+ * RK loop, specter.fpp:985-999): begin records an event, end records another, synchronises and
+ * returns the elapsed device time in milliseconds. */
+int sx_plan_time_begin(sx_plan* plan);
+int sx_plan_time_end(sx_plan* plan, double* ms);
+/* Per-kernel-family device timers, the counterpart of the reference's ffttime / tratime / comtime /
+ * conttime columns of benchmark.txt (fftp_mod.fpp:32-37, specter.fpp:1182-1228).  While enabled an
+ * event is recorded before every kernel launch; sx_plan_stage_times synchronises and returns the
+ * accumulated milliseconds and launch counts per stage id (0 .. sx_stage_count()-1). */
+int sx_stage_count(void);
+const char* sx_stage_name(int id);
+int sx_plan_stage_timing(sx_plan* plan, int on);
+int sx_plan_stage_times(sx_plan* plan, double* ms, long long* counts, int n);
 /* multi-GPU: 128-byte NCCL unique id created on rank 0 and shared by the caller
  * (MPI_BCAST in the Fortran driver, torch.distributed in the Python harness) */
 int sx_nccl_unique_id(void* id128);

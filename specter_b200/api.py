@@ -50,6 +50,12 @@ SIGNATURES = {
     "sx_range": [_I, _I, _I, _I, _PI, _PI],
     "sx_plan_launch_count": [_P],
     "sx_plan_synchronize": [_P],
+    "sx_plan_time_begin": [_P],
+    "sx_plan_time_end": [_P, _PD],
+    "sx_stage_count": [],
+    "sx_stage_name": [_I],
+    "sx_plan_stage_timing": [_P, _I],
+    "sx_plan_stage_times": [_P, _PD, C.POINTER(C.c_longlong), _I],
     "sx_nccl_unique_id": [_D],
     "sx_plan_set_comm": [_P, _D],
     "sx_malloc": [_P, C.c_size_t, C.POINTER(_D)],
@@ -87,7 +93,7 @@ SIGNATURES = {
     "sx_hd_rkstep2": [_P, _I, _F, _F, _PD, _PD, _I],
     "sx_hd_step_host": [_P, _D, _D, _D, _D, _D, _D, _D, _F, _F, _PD, _PD],
 }
-_RESTYPES = {"sx_last_error": C.c_char_p, "sx_version": C.c_char_p,
+_RESTYPES = {"sx_stage_name": C.c_char_p, "sx_last_error": C.c_char_p, "sx_version": C.c_char_p,
              "sx_plan_launch_count": C.c_ulonglong, "sx_spectral_bytes": C.c_size_t,
              "sx_real_bytes": C.c_size_t}
 
@@ -101,7 +107,7 @@ class Library:
                 f"{path} not found: build the CUDA extension first (python -m specter_b200.build); "
                 "specter_b200 has no CPU fallback")
         self.path = path
-        self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        self.dll = C.CDLL(path)
         for name, args in SIGNATURES.items():
             fn = getattr(self.dll, name)  # AttributeError if the ABI is incomplete
             fn.argtypes = args
@@ -146,6 +152,19 @@ class DeviceArray:
         ptr = C.c_void_p()
         plan.lib.check(plan.lib.dll.sx_malloc(plan.handle, max(self.nbytes, 16), C.byref(ptr)))
         self.ptr = ptr
+        self.owned = True
+
+    @classmethod
+    def view(cls, plan: "Plan", kind: str, ptr) -> "DeviceArray":
+        """Wrap plan-owned device memory (not freed by this object)."""
+        self = cls.__new__(cls)
+        self.plan, self.kind = plan, kind
+        self.shape = plan.cshape if kind == "spectral" else plan.rshape
+        self.dtype = np.complex128 if kind == "spectral" else np.float64
+        self.nbytes = int(np.prod(self.shape)) * np.dtype(self.dtype).itemsize
+        self.ptr = ptr
+        self.owned = False
+        return self
 
     def put(self, host: np.ndarray) -> "DeviceArray":
         h = np.ascontiguousarray(host, dtype=self.dtype)
@@ -160,9 +179,9 @@ class DeviceArray:
         return out
 
     def free(self):
-        if self.ptr:
+        if self.ptr and self.owned and self.plan.handle:
             self.plan.lib.dll.sx_free(self.plan.handle, self.ptr)
-            self.ptr = None
+        self.ptr = None
 
 
 def _vec2(v):
@@ -187,6 +206,7 @@ class Plan:
         self.cshape = (self.nxl, ny, nz)
         self.rshape = (self.nzl, ny, nx)
         self._arrays = []
+        self._pinned = []
 
     # ---- memory ----
     def spectral(self, host: Optional[np.ndarray] = None) -> DeviceArray:
@@ -199,8 +219,21 @@ class Plan:
         self._arrays.append(a)
         return a.put(host) if host is not None else a
 
+    def pinned_like(self, a: np.ndarray) -> np.ndarray:
+        """A page-locked host copy of `a` (cudaMallocHost through the C ABI), freed by close()."""
+        ptr = C.c_void_p()
+        self.lib.check(self.lib.dll.sx_malloc_host(max(a.nbytes, 16), C.byref(ptr)))
+        self._pinned.append(ptr)
+        buf = (C.c_char * a.nbytes).from_address(ptr.value)
+        out = np.frombuffer(buf, dtype=a.dtype).reshape(a.shape)
+        out[...] = a
+        return out
+
     def close(self):
         if self.handle:
+            for q in self._pinned:
+                self.lib.dll.sx_free_host(q)
+            self._pinned = []
             for a in self._arrays:
                 a.free()
             self._arrays = []
@@ -215,6 +248,26 @@ class Plan:
 
     def synchronize(self):
         self.lib.check(self.lib.dll.sx_plan_synchronize(self.handle))
+
+    def time_begin(self):
+        self._call("sx_plan_time_begin")
+
+    def time_end(self) -> float:
+        """Elapsed device milliseconds on the plan's stream since time_begin (synchronises)."""
+        ms = C.c_double()
+        self._call("sx_plan_time_end", C.byref(ms))
+        return ms.value
+
+    def stage_timing(self, on: bool):
+        self._call("sx_plan_stage_timing", 1 if on else 0)
+
+    def stage_times(self) -> dict:
+        """{stage name: (milliseconds, launches)} accumulated since stage_timing(True)."""
+        n = self.lib.dll.sx_stage_count()
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        self._call("sx_plan_stage_times", ms, cnt, n)
+        return {self.lib.dll.sx_stage_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i]}
 
     @property
     def launch_count(self) -> int:
@@ -311,6 +364,12 @@ class Plan:
         out = [np.empty(self.cshape, dtype=np.complex128) for _ in range(4)]
         self._call("sx_hd_get_state", *[a.ctypes.data for a in out])
         return out
+
+    def hd_field(self, which: int) -> DeviceArray:
+        """Plan-owned HD state as a device array: 0..2 v, 3 pr, 4..6 f, 7..9 RK base."""
+        ptr = C.c_void_p()
+        self._call("sx_hd_state_ptr", which, C.byref(ptr))
+        return DeviceArray.view(self, "spectral", ptr)
 
     def hd_rkstep1(self):
         self._call("sx_hd_rkstep1")

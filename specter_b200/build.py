@@ -59,7 +59,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if pr.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+    cmd = [nvcc, "-shared", "-Xlinker", "-Bsymbolic", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 
@@ -82,7 +82,7 @@ def build_emu(force: bool = False) -> str:
         if pr.returncode:
             sys.stderr.write(out)
             raise RuntimeError("g++ (emu) failed: " + " ".join(cmd))
-    subprocess.check_call(["g++", "-shared", "-o", EMU_LIB] + objs + ["-lpthread", "-latomic"])
+    subprocess.check_call(["g++", "-shared", "-Wl,-Bsymbolic", "-o", EMU_LIB] + objs + ["-lpthread", "-latomic"])
     return EMU_LIB
 
 

@@ -71,6 +71,40 @@ static int upload_twiddles(int n, cplx** d) {
   return upload(d, h.data(), (size_t)cnt + 1);
 }
 
+const char* stage_name(int id) {
+  static const char* names[ST_COUNT] = {"other", "zfft", "yfft", "xfft", "elementwise", "reduce", "zinv_tile",
+                                        "yinv_tile", "xpass", "yfwd_tile", "zfwd_rk", "project", "exchange"};
+  return (id >= 0 && id < ST_COUNT) ? names[id] : "?";
+}
+int stage_mark_slow(Plan& p, int id) {
+  StageTimer& t = p.timer;
+  if (t.n == t.ev.size()) {
+    cudaEvent_t e;
+    SX_CUDA_CHECK(cudaEventCreate(&e));
+    t.ev.push_back(e);
+    t.ids.push_back(0);
+  }
+  SX_CUDA_CHECK(cudaEventRecord(t.ev[t.n], p.stream));
+  t.ids[t.n] = id;
+  t.n++;
+  if (t.n >= 8192) return stage_flush(p);
+  return 0;
+}
+int stage_flush(Plan& p) {
+  StageTimer& t = p.timer;
+  if (t.n == 0) return 0;
+  if (stage_mark_slow(p, -1)) return 1;  // closing event
+  SX_CUDA_CHECK(cudaEventSynchronize(t.ev[t.n - 1]));
+  for (size_t i = 0; i + 1 < t.n; ++i) {
+    float f = 0.f;
+    SX_CUDA_CHECK(cudaEventElapsedTime(&f, t.ev[i], t.ev[i + 1]));
+    const int id = t.ids[i];
+    if (id >= 0 && id < ST_COUNT) { t.ms[id] += f; t.cnt[id]++; }
+  }
+  t.n = 0;
+  return 0;
+}
+
 int plan_cwork(Plan& p, int idx, cplx** out) {
   if ((int)p.cwork.size() <= idx) p.cwork.resize(idx + 1, nullptr);
   if (!p.cwork[idx]) SX_CUDA_CHECK(cudaMalloc((void**)&p.cwork[idx], p.csize() * sizeof(cplx)));
@@ -135,6 +169,7 @@ static int plan_init(Plan& p, const sx_config& c) {
   }
   SX_CUDA_CHECK(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
   if (upload(&p.d_kx, p.h_kx.data(), p.h_kx.size())) return 1;
+  if (upload(&p.d_kxg, kxf.data(), (size_t)p.nxh)) return 1;
   if (upload(&p.d_ky, p.h_ky.data(), p.h_ky.size())) return 1;
   if (upload(&p.d_kz, p.h_kz.data(), p.h_kz.size())) return 1;
   if (upload(&p.d_fx, fx.data(), fx.size())) return 1;
@@ -153,11 +188,15 @@ static int plan_init(Plan& p, const sx_config& c) {
 
 static void plan_release(Plan& p) {
   hd_state_free(p);
+  fused_free(p);
+  for (auto e : p.timer.ev) cudaEventDestroy(e);
   for (auto* q : p.cwork) if (q) cudaFree(q);
   for (auto* q : p.rwork) if (q) cudaFree(q);
-  void* tabs[] = {p.d_kx, p.d_ky, p.d_kz, p.d_fx, p.d_fy, p.d_fz, p.d_z, p.d_dir, p.tw_x, p.tw_y, p.tw_z, p.d_red};
+  void* tabs[] = {p.d_kxg, p.d_kx, p.d_ky, p.d_kz, p.d_fx, p.d_fy, p.d_fz, p.d_z, p.d_dir, p.tw_x, p.tw_y, p.tw_z, p.d_red};
   for (void* q : tabs) if (q) cudaFree(q);
   if (p.h_red) cudaFreeHost(p.h_red);
+  if (p.ev_t0) cudaEventDestroy(p.ev_t0);
+  if (p.ev_t1) cudaEventDestroy(p.ev_t1);
   if (p.stream) cudaStreamDestroy(p.stream);
 }
 
@@ -405,6 +444,39 @@ int sx_range(int n1, int n2, int nprocs, int irank, int* sta, int* end) {
 }
 unsigned long long sx_plan_launch_count(const sx_plan* plan) { return plan ? plan->p.launches : 0ULL; }
 int sx_plan_synchronize(sx_plan* plan) { SX_PLAN(plan); SX_CUDA_CHECK(cudaStreamSynchronize(p.stream)); return 0; }
+
+int sx_plan_time_begin(sx_plan* plan) {
+  SX_PLAN(plan);
+  if (!p.ev_t0) { SX_CUDA_CHECK(cudaEventCreate(&p.ev_t0)); SX_CUDA_CHECK(cudaEventCreate(&p.ev_t1)); }
+  SX_CUDA_CHECK(cudaEventRecord(p.ev_t0, p.stream));
+  return 0;
+}
+int sx_plan_time_end(sx_plan* plan, double* ms) {
+  SX_PLAN(plan);
+  SX_REQUIRE(p.ev_t0 && ms, "sx_plan_time_end without sx_plan_time_begin");
+  SX_CUDA_CHECK(cudaEventRecord(p.ev_t1, p.stream));
+  SX_CUDA_CHECK(cudaEventSynchronize(p.ev_t1));
+  float f = 0.f;
+  SX_CUDA_CHECK(cudaEventElapsedTime(&f, p.ev_t0, p.ev_t1));
+  *ms = (double)f;
+  return 0;
+}
+
+int sx_stage_count(void) { return ST_COUNT; }
+const char* sx_stage_name(int id) { return stage_name(id); }
+int sx_plan_stage_timing(sx_plan* plan, int on) {
+  SX_PLAN(plan);
+  if (stage_flush(p)) return 1;
+  p.timer.on = on != 0;
+  if (on) for (int i = 0; i < ST_COUNT; ++i) { p.timer.ms[i] = 0; p.timer.cnt[i] = 0; }
+  return 0;
+}
+int sx_plan_stage_times(sx_plan* plan, double* ms, long long* counts, int n) {
+  SX_PLAN(plan);
+  if (stage_flush(p)) return 1;
+  for (int i = 0; i < n && i < ST_COUNT; ++i) { if (ms) ms[i] = p.timer.ms[i]; if (counts) counts[i] = p.timer.cnt[i]; }
+  return 0;
+}
 
 int sx_nccl_unique_id(void*) { sx::set_error("[ERROR] multi-GPU path not built in this version"); return 1; }
 int sx_plan_set_comm(sx_plan*, const void*) { sx::set_error("[ERROR] multi-GPU path not built in this version"); return 1; }

@@ -1,8 +1,776 @@
-// placeholder until the fused path lands
+// The fused HD Runge-Kutta substep (include/hd/hd_rkstep2.f90:3-36 of the reference) as six
+// memory-bound passes.  Every pass is one FFT axis with the neighbouring elementwise work and the
+// slab transposition folded into its load / store pattern:
+//
+//   zinv_tile   v^(kz,ky,kx)      -> z-IFFT of v and of i kz v, physical rows only, written ky-fastest
+//                                    in the exchange layout [rank][kx][z][ky]           (fftp.fpp:1060-1094)
+//   yinv_tile   [kx][z][ky]       -> y-IFFT of (v, i ky v, dz v), written kx-fastest [z][y][kx]
+//   xpass       [z][y][kx] x 9    -> 12 c2r lines (i kx applied on load), (u.grad)u / N^2, 3 r2c lines
+//                                                                           (pseudospec_hd.f90:245-316)
+//   yfwd_tile   [z][y][kx] x 3    -> y-FFT, written ky-fastest [kx][z][ky]
+//   zfwd_rk     [kx][z][ky]       -> FC-Gram continuation + z-FFT (fftp.fpp:757-780), fc_filter
+//                                    (pseudospec_hd.f90:1099-1112), Laplacian + RK update (hd_rkstep2.f90:14-32)
+//   project     per (ky,kx) pencil: no-slip walls + Poisson/Laplace projection, nine z transforms in
+//                                    shared memory (vboundary.f90:116-148, boundary_mod.fpp:197-402)
+//
+// Derivative sharing: d/dx and d/dy commute with the z-IFFT and the transposition, so only v and
+// dz v (6 fields, not 12) cross the transposition; rows above the physical region never do (the
+// products only use k <= pkend, pseudospec_hd.f90:255, and the forward continuation overwrites them).
+//
+// Thread mapping of the "tile" kernels: NP lines per CTA, lane-fastest over the NP lines
+// (p = tid % NP, j = tid / NP, T = N/8 threads per line).  One side of the kernel then moves
+// NP*16 B = 128 B full lines per quarter-warp and the other side 64 B pieces of NP different lines,
+// which is the transposition.
+#include "sx_fft.cuh"
 #include "sx_plan.h"
+
 namespace sx {
-int hd_rkstep2_fused(Plan& p, cplx* const* f, int o, double dt, double nu, const double* zs, const double* ze) {
-  (void)p; (void)f; (void)o; (void)dt; (void)nu; (void)zs; (void)ze;
-  SX_REQUIRE(false, "fused substep not built yet");
+
+// where physical row z lives in the exchange layout [rank][kxl][zl][ky]
+struct ZMap {
+  long long base;  // complex elements before this rank's block
+  int nzl;         // rows held by the owning rank
+  int zl;          // row index inside the owning rank
+  int pad;
+};
+
+struct Fused {
+  int nph = 0;     // physical rows nz - Cz
+  int nzf = 0;     // physical rows owned by this rank in real space (balanced partition)
+  int zf0 = 0;     // first owned physical row (0-based)
+  int nxp = 0;     // padded kx extent of the [z][y][kx] arrays (multiple of 8)
+  size_t wsize = 0;  // complex elements of one exchange-layout slot: nxl * nph * ny
+  size_t vsize = 0;  // complex elements of one [z][y][kx] slot: nzf * ny * nxp
+  ZMap* d_zmap = nullptr;
+  cplx* W[6] = {nullptr};   // z-stage side, exchange layout (v_c, dz v_c)
+  cplx* R[6] = {nullptr};   // y-stage side [kx][zl][ky] (aliases W on one GPU)
+  cplx* V[9] = {nullptr};   // [zl][y][kx]: v, dy v, dz v
+  cplx* X[3] = {nullptr};   // [zl][y][kx]: nonlinear term after the x pass
+  cplx* U[3] = {nullptr};   // y-stage side of the way back [kx][zl][ky]
+  cplx* Uz[3] = {nullptr};  // z-stage side of the way back (aliases U on one GPU)
+};
+
+template <int N> struct TileNP {
+  static constexpr int value = N <= 64 ? 32 : (N == 128 ? 16 : (N <= 1024 ? 8 : 4));
+};
+
+// ------------------------------------------------------------------------------------------
+// zinv_tile: one CTA = NP adjacent ky pencils of one kx.
+// ------------------------------------------------------------------------------------------
+struct ZinvArgs {
+  const cplx* in;   // spectral (nz, ny, nxl)
+  cplx* out0;       // IFFT_z(in), exchange layout
+  cplx* out1;       // IFFT_z(i kz in) or nullptr
+  const double* kz;
+  const ZMap* zmap;
+  int ny, nph;
+};
+
+template <int N, int NP>
+__global__ void __launch_bounds__(NP*(N / 8)) k_zinv_tile(ZinvArgs a, const cplx* __restrict__ tw) {
+  SX_DYN_SMEM(cplx, smem);
+  constexpr int T = N / 8;
+  const int p = threadIdx.x % NP, j = threadIdx.x / NP;
+  const int ky = blockIdx.x * NP + p, kxl = blockIdx.y;
+  const bool active = ky < a.ny;
+  const cplx* src = a.in + ((size_t)kxl * a.ny + (active ? ky : 0)) * N;
+  const SIdxPencil si{p, NP};
+  // destination offsets of this thread's 8 rows (identical for both outputs)
+  long long off[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int z = j + k * T;
+    if (active && z < a.nph) {
+      const ZMap m = a.zmap[z];
+      off[k] = m.base + ((long long)kxl * m.nzl + m.zl) * a.ny + ky;
+    } else {
+      off[k] = -1;
+    }
+  }
+  cplx v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = active ? src[j + k * T] : cmake(0.0, 0.0);
+  fft_regs<N, 1>(v, j, smem, si, tw);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (off[k] >= 0) a.out0[off[k]] = v[k];
+  if (a.out1 != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = j + k * T;
+      const cplx t = active ? src[e] : cmake(0.0, 0.0);  // L1/L2 hit: just read by this CTA
+      const double kk = __ldg(&a.kz[e]);
+      v[k] = cmake(-kk * t.y, kk * t.x);
+    }
+    fft_regs<N, 1>(v, j, smem, si, tw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (off[k] >= 0) a.out1[off[k]] = v[k];
+  }
 }
+
+// ------------------------------------------------------------------------------------------
+// yinv_tile: one CTA = NP adjacent kx lines of one local z row; [kx][zl][ky] -> [zl][y][kx].
+// ------------------------------------------------------------------------------------------
+struct YinvArgs {
+  const cplx* in;   // [kx][zl][ky]
+  cplx* out0;       // IFFT_y(in)          [zl][y][kx]
+  cplx* out1;       // IFFT_y(i ky in) or nullptr
+  const double* ky;
+  int nxh, nxp, nzf;
+};
+
+template <int N, int NP>
+__global__ void __launch_bounds__(NP*(N / 8)) k_yinv_tile(YinvArgs a, const cplx* __restrict__ tw) {
+  SX_DYN_SMEM(cplx, smem);
+  constexpr int T = N / 8;
+  const int p = threadIdx.x % NP, j = threadIdx.x / NP;
+  const int kx = blockIdx.x * NP + p, zl = blockIdx.y;
+  const bool active = kx < a.nxh;
+  const bool store = kx < a.nxp;
+  const cplx* src = a.in + ((size_t)(active ? kx : 0) * a.nzf + zl) * N;
+  const size_t dst = (size_t)zl * N * a.nxp + kx;
+  const SIdxPencil si{p, NP};
+  cplx v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = active ? src[j + k * T] : cmake(0.0, 0.0);
+  fft_regs<N, 1>(v, j, smem, si, tw);
+  if (store) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.out0[dst + (size_t)(j + k * T) * a.nxp] = v[k];
+  }
+  if (a.out1 != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = j + k * T;
+      const cplx t = active ? src[e] : cmake(0.0, 0.0);
+      const double kk = __ldg(&a.ky[e]);
+      v[k] = cmake(-kk * t.y, kk * t.x);
+    }
+    fft_regs<N, 1>(v, j, smem, si, tw);
+    if (store) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a.out1[dst + (size_t)(j + k * T) * a.nxp] = v[k];
+    }
+  }
 }
+
+// ------------------------------------------------------------------------------------------
+// yfwd_tile: [zl][y][kx] -> y-FFT -> [kx][zl][ky]
+// ------------------------------------------------------------------------------------------
+struct YfwdArgs {
+  const cplx* in;
+  cplx* out;
+  int nxh, nxp, nzf;
+};
+
+template <int N, int NP>
+__global__ void __launch_bounds__(NP*(N / 8)) k_yfwd_tile(YfwdArgs a, const cplx* __restrict__ tw) {
+  SX_DYN_SMEM(cplx, smem);
+  constexpr int T = N / 8;
+  const int p = threadIdx.x % NP, j = threadIdx.x / NP;
+  const int kx = blockIdx.x * NP + p, zl = blockIdx.y;
+  const bool active = kx < a.nxh;
+  const size_t src = (size_t)zl * N * a.nxp + (active ? kx : 0);
+  cplx v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = active ? a.in[src + (size_t)(j + k * T) * a.nxp] : cmake(0.0, 0.0);
+  fft_regs<N, -1>(v, j, smem, SIdxPencil{p, NP}, tw);
+  if (active) {
+    cplx* dst = a.out + ((size_t)kx * a.nzf + zl) * N;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[j + k * T] = v[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// xpass (gradre): one CTA = LP pairs of adjacent y lines of one local z row.  Two real lines ride
+// one complex FFT of length nx:  Z(k) = A(k) + i B(k) on the Hermitian-completed spectra.  FFTW's
+// c2r ignores Im of the kx = 0 and kx = nx/2 entries; so do we (after the i kx factor, as the
+// reference applies derivk before the transform).
+// ------------------------------------------------------------------------------------------
+struct XpassArgs {
+  const cplx* V[9];  // v(3), dy v(3), dz v(3)   [zl][y][kx]
+  cplx* X[3];
+  const double* kx;  // GLOBAL kx(1:nx/2+1)
+  int ny, nxp;
+  double tmp;        // 1/(nx ny nz)^2
+};
+
+template <int N, bool DERIV>
+__device__ __forceinline__ void x_load_pair(cplx (&v)[8], const cplx* __restrict__ f, size_t rowA, size_t rowB,
+                                            int t, bool active, const double* __restrict__ kxv) {
+  constexpr int T = N / 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = t + k * T;
+    const int kx = e <= N / 2 ? e : N - e;
+    cplx A = active ? f[rowA + kx] : cmake(0.0, 0.0);
+    cplx B = active ? f[rowB + kx] : cmake(0.0, 0.0);
+    if (DERIV) {
+      const double kk = __ldg(&kxv[kx]);
+      A = cmake(-kk * A.y, kk * A.x);
+      B = cmake(-kk * B.y, kk * B.x);
+    }
+    if (kx == 0 || kx == N / 2) { A.y = 0.0; B.y = 0.0; }
+    if (e > N / 2) { A.y = -A.y; B.y = -B.y; }
+    v[k] = cmake(A.x - B.y, A.y + B.x);
+  }
+}
+
+template <int N, int LP>
+__global__ void __launch_bounds__(LP*(N / 8)) k_xpass_gradre(XpassArgs a, const cplx* __restrict__ tw) {
+  SX_DYN_SMEM(cplx, smem);
+  constexpr int T = N / 8;
+  const int lp = threadIdx.x / T, t = threadIdx.x % T;
+  const int y0 = (blockIdx.x * LP + lp) * 2, zl = blockIdx.y;
+  const bool active = y0 < a.ny;
+  const size_t rowA = ((size_t)zl * a.ny + (active ? y0 : 0)) * a.nxp, rowB = rowA + a.nxp;
+  const SIdxElem si{lp * sidx_elem_stride<N>()};
+  cplx u[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    x_load_pair<N, false>(u[c], a.V[c], rowA, rowB, t, active, a.kx);
+    fft_regs<N, 1>(u[c], t, smem, si, tw);
+  }
+#pragma unroll 1
+  for (int c = 0; c < 3; ++c) {
+    cplx acc[8], g[8];
+    x_load_pair<N, true>(g, a.V[c], rowA, rowB, t, active, a.kx);
+    fft_regs<N, 1>(g, t, smem, si, tw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = cmake(u[0][k].x * g[k].x, u[0][k].y * g[k].y);
+    x_load_pair<N, false>(g, a.V[3 + c], rowA, rowB, t, active, a.kx);
+    fft_regs<N, 1>(g, t, smem, si, tw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = cmake(acc[k].x + u[1][k].x * g[k].x, acc[k].y + u[1][k].y * g[k].y);
+    x_load_pair<N, false>(g, a.V[6 + c], rowA, rowB, t, active, a.kx);
+    fft_regs<N, 1>(g, t, smem, si, tw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      acc[k] = cmake((acc[k].x + u[2][k].x * g[k].x) * a.tmp, (acc[k].y + u[2][k].y * g[k].y) * a.tmp);
+    // forward transform of the packed pair and split into the two half spectra
+    fft_regs<N, -1>(acc, t, smem, si, tw);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) smem[si(t + k * T)] = acc[k];
+    __syncthreads();
+    cplx* out = a.X[c];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int kk = t + k * T;
+      if (kk <= N / 2 && active) {
+        const cplx Zk = acc[k];
+        const cplx Zn = smem[si((N - kk) & (N - 1))];
+        out[rowA + kk] = cmake(0.5 * (Zk.x + Zn.x), 0.5 * (Zk.y - Zn.y));
+        out[rowB + kk] = cmake(0.5 * (Zk.y + Zn.y), -0.5 * (Zk.x - Zn.x));
+      }
+    }
+    // (the next fft_regs starts with a __syncthreads before it writes the exchange buffer)
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// zfwd_rk: one CTA = NP adjacent ky pencils of one kx.  Reads the nonlinear term in the exchange
+// layout, continues it, transforms, filters and performs the RK update of one velocity component.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxDF = 10;
+
+struct ZfwdArgs {
+  const cplx* nl;     // exchange layout [rank][kxl][zl][ky], physical rows
+  cplx* v;            // spectral, in/out
+  const cplx* v0;     // RK base
+  const cplx* f;      // forcing
+  const ZMap* zmap;
+  const double *kx, *ky, *kz;     // kx LOCAL
+  const double *fx, *fy, *fz;     // filter factors (fx LOCAL)
+  const double* dir;  // [C][d]
+  int ny, nph, C, d;
+  double dt, nu, rmp;
+};
+
+// continuation rows of a pencil-fastest tile from the stashed boundary values
+// bnd[q*NP + p]: q in [0,d) = f(1..d), q in [d,2d) = f(n-C-d+1..n-C)
+template <int N, int NP>
+__device__ __forceinline__ void fc_continue_tile(cplx (&v)[8], int j, int p, const cplx* bnd, int nph, int C, int d,
+                                                 const double* __restrict__ dir) {
+  constexpr int T = N / 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = j + k * T;
+    if (e >= nph) {
+      const int ii = e - nph;
+      double ax = 0.0, ay = 0.0;
+      for (int jj = 0; jj < d; ++jj) {
+        const double w1 = __ldg(&dir[ii * d + jj]);
+        const double w2 = __ldg(&dir[(C - 1 - ii) * d + jj]);
+        const cplx f1 = bnd[(d + jj) * NP + p];
+        const cplx f2 = bnd[(d - 1 - jj) * NP + p];
+        ax = fma(w2, f2.x, fma(w1, f1.x, ax));
+        ay = fma(w2, f2.y, fma(w1, f1.y, ay));
+      }
+      v[k] = cmake(ax, ay);
+    }
+  }
+}
+
+template <int N, int NP>
+__device__ __forceinline__ void stash_boundary_tile(const cplx (&v)[8], int j, int p, cplx* bnd, int nph, int d) {
+  constexpr int T = N / 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = j + k * T;
+    if (e < d) bnd[e * NP + p] = v[k];
+    if (e >= nph - d && e < nph) bnd[(d + e - (nph - d)) * NP + p] = v[k];
+  }
+}
+
+template <int N, int NP>
+__global__ void __launch_bounds__(NP*(N / 8)) k_zfwd_rk(ZfwdArgs a, const cplx* __restrict__ tw) {
+  SX_DYN_SMEM(cplx, smem);
+  constexpr int T = N / 8;
+  const int p = threadIdx.x % NP, j = threadIdx.x / NP;
+  const int ky = blockIdx.x * NP + p, kxl = blockIdx.y;
+  const bool active = ky < a.ny;
+  cplx* bnd = smem + (size_t)NP * N;
+  cplx v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int z = j + k * T;
+    if (active && z < a.nph) {
+      const ZMap m = a.zmap[z];
+      v[k] = a.nl[m.base + ((long long)kxl * m.nzl + m.zl) * a.ny + ky];
+    } else {
+      v[k] = cmake(0.0, 0.0);
+    }
+  }
+  stash_boundary_tile<N, NP>(v, j, p, bnd, a.nph, a.d);
+  __syncthreads();
+  fc_continue_tile<N, NP>(v, j, p, bnd, a.nph, a.C, a.d, a.dir);
+  fft_regs<N, -1>(v, j, smem, SIdxPencil{p, NP}, tw);
+  if (active) {
+    const size_t base = ((size_t)kxl * a.ny + ky) * N;
+    const double x = __ldg(&a.kx[kxl]), y = __ldg(&a.ky[ky]);
+    const double f1 = __ldg(&a.fx[kxl]), f2 = __ldg(&a.fy[ky]);
+    const double kh2 = x * x + y * y;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = j + k * T;
+      const double z = __ldg(&a.kz[e]), f3 = __ldg(&a.fz[e]);
+      const double kk2 = kh2 + z * z;
+      const cplx NL = cscale(cscale(cscale(v[k], f1), f2), f3);
+      const cplx L = a.v[base + e], B = a.v0[base + e], F = a.f[base + e];
+      a.v[base + e] = cmake(B.x + a.dt * (a.nu * (-kk2 * L.x) - NL.x + F.x) * a.rmp,
+                            B.y + a.dt * (a.nu * (-kk2 * L.y) - NL.y + F.y) * a.rmp);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// project: v_imposebc_and_project on NPB pencils per CTA, element-fastest mapping.  Everything is
+// local to a (ky,kx) pencil: 2 z-IFFTs + no-slip rows + 2 continued z-FFTs (goto_domain_w_boundaries /
+// noslip_z / goto_3d_fourier), the Poisson particular solution, the wall values of v_z, the
+// closed-form Neumann harmonic correction, the new p' and the final subtraction.
+// ------------------------------------------------------------------------------------------
+struct ProjArgs {
+  cplx *vx, *vy, *vz, *pr;
+  const double *kx, *ky, *kz, *zc, *dir;
+  long npencils;
+  int ny, nph, C, d, has_mean;
+  double Lz, tmp_noslip, inv_nz;
+  double mx0, my0, mx1, my1;  // nx*ny*v_wall (mean mode rows)
+};
+
+template <int N>
+__device__ __forceinline__ void fc_continue_elem(cplx (&v)[8], int j, const cplx* bnd, int nph, int C, int d,
+                                                 const double* __restrict__ dir) {
+  constexpr int T = N / 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = j + k * T;
+    if (e >= nph) {
+      const int ii = e - nph;
+      double ax = 0.0, ay = 0.0;
+      for (int jj = 0; jj < d; ++jj) {
+        const double w1 = __ldg(&dir[ii * d + jj]);
+        const double w2 = __ldg(&dir[(C - 1 - ii) * d + jj]);
+        const cplx f1 = bnd[d + jj];
+        const cplx f2 = bnd[d - 1 - jj];
+        ax = fma(w2, f2.x, fma(w1, f1.x, ax));
+        ay = fma(w2, f2.y, fma(w1, f1.y, ay));
+      }
+      v[k] = cmake(ax, ay);
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void stash_boundary_elem(const cplx (&v)[8], int j, cplx* bnd, int nph, int d) {
+  constexpr int T = N / 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = j + k * T;
+    if (e < d) bnd[e] = v[k];
+    if (e >= nph - d && e < nph) bnd[d + e - (nph - d)] = v[k];
+  }
+}
+
+// continuation + forward transform of a register-resident pencil whose physical rows are final
+template <int N, class SI>
+__device__ __forceinline__ void fc_fft_fwd(cplx (&v)[8], int j, cplx* smem, const SI& si, cplx* bnd, int nph, int C,
+                                           int d, const double* __restrict__ dir, const cplx* __restrict__ tw) {
+  __syncthreads();  // bnd may still be read by a previous continuation
+  stash_boundary_elem<N>(v, j, bnd, nph, d);
+  __syncthreads();
+  fc_continue_elem<N>(v, j, bnd, nph, C, d, dir);
+  fft_regs<N, -1>(v, j, smem, si, tw);
+}
+
+template <int N, int NPB>
+__global__ void __launch_bounds__(NPB*(N / 8)) k_project(ProjArgs a, const cplx* __restrict__ tw) {
+  SX_DYN_SMEM(cplx, smem);
+  constexpr int T = N / 8;
+  constexpr int XS = sidx_elem_stride<N>();
+  const int pl = threadIdx.x / T, j = threadIdx.x % T;
+  const long pencil = (long)blockIdx.x * NPB + pl;
+  const bool active = pencil < a.npencils;
+  const long pc = active ? pencil : 0;
+  const int ky_i = (int)(pc % a.ny), kx_i = (int)(pc / a.ny);
+  const SIdxElem si{pl * XS};
+  // shared: [NPB exchange buffers][NPB x 3 parked pencils][NPB boundary stashes][NPB wall values]
+  cplx* park = smem + (size_t)NPB * XS + (size_t)pl * 3 * N;
+  cplx* bnd = smem + (size_t)NPB * XS + (size_t)NPB * 3 * N + (size_t)pl * 2 * kMaxDF;
+  cplx* wall = smem + (size_t)NPB * XS + (size_t)NPB * 3 * N + (size_t)NPB * 2 * kMaxDF + (size_t)pl * 2;
+  const size_t base = (size_t)pc * N;
+  const double x = __ldg(&a.kx[kx_i]), y = __ldg(&a.ky[ky_i]);
+  const bool mean = a.has_mean && pencil == 0;
+  const int top = a.nph - 1;
+  const cplx pr0 = a.pr[base], prT = a.pr[base + top];
+
+  // ---- no-slip rows of vx, vy in the mixed domain, back to Fourier (vboundary.f90:116-145) ----
+  cplx v[8];
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    const cplx* src = c == 0 ? a.vx : a.vy;
+    const double kc = c == 0 ? x : y;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = active ? src[base + j + k * T] : cmake(0.0, 0.0);
+    fft_regs<N, 1>(v, j, smem, si, tw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = j + k * T;
+      v[k] = cscale(v[k], a.inv_nz);
+      if (e == 0 || e == top) {
+        const cplx P = e == 0 ? pr0 : prT;
+        v[k] = cmake(-kc * P.y * a.tmp_noslip, kc * P.x * a.tmp_noslip);
+        if (mean) v[k] = cmake(e == 0 ? (c == 0 ? a.mx0 : a.my0) : (c == 0 ? a.mx1 : a.my1), 0.0);
+      }
+    }
+    fc_fft_fwd<N>(v, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, tw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) park[c * N + j + k * T] = v[k];
+  }
+  // ---- particular solution and its gradient (boundary_mod.fpp:405-448, 249-259) ----
+  cplx dd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = j + k * T;
+    const double z = __ldg(&a.kz[e]);
+    const double kk2 = x * x + y * y + z * z;
+    cplx A = park[e], B = park[N + e];
+    cplx Cc = active ? a.vz[base + e] : cmake(0.0, 0.0);
+    const cplx s = cmake(x * A.x + y * B.x + z * Cc.x, x * A.y + y * B.y + z * Cc.y);
+    cplx D = cmake(s.y / kk2, -s.x / kk2);
+    if ((mean && e == 0) || !active) D = cmake(0.0, 0.0);
+    A = cmake(A.x + x * D.y, A.y - x * D.x);
+    B = cmake(B.x + y * D.y, B.y - y * D.x);
+    Cc = cmake(Cc.x + z * D.y, Cc.y - z * D.x);
+    park[e] = A;
+    park[N + e] = B;
+    park[2 * N + e] = Cc;
+    dd[k] = D;
+    v[k] = cscale(Cc, a.inv_nz);
+  }
+  // ---- wall values of v_z (boundary_mod.fpp:275-338) ----
+  fft_regs<N, 1>(v, j, smem, si, tw);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = j + k * T;
+    if (e == 0) wall[0] = v[k];
+    if (e == top) wall[1] = v[k];
+  }
+  __syncthreads();
+  const cplx bc1 = wall[0], bc2 = wall[1];
+  // ---- laplace_z, Neumann-Neumann (boundary_mod.fpp:531-560, 635-675) ----
+  const double kh = sqrt(x * x + y * y);
+  cplx c1, c2;
+  if (mean) {
+    c1 = bc1;
+    c2 = cmake(0.0, 0.0);
+  } else {
+    const double e1 = exp(-kh * a.Lz), tt = 1.0 / (kh * (1.0 - exp(-2.0 * kh * a.Lz)));
+    c1 = cmake((bc2.x - bc1.x * e1) * tt, (bc2.y - bc1.y * e1) * tt);
+    c2 = cmake((-bc1.x + bc2.x * e1) * tt, (-bc1.y + bc2.y * e1) * tt);
+  }
+  // p' = IFFT_z(d)/nz + phi  (boundary_mod.fpp:371-380); all nz rows like the reference
+  fft_regs<N, 1>(dd, j, smem, si, tw);
+  cplx ph[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = j + k * T;
+    const double z = __ldg(&a.zc[e]);
+    cplx A, B;
+    if (mean) {
+      A = cmake(c1.x * z + c2.x, 0.0);
+      B = cmake(c1.x, 0.0);
+    } else {
+      const double ep = exp(kh * (z - a.Lz)), em = exp(-kh * z);
+      A = cmake(c1.x * ep + c2.x * em, c1.y * ep + c2.y * em);
+      B = cmake(kh * (c1.x * ep - c2.x * em), kh * (c1.y * ep - c2.y * em));
+    }
+    if (active) a.pr[base + e] = cmake(dd[k].x * a.inv_nz + A.x, dd[k].y * a.inv_nz + A.y);
+    ph[k] = A;
+    v[k] = B;
+  }
+  // ---- subtract the harmonic correction (boundary_mod.fpp:385-399) ----
+  fc_fft_fwd<N>(v, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, tw);   // d(phi)/dz
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = j + k * T;
+      const cplx Cc = park[2 * N + e];
+      a.vz[base + e] = cmake(Cc.x - v[k].x, Cc.y - v[k].y);
+    }
+  }
+  fc_fft_fwd<N>(ph, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, tw);  // phi
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = j + k * T;
+      const cplx A = park[e], B = park[N + e], h = ph[k];
+      a.vx[base + e] = cmake(A.x + x * h.y, A.y - x * h.x);
+      a.vy[base + e] = cmake(B.x + y * h.y, B.y - y * h.x);
+    }
+  }
+}
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+static void range0(int n, int nprocs, int r, int* sta, int* cnt) {  // `range` on [0,n)
+  const int w = n / nprocs, m = n % nprocs;
+  *sta = r * w + (r < m ? r : m);
+  *cnt = w + (m > r ? 1 : 0);
+}
+
+int fused_free(Plan& p) {
+  Fused* f = p.fused;
+  if (!f) return 0;
+  auto rel = [](cplx** a, int n, cplx** alias = nullptr) {
+    for (int i = 0; i < n; ++i) {
+      if (a[i] && (!alias || alias[i] != a[i])) cudaFree(a[i]);
+      a[i] = nullptr;
+    }
+  };
+  rel(f->R, 6, f->W);
+  rel(f->W, 6);
+  rel(f->V, 9);
+  rel(f->X, 3);
+  rel(f->Uz, 3, f->U);
+  rel(f->U, 3);
+  if (f->d_zmap) cudaFree(f->d_zmap);
+  delete f;
+  p.fused = nullptr;
+  return 0;
+}
+
+static int fused_init(Plan& p, Fused** out) {
+  if (p.fused) { *out = p.fused; return 0; }
+  SX_REQUIRE(p.Cz > 0 && p.oz > 0 && p.oz <= kMaxDF, "the fused substep needs a non-periodic z direction (0 < oz <= 10)");
+  Fused* f = new Fused();
+  p.fused = f;
+  f->nph = p.nz - p.Cz;
+  range0(f->nph, p.nprocs, p.myrank, &f->zf0, &f->nzf);
+  f->nxp = (p.nxh + 7) / 8 * 8;
+  f->wsize = (size_t)p.nxl * f->nph * p.ny;
+  f->vsize = (size_t)f->nzf * p.ny * f->nxp;
+  std::vector<ZMap> zm(f->nph);
+  long long base = 0;
+  for (int r = 0; r < p.nprocs; ++r) {
+    int s, c;
+    range0(f->nph, p.nprocs, r, &s, &c);
+    for (int q = 0; q < c; ++q) zm[s + q] = ZMap{base, c, q, 0};
+    base += (long long)p.nxl * c * p.ny;
+  }
+  SX_CUDA_CHECK(cudaMalloc((void**)&f->d_zmap, zm.size() * sizeof(ZMap)));
+  SX_CUDA_CHECK(cudaMemcpy(f->d_zmap, zm.data(), zm.size() * sizeof(ZMap), cudaMemcpyHostToDevice));
+  const size_t rsize = (size_t)p.nxh * f->nzf * p.ny;  // y-stage side [kx][zl][ky]
+  for (int i = 0; i < 6; ++i) {
+    SX_CUDA_CHECK(cudaMalloc((void**)&f->W[i], (f->wsize > rsize ? f->wsize : rsize) * sizeof(cplx)));
+    if (p.nprocs == 1) f->R[i] = f->W[i];
+    else SX_CUDA_CHECK(cudaMalloc((void**)&f->R[i], rsize * sizeof(cplx)));
+  }
+  for (int i = 0; i < 9; ++i) SX_CUDA_CHECK(cudaMalloc((void**)&f->V[i], f->vsize * sizeof(cplx)));
+  for (int i = 0; i < 3; ++i) {
+    SX_CUDA_CHECK(cudaMalloc((void**)&f->X[i], f->vsize * sizeof(cplx)));
+    SX_CUDA_CHECK(cudaMalloc((void**)&f->U[i], (f->wsize > rsize ? f->wsize : rsize) * sizeof(cplx)));
+    if (p.nprocs == 1) f->Uz[i] = f->U[i];
+    else SX_CUDA_CHECK(cudaMalloc((void**)&f->Uz[i], f->wsize * sizeof(cplx)));
+  }
+  *out = f;
+  return 0;
+}
+
+#define SX_FUSED_LAUNCH(p, stage, kfn, grid, threads, smem, ...)                                         \
+  do {                                                                                                   \
+    SX_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+    if (stage_mark((p), (stage))) return 1;                                                              \
+    cudaStream_t st_ = (p).stream;                                                                       \
+    SX_LAUNCH(kfn, grid, dim3(threads), (smem), st_, __VA_ARGS__);                                       \
+    (p).launches++;                                                                                      \
+    SX_KERNEL_CHECK();                                                                                   \
+  } while (0)
+
+template <int N> static int run_zinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
+  constexpr int NP = TileNP<N>::value;
+  ZinvArgs a{in, out0, out1, p.d_kz, f.d_zmap, p.ny, f.nph};
+  const cplx* tw = p.tw_z;
+  auto kfn = k_zinv_tile<N, NP>;
+  SX_FUSED_LAUNCH(p, ST_ZINV, kfn, dim3(cdiv(p.ny, NP), p.nxl), NP * (N / 8), (size_t)NP * N * sizeof(cplx), a, tw);
+  return 0;
+}
+template <int N> static int run_yinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
+  constexpr int NP = TileNP<N>::value;
+  if (f.nzf == 0) return 0;
+  YinvArgs a{in, out0, out1, p.d_ky, p.nxh, f.nxp, f.nzf};
+  const cplx* tw = p.tw_y;
+  auto kfn = k_yinv_tile<N, NP>;
+  SX_FUSED_LAUNCH(p, ST_YINV, kfn, dim3(cdiv(f.nxp, NP), f.nzf), NP * (N / 8), (size_t)NP * N * sizeof(cplx), a, tw);
+  return 0;
+}
+template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* out) {
+  constexpr int NP = TileNP<N>::value;
+  if (f.nzf == 0) return 0;
+  YfwdArgs a{in, out, p.nxh, f.nxp, f.nzf};
+  const cplx* tw = p.tw_y;
+  auto kfn = k_yfwd_tile<N, NP>;
+  SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(cdiv(p.nxh, NP), f.nzf), NP * (N / 8), (size_t)NP * N * sizeof(cplx), a, tw);
+  return 0;
+}
+template <int N> static int run_xpass(Plan& p, Fused& f, const double* d_kx_global) {
+  constexpr int T = N / 8;
+  constexpr int LP = T >= 256 ? 1 : (256 / T > 32 ? 32 : 256 / T);
+  if (f.nzf == 0) return 0;
+  XpassArgs a;
+  for (int i = 0; i < 9; ++i) a.V[i] = f.V[i];
+  for (int i = 0; i < 3; ++i) a.X[i] = f.X[i];
+  a.kx = d_kx_global;
+  a.ny = p.ny;
+  a.nxp = f.nxp;
+  const double Ntot = (double)p.nx * (double)p.ny * (double)p.nz;
+  a.tmp = 1.0 / (Ntot * Ntot);
+  const cplx* tw = p.tw_x;
+  auto kfn = k_xpass_gradre<N, LP>;
+  SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(cdiv(p.ny, 2 * LP), f.nzf), LP * T,
+                  (size_t)LP * sidx_elem_stride<N>() * sizeof(cplx), a, tw);
+  return 0;
+}
+template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, cplx* v, const cplx* v0, const cplx* frc,
+                                        double dt, double nu, double rmp) {
+  constexpr int NP = TileNP<N>::value;
+  ZfwdArgs a{nl, v, v0, frc, f.d_zmap, p.d_kx, p.d_ky, p.d_kz, p.d_fx, p.d_fy, p.d_fz, p.d_dir,
+             p.ny, f.nph, p.Cz, p.oz, dt, nu, rmp};
+  const cplx* tw = p.tw_z;
+  auto kfn = k_zfwd_rk<N, NP>;
+  const size_t smem = ((size_t)NP * N + (size_t)2 * kMaxDF * NP) * sizeof(cplx);
+  SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(cdiv(p.ny, NP), p.nxl), NP * (N / 8), smem, a, tw);
+  return 0;
+}
+template <int N> static int run_project(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
+                                        const double* zs, const double* ze) {
+  constexpr int T = N / 8;
+  constexpr int NPB = T >= 128 ? 1 : 128 / T;
+  double tmp = 1.0 / (double)o;
+  if (o != p.ord) tmp = (double)(o + 1) * tmp;   // vboundary.f90:195-196
+  const double sc = (double)p.nx * (double)p.ny;
+  ProjArgs a{vx, vy, vz, pr, p.d_kx, p.d_ky, p.d_kz, p.d_z, p.d_dir, (long)p.ny * p.nxl,
+             p.ny, f.nph, p.Cz, p.oz, p.ista == 1 ? 1 : 0, p.Lz, tmp, 1.0 / (double)p.nz,
+             sc * (zs ? zs[0] : 0.0), sc * (zs ? zs[1] : 0.0), sc * (ze ? ze[0] : 0.0), sc * (ze ? ze[1] : 0.0)};
+  const cplx* tw = p.tw_z;
+  auto kfn = k_project<N, NPB>;
+  const size_t smem = ((size_t)NPB * sidx_elem_stride<N>() + (size_t)NPB * 3 * N + (size_t)NPB * 2 * kMaxDF + (size_t)NPB * 2) * sizeof(cplx);
+  const unsigned grid = (unsigned)((a.npencils + NPB - 1) / NPB);
+  SX_FUSED_LAUNCH(p, ST_PROJECT, kfn, dim3(grid), NPB * T, smem, a, tw);
+  return 0;
+}
+
+#define SX_SIZE_SWITCH(n, CALL)                 \
+  switch (n) {                                  \
+    case 16: return CALL(16);                   \
+    case 32: return CALL(32);                   \
+    case 64: return CALL(64);                   \
+    case 128: return CALL(128);                 \
+    case 256: return CALL(256);                 \
+    case 512: return CALL(512);                 \
+    case 1024: return CALL(1024);               \
+    case 2048: return CALL(2048);               \
+  }                                             \
+  SX_REQUIRE(false, "unsupported transform length (power of two in [16,2048])")
+
+static int zinv(Plan& p, Fused& f, const cplx* in, cplx* o0, cplx* o1) {
+#define C_(N) run_zinv<N>(p, f, in, o0, o1)
+  SX_SIZE_SWITCH(p.nz, C_);
+#undef C_
+}
+static int yinv(Plan& p, Fused& f, const cplx* in, cplx* o0, cplx* o1) {
+#define C_(N) run_yinv<N>(p, f, in, o0, o1)
+  SX_SIZE_SWITCH(p.ny, C_);
+#undef C_
+}
+static int yfwd(Plan& p, Fused& f, const cplx* in, cplx* out) {
+#define C_(N) run_yfwd<N>(p, f, in, out)
+  SX_SIZE_SWITCH(p.ny, C_);
+#undef C_
+}
+static int xpass(Plan& p, Fused& f, const double* kxg) {
+#define C_(N) run_xpass<N>(p, f, kxg)
+  SX_SIZE_SWITCH(p.nx, C_);
+#undef C_
+}
+static int zfwd_rk(Plan& p, Fused& f, const cplx* nl, cplx* v, const cplx* v0, const cplx* frc, double dt, double nu,
+                   double rmp) {
+#define C_(N) run_zfwd_rk<N>(p, f, nl, v, v0, frc, dt, nu, rmp)
+  SX_SIZE_SWITCH(p.nz, C_);
+#undef C_
+}
+static int project(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o, const double* zs, const double* ze) {
+#define C_(N) run_project<N>(p, f, vx, vy, vz, pr, o, zs, ze)
+  SX_SIZE_SWITCH(p.nz, C_);
+#undef C_
+}
+
+int exchange_to_real(Plan& p, Fused& f, int slot);   // sx_comm.cu: W[slot] -> R[slot]
+int exchange_to_spec(Plan& p, Fused& f, int slot);   // sx_comm.cu: U[slot] -> Uz[slot]
+
+// hd_rkstep2.f90:3-36.  st[0..2] v, st[3] pr, st[4..6] f, st[7..9] RK base.
+int hd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, const double* zs, const double* ze) {
+  Fused* fp;
+  if (fused_init(p, &fp)) return 1;
+  Fused& f = *fp;
+  SX_REQUIRE(p.nprocs == 1, "multi-GPU exchange not linked in this build");
+  const double rmp = 1.0 / (double)o;
+  for (int c = 0; c < 3; ++c)
+    if (zinv(p, f, st[c], f.W[2 * c], f.W[2 * c + 1])) return 1;
+  for (int c = 0; c < 3; ++c) {
+    if (yinv(p, f, f.R[2 * c], f.V[c], f.V[3 + c])) return 1;
+    if (yinv(p, f, f.R[2 * c + 1], f.V[6 + c], nullptr)) return 1;
+  }
+  if (xpass(p, f, p.d_kxg)) return 1;
+  for (int c = 0; c < 3; ++c)
+    if (yfwd(p, f, f.X[c], f.U[c])) return 1;
+  for (int c = 0; c < 3; ++c)
+    if (zfwd_rk(p, f, f.Uz[c], st[c], st[7 + c], st[4 + c], dt, nu, rmp)) return 1;
+  return project(p, f, st[0], st[1], st[2], st[3], o, zs, ze);
+}
+
+}  // namespace sx

@@ -102,6 +102,7 @@ template <int N> static int zfft_dispatch(Plan& p, const ZArgs& a, int dir, bool
   if (grid == 0) return 0;
   const cplx* tw = p.tw_z;
   cudaStream_t st = p.stream;
+  if (stage_mark(p, ST_ZFFT)) return 1;
 #define SX_Z_CASE(D, CT)                                                                          \
   {                                                                                               \
     auto kfn = zfft_kernel<N, D, CT>;                                                             \
@@ -183,6 +184,7 @@ template <int N> static int yfft_dispatch(Plan& p, const YArgs& a, int dir) {
   if (grid.x == 0 || grid.y == 0) return 0;
   const cplx* tw = p.tw_y;
   cudaStream_t st = p.stream;
+  if (stage_mark(p, ST_YFFT)) return 1;
   if (dir < 0) {
     auto kfn = yfft_kernel<N, -1, NP>;
     SX_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -320,6 +322,7 @@ template <int N> static int xfft_dispatch(Plan& p, const XArgs& a, bool c2r) {
   if (grid.x == 0) return 0;
   const cplx* tw = p.tw_x;
   cudaStream_t st = p.stream;
+  if (stage_mark(p, ST_XFFT)) return 1;
   if (c2r) {
     auto kfn = xfft_c2r_kernel<N, NP>;
     SX_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -315,6 +315,7 @@ __global__ void k_reduce_phys(Dims d, const cplx* __restrict__ a, const cplx* __
   do {                                                                         \
     auto kfn = kernel;                                                         \
     cudaStream_t st_ = (p).stream;                                             \
+    if (stage_mark((p), ST_EW)) return 1;                                      \
     SX_LAUNCH(kfn, dim3(ew_grid(n)), dim3(256), 0, st_, __VA_ARGS__);          \
     (p).launches++;                                                            \
     SX_KERNEL_CHECK();                                                         \
@@ -445,6 +446,7 @@ int op_reduce_phys(Plan& p, const cplx* a, const cplx* b, int mode, int row, dou
   double* partial = p.d_red;
   cudaStream_t st = p.stream;
   auto kfn = k_reduce_phys;
+  if (stage_mark(p, ST_REDUCE)) return 1;
   SX_LAUNCH(kfn, dim3(blocks), dim3(256), 256 * sizeof(double), st, dm, a, b, mode, nph, row, first, scale,
             partial);
   p.launches++;

@@ -7,6 +7,24 @@
 namespace sx {
 
 struct HdState;  // fused-path device state (sx_rkstep.cu)
+struct Fused;    // fused-path work buffers and slab maps (sx_fused.cu)
+
+// Per-stage CUDA-event timers (the reference's ffttime/tratime/comtime/conttime counters,
+// fftp_mod.fpp:32-37, re-cast per kernel family).
+enum Stage {
+  ST_OTHER = 0, ST_ZFFT, ST_YFFT, ST_XFFT, ST_EW, ST_REDUCE,          // per-operator path
+  ST_ZINV, ST_YINV, ST_XPASS, ST_YFWD, ST_ZFWD_RK, ST_PROJECT, ST_EXCHANGE,  // fused substep
+  ST_COUNT
+};
+const char* stage_name(int id);
+struct StageTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ids;
+  size_t n = 0;
+  double ms[ST_COUNT] = {0};
+  long long cnt[ST_COUNT] = {0};
+};
 
 struct Plan {
   // configuration (mirrors FCPLAN + grid/kes modules of the reference)
@@ -20,10 +38,12 @@ struct Plan {
   std::vector<double> h_kx, h_ky, h_kz, h_z, h_dir, h_neu, h_neu2;
   // device tables
   double *d_kx = nullptr, *d_ky = nullptr, *d_kz = nullptr;  // kx is the LOCAL slab kx(ista:iend)
+  double* d_kxg = nullptr;                                    // GLOBAL kx(1:nx/2+1)
   double *d_fx = nullptr, *d_fy = nullptr, *d_fz = nullptr;  // fc_filter separable factors
   double *d_z = nullptr, *d_dir = nullptr;
   cplx *tw_x = nullptr, *tw_y = nullptr, *tw_z = nullptr;
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // sx_plan_time_begin/end
   // scratch pool (lazily grown): complex spectral-sized and real-sized work arrays
   std::vector<cplx*> cwork;
   std::vector<double*> rwork;
@@ -31,12 +51,19 @@ struct Plan {
   double* h_red = nullptr;   // pinned host landing zone
   int red_blocks = 0;
   HdState* hd = nullptr;
+  Fused* fused = nullptr;
+  StageTimer timer;
   unsigned long long launches = 0;  // kernels launched by this plan (bench "gpu_launches")
 
   size_t csize() const { return (size_t)nz * ny * nxl; }   // complex elements per spectral field
   size_t rsize() const { return (size_t)nx * ny * nzl; }   // doubles per real field
   int nphys() const { return nz - Cz; }
 };
+
+// stage timing: call stage_mark right before a kernel launch
+int stage_mark_slow(Plan& p, int id);
+inline int stage_mark(Plan& p, int id) { return p.timer.on ? stage_mark_slow(p, id) : 0; }
+int stage_flush(Plan& p);
 
 // scratch management
 int plan_cwork(Plan& p, int idx, cplx** out);
@@ -84,6 +111,7 @@ int gradre(Plan& p, const cplx* a, const cplx* b, const cplx* c, cplx* d, cplx* 
 int v_imposebc_and_project(Plan& p, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int rki, const double* zs,
                            const double* ze);
 int hd_state_free(Plan& p);
+int fused_free(Plan& p);
 
 }  // namespace sx
 

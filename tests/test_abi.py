@@ -1,0 +1,60 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/specter_b200.h declares;
+the ctypes table of the host-side mirror agrees with the header; plan creation fails loudly
+(no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from specter_b200 import api, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "specter_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_bindings_agree():
+    names = header_functions()
+    assert len(names) > 40
+    assert sorted(api.SIGNATURES) == names
+
+
+def test_cuda_library_exports_every_symbol():
+    lib = build.build_cuda()
+    dll = ctypes.CDLL(lib)
+    for name in header_functions():
+        assert hasattr(dll, name), name
+    dll.sx_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in dll.sx_version()
+
+
+def test_no_cpu_fallback(tables):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.SpecterError):
+        api.Plan(16, 16, 64, 25, 5, tdir=tables)
+
+
+def test_argument_errors_on_emulated_build(emu_lib, tables):
+    with pytest.raises(api.SpecterError, match="power"):
+        api.Plan(24, 16, 64, 25, 5, tdir=tables, lib=emu_lib)
+    with pytest.raises(api.SpecterError, match="table"):
+        api.Plan(16, 16, 64, 25, 5, tdir="/nonexistent", lib=emu_lib)
+    with pytest.raises(api.SpecterError, match="Mismatch"):
+        api.Plan(16, 16, 64, 25, 0, tdir=tables, lib=emu_lib)
+    p = api.Plan(16, 16, 64, 25, 5, tdir=tables, lib=emu_lib)
+    a = p.spectral()
+    with pytest.raises(api.SpecterError, match="dir"):
+        p.derivk(a, a, 4)
+    with pytest.raises(api.SpecterError, match="Unsupported BC"):
+        p.sol_project(a, a, a, a, 1, 1, 1)
+    with pytest.raises(api.SpecterError, match="substep"):
+        p.hd_rkstep2(3, 1e-3, 1e-3)
+    assert api.sx_range(1, 33, 8, 0, lib=emu_lib) == (1, 5)
+    p.close()

@@ -1,0 +1,53 @@
+"""CPU (no GPU): the kernel SOURCES under the CPU-thread emulation vs the oracle, small grids.
+Checks index math, barrier structure and the host-side composition; the GPU parity proper is
+test_parity_gpu.py."""
+import pytest
+
+import parity_cases as P
+
+SMALL = (32, 16, 64)
+
+
+def test_fft1d_z(emu_lib, tables):
+    P.case_fft1d_z(emu_lib, tables, SMALL)
+    P.case_fft1d_z(emu_lib, tables, (16, 16, 128), Cz=25)
+    P.case_fft1d_z(emu_lib, tables, (16, 16, 32), Cz=0)
+
+
+def test_fft3d(emu_lib, tables):
+    P.case_fft3d(emu_lib, tables, SMALL)
+    P.case_fft3d(emu_lib, tables, (16, 32, 64))
+    P.case_fft3d(emu_lib, tables, (64, 16, 16), Cz=0)
+
+
+def test_fft_known_answer(emu_lib, tables):
+    P.case_fft_known_answer(emu_lib, tables, 32)
+
+
+def test_spectral_ops(emu_lib, tables):
+    P.case_spectral_ops(emu_lib, tables, SMALL)
+
+
+def test_nonlinear(emu_lib, tables):
+    P.case_nonlinear(emu_lib, tables, SMALL)
+
+
+def test_projection(emu_lib, tables):
+    P.case_projection(emu_lib, tables, SMALL)
+
+
+def test_diagnostics(emu_lib, tables):
+    P.case_diagnostics(emu_lib, tables, SMALL)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_hd_substeps(emu_lib, tables, impl):
+    P.case_hd_substeps(emu_lib, tables, SMALL, ord=2, nsteps=2, impl=impl)
+
+
+def test_hd_substeps_rk4_moving_walls(emu_lib, tables):
+    P.case_hd_substeps(emu_lib, tables, (16, 16, 64), ord=4, nsteps=1, impl=0, walls=((0.2, -0.1), (-0.3, 0.1)))
+
+
+def test_hd_step_host(emu_lib, tables):
+    P.case_hd_step_host(emu_lib, tables, SMALL)

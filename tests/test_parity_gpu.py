@@ -1,0 +1,67 @@
+"""GPU parity proper: the nvcc-built sm_100a library through the C ABI against the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import parity_cases as P
+
+pytestmark = pytest.mark.gpu
+CFG1 = (64, 64, 64)  # BASELINE.json configs[0]
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_fft1d_z(cuda_lib, tables):
+    for shape in (CFG1, (32, 16, 128), (16, 32, 256), (16, 16, 512), (16, 16, 1024)):
+        P.case_fft1d_z(cuda_lib, tables, shape)
+    P.case_fft1d_z(cuda_lib, tables, (16, 16, 32), Cz=0)
+
+
+def test_fft3d(cuda_lib, tables):
+    for shape in (CFG1, (128, 32, 64), (32, 256, 64), (512, 16, 64), (16, 512, 128)):
+        P.case_fft3d(cuda_lib, tables, shape)
+    P.case_fft3d(cuda_lib, tables, (64, 32, 32), Cz=0)
+
+
+def test_fft_known_answer(cuda_lib, tables):
+    P.case_fft_known_answer(cuda_lib, tables, 64)
+
+
+def test_spectral_ops(cuda_lib, tables):
+    P.case_spectral_ops(cuda_lib, tables, CFG1)
+
+
+def test_nonlinear(cuda_lib, tables):
+    P.case_nonlinear(cuda_lib, tables, CFG1)
+    P.case_nonlinear(cuda_lib, tables, (128, 64, 128))
+
+
+def test_projection(cuda_lib, tables):
+    P.case_projection(cuda_lib, tables, CFG1)
+
+
+def test_diagnostics(cuda_lib, tables):
+    P.case_diagnostics(cuda_lib, tables, CFG1)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_hd_substeps_cfg1(cuda_lib, tables, impl):
+    P.case_hd_substeps(cuda_lib, tables, CFG1, ord=2, nsteps=3, impl=impl)
+
+
+def test_hd_substeps_rk4(cuda_lib, tables):
+    P.case_hd_substeps(cuda_lib, tables, (128, 128, 128), ord=4, nsteps=1, impl=0)
+    P.case_hd_substeps(cuda_lib, tables, (64, 32, 256), ord=4, nsteps=1, impl=0, walls=((0.2, -0.1), (-0.3, 0.1)))
+
+
+def test_hd_step_host(cuda_lib, tables):
+    P.case_hd_step_host(cuda_lib, tables, CFG1)
+
+
+def test_hd_diagnostics_100_steps_cfg1(cuda_lib, tables):
+    """Config 1, 100 RK2 steps: balance.txt / noslip_diagnostic columns vs the committed oracle goldens."""
+    with open(os.path.join(GOLD, "hd64_diag100.json")) as f:
+        gold = json.load(f)
+    rows = P.case_hd_diagnostics_100(cuda_lib, tables, CFG1, nsteps=100, ord=2, impl=0, golden=gold["rows"])
+    assert rows.shape[0] == 10
