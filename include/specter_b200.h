@@ -65,6 +65,16 @@ int sx_plan_stage_times(sx_plan* plan, double* ms, long long* counts, int n);
  * (MPI_BCAST in the Fortran driver, torch.distributed in the Python harness) */
 int sx_nccl_unique_id(void* id128);
 int sx_plan_set_comm(sx_plan* plan, const void* id128);
+/* Alternative transport (e.g. CUDA-aware MPI_Alltoallv / MPI_Allreduce from the Fortran driver, or
+ * torch.distributed in the test-suite).  Buffers are device pointers, displacements and counts are in
+ * BYTES per peer rank; the all-reduce sums n doubles in a host array in place.  Return 0 on success. */
+typedef int (*sx_alltoallv_fn)(void* user, const void* sendbuf, const size_t* sdispl, const size_t* scount,
+                               void* recvbuf, const size_t* rdispl, const size_t* rcount, int nprocs);
+typedef int (*sx_allreduce_fn)(void* user, double* inout_host, int n);
+int sx_plan_set_comm_callbacks(sx_plan* plan, sx_alltoallv_fn alltoallv, sx_allreduce_fn allreduce, void* user);
+/* bytes this rank sent to peers, device milliseconds spent in exchanges (only accumulated while
+ * sx_plan_stage_timing is on) and the number of exchanges since the last reset */
+int sx_plan_comm_stats(sx_plan* plan, double* bytes_sent, double* ms, long long* exchanges, int reset);
 
 /* device memory helpers so a host language needs no CUDA runtime of its own */
 int sx_malloc(sx_plan* plan, size_t bytes, void** dptr);

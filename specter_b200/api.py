@@ -58,6 +58,8 @@ SIGNATURES = {
     "sx_plan_stage_times": [_P, _PD, C.POINTER(C.c_longlong), _I],
     "sx_nccl_unique_id": [_D],
     "sx_plan_set_comm": [_P, _D],
+    "sx_plan_set_comm_callbacks": [_P, _D, _D, _D],
+    "sx_plan_comm_stats": [_P, _PD, _PD, C.POINTER(C.c_longlong), _I],
     "sx_malloc": [_P, C.c_size_t, C.POINTER(_D)],
     "sx_free": [_P, _D],
     "sx_malloc_host": [C.c_size_t, C.POINTER(_D)],
@@ -228,6 +230,53 @@ class Plan:
         out = np.frombuffer(buf, dtype=a.dtype).reshape(a.shape)
         out[...] = a
         return out
+
+    # ---- multi-GPU ----
+    def init_comm_torch(self, dist):
+        """Create the plan's own NCCL communicator; the 128-byte unique id travels over the caller's
+        torch.distributed group (the Fortran driver would MPI_BCAST it)."""
+        import torch
+        buf = (C.c_char * 128)()
+        if dist.get_rank() == 0:
+            self.lib.check(self.lib.dll.sx_nccl_unique_id(buf))
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().tolist())
+        self._call("sx_plan_set_comm", C.c_char_p(raw))
+
+    def set_comm_callbacks(self, alltoallv, allreduce):
+        """Route the slab exchange through caller code: alltoallv(send_ptr, sdispl, scount, recv_ptr,
+        rdispl, rcount) with byte offsets per rank, allreduce(ptr, n) summing n host doubles in place."""
+        A2A = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p,
+                          C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_int)
+        ARD = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int)
+
+        def a2a(user, send, sd, sc, recv, rd, rc, n):
+            try:
+                alltoallv(send, [sd[i] for i in range(n)], [sc[i] for i in range(n)], recv,
+                          [rd[i] for i in range(n)], [rc[i] for i in range(n)])
+                return 0
+            except Exception as e:  # pragma: no cover
+                print("alltoallv callback failed:", e)
+                return 1
+
+        def ard(user, ptr, n):
+            try:
+                allreduce(ptr, n)
+                return 0
+            except Exception as e:  # pragma: no cover
+                print("allreduce callback failed:", e)
+                return 1
+
+        self._cb = (A2A(a2a), ARD(ard))  # keep alive
+        self._call("sx_plan_set_comm_callbacks", C.cast(self._cb[0], C.c_void_p), C.cast(self._cb[1], C.c_void_p), None)
+
+    def comm_stats(self, reset=False):
+        b, ms, n = C.c_double(), C.c_double(), C.c_longlong()
+        self._call("sx_plan_comm_stats", C.byref(b), C.byref(ms), C.byref(n), 1 if reset else 0)
+        return {"bytes_sent": b.value, "ms": ms.value, "exchanges": n.value}
 
     def close(self):
         if self.handle:

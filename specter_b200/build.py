@@ -59,7 +59,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if pr.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nvcc, "-shared", "-Xlinker", "-Bsymbolic", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+    cmd = [nvcc, "-shared", "-Xlinker", "-Bsymbolic", "-o", LIB] + objs + ["-lcudart", "-lnccl", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

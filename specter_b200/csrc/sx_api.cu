@@ -1,6 +1,7 @@
 // C ABI (include/specter_b200.h): plan construction and the per-operator entry points that
 // mirror the reference's fftp / pseudo / boundary modules, composed from the kernels in
 // sx_kernels_fft.cu and sx_kernels_ops.cu.
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <mutex>
@@ -126,7 +127,6 @@ static int plan_init(Plan& p, const sx_config& c) {
              "Mismatch in continuation or matching points in z direction. Aborting...");
   SX_REQUIRE(c.Cz == 0 || (c.oz <= 10 && c.Cz + 2 * c.oz < c.nz), "invalid Cz/oz for this nz");
   SX_REQUIRE(c.nprocs >= 1 && c.myrank >= 0 && c.myrank < c.nprocs, "invalid nprocs/myrank");
-  SX_REQUIRE(c.nprocs == 1, "nprocs > 1 needs sx_plan_set_comm (multi-GPU path not built in this version)");
   SX_REQUIRE(c.ord >= 1, "ord must be >= 1");
   p.nx = c.nx; p.ny = c.ny; p.nz = c.nz; p.Cz = c.Cz; p.oz = c.oz; p.ord = c.ord;
   p.Lx = c.Lx; p.Ly = c.Ly; p.Lz = c.Lz;
@@ -180,6 +180,8 @@ static int plan_init(Plan& p, const sx_config& c) {
   if (upload_twiddles(p.nx, &p.tw_x)) return 1;
   if (upload_twiddles(p.ny, &p.tw_y)) return 1;
   if (upload_twiddles(p.nz, &p.tw_z)) return 1;
+  if (const char* e = getenv("SX_TILE_NP")) p.knob_np = atoi(e);
+  if (const char* e = getenv("SX_TILE_MINB")) p.knob_minb = atoi(e);
   p.red_blocks = 148 * 4;
   SX_CUDA_CHECK(cudaMalloc((void**)&p.d_red, p.red_blocks * sizeof(double)));
   SX_CUDA_CHECK(cudaMallocHost((void**)&p.h_red, p.red_blocks * sizeof(double)));
@@ -189,6 +191,7 @@ static int plan_init(Plan& p, const sx_config& c) {
 static void plan_release(Plan& p) {
   hd_state_free(p);
   fused_free(p);
+  comm_free(p);
   for (auto e : p.timer.ev) cudaEventDestroy(e);
   for (auto* q : p.cwork) if (q) cudaFree(q);
   for (auto* q : p.rwork) if (q) cudaFree(q);
@@ -210,11 +213,15 @@ int fft1d_z_fwd(Plan& p, cplx* a) {  // fftp1d_real_to_complex_z
 int fft1d_z_bwd(Plan& p, const cplx* in, cplx* out, double scale_phys) {  // fftp1d_complex_to_real_z
   return launch_zfft(p, in, out, (long)p.ny * p.nxl, +1, false, scale_phys, 1.0);
 }
+#define SX_SINGLE_RANK(p, what) \
+  SX_REQUIRE((p).nprocs == 1, what ": the per-operator xy transforms are single-rank in this version (the fused substep is slab-parallel)")
 int fft2d_xy_r2c(Plan& p, const double* r, cplx* out, int nz_active) {
+  SX_SINGLE_RANK(p, "fftp2d_real_to_complex_xy");
   if (launch_x_r2c(p, r, out, p.nz, nz_active, 1.0)) return 1;
   return launch_yfft(p, out, out, p.nz, p.nxh, nz_active, -1, 1.0);
 }
 int fft2d_xy_c2r(Plan& p, cplx* mixed_destroyed, double* r, int nz_active) {
+  SX_SINGLE_RANK(p, "fftp2d_complex_to_real_xy");
   if (launch_yfft(p, mixed_destroyed, mixed_destroyed, p.nz, p.nxh, nz_active, +1, 1.0)) return 1;
   return launch_x_c2r(p, mixed_destroyed, r, p.nz, nz_active, 1.0);
 }
@@ -478,8 +485,6 @@ int sx_plan_stage_times(sx_plan* plan, double* ms, long long* counts, int n) {
   return 0;
 }
 
-int sx_nccl_unique_id(void*) { sx::set_error("[ERROR] multi-GPU path not built in this version"); return 1; }
-int sx_plan_set_comm(sx_plan*, const void*) { sx::set_error("[ERROR] multi-GPU path not built in this version"); return 1; }
 
 int sx_malloc(sx_plan* plan, size_t bytes, void** dptr) { SX_PLAN(plan); SX_CUDA_CHECK(cudaSetDevice(p.device)); SX_CUDA_CHECK(cudaMalloc(dptr, bytes)); return 0; }
 int sx_free(sx_plan* plan, void* dptr) { SX_PLAN(plan); SX_CUDA_CHECK(cudaStreamSynchronize(p.stream)); SX_CUDA_CHECK(cudaFree(dptr)); return 0; }

@@ -1,0 +1,242 @@
+// Slab exchange between the z-stage (kx-slabs, all z) and the xy-stage (z-slabs, all kx), and the
+// scalar reductions of the diagnostics.  Replaces the reference's ring of MPI_ISEND/MPI_IRECV with
+// derived datatypes (fftp/fftp.fpp:478-499, 670-691, 887-907, 1024-1044) and its MPI_REDUCE calls
+// (e.g. pseudospec_hd.f90:631).
+//
+// The FFT kernels on both sides already write / read the per-destination blocks contiguously
+// ([rank][kxl][zl][ky] on the z side, [kx][zl][ky] on the xy side), so the exchange is a plain
+// all-to-all-v of contiguous blocks: one ncclGroup of ncclSend/ncclRecv on a dedicated stream,
+// ordered against the compute stream with events so that the exchange of field c overlaps the
+// transforms of field c+1.  No packing kernels, no host staging.
+//
+// A caller may instead install callbacks (sx_plan_set_comm_callbacks): the Fortran/MPI driver can
+// route the blocks through CUDA-aware MPI_Alltoallv, and the CPU test-suite routes them through
+// torch.distributed/gloo under the kernel emulation.
+#include <cstring>
+#include <vector>
+
+#include "../../include/specter_b200.h"
+#include "sx_plan.h"
+#ifndef SX_EMU
+#include <nccl.h>
+#endif
+
+namespace sx {
+
+struct Comm {
+#ifndef SX_EMU
+  ncclComm_t nccl = nullptr;
+#endif
+  cudaStream_t stream = nullptr;
+  sx_alltoallv_fn a2a = nullptr;
+  sx_allreduce_fn allred = nullptr;
+  void* user = nullptr;
+  cudaEvent_t ready[16] = {nullptr}, done[16] = {nullptr};
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  double* d_scal = nullptr;
+  double* h_scal = nullptr;
+  // accounting for the NVLink roofline
+  double bytes_sent = 0.0, ms = 0.0;
+  long long exchanges = 0;
+};
+
+int comm_free(Plan& p) {
+  Comm* c = p.comm;
+  if (!c) return 0;
+#ifndef SX_EMU
+  if (c->nccl) ncclCommDestroy(c->nccl);
+#endif
+  for (int i = 0; i < 16; ++i) {
+    if (c->ready[i]) cudaEventDestroy(c->ready[i]);
+    if (c->done[i]) cudaEventDestroy(c->done[i]);
+  }
+  if (c->t0) cudaEventDestroy(c->t0);
+  if (c->t1) cudaEventDestroy(c->t1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->d_scal) cudaFree(c->d_scal);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  delete c;
+  p.comm = nullptr;
+  return 0;
+}
+
+static int comm_get(Plan& p, Comm** out) {
+  if (!p.comm) {
+    Comm* c = new Comm();
+    p.comm = c;
+    SX_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; ++i) {
+      SX_CUDA_CHECK(cudaEventCreate(&c->ready[i]));
+      SX_CUDA_CHECK(cudaEventCreate(&c->done[i]));
+    }
+    SX_CUDA_CHECK(cudaEventCreate(&c->t0));
+    SX_CUDA_CHECK(cudaEventCreate(&c->t1));
+    SX_CUDA_CHECK(cudaMalloc((void**)&c->d_scal, 64 * sizeof(double)));
+    SX_CUDA_CHECK(cudaMallocHost((void**)&c->h_scal, 64 * sizeof(double)));
+  }
+  *out = p.comm;
+  return 0;
+}
+
+bool comm_ready(const Plan& p) {
+  if (p.nprocs == 1) return true;
+  if (!p.comm) return false;
+#ifndef SX_EMU
+  if (p.comm->nccl) return true;
+#endif
+  return p.comm->a2a != nullptr;
+}
+
+// All-to-all-v of contiguous blocks; displacements and counts in complex elements.  `ev` selects the
+// event pair (one per buffer in flight).  Asynchronous with respect to the compute stream: the data
+// may be read only after exchange_wait(ev).
+int exchange_begin(Plan& p, int ev, const cplx* send, cplx* recv, const size_t* sdispl, const size_t* scount,
+                   const size_t* rdispl, const size_t* rcount) {
+  SX_REQUIRE(p.nprocs > 1, "exchange on a single-rank plan");
+  SX_REQUIRE(comm_ready(p), "multi-rank plan without a communicator: call sx_plan_set_comm or sx_plan_set_comm_callbacks");
+  SX_REQUIRE(ev >= 0 && ev < 16, "exchange: bad event slot");
+  Comm& c = *p.comm;
+  if (stage_mark(p, ST_EXCHANGE)) return 1;
+  double sent = 0.0;
+  for (int r = 0; r < p.nprocs; ++r)
+    if (r != p.myrank) sent += (double)scount[r] * sizeof(cplx);
+  c.bytes_sent += sent;
+  c.exchanges++;
+  if (c.a2a) {
+    // caller-provided transport: complete the producing kernels, hand over byte displacements
+    SX_CUDA_CHECK(cudaStreamSynchronize(p.stream));
+    std::vector<size_t> sd(p.nprocs), sc(p.nprocs), rd(p.nprocs), rc(p.nprocs);
+    for (int r = 0; r < p.nprocs; ++r) {
+      sd[r] = sdispl[r] * sizeof(cplx); sc[r] = scount[r] * sizeof(cplx);
+      rd[r] = rdispl[r] * sizeof(cplx); rc[r] = rcount[r] * sizeof(cplx);
+    }
+    const int rc_ = c.a2a(c.user, send, sd.data(), sc.data(), recv, rd.data(), rc.data(), p.nprocs);
+    SX_REQUIRE(rc_ == 0, "the all-to-all callback reported an error");
+    return 0;
+  }
+#ifndef SX_EMU
+  SX_CUDA_CHECK(cudaEventRecord(c.ready[ev], p.stream));
+  SX_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ready[ev], 0));
+  const bool timing = p.timer.on;
+  if (timing) SX_CUDA_CHECK(cudaEventRecord(c.t0, c.stream));
+  ncclResult_t st = ncclGroupStart();
+  for (int q = 0; q < p.nprocs && st == ncclSuccess; ++q) {
+    // start with the neighbour so that all pairs are busy (any order is correct inside a group)
+    const int r = (p.myrank + q) % p.nprocs, s = (p.myrank - q + p.nprocs) % p.nprocs;
+    if (scount[r]) st = ncclSend(send + sdispl[r], scount[r] * 2, ncclDouble, r, c.nccl, c.stream);
+    if (st == ncclSuccess && rcount[s]) st = ncclRecv(recv + rdispl[s], rcount[s] * 2, ncclDouble, s, c.nccl, c.stream);
+  }
+  ncclResult_t st2 = ncclGroupEnd();
+  SX_REQUIRE(st == ncclSuccess && st2 == ncclSuccess,
+             std::string("NCCL all-to-all failed: ") + ncclGetErrorString(st != ncclSuccess ? st : st2));
+  if (timing) {
+    SX_CUDA_CHECK(cudaEventRecord(c.t1, c.stream));
+    SX_CUDA_CHECK(cudaEventSynchronize(c.t1));
+    float f = 0.f;
+    SX_CUDA_CHECK(cudaEventElapsedTime(&f, c.t0, c.t1));
+    c.ms += f;
+  }
+  SX_CUDA_CHECK(cudaEventRecord(c.done[ev], c.stream));
+  p.launches++;
+  return 0;
+#else
+  SX_REQUIRE(false, "the emulated build has no NCCL: install callbacks with sx_plan_set_comm_callbacks");
+#endif
+}
+
+int exchange_wait(Plan& p, int ev) {
+  Comm& c = *p.comm;
+  if (c.a2a) return 0;
+  SX_CUDA_CHECK(cudaStreamWaitEvent(p.stream, c.done[ev], 0));
+  return 0;
+}
+
+// Sum of n doubles over all ranks (result on every rank).
+int allreduce_sum(Plan& p, double* v, int n) {
+  if (p.nprocs == 1) return 0;
+  SX_REQUIRE(comm_ready(p), "multi-rank plan without a communicator: call sx_plan_set_comm or sx_plan_set_comm_callbacks");
+  SX_REQUIRE(n <= 64, "allreduce_sum: at most 64 values");
+  Comm& c = *p.comm;
+  if (c.allred) {
+    SX_REQUIRE(c.allred(c.user, v, n) == 0, "the all-reduce callback reported an error");
+    return 0;
+  }
+#ifndef SX_EMU
+  for (int i = 0; i < n; ++i) c.h_scal[i] = v[i];
+  SX_CUDA_CHECK(cudaMemcpyAsync(c.d_scal, c.h_scal, n * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+  ncclResult_t st = ncclAllReduce(c.d_scal, c.d_scal, n, ncclDouble, ncclSum, c.nccl, p.stream);
+  SX_REQUIRE(st == ncclSuccess, std::string("ncclAllReduce failed: ") + ncclGetErrorString(st));
+  SX_CUDA_CHECK(cudaMemcpyAsync(c.h_scal, c.d_scal, n * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+  SX_CUDA_CHECK(cudaStreamSynchronize(p.stream));
+  for (int i = 0; i < n; ++i) v[i] = c.h_scal[i];
+  return 0;
+#else
+  SX_REQUIRE(false, "the emulated build has no NCCL: install callbacks with sx_plan_set_comm_callbacks");
+#endif
+}
+
+}  // namespace sx
+
+using namespace sx;
+#define SX_PLAN(pl) \
+  if (!(pl)) { sx::set_error("[ERROR] null plan"); return 1; } \
+  sx::Plan& p = (pl)->p
+
+extern "C" {
+
+int sx_nccl_unique_id(void* id128) {
+#ifndef SX_EMU
+  SX_REQUIRE(id128 != nullptr, "sx_nccl_unique_id: null buffer");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  ncclUniqueId id;
+  ncclResult_t st = ncclGetUniqueId(&id);
+  SX_REQUIRE(st == ncclSuccess, std::string("ncclGetUniqueId failed: ") + ncclGetErrorString(st));
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+#else
+  (void)id128;
+  SX_REQUIRE(false, "the emulated build has no NCCL");
+#endif
+}
+
+int sx_plan_set_comm(sx_plan* plan, const void* id128) {
+  SX_PLAN(plan);
+#ifndef SX_EMU
+  SX_REQUIRE(id128 != nullptr, "sx_plan_set_comm: null id");
+  Comm* c;
+  if (comm_get(p, &c)) return 1;
+  SX_REQUIRE(c->nccl == nullptr, "sx_plan_set_comm: communicator already set");
+  SX_CUDA_CHECK(cudaSetDevice(p.device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclResult_t st = ncclCommInitRank(&c->nccl, p.nprocs, id, p.myrank);
+  SX_REQUIRE(st == ncclSuccess, std::string("ncclCommInitRank failed: ") + ncclGetErrorString(st));
+  return 0;
+#else
+  (void)id128;
+  SX_REQUIRE(false, "the emulated build has no NCCL: use sx_plan_set_comm_callbacks");
+#endif
+}
+
+int sx_plan_set_comm_callbacks(sx_plan* plan, sx_alltoallv_fn alltoallv, sx_allreduce_fn allreduce, void* user) {
+  SX_PLAN(plan);
+  SX_REQUIRE(alltoallv != nullptr && allreduce != nullptr, "sx_plan_set_comm_callbacks: null callback");
+  Comm* c;
+  if (comm_get(p, &c)) return 1;
+  c->a2a = alltoallv;
+  c->allred = allreduce;
+  c->user = user;
+  return 0;
+}
+
+int sx_plan_comm_stats(sx_plan* plan, double* bytes_sent, double* ms, long long* exchanges, int reset) {
+  SX_PLAN(plan);
+  Comm* c = p.comm;
+  if (bytes_sent) *bytes_sent = c ? c->bytes_sent : 0.0;
+  if (ms) *ms = c ? c->ms : 0.0;
+  if (exchanges) *exchanges = c ? c->exchanges : 0;
+  if (c && reset) { c->bytes_sent = 0.0; c->ms = 0.0; c->exchanges = 0; }
+  return 0;
+}
+
+}  // extern "C"

@@ -48,6 +48,8 @@ struct Fused {
   cplx* X[3] = {nullptr};   // [zl][y][kx]: nonlinear term after the x pass
   cplx* U[3] = {nullptr};   // y-stage side of the way back [kx][zl][ky]
   cplx* Uz[3] = {nullptr};  // z-stage side of the way back (aliases U on one GPU)
+  // all-to-all-v block tables in complex elements: z side [rank][kxl][zl_r][ky], xy side [kx][zl][ky]
+  std::vector<size_t> z_displ, z_count, x_displ, x_count;
 };
 
 template <int N> struct TileNP {
@@ -66,8 +68,8 @@ struct ZinvArgs {
   int ny, nph;
 };
 
-template <int N, int NP>
-__global__ void __launch_bounds__(NP*(N / 8)) k_zinv_tile(ZinvArgs a, const cplx* __restrict__ tw) {
+template <int N, int NP, int MINB>
+__global__ void __launch_bounds__(NP*(N / 8), MINB) k_zinv_tile(ZinvArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8;
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
@@ -120,8 +122,8 @@ struct YinvArgs {
   int nxh, nxp, nzf;
 };
 
-template <int N, int NP>
-__global__ void __launch_bounds__(NP*(N / 8)) k_yinv_tile(YinvArgs a, const cplx* __restrict__ tw) {
+template <int N, int NP, int MINB>
+__global__ void __launch_bounds__(NP*(N / 8), MINB) k_yinv_tile(YinvArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8;
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
@@ -164,8 +166,8 @@ struct YfwdArgs {
   int nxh, nxp, nzf;
 };
 
-template <int N, int NP>
-__global__ void __launch_bounds__(NP*(N / 8)) k_yfwd_tile(YfwdArgs a, const cplx* __restrict__ tw) {
+template <int N, int NP, int MINB>
+__global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tile(YfwdArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8;
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
@@ -325,8 +327,8 @@ __device__ __forceinline__ void stash_boundary_tile(const cplx (&v)[8], int j, i
   }
 }
 
-template <int N, int NP>
-__global__ void __launch_bounds__(NP*(N / 8)) k_zfwd_rk(ZfwdArgs a, const cplx* __restrict__ tw) {
+template <int N, int NP, int MINB>
+__global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8;
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
@@ -602,6 +604,16 @@ static int fused_init(Plan& p, Fused** out) {
     for (int q = 0; q < c; ++q) zm[s + q] = ZMap{base, c, q, 0};
     base += (long long)p.nxl * c * p.ny;
   }
+  f->z_displ.resize(p.nprocs); f->z_count.resize(p.nprocs); f->x_displ.resize(p.nprocs); f->x_count.resize(p.nprocs);
+  for (int r = 0; r < p.nprocs; ++r) {
+    int s, c, xs, xc;
+    range0(f->nph, p.nprocs, r, &s, &c);
+    range0(p.nxh, p.nprocs, r, &xs, &xc);
+    f->z_displ[r] = c ? (size_t)zm[s].base : 0;
+    f->z_count[r] = (size_t)p.nxl * c * p.ny;
+    f->x_displ[r] = (size_t)xs * f->nzf * p.ny;
+    f->x_count[r] = (size_t)xc * f->nzf * p.ny;
+  }
   SX_CUDA_CHECK(cudaMalloc((void**)&f->d_zmap, zm.size() * sizeof(ZMap)));
   SX_CUDA_CHECK(cudaMemcpy(f->d_zmap, zm.data(), zm.size() * sizeof(ZMap), cudaMemcpyHostToDevice));
   const size_t rsize = (size_t)p.nxh * f->nzf * p.ny;  // y-stage side [kx][zl][ky]
@@ -631,31 +643,42 @@ static int fused_init(Plan& p, Fused** out) {
     SX_KERNEL_CHECK();                                                                                   \
   } while (0)
 
-template <int N> static int run_zinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
-  constexpr int NP = TileNP<N>::value;
+template <int N, int NP, int MINB> static int run_zinv_v(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
   ZinvArgs a{in, out0, out1, p.d_kz, f.d_zmap, p.ny, f.nph};
   const cplx* tw = p.tw_z;
-  auto kfn = k_zinv_tile<N, NP>;
+  auto kfn = k_zinv_tile<N, NP, MINB>;
   SX_FUSED_LAUNCH(p, ST_ZINV, kfn, dim3(cdiv(p.ny, NP), p.nxl), NP * (N / 8), (size_t)NP * N * sizeof(cplx), a, tw);
   return 0;
 }
-template <int N> static int run_yinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
-  constexpr int NP = TileNP<N>::value;
+#define SX_VARIANTS(fn, ...)                                                             \
+  constexpr int NP0 = TileNP<N>::value;                                                  \
+  constexpr int NP4 = N == 512 ? 4 : NP0;                                                \
+  if (N == 512 && p.knob_np == 4) return p.knob_minb >= 4 ? fn<N, NP4, (N == 512 ? 4 : 1)>(__VA_ARGS__) : fn<N, NP4, (N == 512 ? 2 : 1)>(__VA_ARGS__); \
+  return p.knob_minb == 2 ? fn<N, NP0, (N <= 512 ? 2 : 1)>(__VA_ARGS__) : fn<N, NP0, 1>(__VA_ARGS__)
+template <int N> static int run_zinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
+  SX_VARIANTS(run_zinv_v, p, f, in, out0, out1);
+}
+template <int N, int NP, int MINB> static int run_yinv_v(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
   if (f.nzf == 0) return 0;
   YinvArgs a{in, out0, out1, p.d_ky, p.nxh, f.nxp, f.nzf};
   const cplx* tw = p.tw_y;
-  auto kfn = k_yinv_tile<N, NP>;
+  auto kfn = k_yinv_tile<N, NP, MINB>;
   SX_FUSED_LAUNCH(p, ST_YINV, kfn, dim3(cdiv(f.nxp, NP), f.nzf), NP * (N / 8), (size_t)NP * N * sizeof(cplx), a, tw);
   return 0;
 }
-template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* out) {
-  constexpr int NP = TileNP<N>::value;
+template <int N> static int run_yinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
+  SX_VARIANTS(run_yinv_v, p, f, in, out0, out1);
+}
+template <int N, int NP, int MINB> static int run_yfwd_v(Plan& p, Fused& f, const cplx* in, cplx* out) {
   if (f.nzf == 0) return 0;
   YfwdArgs a{in, out, p.nxh, f.nxp, f.nzf};
   const cplx* tw = p.tw_y;
-  auto kfn = k_yfwd_tile<N, NP>;
+  auto kfn = k_yfwd_tile<N, NP, MINB>;
   SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(cdiv(p.nxh, NP), f.nzf), NP * (N / 8), (size_t)NP * N * sizeof(cplx), a, tw);
   return 0;
+}
+template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* out) {
+  SX_VARIANTS(run_yfwd_v, p, f, in, out);
 }
 template <int N> static int run_xpass(Plan& p, Fused& f, const double* d_kx_global) {
   constexpr int T = N / 8;
@@ -675,16 +698,19 @@ template <int N> static int run_xpass(Plan& p, Fused& f, const double* d_kx_glob
                   (size_t)LP * sidx_elem_stride<N>() * sizeof(cplx), a, tw);
   return 0;
 }
-template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, cplx* v, const cplx* v0, const cplx* frc,
+template <int N, int NP, int MINB> static int run_zfwd_rk_v(Plan& p, Fused& f, const cplx* nl, cplx* v, const cplx* v0, const cplx* frc,
                                         double dt, double nu, double rmp) {
-  constexpr int NP = TileNP<N>::value;
   ZfwdArgs a{nl, v, v0, frc, f.d_zmap, p.d_kx, p.d_ky, p.d_kz, p.d_fx, p.d_fy, p.d_fz, p.d_dir,
              p.ny, f.nph, p.Cz, p.oz, dt, nu, rmp};
   const cplx* tw = p.tw_z;
-  auto kfn = k_zfwd_rk<N, NP>;
+  auto kfn = k_zfwd_rk<N, NP, MINB>;
   const size_t smem = ((size_t)NP * N + (size_t)2 * kMaxDF * NP) * sizeof(cplx);
   SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(cdiv(p.ny, NP), p.nxl), NP * (N / 8), smem, a, tw);
   return 0;
+}
+template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, cplx* v, const cplx* v0, const cplx* frc,
+                                        double dt, double nu, double rmp) {
+  SX_VARIANTS(run_zfwd_rk_v, p, f, nl, v, v0, frc, dt, nu, rmp);
 }
 template <int N> static int run_project(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
                                         const double* zs, const double* ze) {
@@ -749,27 +775,43 @@ static int project(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, in
 #undef C_
 }
 
-int exchange_to_real(Plan& p, Fused& f, int slot);   // sx_comm.cu: W[slot] -> R[slot]
-int exchange_to_spec(Plan& p, Fused& f, int slot);   // sx_comm.cu: U[slot] -> Uz[slot]
+// W[slot] (z side, [rank][kxl][zl][ky]) -> R[slot] (xy side, [kx][zl][ky]); event slots 0..5
+static int to_real_begin(Plan& p, Fused& f, int slot) {
+  if (p.nprocs == 1) return 0;
+  return exchange_begin(p, slot, f.W[slot], f.R[slot], f.z_displ.data(), f.z_count.data(), f.x_displ.data(), f.x_count.data());
+}
+// U[slot] (xy side) -> Uz[slot] (z side); event slots 6..8
+static int to_spec_begin(Plan& p, Fused& f, int slot) {
+  if (p.nprocs == 1) return 0;
+  return exchange_begin(p, 6 + slot, f.U[slot], f.Uz[slot], f.x_displ.data(), f.x_count.data(), f.z_displ.data(), f.z_count.data());
+}
+static int ex_wait(Plan& p, int ev) { return p.nprocs == 1 ? 0 : exchange_wait(p, ev); }
 
 // hd_rkstep2.f90:3-36.  st[0..2] v, st[3] pr, st[4..6] f, st[7..9] RK base.
 int hd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, const double* zs, const double* ze) {
   Fused* fp;
   if (fused_init(p, &fp)) return 1;
   Fused& f = *fp;
-  SX_REQUIRE(p.nprocs == 1, "multi-GPU exchange not linked in this build");
+  SX_REQUIRE(comm_ready(p), "multi-rank plan without a communicator: call sx_plan_set_comm or sx_plan_set_comm_callbacks");
   const double rmp = 1.0 / (double)o;
-  for (int c = 0; c < 3; ++c)
-    if (zinv(p, f, st[c], f.W[2 * c], f.W[2 * c + 1])) return 1;
   for (int c = 0; c < 3; ++c) {
+    if (zinv(p, f, st[c], f.W[2 * c], f.W[2 * c + 1])) return 1;
+    if (to_real_begin(p, f, 2 * c) || to_real_begin(p, f, 2 * c + 1)) return 1;
+  }
+  for (int c = 0; c < 3; ++c) {
+    if (ex_wait(p, 2 * c) || ex_wait(p, 2 * c + 1)) return 1;
     if (yinv(p, f, f.R[2 * c], f.V[c], f.V[3 + c])) return 1;
     if (yinv(p, f, f.R[2 * c + 1], f.V[6 + c], nullptr)) return 1;
   }
   if (xpass(p, f, p.d_kxg)) return 1;
-  for (int c = 0; c < 3; ++c)
+  for (int c = 0; c < 3; ++c) {
     if (yfwd(p, f, f.X[c], f.U[c])) return 1;
-  for (int c = 0; c < 3; ++c)
+    if (to_spec_begin(p, f, c)) return 1;
+  }
+  for (int c = 0; c < 3; ++c) {
+    if (ex_wait(p, 6 + c)) return 1;
     if (zfwd_rk(p, f, f.Uz[c], st[c], st[7 + c], st[4 + c], dt, nu, rmp)) return 1;
+  }
   return project(p, f, st[0], st[1], st[2], st[3], o, zs, ze);
 }
 

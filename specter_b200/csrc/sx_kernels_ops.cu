@@ -455,6 +455,7 @@ int op_reduce_phys(Plan& p, const cplx* a, const cplx* b, int mode, int row, dou
   SX_CUDA_CHECK(cudaStreamSynchronize(p.stream));
   double s = 0.0;
   for (int i = 0; i < blocks; ++i) s += p.h_red[i];
+  if (allreduce_sum(p, &s, 1)) return 1;  // the reference: MPI_REDUCE to rank 0 (pseudospec_hd.f90:631)
   *result = s;
   return 0;
 }

@@ -8,6 +8,7 @@ namespace sx {
 
 struct HdState;  // fused-path device state (sx_rkstep.cu)
 struct Fused;    // fused-path work buffers and slab maps (sx_fused.cu)
+struct Comm;     // NCCL communicator / transport callbacks (sx_comm.cu)
 
 // Per-stage CUDA-event timers (the reference's ffttime/tratime/comtime/conttime counters,
 // fftp_mod.fpp:32-37, re-cast per kernel family).
@@ -52,7 +53,9 @@ struct Plan {
   int red_blocks = 0;
   HdState* hd = nullptr;
   Fused* fused = nullptr;
+  Comm* comm = nullptr;
   StageTimer timer;
+  int knob_np = 0, knob_minb = 1;   // tuning experiments (env SX_TILE_NP, SX_TILE_MINB)
   unsigned long long launches = 0;  // kernels launched by this plan (bench "gpu_launches")
 
   size_t csize() const { return (size_t)nz * ny * nxl; }   // complex elements per spectral field
@@ -112,6 +115,12 @@ int v_imposebc_and_project(Plan& p, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int 
                            const double* ze);
 int hd_state_free(Plan& p);
 int fused_free(Plan& p);
+int comm_free(Plan& p);
+bool comm_ready(const Plan& p);
+int exchange_begin(Plan& p, int ev, const cplx* send, cplx* recv, const size_t* sdispl, const size_t* scount,
+                   const size_t* rdispl, const size_t* rcount);
+int exchange_wait(Plan& p, int ev);
+int allreduce_sum(Plan& p, double* v, int n);
 
 }  // namespace sx
 
