@@ -136,6 +136,11 @@ static int plan_init(Plan& p, const sx_config& c) {
   SX_REQUIRE(ndev > 0, "no CUDA device: specter_b200 has no CPU fallback");
   p.device = c.device >= 0 ? c.device : c.myrank % ndev;
   SX_CUDA_CHECK(cudaSetDevice(p.device));
+#ifndef SX_EMU
+  SX_CUDA_CHECK(cudaDeviceGetAttribute(&p.num_sms, cudaDevAttrMultiProcessorCount, p.device));
+#else
+  p.num_sms = 3;  // small persistent grids so that the tile loops are exercised
+#endif
   p.nxh = p.nx / 2 + 1;
   range_(1, p.nxh, p.nprocs, p.myrank, &p.ista, &p.iend);
   range_(1, p.nz, p.nprocs, p.myrank, &p.ksta, &p.kend);

@@ -21,6 +21,20 @@ namespace sx {
 
 typedef double2 cplx;
 
+// ---- cp.async (LDGSTS) 16-byte copies global -> shared, used for software prefetch --------------
+#ifndef SX_EMU
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+#else
+inline void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
+#endif
+
 __host__ __device__ __forceinline__ cplx cmake(double x, double y) { return make_double2(x, y); }
 __host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }

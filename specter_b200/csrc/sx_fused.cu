@@ -52,12 +52,23 @@ struct Fused {
   std::vector<size_t> z_displ, z_count, x_displ, x_count;
 };
 
+// lines per CTA of the tile kernels: 256 threads up to N = 512 (64 B pieces on the strided side --
+// measured FASTER on B200 than 128 B pieces with twice the CTA footprint), 4 lines beyond
 template <int N> struct TileNP {
-  static constexpr int value = N <= 64 ? 32 : (N == 128 ? 16 : (N <= 1024 ? 8 : 4));
+  static constexpr int value = N <= 64 ? 32 : (N == 128 ? 16 : (N == 256 ? 8 : 4));
+};
+template <int N> struct TileMinB {  // CTAs per SM the register budget is capped for
+  static constexpr int value = N <= 512 ? 3 : (N == 1024 ? 1 : 1);
 };
 
+// Every tile kernel is persistent (grid = a multiple of the SM count, tiles strided by gridDim) and
+// software-pipelined: while tile t is transformed, the 8 values per thread of tile t+gridDim are in
+// flight as 16-byte cp.async copies into thread-private shared-memory slots (slot k of thread tid at
+// stage[k*NT + tid]: conflict free, and no barrier is needed because only the issuing thread reads
+// them).  The registers are the second pipeline stage.
+
 // ------------------------------------------------------------------------------------------
-// zinv_tile: one CTA = NP adjacent ky pencils of one kx.
+// zinv_tile: one tile = NP adjacent ky pencils of one kx.
 // ------------------------------------------------------------------------------------------
 struct ZinvArgs {
   const cplx* in;   // spectral (nz, ny, nxl)
@@ -65,54 +76,71 @@ struct ZinvArgs {
   cplx* out1;       // IFFT_z(i kz in) or nullptr
   const double* kz;
   const ZMap* zmap;
-  int ny, nph;
+  int ny, nxl, nph;
 };
 
 template <int N, int NP, int MINB>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zinv_tile(ZinvArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
-  constexpr int T = N / 8;
+  constexpr int T = N / 8, NT = NP * T;
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
-  const int ky = blockIdx.x * NP + p, kxl = blockIdx.y;
-  const bool active = ky < a.ny;
-  const cplx* src = a.in + ((size_t)kxl * a.ny + (active ? ky : 0)) * N;
+  cplx* slot = smem + (size_t)NP * N + threadIdx.x;
   const SIdxPencil si{p, NP};
-  // destination offsets of this thread's 8 rows (identical for both outputs)
-  long long off[8];
+  const int tiles_y = cdiv(a.ny, NP), ntiles = tiles_y * a.nxl;
+  auto issue = [&](int t) {
+    const int ky = (t % tiles_y) * NP + p, kxl = t / tiles_y;
+    if (ky < a.ny) {
+      const cplx* src = a.in + ((size_t)kxl * a.ny + ky) * N + j;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int z = j + k * T;
-    if (active && z < a.nph) {
-      const ZMap m = a.zmap[z];
-      off[k] = m.base + ((long long)kxl * m.nzl + m.zl) * a.ny + ky;
+      for (int k = 0; k < 8; ++k) cp_async16(slot + k * NT, src + k * T);
     } else {
-      off[k] = -1;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) slot[k * NT] = cmake(0.0, 0.0);
     }
-  }
-  cplx v[8];
+    cp_async_commit();
+  };
+  int t = blockIdx.x;
+  if (t < ntiles) issue(t);
+  for (; t < ntiles; t += gridDim.x) {
+    const int ky = (t % tiles_y) * NP + p, kxl = t / tiles_y;
+    const bool active = ky < a.ny;
+    cplx v[8];
+    cp_async_wait_all();
+    if (a.out1 != nullptr) {
+      // derivative first: the slots still hold this tile
 #pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = active ? src[j + k * T] : cmake(0.0, 0.0);
-  fft_regs<N, 1>(v, j, smem, si, tw);
+      for (int k = 0; k < 8; ++k) {
+        const cplx q = slot[k * NT];
+        const double kk = __ldg(&a.kz[j + k * T]);
+        v[k] = cmake(-kk * q.y, kk * q.x);
+      }
+      fft_regs<N, 1>(v, j, smem, si, tw);
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
-    if (off[k] >= 0) a.out0[off[k]] = v[k];
-  if (a.out1 != nullptr) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int e = j + k * T;
-      const cplx t = active ? src[e] : cmake(0.0, 0.0);  // L1/L2 hit: just read by this CTA
-      const double kk = __ldg(&a.kz[e]);
-      v[k] = cmake(-kk * t.y, kk * t.x);
+      for (int k = 0; k < 8; ++k) {
+        const int z = j + k * T;
+        if (active && z < a.nph) {
+          const ZMap m = a.zmap[z];
+          a.out1[m.base + ((long long)kxl * m.nzl + m.zl) * a.ny + ky] = v[k];
+        }
+      }
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+    if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
     fft_regs<N, 1>(v, j, smem, si, tw);
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (off[k] >= 0) a.out1[off[k]] = v[k];
+    for (int k = 0; k < 8; ++k) {
+      const int z = j + k * T;
+      if (active && z < a.nph) {
+        const ZMap m = a.zmap[z];
+        a.out0[m.base + ((long long)kxl * m.nzl + m.zl) * a.ny + ky] = v[k];
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// yinv_tile: one CTA = NP adjacent kx lines of one local z row; [kx][zl][ky] -> [zl][y][kx].
+// yinv_tile: one tile = NP adjacent kx lines of one local z row; [kx][zl][ky] -> [zl][y][kx].
 // ------------------------------------------------------------------------------------------
 struct YinvArgs {
   const cplx* in;   // [kx][zl][ky]
@@ -125,34 +153,51 @@ struct YinvArgs {
 template <int N, int NP, int MINB>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yinv_tile(YinvArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
-  constexpr int T = N / 8;
+  constexpr int T = N / 8, NT = NP * T;
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
-  const int kx = blockIdx.x * NP + p, zl = blockIdx.y;
-  const bool active = kx < a.nxh;
-  const bool store = kx < a.nxp;
-  const cplx* src = a.in + ((size_t)(active ? kx : 0) * a.nzf + zl) * N;
-  const size_t dst = (size_t)zl * N * a.nxp + kx;
+  cplx* slot = smem + (size_t)NP * N + threadIdx.x;
   const SIdxPencil si{p, NP};
-  cplx v[8];
+  const int tiles_x = cdiv(a.nxp, NP), ntiles = tiles_x * a.nzf;
+  auto issue = [&](int t) {
+    const int kx = (t % tiles_x) * NP + p, zl = t / tiles_x;
+    if (kx < a.nxh) {
+      const cplx* src = a.in + ((size_t)kx * a.nzf + zl) * N + j;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = active ? src[j + k * T] : cmake(0.0, 0.0);
-  fft_regs<N, 1>(v, j, smem, si, tw);
-  if (store) {
+      for (int k = 0; k < 8; ++k) cp_async16(slot + k * NT, src + k * T);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a.out0[dst + (size_t)(j + k * T) * a.nxp] = v[k];
-  }
-  if (a.out1 != nullptr) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int e = j + k * T;
-      const cplx t = active ? src[e] : cmake(0.0, 0.0);
-      const double kk = __ldg(&a.ky[e]);
-      v[k] = cmake(-kk * t.y, kk * t.x);
+      for (int k = 0; k < 8; ++k) slot[k * NT] = cmake(0.0, 0.0);
     }
+    cp_async_commit();
+  };
+  int t = blockIdx.x;
+  if (t < ntiles) issue(t);
+  for (; t < ntiles; t += gridDim.x) {
+    const int kx = (t % tiles_x) * NP + p, zl = t / tiles_x;
+    const bool store = kx < a.nxp;
+    const size_t dst = (size_t)zl * N * a.nxp + kx;
+    cplx v[8];
+    cp_async_wait_all();
+    if (a.out1 != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const cplx q = slot[k * NT];
+        const double kk = __ldg(&a.ky[j + k * T]);
+        v[k] = cmake(-kk * q.y, kk * q.x);
+      }
+      fft_regs<N, 1>(v, j, smem, si, tw);
+      if (store) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.out1[dst + (size_t)(j + k * T) * a.nxp] = v[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+    if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
     fft_regs<N, 1>(v, j, smem, si, tw);
     if (store) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a.out1[dst + (size_t)(j + k * T) * a.nxp] = v[k];
+      for (int k = 0; k < 8; ++k) a.out0[dst + (size_t)(j + k * T) * a.nxp] = v[k];
     }
   }
 }
@@ -169,19 +214,37 @@ struct YfwdArgs {
 template <int N, int NP, int MINB>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tile(YfwdArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
-  constexpr int T = N / 8;
+  constexpr int T = N / 8, NT = NP * T;
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
-  const int kx = blockIdx.x * NP + p, zl = blockIdx.y;
-  const bool active = kx < a.nxh;
-  const size_t src = (size_t)zl * N * a.nxp + (active ? kx : 0);
-  cplx v[8];
+  cplx* slot = smem + (size_t)NP * N + threadIdx.x;
+  const int tiles_x = cdiv(a.nxh, NP), ntiles = tiles_x * a.nzf;
+  auto issue = [&](int t) {
+    const int kx = (t % tiles_x) * NP + p, zl = t / tiles_x;
+    if (kx < a.nxh) {
+      const cplx* src = a.in + ((size_t)zl * N + j) * a.nxp + kx;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = active ? a.in[src + (size_t)(j + k * T) * a.nxp] : cmake(0.0, 0.0);
-  fft_regs<N, -1>(v, j, smem, SIdxPencil{p, NP}, tw);
-  if (active) {
-    cplx* dst = a.out + ((size_t)kx * a.nzf + zl) * N;
+      for (int k = 0; k < 8; ++k) cp_async16(slot + k * NT, src + (size_t)k * T * a.nxp);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dst[j + k * T] = v[k];
+      for (int k = 0; k < 8; ++k) slot[k * NT] = cmake(0.0, 0.0);
+    }
+    cp_async_commit();
+  };
+  int t = blockIdx.x;
+  if (t < ntiles) issue(t);
+  for (; t < ntiles; t += gridDim.x) {
+    const int kx = (t % tiles_x) * NP + p, zl = t / tiles_x;
+    cplx v[8];
+    cp_async_wait_all();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+    if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
+    fft_regs<N, -1>(v, j, smem, SIdxPencil{p, NP}, tw);
+    if (kx < a.nxh) {
+      cplx* dst = a.out + ((size_t)kx * a.nzf + zl) * N;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[j + k * T] = v[k];
+    }
   }
 }
 
@@ -195,80 +258,110 @@ struct XpassArgs {
   const cplx* V[9];  // v(3), dy v(3), dz v(3)   [zl][y][kx]
   cplx* X[3];
   const double* kx;  // GLOBAL kx(1:nx/2+1)
-  int ny, nxp;
+  int ny, nxp, nzf;
   double tmp;        // 1/(nx ny nz)^2
 };
 
-template <int N, bool DERIV>
-__device__ __forceinline__ void x_load_pair(cplx (&v)[8], const cplx* __restrict__ f, size_t rowA, size_t rowB,
-                                            int t, bool active, const double* __restrict__ kxv) {
-  constexpr int T = N / 8;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int e = t + k * T;
-    const int kx = e <= N / 2 ? e : N - e;
-    cplx A = active ? f[rowA + kx] : cmake(0.0, 0.0);
-    cplx B = active ? f[rowB + kx] : cmake(0.0, 0.0);
-    if (DERIV) {
-      const double kk = __ldg(&kxv[kx]);
-      A = cmake(-kk * A.y, kk * A.x);
-      B = cmake(-kk * B.y, kk * B.x);
-    }
-    if (kx == 0 || kx == N / 2) { A.y = 0.0; B.y = 0.0; }
-    if (e > N / 2) { A.y = -A.y; B.y = -B.y; }
-    v[k] = cmake(A.x - B.y, A.y + B.x);
-  }
-}
-
+// One CTA = LP pairs of adjacent y lines; persistent over (z row, y group).  The 12 inverse
+// transforms of a group are a software pipeline: while transform m runs, the two spectral rows of
+// transform m+1 are in flight as cp.async copies into thread-private slots.  The three velocity
+// lines are parked in thread-private shared memory, so the register file only holds one transform
+// and one accumulator.
 template <int N, int LP>
-__global__ void __launch_bounds__(LP*(N / 8)) k_xpass_gradre(XpassArgs a, const cplx* __restrict__ tw) {
+__global__ void __launch_bounds__(LP*(N / 8), (N <= 1024 ? 2 : 1)) k_xpass_gradre(XpassArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
-  constexpr int T = N / 8;
+  constexpr int T = N / 8, NT = LP * T, XS = sidx_elem_stride<N>();
   const int lp = threadIdx.x / T, t = threadIdx.x % T;
-  const int y0 = (blockIdx.x * LP + lp) * 2, zl = blockIdx.y;
-  const bool active = y0 < a.ny;
-  const size_t rowA = ((size_t)zl * a.ny + (active ? y0 : 0)) * a.nxp, rowB = rowA + a.nxp;
-  const SIdxElem si{lp * sidx_elem_stride<N>()};
-  cplx u[3][8];
+  const SIdxElem si{lp * XS};
+  cplx* park = smem + (size_t)LP * XS + threadIdx.x;            // park[(c*8+k)*NT]
+  cplx* slot = smem + (size_t)LP * XS + (size_t)24 * NT + threadIdx.x;  // slot[(2k+h)*NT]
+  const int groups_y = cdiv(a.ny, 2 * LP), ngroups = groups_y * a.nzf;
+  auto field_of = [&](int m) -> const cplx* {
+    if (m < 3) return a.V[m];
+    const int c = (m - 3) / 3, d = (m - 3) % 3;
+    return a.V[d * 3 + c];
+  };
+  auto issue = [&](int g, int m) {
+    const int y0 = ((g % groups_y) * LP + lp) * 2, zl = g / groups_y;
+    if (y0 < a.ny) {
+      const cplx* rowA = field_of(m) + ((size_t)zl * a.ny + y0) * a.nxp;
+      const cplx* rowB = rowA + a.nxp;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    x_load_pair<N, false>(u[c], a.V[c], rowA, rowB, t, active, a.kx);
-    fft_regs<N, 1>(u[c], t, smem, si, tw);
-  }
+      for (int k = 0; k < 8; ++k) {
+        const int e = t + k * T;
+        const int kx = e <= N / 2 ? e : N - e;
+        cp_async16(slot + (2 * k) * NT, rowA + kx);
+        cp_async16(slot + (2 * k + 1) * NT, rowB + kx);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) slot[k * NT] = cmake(0.0, 0.0);
+    }
+    cp_async_commit();
+  };
+  int g = blockIdx.x;
+  if (g < ngroups) issue(g, 0);
+  for (; g < ngroups; g += gridDim.x) {
+    const int y0 = ((g % groups_y) * LP + lp) * 2, zl = g / groups_y;
+    const bool active = y0 < a.ny;
+    const size_t rowA = ((size_t)zl * a.ny + (active ? y0 : 0)) * a.nxp, rowB = rowA + a.nxp;
+    cplx acc[8];
 #pragma unroll 1
-  for (int c = 0; c < 3; ++c) {
-    cplx acc[8], g[8];
-    x_load_pair<N, true>(g, a.V[c], rowA, rowB, t, active, a.kx);
-    fft_regs<N, 1>(g, t, smem, si, tw);
+    for (int m = 0; m < 12; ++m) {
+      const bool deriv = m >= 3 && (m - 3) % 3 == 0;
+      cplx v[8];
+      cp_async_wait_all();
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = cmake(u[0][k].x * g[k].x, u[0][k].y * g[k].y);
-    x_load_pair<N, false>(g, a.V[3 + c], rowA, rowB, t, active, a.kx);
-    fft_regs<N, 1>(g, t, smem, si, tw);
+      for (int k = 0; k < 8; ++k) {
+        const int e = t + k * T;
+        const int kx = e <= N / 2 ? e : N - e;
+        cplx A = slot[(2 * k) * NT], B = slot[(2 * k + 1) * NT];
+        if (deriv) {
+          const double kk = __ldg(&a.kx[kx]);
+          A = cmake(-kk * A.y, kk * A.x);
+          B = cmake(-kk * B.y, kk * B.x);
+        }
+        if (kx == 0 || kx == N / 2) { A.y = 0.0; B.y = 0.0; }
+        if (e > N / 2) { A.y = -A.y; B.y = -B.y; }
+        v[k] = cmake(A.x - B.y, A.y + B.x);
+      }
+      if (m < 11) issue(g, m + 1);
+      else if (g + (int)gridDim.x < ngroups) issue(g + gridDim.x, 0);
+      fft_regs<N, 1>(v, t, smem, si, tw);
+      if (m < 3) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = cmake(acc[k].x + u[1][k].x * g[k].x, acc[k].y + u[1][k].y * g[k].y);
-    x_load_pair<N, false>(g, a.V[6 + c], rowA, rowB, t, active, a.kx);
-    fft_regs<N, 1>(g, t, smem, si, tw);
+        for (int k = 0; k < 8; ++k) park[(m * 8 + k) * NT] = v[k];
+      } else {
+        const int c = (m - 3) / 3, d = (m - 3) % 3;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      acc[k] = cmake((acc[k].x + u[2][k].x * g[k].x) * a.tmp, (acc[k].y + u[2][k].y * g[k].y) * a.tmp);
-    // forward transform of the packed pair and split into the two half spectra
-    fft_regs<N, -1>(acc, t, smem, si, tw);
-    __syncthreads();
+        for (int k = 0; k < 8; ++k) {
+          const cplx u = park[(d * 8 + k) * NT];
+          if (d == 0) acc[k] = cmake(u.x * v[k].x, u.y * v[k].y);
+          else acc[k] = cmake(acc[k].x + u.x * v[k].x, acc[k].y + u.y * v[k].y);
+        }
+        if (d == 2) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) smem[si(t + k * T)] = acc[k];
-    __syncthreads();
-    cplx* out = a.X[c];
+          for (int k = 0; k < 8; ++k) acc[k] = cmake(acc[k].x * a.tmp, acc[k].y * a.tmp);
+          // forward transform of the packed pair and split into the two half spectra
+          fft_regs<N, -1>(acc, t, smem, si, tw);
+          __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int kk = t + k * T;
-      if (kk <= N / 2 && active) {
-        const cplx Zk = acc[k];
-        const cplx Zn = smem[si((N - kk) & (N - 1))];
-        out[rowA + kk] = cmake(0.5 * (Zk.x + Zn.x), 0.5 * (Zk.y - Zn.y));
-        out[rowB + kk] = cmake(0.5 * (Zk.y + Zn.y), -0.5 * (Zk.x - Zn.x));
+          for (int k = 0; k < 8; ++k) smem[si(t + k * T)] = acc[k];
+          __syncthreads();
+          cplx* out = a.X[c];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int kk = t + k * T;
+            if (kk <= N / 2 && active) {
+              const cplx Zk = acc[k];
+              const cplx Zn = smem[si((N - kk) & (N - 1))];
+              out[rowA + kk] = cmake(0.5 * (Zk.x + Zn.x), 0.5 * (Zk.y - Zn.y));
+              out[rowB + kk] = cmake(0.5 * (Zk.y + Zn.y), -0.5 * (Zk.x - Zn.x));
+            }
+          }
+        }
       }
     }
-    // (the next fft_regs starts with a __syncthreads before it writes the exchange buffer)
   }
 }
 
@@ -287,7 +380,7 @@ struct ZfwdArgs {
   const double *kx, *ky, *kz;     // kx LOCAL
   const double *fx, *fy, *fz;     // filter factors (fx LOCAL)
   const double* dir;  // [C][d]
-  int ny, nph, C, d;
+  int ny, nxl, nph, C, d;
   double dt, nu, rmp;
 };
 
@@ -330,40 +423,55 @@ __device__ __forceinline__ void stash_boundary_tile(const cplx (&v)[8], int j, i
 template <int N, int NP, int MINB>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
-  constexpr int T = N / 8;
+  constexpr int T = N / 8, NT = NP * T;
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
-  const int ky = blockIdx.x * NP + p, kxl = blockIdx.y;
-  const bool active = ky < a.ny;
   cplx* bnd = smem + (size_t)NP * N;
-  cplx v[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int z = j + k * T;
-    if (active && z < a.nph) {
-      const ZMap m = a.zmap[z];
-      v[k] = a.nl[m.base + ((long long)kxl * m.nzl + m.zl) * a.ny + ky];
-    } else {
-      v[k] = cmake(0.0, 0.0);
-    }
-  }
-  stash_boundary_tile<N, NP>(v, j, p, bnd, a.nph, a.d);
-  __syncthreads();
-  fc_continue_tile<N, NP>(v, j, p, bnd, a.nph, a.C, a.d, a.dir);
-  fft_regs<N, -1>(v, j, smem, SIdxPencil{p, NP}, tw);
-  if (active) {
-    const size_t base = ((size_t)kxl * a.ny + ky) * N;
-    const double x = __ldg(&a.kx[kxl]), y = __ldg(&a.ky[ky]);
-    const double f1 = __ldg(&a.fx[kxl]), f2 = __ldg(&a.fy[ky]);
-    const double kh2 = x * x + y * y;
+  cplx* slot = bnd + (size_t)2 * kMaxDF * NP + threadIdx.x;
+  const int tiles_y = cdiv(a.ny, NP), ntiles = tiles_y * a.nxl;
+  auto issue = [&](int t) {
+    const int ky = (t % tiles_y) * NP + p, kxl = t / tiles_y;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int e = j + k * T;
-      const double z = __ldg(&a.kz[e]), f3 = __ldg(&a.fz[e]);
-      const double kk2 = kh2 + z * z;
-      const cplx NL = cscale(cscale(cscale(v[k], f1), f2), f3);
-      const cplx L = a.v[base + e], B = a.v0[base + e], F = a.f[base + e];
-      a.v[base + e] = cmake(B.x + a.dt * (a.nu * (-kk2 * L.x) - NL.x + F.x) * a.rmp,
-                            B.y + a.dt * (a.nu * (-kk2 * L.y) - NL.y + F.y) * a.rmp);
+      const int z = j + k * T;
+      if (ky < a.ny && z < a.nph) {
+        const ZMap m = a.zmap[z];
+        cp_async16(slot + k * NT, a.nl + m.base + ((long long)kxl * m.nzl + m.zl) * a.ny + ky);
+      } else {
+        slot[k * NT] = cmake(0.0, 0.0);
+      }
+    }
+    cp_async_commit();
+  };
+  int t = blockIdx.x;
+  if (t < ntiles) issue(t);
+  for (; t < ntiles; t += gridDim.x) {
+    const int ky = (t % tiles_y) * NP + p, kxl = t / tiles_y;
+    const bool active = ky < a.ny;
+    cplx v[8];
+    cp_async_wait_all();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+    if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
+    __syncthreads();  // bnd and the exchange buffer of the previous tile are free
+    stash_boundary_tile<N, NP>(v, j, p, bnd, a.nph, a.d);
+    __syncthreads();
+    fc_continue_tile<N, NP>(v, j, p, bnd, a.nph, a.C, a.d, a.dir);
+    fft_regs<N, -1>(v, j, smem, SIdxPencil{p, NP}, tw);
+    if (active) {
+      const size_t base = ((size_t)kxl * a.ny + ky) * N;
+      const double x = __ldg(&a.kx[kxl]), y = __ldg(&a.ky[ky]);
+      const double f1 = __ldg(&a.fx[kxl]), f2 = __ldg(&a.fy[ky]);
+      const double kh2 = x * x + y * y;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = j + k * T;
+        const double z = __ldg(&a.kz[e]), f3 = __ldg(&a.fz[e]);
+        const double kk2 = kh2 + z * z;
+        const cplx NL = cscale(cscale(cscale(v[k], f1), f2), f3);
+        const cplx L = a.v[base + e], B = a.v0[base + e], F = a.f[base + e];
+        a.v[base + e] = cmake(B.x + a.dt * (a.nu * (-kk2 * L.x) - NL.x + F.x) * a.rmp,
+                              B.y + a.dt * (a.nu * (-kk2 * L.y) - NL.y + F.y) * a.rmp);
+      }
     }
   }
 }
@@ -429,130 +537,149 @@ __device__ __forceinline__ void fc_fft_fwd(cplx (&v)[8], int j, cplx* smem, cons
 }
 
 template <int N, int NPB>
-__global__ void __launch_bounds__(NPB*(N / 8)) k_project(ProjArgs a, const cplx* __restrict__ tw) {
+__global__ void __launch_bounds__(NPB*(N / 8), (N <= 512 ? 3 : 1)) k_project(ProjArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
-  constexpr int T = N / 8;
+  constexpr int T = N / 8, NT = NPB * T;
   constexpr int XS = sidx_elem_stride<N>();
   const int pl = threadIdx.x / T, j = threadIdx.x % T;
-  const long pencil = (long)blockIdx.x * NPB + pl;
-  const bool active = pencil < a.npencils;
-  const long pc = active ? pencil : 0;
-  const int ky_i = (int)(pc % a.ny), kx_i = (int)(pc / a.ny);
   const SIdxElem si{pl * XS};
-  // shared: [NPB exchange buffers][NPB x 3 parked pencils][NPB boundary stashes][NPB wall values]
-  cplx* park = smem + (size_t)NPB * XS + (size_t)pl * 3 * N;
-  cplx* bnd = smem + (size_t)NPB * XS + (size_t)NPB * 3 * N + (size_t)pl * 2 * kMaxDF;
-  cplx* wall = smem + (size_t)NPB * XS + (size_t)NPB * 3 * N + (size_t)NPB * 2 * kMaxDF + (size_t)pl * 2;
-  const size_t base = (size_t)pc * N;
-  const double x = __ldg(&a.kx[kx_i]), y = __ldg(&a.ky[ky_i]);
-  const bool mean = a.has_mean && pencil == 0;
+  // shared: [NPB exchange buffers][2 parked fields, thread-private][prefetch slots][boundary stashes][wall values]
+  cplx* park = smem + (size_t)NPB * XS + threadIdx.x;                      // park[(c*8+k)*NT]
+  cplx* slot = smem + (size_t)NPB * XS + (size_t)16 * NT + threadIdx.x;    // slot[k*NT]
+  cplx* bnd = smem + (size_t)NPB * XS + (size_t)24 * NT + (size_t)pl * 2 * kMaxDF;
+  cplx* wall = smem + (size_t)NPB * XS + (size_t)24 * NT + (size_t)NPB * 2 * kMaxDF + (size_t)pl * 2;
   const int top = a.nph - 1;
-  const cplx pr0 = a.pr[base], prT = a.pr[base + top];
-
-  // ---- no-slip rows of vx, vy in the mixed domain, back to Fourier (vboundary.f90:116-145) ----
-  cplx v[8];
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    const cplx* src = c == 0 ? a.vx : a.vy;
-    const double kc = c == 0 ? x : y;
+  const long ngroups = (a.npencils + NPB - 1) / NPB;
+  auto issue = [&](long g, const cplx* field) {
+    const long pencil = g * NPB + pl;
+    if (pencil < a.npencils) {
+      const cplx* src = field + (size_t)pencil * N + j;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = active ? src[base + j + k * T] : cmake(0.0, 0.0);
+      for (int k = 0; k < 8; ++k) cp_async16(slot + k * NT, src + k * T);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) slot[k * NT] = cmake(0.0, 0.0);
+    }
+    cp_async_commit();
+  };
+  long g = blockIdx.x;
+  if (g < ngroups) issue(g, a.vx);
+  for (; g < ngroups; g += gridDim.x) {
+    const long pencil = g * NPB + pl;
+    const bool active = pencil < a.npencils;
+    const long pc = active ? pencil : 0;
+    const int ky_i = (int)(pc % a.ny), kx_i = (int)(pc / a.ny);
+    const size_t base = (size_t)pc * N;
+    const double x = __ldg(&a.kx[kx_i]), y = __ldg(&a.ky[ky_i]);
+    const bool mean = a.has_mean && pencil == 0;
+    const cplx pr0 = a.pr[base], prT = a.pr[base + top];
+
+    // ---- no-slip rows of vx, vy in the mixed domain, back to Fourier (vboundary.f90:116-145) ----
+    cplx v[8];
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      const double kc = c == 0 ? x : y;
+      cp_async_wait_all();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+      issue(g, c == 0 ? a.vy : a.vz);
+      fft_regs<N, 1>(v, j, smem, si, tw);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = j + k * T;
+        v[k] = cscale(v[k], a.inv_nz);
+        if (e == 0 || e == top) {
+          const cplx P = e == 0 ? pr0 : prT;
+          v[k] = cmake(-kc * P.y * a.tmp_noslip, kc * P.x * a.tmp_noslip);
+          if (mean) v[k] = cmake(e == 0 ? (c == 0 ? a.mx0 : a.my0) : (c == 0 ? a.mx1 : a.my1), 0.0);
+        }
+      }
+      fc_fft_fwd<N>(v, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, tw);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) park[(c * 8 + k) * NT] = v[k];
+    }
+    // ---- particular solution and its gradient (boundary_mod.fpp:405-448, 249-259) ----
+    cplx dd[8], cz[8];
+    cp_async_wait_all();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cz[k] = slot[k * NT];
+    if (g + (long)gridDim.x < ngroups) issue(g + gridDim.x, a.vx);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = j + k * T;
+      const double z = __ldg(&a.kz[e]);
+      const double kk2 = x * x + y * y + z * z;
+      cplx A = park[k * NT], B = park[(8 + k) * NT];
+      cplx Cc = cz[k];
+      const cplx s = cmake(x * A.x + y * B.x + z * Cc.x, x * A.y + y * B.y + z * Cc.y);
+      cplx D = cmake(s.y / kk2, -s.x / kk2);
+      if ((mean && e == 0) || !active) D = cmake(0.0, 0.0);
+      A = cmake(A.x + x * D.y, A.y - x * D.x);
+      B = cmake(B.x + y * D.y, B.y - y * D.x);
+      Cc = cmake(Cc.x + z * D.y, Cc.y - z * D.x);
+      park[k * NT] = A;
+      park[(8 + k) * NT] = B;
+      cz[k] = Cc;
+      dd[k] = D;
+      v[k] = cscale(Cc, a.inv_nz);
+    }
+    // ---- wall values of v_z (boundary_mod.fpp:275-338) ----
     fft_regs<N, 1>(v, j, smem, si, tw);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int e = j + k * T;
-      v[k] = cscale(v[k], a.inv_nz);
-      if (e == 0 || e == top) {
-        const cplx P = e == 0 ? pr0 : prT;
-        v[k] = cmake(-kc * P.y * a.tmp_noslip, kc * P.x * a.tmp_noslip);
-        if (mean) v[k] = cmake(e == 0 ? (c == 0 ? a.mx0 : a.my0) : (c == 0 ? a.mx1 : a.my1), 0.0);
+      if (e == 0) wall[0] = v[k];
+      if (e == top) wall[1] = v[k];
+    }
+    __syncthreads();
+    const cplx bc1 = wall[0], bc2 = wall[1];
+    // ---- laplace_z, Neumann-Neumann (boundary_mod.fpp:531-560, 635-675) ----
+    const double kh = sqrt(x * x + y * y);
+    cplx c1, c2;
+    if (mean) {
+      c1 = bc1;
+      c2 = cmake(0.0, 0.0);
+    } else {
+      const double e1 = exp(-kh * a.Lz), tt = 1.0 / (kh * (1.0 - exp(-2.0 * kh * a.Lz)));
+      c1 = cmake((bc2.x - bc1.x * e1) * tt, (bc2.y - bc1.y * e1) * tt);
+      c2 = cmake((-bc1.x + bc2.x * e1) * tt, (-bc1.y + bc2.y * e1) * tt);
+    }
+    // p' = IFFT_z(d)/nz + phi  (boundary_mod.fpp:371-380); all nz rows like the reference
+    fft_regs<N, 1>(dd, j, smem, si, tw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = j + k * T;
+      const double z = __ldg(&a.zc[e]);
+      cplx A, B;
+      if (mean) {
+        A = cmake(c1.x * z + c2.x, 0.0);
+        B = cmake(c1.x, 0.0);
+      } else {
+        const double ep = exp(kh * (z - a.Lz)), em = exp(-kh * z);
+        A = cmake(c1.x * ep + c2.x * em, c1.y * ep + c2.y * em);
+        B = cmake(kh * (c1.x * ep - c2.x * em), kh * (c1.y * ep - c2.y * em));
+      }
+      if (active) a.pr[base + e] = cmake(dd[k].x * a.inv_nz + A.x, dd[k].y * a.inv_nz + A.y);
+      dd[k] = A;   // phi
+      v[k] = B;    // d(phi)/dz
+    }
+    // ---- subtract the harmonic correction (boundary_mod.fpp:385-399) ----
+    fc_fft_fwd<N>(v, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, tw);
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a.vz[base + j + k * T] = cmake(cz[k].x - v[k].x, cz[k].y - v[k].y);
+    }
+    fc_fft_fwd<N>(dd, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, tw);
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = j + k * T;
+        const cplx A = park[k * NT], B = park[(8 + k) * NT], h = dd[k];
+        a.vx[base + e] = cmake(A.x + x * h.y, A.y - x * h.x);
+        a.vy[base + e] = cmake(B.x + y * h.y, B.y - y * h.x);
       }
     }
-    fc_fft_fwd<N>(v, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, tw);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) park[c * N + j + k * T] = v[k];
-  }
-  // ---- particular solution and its gradient (boundary_mod.fpp:405-448, 249-259) ----
-  cplx dd[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int e = j + k * T;
-    const double z = __ldg(&a.kz[e]);
-    const double kk2 = x * x + y * y + z * z;
-    cplx A = park[e], B = park[N + e];
-    cplx Cc = active ? a.vz[base + e] : cmake(0.0, 0.0);
-    const cplx s = cmake(x * A.x + y * B.x + z * Cc.x, x * A.y + y * B.y + z * Cc.y);
-    cplx D = cmake(s.y / kk2, -s.x / kk2);
-    if ((mean && e == 0) || !active) D = cmake(0.0, 0.0);
-    A = cmake(A.x + x * D.y, A.y - x * D.x);
-    B = cmake(B.x + y * D.y, B.y - y * D.x);
-    Cc = cmake(Cc.x + z * D.y, Cc.y - z * D.x);
-    park[e] = A;
-    park[N + e] = B;
-    park[2 * N + e] = Cc;
-    dd[k] = D;
-    v[k] = cscale(Cc, a.inv_nz);
-  }
-  // ---- wall values of v_z (boundary_mod.fpp:275-338) ----
-  fft_regs<N, 1>(v, j, smem, si, tw);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int e = j + k * T;
-    if (e == 0) wall[0] = v[k];
-    if (e == top) wall[1] = v[k];
-  }
-  __syncthreads();
-  const cplx bc1 = wall[0], bc2 = wall[1];
-  // ---- laplace_z, Neumann-Neumann (boundary_mod.fpp:531-560, 635-675) ----
-  const double kh = sqrt(x * x + y * y);
-  cplx c1, c2;
-  if (mean) {
-    c1 = bc1;
-    c2 = cmake(0.0, 0.0);
-  } else {
-    const double e1 = exp(-kh * a.Lz), tt = 1.0 / (kh * (1.0 - exp(-2.0 * kh * a.Lz)));
-    c1 = cmake((bc2.x - bc1.x * e1) * tt, (bc2.y - bc1.y * e1) * tt);
-    c2 = cmake((-bc1.x + bc2.x * e1) * tt, (-bc1.y + bc2.y * e1) * tt);
-  }
-  // p' = IFFT_z(d)/nz + phi  (boundary_mod.fpp:371-380); all nz rows like the reference
-  fft_regs<N, 1>(dd, j, smem, si, tw);
-  cplx ph[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int e = j + k * T;
-    const double z = __ldg(&a.zc[e]);
-    cplx A, B;
-    if (mean) {
-      A = cmake(c1.x * z + c2.x, 0.0);
-      B = cmake(c1.x, 0.0);
-    } else {
-      const double ep = exp(kh * (z - a.Lz)), em = exp(-kh * z);
-      A = cmake(c1.x * ep + c2.x * em, c1.y * ep + c2.y * em);
-      B = cmake(kh * (c1.x * ep - c2.x * em), kh * (c1.y * ep - c2.y * em));
-    }
-    if (active) a.pr[base + e] = cmake(dd[k].x * a.inv_nz + A.x, dd[k].y * a.inv_nz + A.y);
-    ph[k] = A;
-    v[k] = B;
-  }
-  // ---- subtract the harmonic correction (boundary_mod.fpp:385-399) ----
-  fc_fft_fwd<N>(v, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, tw);   // d(phi)/dz
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int e = j + k * T;
-      const cplx Cc = park[2 * N + e];
-      a.vz[base + e] = cmake(Cc.x - v[k].x, Cc.y - v[k].y);
-    }
-  }
-  fc_fft_fwd<N>(ph, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, tw);  // phi
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int e = j + k * T;
-      const cplx A = park[e], B = park[N + e], h = ph[k];
-      a.vx[base + e] = cmake(A.x + x * h.y, A.y - x * h.x);
-      a.vy[base + e] = cmake(B.x + y * h.y, B.y - y * h.x);
-    }
+    __syncthreads();  // wall / bnd are rewritten by the next group
   }
 }
 
@@ -643,46 +770,57 @@ static int fused_init(Plan& p, Fused** out) {
     SX_KERNEL_CHECK();                                                                                   \
   } while (0)
 
-template <int N, int NP, int MINB> static int run_zinv_v(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
-  ZinvArgs a{in, out0, out1, p.d_kz, f.d_zmap, p.ny, f.nph};
-  const cplx* tw = p.tw_z;
-  auto kfn = k_zinv_tile<N, NP, MINB>;
-  SX_FUSED_LAUNCH(p, ST_ZINV, kfn, dim3(cdiv(p.ny, NP), p.nxl), NP * (N / 8), (size_t)NP * N * sizeof(cplx), a, tw);
+// persistent grid: CTAs per SM from the occupancy calculator, times the SM count
+template <class K> static int persistent_grid(Plan& p, K kfn, int threads, size_t smem, int ntiles, int* grid) {
+  SX_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+#ifndef SX_EMU
+  SX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+#endif
+  const int g = per_sm * p.num_sms;
+  *grid = ntiles < g ? ntiles : g;
   return 0;
 }
-#define SX_VARIANTS(fn, ...)                                                             \
-  constexpr int NP0 = TileNP<N>::value;                                                  \
-  constexpr int NP4 = N == 512 ? 4 : NP0;                                                \
-  if (N == 512 && p.knob_np == 4) return p.knob_minb >= 4 ? fn<N, NP4, (N == 512 ? 4 : 1)>(__VA_ARGS__) : fn<N, NP4, (N == 512 ? 2 : 1)>(__VA_ARGS__); \
-  return p.knob_minb == 2 ? fn<N, NP0, (N <= 512 ? 2 : 1)>(__VA_ARGS__) : fn<N, NP0, 1>(__VA_ARGS__)
+
 template <int N> static int run_zinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
-  SX_VARIANTS(run_zinv_v, p, f, in, out0, out1);
+  constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
+  ZinvArgs a{in, out0, out1, p.d_kz, f.d_zmap, p.ny, p.nxl, f.nph};
+  const cplx* tw = p.tw_z;
+  auto kfn = k_zinv_tile<N, NP, MINB>;
+  const size_t smem = (size_t)2 * NP * N * sizeof(cplx);
+  int grid;
+  if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
+  SX_FUSED_LAUNCH(p, ST_ZINV, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  return 0;
 }
-template <int N, int NP, int MINB> static int run_yinv_v(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
+template <int N> static int run_yinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
+  constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
   if (f.nzf == 0) return 0;
   YinvArgs a{in, out0, out1, p.d_ky, p.nxh, f.nxp, f.nzf};
   const cplx* tw = p.tw_y;
   auto kfn = k_yinv_tile<N, NP, MINB>;
-  SX_FUSED_LAUNCH(p, ST_YINV, kfn, dim3(cdiv(f.nxp, NP), f.nzf), NP * (N / 8), (size_t)NP * N * sizeof(cplx), a, tw);
+  const size_t smem = (size_t)2 * NP * N * sizeof(cplx);
+  int grid;
+  if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(f.nxp, NP) * f.nzf, &grid)) return 1;
+  SX_FUSED_LAUNCH(p, ST_YINV, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   return 0;
 }
-template <int N> static int run_yinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
-  SX_VARIANTS(run_yinv_v, p, f, in, out0, out1);
-}
-template <int N, int NP, int MINB> static int run_yfwd_v(Plan& p, Fused& f, const cplx* in, cplx* out) {
+template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* out) {
+  constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
   if (f.nzf == 0) return 0;
   YfwdArgs a{in, out, p.nxh, f.nxp, f.nzf};
   const cplx* tw = p.tw_y;
   auto kfn = k_yfwd_tile<N, NP, MINB>;
-  SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(cdiv(p.nxh, NP), f.nzf), NP * (N / 8), (size_t)NP * N * sizeof(cplx), a, tw);
+  const size_t smem = (size_t)2 * NP * N * sizeof(cplx);
+  int grid;
+  if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.nxh, NP) * f.nzf, &grid)) return 1;
+  SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   return 0;
-}
-template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* out) {
-  SX_VARIANTS(run_yfwd_v, p, f, in, out);
 }
 template <int N> static int run_xpass(Plan& p, Fused& f, const double* d_kx_global) {
   constexpr int T = N / 8;
-  constexpr int LP = T >= 256 ? 1 : (256 / T > 32 ? 32 : 256 / T);
+  constexpr int LP = T >= 128 ? 1 : 128 / T;
   if (f.nzf == 0) return 0;
   XpassArgs a;
   for (int i = 0; i < 9; ++i) a.V[i] = f.V[i];
@@ -690,27 +828,29 @@ template <int N> static int run_xpass(Plan& p, Fused& f, const double* d_kx_glob
   a.kx = d_kx_global;
   a.ny = p.ny;
   a.nxp = f.nxp;
+  a.nzf = f.nzf;
   const double Ntot = (double)p.nx * (double)p.ny * (double)p.nz;
   a.tmp = 1.0 / (Ntot * Ntot);
   const cplx* tw = p.tw_x;
   auto kfn = k_xpass_gradre<N, LP>;
-  SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(cdiv(p.ny, 2 * LP), f.nzf), LP * T,
-                  (size_t)LP * sidx_elem_stride<N>() * sizeof(cplx), a, tw);
-  return 0;
-}
-template <int N, int NP, int MINB> static int run_zfwd_rk_v(Plan& p, Fused& f, const cplx* nl, cplx* v, const cplx* v0, const cplx* frc,
-                                        double dt, double nu, double rmp) {
-  ZfwdArgs a{nl, v, v0, frc, f.d_zmap, p.d_kx, p.d_ky, p.d_kz, p.d_fx, p.d_fy, p.d_fz, p.d_dir,
-             p.ny, f.nph, p.Cz, p.oz, dt, nu, rmp};
-  const cplx* tw = p.tw_z;
-  auto kfn = k_zfwd_rk<N, NP, MINB>;
-  const size_t smem = ((size_t)NP * N + (size_t)2 * kMaxDF * NP) * sizeof(cplx);
-  SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(cdiv(p.ny, NP), p.nxl), NP * (N / 8), smem, a, tw);
+  const size_t smem = ((size_t)LP * sidx_elem_stride<N>() + (size_t)40 * LP * T) * sizeof(cplx);
+  int grid;
+  if (persistent_grid(p, kfn, LP * T, smem, cdiv(p.ny, 2 * LP) * f.nzf, &grid)) return 1;
+  SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(grid), LP * T, smem, a, tw);
   return 0;
 }
 template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, cplx* v, const cplx* v0, const cplx* frc,
                                         double dt, double nu, double rmp) {
-  SX_VARIANTS(run_zfwd_rk_v, p, f, nl, v, v0, frc, dt, nu, rmp);
+  constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
+  ZfwdArgs a{nl, v, v0, frc, f.d_zmap, p.d_kx, p.d_ky, p.d_kz, p.d_fx, p.d_fy, p.d_fz, p.d_dir,
+             p.ny, p.nxl, f.nph, p.Cz, p.oz, dt, nu, rmp};
+  const cplx* tw = p.tw_z;
+  auto kfn = k_zfwd_rk<N, NP, MINB>;
+  const size_t smem = ((size_t)2 * NP * N + (size_t)2 * kMaxDF * NP) * sizeof(cplx);
+  int grid;
+  if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
+  SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  return 0;
 }
 template <int N> static int run_project(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
                                         const double* zs, const double* ze) {
@@ -724,8 +864,10 @@ template <int N> static int run_project(Plan& p, Fused& f, cplx* vx, cplx* vy, c
              sc * (zs ? zs[0] : 0.0), sc * (zs ? zs[1] : 0.0), sc * (ze ? ze[0] : 0.0), sc * (ze ? ze[1] : 0.0)};
   const cplx* tw = p.tw_z;
   auto kfn = k_project<N, NPB>;
-  const size_t smem = ((size_t)NPB * sidx_elem_stride<N>() + (size_t)NPB * 3 * N + (size_t)NPB * 2 * kMaxDF + (size_t)NPB * 2) * sizeof(cplx);
-  const unsigned grid = (unsigned)((a.npencils + NPB - 1) / NPB);
+  const size_t smem = ((size_t)NPB * sidx_elem_stride<N>() + (size_t)24 * NPB * T + (size_t)NPB * 2 * kMaxDF + (size_t)NPB * 2) * sizeof(cplx);
+  const int ngroups = (int)((a.npencils + NPB - 1) / NPB);
+  int grid;
+  if (persistent_grid(p, kfn, NPB * T, smem, ngroups, &grid)) return 1;
   SX_FUSED_LAUNCH(p, ST_PROJECT, kfn, dim3(grid), NPB * T, smem, a, tw);
   return 0;
 }

@@ -55,6 +55,7 @@ struct Plan {
   Fused* fused = nullptr;
   Comm* comm = nullptr;
   StageTimer timer;
+  int num_sms = 148;                // multiProcessorCount of the device
   int knob_np = 0, knob_minb = 1;   // tuning experiments (env SX_TILE_NP, SX_TILE_MINB)
   unsigned long long launches = 0;  // kernels launched by this plan (bench "gpu_launches")
 
