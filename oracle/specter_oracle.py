@@ -653,11 +653,11 @@ _CR_ROOTS = [np.float64(np.float32(v)) for v in (
     17.27875966, 20.42035225, 23.56194490, 26.70353756)]
 
 
-def initialv(g: Grid, seed=1000, kdn=2.0, kup=4.0, vparam0=1.0, vparam1=2.0, u0=1.0):
+def initialv(g: Grid, seed=1000, kdn=2.0, kup=4.0, vparam0=1.0, vparam1=2.0, u0=1.0, rnd=None):
     """Chandrasekhar-Reid no-slip solenoidal noise, initialv.f90:25-203 (1 rank,
     single-stream randu order).  Returns vx,vy,vz in (kz,ky,kx)."""
     assert g.nprocs == 1
-    rnd = Randu(seed)
+    rnd = rnd or Randu(seed)
     nph = g.nz - g.Cz
     z = g.z[:nph]
     Lz = g.Lz
@@ -744,3 +744,256 @@ def analytic_field(g: Grid, kind="sin"):
     if kind == "sin":
         return np.sin(4 * x) * np.cos(8 * y) * np.sin(6 * z)
     return np.sin(4 * x) * np.cos(8 * y) * np.exp(0.4 * z / g.Lz)
+
+
+# ============================================================================
+# Boussinesq and vector-potential MHD            (configs 3 and 4 of BASELINE.json)
+# ============================================================================
+def advect(g: Grid, a, b, c, d):
+    """A.grad(d), pseudospec_phd.f90:23-113."""
+    ph = _phys(g)
+    r3 = np.zeros(g.rshape())
+    for comp, dir_ in ((a, 1), (b, 2), (c, 3)):
+        r1 = fftp3d_complex_to_real(g, comp)
+        r2 = fftp3d_complex_to_real(g, derivk(g, d, dir_))
+        r3[ph] += r1[ph] * r2[ph]
+    r3[ph] *= 1.0 / g.N ** 2
+    return fftp3d_real_to_complex(g, r3)
+
+
+def vector(g: Grid, a, b, c, d, e, f):
+    """A x B in real space, pseudospec_mhd.f90:22-105."""
+    ph = _phys(g)
+    r1 = fftp3d_complex_to_real(g, a); r2 = fftp3d_complex_to_real(g, b); r3 = fftp3d_complex_to_real(g, c)
+    r4 = fftp3d_complex_to_real(g, d); r5 = fftp3d_complex_to_real(g, e); r6 = fftp3d_complex_to_real(g, f)
+    tmp = 1.0 / g.N ** 2
+    o1 = np.zeros(g.rshape()); o2 = np.zeros(g.rshape()); o3 = np.zeros(g.rshape())
+    o1[ph] = (r2[ph] * r6[ph] - r5[ph] * r3[ph]) * tmp
+    o2[ph] = (r3[ph] * r4[ph] - r6[ph] * r1[ph]) * tmp
+    o3[ph] = (r1[ph] * r5[ph] - r4[ph] * r2[ph]) * tmp
+    return (fftp3d_real_to_complex(g, o1), fftp3d_real_to_complex(g, o2), fftp3d_real_to_complex(g, o3))
+
+
+def variance(g: Grid, a, kin: int) -> float:
+    """pseudospec_phd.f90:116-196."""
+    tmp = 1.0 / g.N ** 2 / float(g.nz - g.Cz)
+    at = a.copy() if kin == 1 else g.kk2 * a
+    return _mean_phys(g, _abs2_iz(g, at), tmp)
+
+
+def normsca(g: Grid, a, b: float, kin: int):
+    """pseudospec_phd.f90:324-368."""
+    a *= np.sqrt(b / variance(g, a, kin))
+
+
+def s_imposebc(g: Grid, th):
+    """sboundary.f90:67-119 with `constant' walls (s_constant_z :122-165 sets the rows to 0)."""
+    goto_domain_w_boundaries(g, th)
+    th[:, :, 0] = 0.0
+    th[:, :, g.nz - g.Cz - 1] = 0.0
+    goto_3d_fourier(g, th)
+
+
+@dataclass
+class BoussState(HDState):
+    th: np.ndarray = None
+    fs: np.ndarray = None
+
+
+def bouss_rkstep2(g: Grid, s: BoussState, C1, C2, C3, C7, o: int, dt: float, nu: float, kappa: float,
+                  xmom: float = 1.0, xtemp: float = 1.0, v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0)):
+    """include/bouss/bouss_rkstep2.f90:3-59, including the theta `hack' (:57-59)."""
+    rmp = 1.0 / float(o)
+    C4, C5, C6 = gradre(g, s.vx, s.vy, s.vz)
+    C8 = advect(g, s.vx, s.vy, s.vz, s.th)
+    C6 = C6 - xmom * s.th
+    C8 = C8 - xtemp * s.vz
+    for q in (C4, C5, C6, C8):
+        fc_filter(g, q)
+    s.vx = laplak(g, s.vx); s.vy = laplak(g, s.vy); s.vz = laplak(g, s.vz); s.th = laplak(g, s.th)
+    s.vx = C1 + dt * (nu * s.vx - C4 + s.fx) * rmp
+    s.vy = C2 + dt * (nu * s.vy - C5 + s.fy) * rmp
+    s.vz = C3 + dt * (nu * s.vz - C6 + s.fz) * rmp
+    s.th = C7 + dt * (kappa * s.th - C8 + s.fs) * rmp
+    s.pr = v_imposebc_and_project(g, s.vx, s.vy, s.vz, s.pr, o, v_zsta, v_zend)
+    s_imposebc(g, s.th)
+    fc_filter(g, s.th)
+    R1 = fftp3d_complex_to_real(g, s.th)
+    R1 = R1 / g.nx / g.ny / g.nz
+    s.th = fftp3d_real_to_complex(g, R1)
+
+
+def bouss_step(g: Grid, s: BoussState, dt, nu, kappa, on_substep=None, **kw):
+    C1 = s.vx.copy(); C2 = s.vy.copy(); C3 = s.vz.copy(); C7 = s.th.copy()
+    for o in range(g.ord, 0, -1):
+        bouss_rkstep2(g, s, C1, C2, C3, C7, o, dt, nu, kappa, **kw)
+        if on_substep is not None:
+            on_substep(o, s)
+
+
+def initials(g: Grid, rnd: "Randu", c0=0.5, skdn=3.0, skup=8.0, cparam0=1.0, cparam1=2.0):
+    """examples/initials.f90_random (1 rank).  Note rmp uses kk2 at z-INDEX kk (as written there)."""
+    nph = g.nz - g.Cz
+    z = g.z[:nph]
+    pi, Lz, ny = np.pi, g.Lz, g.ny
+    th = np.zeros(g.cshape(), dtype=np.complex128)
+    for kk in range(int(cparam0), int(cparam1) + 1):
+        def put(i, j, mirror):
+            k2 = g.kk2[i, j, 0]
+            if not (k2 <= skup ** 2 and k2 >= skdn ** 2):
+                return
+            rmq = 2 * pi * rnd()
+            rmp = 1.0 / np.sqrt(g.kk2[i, j, kk - 1])
+            ph = np.cos(rmq) + IM * np.sin(rmq)
+            th[i, j, :nph] = rmp * ph * np.sin(2 * kk * pi / Lz * z)
+            th[i, j, :nph] = th[i, j, :nph] + rmp * ph * np.sin((2 * kk - 1) * pi / Lz * z)
+            if mirror:
+                th[i, (ny - j) % ny, :nph] = np.conj(th[i, j, :nph])
+        for j in range(1, ny // 2 + 1):
+            put(0, j, True)
+        for i in range(1, g.nxl):
+            for j in range(ny):
+                put(i, j, False)
+    fftp1d_real_to_complex_z(g, th)
+    normsca(g, th, c0, 1)
+    return th
+
+
+def make_bouss_state(g: Grid, seed=1000, **ic) -> BoussState:
+    """Velocity from initialv, then theta from the same randu stream (specter.fpp:846-874 order)."""
+    rnd = Randu(seed)
+    vx, vy, vz = initialv(g, rnd=rnd, **ic)
+    th = initials(g, rnd)
+    fx, fy, fz = initialfv(g)
+    z = np.zeros(g.cshape(), dtype=np.complex128)
+    return BoussState(vx, vy, vz, z.copy(), fx, fy, fz, th, z.copy())
+
+
+def neumann_reconstruct(g: Grid, f, boun: int, order: int):
+    """fcgram_mod.f90:368-511, z branches (:456-499).  boun 5 = z=0, 6 = z=Lz; the prescribed normal
+    derivative sits in the wall row on entry."""
+    neu = g.neu if order == 1 else g.neu2
+    d = g.oz
+    if boun == 5:
+        acc = neu[d - 1] * f[:, :, 0]
+        for k in range(1, d):
+            acc = acc + neu[k - 1] * f[:, :, d - k]          # f(dz+1-k)
+        f[:, :, 0] = acc
+    elif boun == 6:
+        top = g.nz - g.Cz - 1
+        acc = neu[d - 1] * f[:, :, top]
+        for k in range(1, d):
+            acc = acc + neu[k - 1] * f[:, :, top - d + k]    # f(nz-Cz-dz+k)
+        f[:, :, top] = acc
+    else:
+        raise ValueError("[ERROR] Neumann reconstruction not performed.")
+
+
+def a_imposebc_and_project(g: Grid, ax, ay, az, bczsta: int = 0, bczend: int = 0):
+    """bboundary.f90:100-189 for conducting walls (bc kind 0) at both ends.  Returns ph."""
+    if bczsta != 0 or bczend != 0:
+        raise ValueError("[ERROR] Unsupported boundary conditions in Z direction (oracle: conducting only).")
+    if g.ista == 1:
+        az[0, 0, 0] = 0.0
+    top = g.nz - g.Cz - 1
+    goto_domain_w_boundaries(g, ax, ay)
+    for ind in (0, top):                                   # int_conducting_z :192-236
+        ax[:, :, ind] = 0.0
+        ay[:, :, ind] = 0.0
+    goto_3d_fourier(g, ax, ay)
+    ph = sol_project(g, ax, ay, az, 0, 0, 0)
+    goto_domain_w_boundaries(g, ax, ay, az)
+    for pos, ind in ((0, 0), (1, top)):                     # conducting_z :239-290
+        ax[:, :, ind] = 0.0
+        ay[:, :, ind] = 0.0
+        az[:, :, ind] = 0.0
+        neumann_reconstruct(g, ax, 5 + pos, 2)
+        neumann_reconstruct(g, ay, 5 + pos, 2)
+        neumann_reconstruct(g, az, 5 + pos, 1)
+    goto_3d_fourier(g, ax, ay, az)
+    return ph
+
+
+@dataclass
+class MhdState(HDState):
+    ax: np.ndarray = None
+    ay: np.ndarray = None
+    az: np.ndarray = None
+    ph: np.ndarray = None
+    mx: np.ndarray = None
+    my: np.ndarray = None
+    mz: np.ndarray = None
+
+
+def mhd_rkstep2(g: Grid, s: MhdState, C1, C2, C3, C9, C10, C11, o: int, dt: float, nu: float, mu: float,
+                b0=(0.0, 0.0, 0.0)):
+    """include/mhd/mhd_rkstep2.f90:3-84 (ax,ay,az hold J when the RK update reads them)."""
+    rmp = 1.0 / float(o)
+    C12 = curlk(g, s.ay, s.az, 1); C13 = curlk(g, s.ax, s.az, 2); C14 = curlk(g, s.ax, s.ay, 3)
+    if g.ista == 1:
+        C12[0, 0, 0] = b0[0] * g.N; C13[0, 0, 0] = b0[1] * g.N; C14[0, 0, 0] = b0[2] * g.N
+    s.ax = curlk(g, C13, C14, 1); s.ay = curlk(g, C12, C14, 2); s.az = curlk(g, C12, C13, 3)
+    C4, C5, C6 = prodre(g, s.vx, s.vy, s.vz)
+    C15, C16, C17 = vector(g, s.ax, s.ay, s.az, C12, C13, C14)
+    C4 = C4 - C15; C5 = C5 - C16; C6 = C6 - C17
+    for q in (C4, C5, C6):
+        fc_filter(g, q)
+    C15, C16, C17 = vector(g, s.vx, s.vy, s.vz, C12, C13, C14)
+    for q in (C15, C16, C17):
+        fc_filter(g, q)
+    s.vx = laplak(g, s.vx); s.vy = laplak(g, s.vy); s.vz = laplak(g, s.vz)
+    s.vx = C1 + dt * (nu * s.vx - C4 + s.fx) * rmp
+    s.vy = C2 + dt * (nu * s.vy - C5 + s.fy) * rmp
+    s.vz = C3 + dt * (nu * s.vz - C6 + s.fz) * rmp
+    s.ax = C9 + dt * (-mu * s.ax + C15 + s.mx) * rmp
+    s.ay = C10 + dt * (-mu * s.ay + C16 + s.my) * rmp
+    s.az = C11 + dt * (-mu * s.az + C17 + s.mz) * rmp
+    s.pr = v_imposebc_and_project(g, s.vx, s.vy, s.vz, s.pr, o)
+    s.ph = a_imposebc_and_project(g, s.ax, s.ay, s.az)
+
+
+def mhd_step(g: Grid, s: MhdState, dt, nu, mu, on_substep=None, **kw):
+    C = [q.copy() for q in (s.vx, s.vy, s.vz, s.ax, s.ay, s.az)]
+    for o in range(g.ord, 0, -1):
+        mhd_rkstep2(g, s, *C, o, dt, nu, mu, **kw)
+        if on_substep is not None:
+            on_substep(o, s)
+
+
+def initialb(g: Grid, rnd: "Randu", a0=1.0, mkdn=2.0, mkup=4.0, aparam0=1.0, aparam1=2.0):
+    """initialb.f90 (1 rank): toroidal vector potential from a random stream function."""
+    nph = g.nz - g.Cz
+    z = g.z[:nph]
+    pi, Lz, ny = np.pi, g.Lz, g.ny
+    C3 = np.zeros(g.cshape(), dtype=np.complex128)
+    for kk in range(int(aparam0), int(aparam1) + 1):
+        def put(i, j, mirror):
+            k2 = g.kk2[i, j, 0]
+            if not (k2 <= mkup ** 2 and k2 >= mkdn ** 2):
+                return
+            rmp = 2 * pi * rnd()
+            rmq = rnd() / np.sqrt(k2 + kk ** 2 * pi ** 2 / Lz ** 2) ** 2
+            C3[i, j, :nph] = rmq * (np.cos(rmp) + IM * np.sin(rmp)) * np.sin(kk * pi * z / Lz)
+            if mirror:
+                C3[i, (ny - j) % ny, :nph] = np.conj(C3[i, j, :nph])
+        for j in range(1, ny // 2 + 1):
+            put(0, j, True)
+        for i in range(1, g.nxl):
+            for j in range(ny):
+                put(i, j, False)
+    ax = derivk(g, C3, 2)
+    ay = derivk(g, -C3, 1)
+    az = np.zeros_like(ax)
+    fftp1d_real_to_complex_z(g, ax); fftp1d_real_to_complex_z(g, ay); fftp1d_real_to_complex_z(g, az)
+    normvec(g, ax, ay, az, a0, 0)
+    return ax, ay, az
+
+
+def make_mhd_state(g: Grid, seed=1000, **ic) -> MhdState:
+    if g.neu is None:
+        g.load_neumann()
+    rnd = Randu(seed)
+    vx, vy, vz = initialv(g, rnd=rnd, **ic)
+    ax, ay, az = initialb(g, rnd)
+    z = np.zeros(g.cshape(), dtype=np.complex128)
+    return MhdState(vx, vy, vz, z.copy(), z.copy(), z.copy(), z.copy(), ax, ay, az, z.copy(), z.copy(), z.copy(), z.copy())

@@ -19,7 +19,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libspecter_b200.so")
+LIB_PATH = os.environ.get("SPECTER_B200_LIB") or os.path.join(_HERE, "csrc", "libspecter_b200.so")
 
 
 class SpecterError(RuntimeError):

@@ -185,6 +185,9 @@ static int plan_init(Plan& p, const sx_config& c) {
   if (upload_twiddles(p.nx, &p.tw_x)) return 1;
   if (upload_twiddles(p.ny, &p.tw_y)) return 1;
   if (upload_twiddles(p.nz, &p.tw_z)) return 1;
+  if (const char* e = getenv("SX_ZF")) p.knob_zf = atoi(e);
+  if (const char* e = getenv("SX_XP")) p.knob_xp = atoi(e);
+  if (const char* e = getenv("SX_PJ")) p.knob_pj = atoi(e);
   if (const char* e = getenv("SX_TILE_NP")) p.knob_np = atoi(e);
   if (const char* e = getenv("SX_TILE_MINB")) p.knob_minb = atoi(e);
   p.red_blocks = 148 * 4;

@@ -27,11 +27,10 @@
 namespace sx {
 
 // where physical row z lives in the exchange layout [rank][kxl][zl][ky]
-struct ZMap {
+struct alignas(16) ZMap {
   long long base;  // complex elements before this rank's block
   int nzl;         // rows held by the owning rank
   int zl;          // row index inside the owning rank
-  int pad;
 };
 
 struct Fused {
@@ -55,7 +54,7 @@ struct Fused {
 // lines per CTA of the tile kernels: 256 threads up to N = 512 (64 B pieces on the strided side --
 // measured FASTER on B200 than 128 B pieces with twice the CTA footprint), 4 lines beyond
 template <int N> struct TileNP {
-  static constexpr int value = N <= 64 ? 32 : (N == 128 ? 16 : (N == 256 ? 8 : 4));
+  static constexpr int value = N <= 64 ? 32 : (N == 128 ? 16 : (N == 256 ? 8 : (N <= 1024 ? 4 : 2)));
 };
 template <int N> struct TileMinB {  // CTAs per SM the register budget is capped for
   static constexpr int value = N <= 512 ? 3 : (N == 1024 ? 1 : 1);
@@ -85,6 +84,9 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zinv_tile(ZinvArgs a, cons
   constexpr int T = N / 8, NT = NP * T;
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
   cplx* slot = smem + (size_t)NP * N + threadIdx.x;
+  ZMap* zm = reinterpret_cast<ZMap*>(smem + (size_t)2 * NP * N);  // row table, read with one LDS.128
+  for (int z = threadIdx.x; z < a.nph; z += NT) zm[z] = a.zmap[z];
+  __syncthreads();
   const SIdxPencil si{p, NP};
   const int tiles_y = cdiv(a.ny, NP), ntiles = tiles_y * a.nxl;
   auto issue = [&](int t) {
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zinv_tile(ZinvArgs a, cons
       for (int k = 0; k < 8; ++k) {
         const int z = j + k * T;
         if (active && z < a.nph) {
-          const ZMap m = a.zmap[z];
+          const ZMap m = zm[z];
           a.out1[m.base + ((long long)kxl * m.nzl + m.zl) * a.ny + ky] = v[k];
         }
       }
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zinv_tile(ZinvArgs a, cons
     for (int k = 0; k < 8; ++k) {
       const int z = j + k * T;
       if (active && z < a.nph) {
-        const ZMap m = a.zmap[z];
+        const ZMap m = zm[z];
         a.out0[m.base + ((long long)kxl * m.nzl + m.zl) * a.ny + ky] = v[k];
       }
     }
@@ -267,8 +269,8 @@ struct XpassArgs {
 // transform m+1 are in flight as cp.async copies into thread-private slots.  The three velocity
 // lines are parked in thread-private shared memory, so the register file only holds one transform
 // and one accumulator.
-template <int N, int LP>
-__global__ void __launch_bounds__(LP*(N / 8), (N <= 1024 ? 2 : 1)) k_xpass_gradre(XpassArgs a, const cplx* __restrict__ tw) {
+template <int N, int LP, bool PF, int MINB>
+__global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_gradre(XpassArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8, NT = LP * T, XS = sidx_elem_stride<N>();
   const int lp = threadIdx.x / T, t = threadIdx.x % T;
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(LP*(N / 8), (N <= 1024 ? 2 : 1)) k_xpass_gradr
     return a.V[d * 3 + c];
   };
   auto issue = [&](int g, int m) {
+    if (!PF) return;
     const int y0 = ((g % groups_y) * LP + lp) * 2, zl = g / groups_y;
     if (y0 < a.ny) {
       const cplx* rowA = field_of(m) + ((size_t)zl * a.ny + y0) * a.nxp;
@@ -310,12 +313,21 @@ __global__ void __launch_bounds__(LP*(N / 8), (N <= 1024 ? 2 : 1)) k_xpass_gradr
     for (int m = 0; m < 12; ++m) {
       const bool deriv = m >= 3 && (m - 3) % 3 == 0;
       cplx v[8];
-      cp_async_wait_all();
+      if (PF) cp_async_wait_all();
+      const cplx* fA = field_of(m) + rowA;
+      const cplx* fB = fA + a.nxp;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int e = t + k * T;
         const int kx = e <= N / 2 ? e : N - e;
-        cplx A = slot[(2 * k) * NT], B = slot[(2 * k + 1) * NT];
+        cplx A, B;
+        if (PF) {
+          A = slot[(2 * k) * NT];
+          B = slot[(2 * k + 1) * NT];
+        } else {
+          A = active ? fA[kx] : cmake(0.0, 0.0);
+          B = active ? fB[kx] : cmake(0.0, 0.0);
+        }
         if (deriv) {
           const double kk = __ldg(&a.kx[kx]);
           A = cmake(-kk * A.y, kk * A.x);
@@ -420,13 +432,16 @@ __device__ __forceinline__ void stash_boundary_tile(const cplx (&v)[8], int j, i
   }
 }
 
-template <int N, int NP, int MINB>
+template <int N, int NP, int MINB, bool HOIST>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8, NT = NP * T;
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
   cplx* bnd = smem + (size_t)NP * N;
   cplx* slot = bnd + (size_t)2 * kMaxDF * NP + threadIdx.x;
+  ZMap* zm = reinterpret_cast<ZMap*>(bnd + (size_t)2 * kMaxDF * NP + (size_t)NP * N);
+  for (int z = threadIdx.x; z < a.nph; z += NT) zm[z] = a.zmap[z];
+  __syncthreads();
   const int tiles_y = cdiv(a.ny, NP), ntiles = tiles_y * a.nxl;
   auto issue = [&](int t) {
     const int ky = (t % tiles_y) * NP + p, kxl = t / tiles_y;
@@ -434,7 +449,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
     for (int k = 0; k < 8; ++k) {
       const int z = j + k * T;
       if (ky < a.ny && z < a.nph) {
-        const ZMap m = a.zmap[z];
+        const ZMap m = zm[z];
         cp_async16(slot + k * NT, a.nl + m.base + ((long long)kxl * m.nzl + m.zl) * a.ny + ky);
       } else {
         slot[k * NT] = cmake(0.0, 0.0);
@@ -452,13 +467,25 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
     if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
+    // the three spectral pencils of the RK update: issued before the transform so that their latency
+    // is covered by it (HOIST), or loaded at the point of use
+    const size_t base = ((size_t)kxl * a.ny + (active ? ky : 0)) * N;
+    cplx L[8], B[8], F[8];
+    if (HOIST) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = j + k * T;
+        L[k] = a.v[base + e];
+        B[k] = a.v0[base + e];
+        F[k] = a.f[base + e];
+      }
+    }
     __syncthreads();  // bnd and the exchange buffer of the previous tile are free
     stash_boundary_tile<N, NP>(v, j, p, bnd, a.nph, a.d);
     __syncthreads();
     fc_continue_tile<N, NP>(v, j, p, bnd, a.nph, a.C, a.d, a.dir);
     fft_regs<N, -1>(v, j, smem, SIdxPencil{p, NP}, tw);
     if (active) {
-      const size_t base = ((size_t)kxl * a.ny + ky) * N;
       const double x = __ldg(&a.kx[kxl]), y = __ldg(&a.ky[ky]);
       const double f1 = __ldg(&a.fx[kxl]), f2 = __ldg(&a.fy[ky]);
       const double kh2 = x * x + y * y;
@@ -468,9 +495,9 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
         const double z = __ldg(&a.kz[e]), f3 = __ldg(&a.fz[e]);
         const double kk2 = kh2 + z * z;
         const cplx NL = cscale(cscale(cscale(v[k], f1), f2), f3);
-        const cplx L = a.v[base + e], B = a.v0[base + e], F = a.f[base + e];
-        a.v[base + e] = cmake(B.x + a.dt * (a.nu * (-kk2 * L.x) - NL.x + F.x) * a.rmp,
-                              B.y + a.dt * (a.nu * (-kk2 * L.y) - NL.y + F.y) * a.rmp);
+        const cplx Lk = HOIST ? L[k] : a.v[base + e], Bk = HOIST ? B[k] : a.v0[base + e], Fk = HOIST ? F[k] : a.f[base + e];
+        a.v[base + e] = cmake(Bk.x + a.dt * (a.nu * (-kk2 * Lk.x) - NL.x + Fk.x) * a.rmp,
+                              Bk.y + a.dt * (a.nu * (-kk2 * Lk.y) - NL.y + Fk.y) * a.rmp);
       }
     }
   }
@@ -536,8 +563,8 @@ __device__ __forceinline__ void fc_fft_fwd(cplx (&v)[8], int j, cplx* smem, cons
   fft_regs<N, -1>(v, j, smem, si, tw);
 }
 
-template <int N, int NPB>
-__global__ void __launch_bounds__(NPB*(N / 8), (N <= 512 ? 3 : 1)) k_project(ProjArgs a, const cplx* __restrict__ tw) {
+template <int N, int NPB, bool PF, int MINB>
+__global__ void __launch_bounds__(NPB*(N / 8), MINB) k_project(ProjArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8, NT = NPB * T;
   constexpr int XS = sidx_elem_stride<N>();
@@ -551,6 +578,7 @@ __global__ void __launch_bounds__(NPB*(N / 8), (N <= 512 ? 3 : 1)) k_project(Pro
   const int top = a.nph - 1;
   const long ngroups = (a.npencils + NPB - 1) / NPB;
   auto issue = [&](long g, const cplx* field) {
+    if (!PF) return;
     const long pencil = g * NPB + pl;
     if (pencil < a.npencils) {
       const cplx* src = field + (size_t)pencil * N + j;
@@ -579,10 +607,16 @@ __global__ void __launch_bounds__(NPB*(N / 8), (N <= 512 ? 3 : 1)) k_project(Pro
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       const double kc = c == 0 ? x : y;
-      cp_async_wait_all();
+      if (PF) {
+        cp_async_wait_all();
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
-      issue(g, c == 0 ? a.vy : a.vz);
+        for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+        issue(g, c == 0 ? a.vy : a.vz);
+      } else {
+        const cplx* src = c == 0 ? a.vx : a.vy;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = active ? src[base + j + k * T] : cmake(0.0, 0.0);
+      }
       fft_regs<N, 1>(v, j, smem, si, tw);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -600,10 +634,15 @@ __global__ void __launch_bounds__(NPB*(N / 8), (N <= 512 ? 3 : 1)) k_project(Pro
     }
     // ---- particular solution and its gradient (boundary_mod.fpp:405-448, 249-259) ----
     cplx dd[8], cz[8];
-    cp_async_wait_all();
+    if (PF) {
+      cp_async_wait_all();
 #pragma unroll
-    for (int k = 0; k < 8; ++k) cz[k] = slot[k * NT];
-    if (g + (long)gridDim.x < ngroups) issue(g + gridDim.x, a.vx);
+      for (int k = 0; k < 8; ++k) cz[k] = slot[k * NT];
+      if (g + (long)gridDim.x < ngroups) issue(g + gridDim.x, a.vx);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cz[k] = active ? a.vz[base + j + k * T] : cmake(0.0, 0.0);
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int e = j + k * T;
@@ -728,7 +767,7 @@ static int fused_init(Plan& p, Fused** out) {
   for (int r = 0; r < p.nprocs; ++r) {
     int s, c;
     range0(f->nph, p.nprocs, r, &s, &c);
-    for (int q = 0; q < c; ++q) zm[s + q] = ZMap{base, c, q, 0};
+    for (int q = 0; q < c; ++q) zm[s + q] = ZMap{base, c, q};
     base += (long long)p.nxl * c * p.ny;
   }
   f->z_displ.resize(p.nprocs); f->z_count.resize(p.nprocs); f->x_displ.resize(p.nprocs); f->x_count.resize(p.nprocs);
@@ -788,7 +827,7 @@ template <int N> static int run_zinv(Plan& p, Fused& f, const cplx* in, cplx* ou
   ZinvArgs a{in, out0, out1, p.d_kz, f.d_zmap, p.ny, p.nxl, f.nph};
   const cplx* tw = p.tw_z;
   auto kfn = k_zinv_tile<N, NP, MINB>;
-  const size_t smem = (size_t)2 * NP * N * sizeof(cplx);
+  const size_t smem = (size_t)2 * NP * N * sizeof(cplx) + (size_t)N * sizeof(ZMap);
   int grid;
   if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
   SX_FUSED_LAUNCH(p, ST_ZINV, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
@@ -818,9 +857,8 @@ template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* ou
   SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   return 0;
 }
-template <int N> static int run_xpass(Plan& p, Fused& f, const double* d_kx_global) {
+template <int N, int LP, bool PF, int MINB> static int run_xpass_v(Plan& p, Fused& f, const double* d_kx_global) {
   constexpr int T = N / 8;
-  constexpr int LP = T >= 128 ? 1 : 128 / T;
   if (f.nzf == 0) return 0;
   XpassArgs a;
   for (int i = 0; i < 9; ++i) a.V[i] = f.V[i];
@@ -832,12 +870,26 @@ template <int N> static int run_xpass(Plan& p, Fused& f, const double* d_kx_glob
   const double Ntot = (double)p.nx * (double)p.ny * (double)p.nz;
   a.tmp = 1.0 / (Ntot * Ntot);
   const cplx* tw = p.tw_x;
-  auto kfn = k_xpass_gradre<N, LP>;
-  const size_t smem = ((size_t)LP * sidx_elem_stride<N>() + (size_t)40 * LP * T) * sizeof(cplx);
+  auto kfn = k_xpass_gradre<N, LP, PF, MINB>;
+  const size_t smem = ((size_t)LP * sidx_elem_stride<N>() + (size_t)(PF ? 40 : 24) * LP * T) * sizeof(cplx);
   int grid;
   if (persistent_grid(p, kfn, LP * T, smem, cdiv(p.ny, 2 * LP) * f.nzf, &grid)) return 1;
   SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(grid), LP * T, smem, a, tw);
   return 0;
+}
+template <int N> static int run_xpass(Plan& p, Fused& f, const double* d_kx_global) {
+  constexpr int T = N / 8;
+  constexpr int LP = T >= 128 ? 1 : 128 / T;
+  if constexpr (N == 512) {
+    switch (p.knob_xp) {
+      case 1: return run_xpass_v<N, 1, true, 4>(p, f, d_kx_global);
+      case 2: return run_xpass_v<N, 1, false, 6>(p, f, d_kx_global);
+      case 3: return run_xpass_v<N, 2, false, 3>(p, f, d_kx_global);
+      case 4: return run_xpass_v<N, 1, false, 4>(p, f, d_kx_global);
+      default: break;
+    }
+  }
+  return run_xpass_v<N, LP, true, (N <= 1024 ? 2 : 1)>(p, f, d_kx_global);
 }
 template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, cplx* v, const cplx* v0, const cplx* frc,
                                         double dt, double nu, double rmp) {
@@ -845,17 +897,22 @@ template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, cplx*
   ZfwdArgs a{nl, v, v0, frc, f.d_zmap, p.d_kx, p.d_ky, p.d_kz, p.d_fx, p.d_fy, p.d_fz, p.d_dir,
              p.ny, p.nxl, f.nph, p.Cz, p.oz, dt, nu, rmp};
   const cplx* tw = p.tw_z;
-  auto kfn = k_zfwd_rk<N, NP, MINB>;
-  const size_t smem = ((size_t)2 * NP * N + (size_t)2 * kMaxDF * NP) * sizeof(cplx);
+  const size_t smem = ((size_t)2 * NP * N + (size_t)2 * kMaxDF * NP) * sizeof(cplx) + (size_t)N * sizeof(ZMap);
   int grid;
+  if (N == 512 && p.knob_zf == 1) {
+    auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), true>;
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
+    SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+    return 0;
+  }
+  auto kfn = k_zfwd_rk<N, NP, MINB, false>;
   if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
   SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   return 0;
 }
-template <int N> static int run_project(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
+template <int N, int NPB, bool PF, int MINB> static int run_project_v(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
                                         const double* zs, const double* ze) {
   constexpr int T = N / 8;
-  constexpr int NPB = T >= 128 ? 1 : 128 / T;
   double tmp = 1.0 / (double)o;
   if (o != p.ord) tmp = (double)(o + 1) * tmp;   // vboundary.f90:195-196
   const double sc = (double)p.nx * (double)p.ny;
@@ -863,13 +920,28 @@ template <int N> static int run_project(Plan& p, Fused& f, cplx* vx, cplx* vy, c
              p.ny, f.nph, p.Cz, p.oz, p.ista == 1 ? 1 : 0, p.Lz, tmp, 1.0 / (double)p.nz,
              sc * (zs ? zs[0] : 0.0), sc * (zs ? zs[1] : 0.0), sc * (ze ? ze[0] : 0.0), sc * (ze ? ze[1] : 0.0)};
   const cplx* tw = p.tw_z;
-  auto kfn = k_project<N, NPB>;
+  auto kfn = k_project<N, NPB, PF, MINB>;
   const size_t smem = ((size_t)NPB * sidx_elem_stride<N>() + (size_t)24 * NPB * T + (size_t)NPB * 2 * kMaxDF + (size_t)NPB * 2) * sizeof(cplx);
   const int ngroups = (int)((a.npencils + NPB - 1) / NPB);
   int grid;
   if (persistent_grid(p, kfn, NPB * T, smem, ngroups, &grid)) return 1;
   SX_FUSED_LAUNCH(p, ST_PROJECT, kfn, dim3(grid), NPB * T, smem, a, tw);
   return 0;
+}
+template <int N> static int run_project(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
+                                        const double* zs, const double* ze) {
+  constexpr int T = N / 8;
+  constexpr int NPB = T >= 128 ? 1 : 128 / T;
+  if constexpr (N == 512) {
+    switch (p.knob_pj) {
+      case 1: return run_project_v<N, 1, true, 6>(p, f, vx, vy, vz, pr, o, zs, ze);
+      case 2: return run_project_v<N, 1, false, 8>(p, f, vx, vy, vz, pr, o, zs, ze);
+      case 3: return run_project_v<N, 2, false, 4>(p, f, vx, vy, vz, pr, o, zs, ze);
+      case 4: return run_project_v<N, 1, true, 8>(p, f, vx, vy, vz, pr, o, zs, ze);
+      default: break;
+    }
+  }
+  return run_project_v<N, NPB, true, (N <= 512 ? 3 : 1)>(p, f, vx, vy, vz, pr, o, zs, ze);
 }
 
 #define SX_SIZE_SWITCH(n, CALL)                 \

@@ -155,3 +155,51 @@ def test_hd_step_invariants(g):
     print("vdiag", div, vt0, vtL, vn0, vnL)
     assert div < 1e-8 and vn0 < 1e-25 and vnL < 1e-25   # div limited by FC(5) accuracy
     assert vt0 < 1e-4 and vtL < 1e-4                    # slip error O(dt^2) of the p' prediction
+
+
+def test_fc_neumann_reconstruction(g):
+    # tests/fc_neumann.f90 (order 1) and fc_neumann2.f90 (order 2): wall values recovered from the
+    # prescribed normal derivative; thresholds from a first CPU run (FC(5) accuracy at 39 points)
+    if g.neu is None:
+        g.load_neumann()
+    nph = g.nz - g.Cz
+    x, y, z = g.x[None, None, :], g.y[None, :, None], g.z[:, None, None]
+    r1 = np.sin(4 * x) * np.cos(8 * y) * np.sin(6 * z)
+    dz1 = 6 * np.sin(4 * x) * np.cos(8 * y) * np.cos(6 * z)
+    dz2 = -36 * r1
+    for order, deriv, tol in ((1, dz1, 5e-4), (2, dz2, 5e-2)):
+        c1 = O.fftp2d_real_to_complex_xy(g, r1)
+        c3 = O.fftp2d_real_to_complex_xy(g, deriv)
+        sign = -1.0 if order == 1 else 1.0          # d/dz = -d/dn at z=0 for odd orders
+        c1[:, :, 0] = sign * c3[:, :, 0]
+        c1[:, :, nph - 1] = c3[:, :, nph - 1]
+        O.neumann_reconstruct(g, c1, 5, order)
+        O.neumann_reconstruct(g, c1, 6, order)
+        back = O.fftp2d_complex_to_real_xy(g, c1) / g.nx / g.ny
+        e0 = np.abs(back[0] - r1[0]).max()
+        eL = np.abs(back[nph - 1] - r1[nph - 1]).max()
+        print("neumann order", order, e0, eL)
+        assert e0 < tol and eL < tol, (order, e0, eL)
+
+
+def test_bouss_and_mhd_substep_invariants(tables):
+    g = O.Grid(32, 32, 64, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, ord=2)
+    s = O.make_bouss_state(g)
+    assert abs(O.variance(g, s.th, 1) - 0.5) < 1e-12          # normsca(c0 = 0.5)
+    O.bouss_step(g, s, 1e-3, 1e-3, 1e-3)
+    th = s.th.copy()
+    O.fftp1d_complex_to_real_z(g, th)
+    nph = g.nz - g.Cz
+    wall = max(np.abs(th[:, :, 0]).max(), np.abs(th[:, :, nph - 1]).max())
+    # `constant' walls set theta = 0; the fc_filter and the theta `hack' that follow (bouss_rkstep2.f90:54-59)
+    # perturb it again at the 1e-5 level
+    assert wall < 1e-3 * np.abs(th[:, :, :nph]).max()
+    assert O.vdiagnostic(g, s.vx, s.vy, s.vz)[0] < 1e-8
+    m = O.make_mhd_state(g)
+    assert abs(O.energy(g, m.ax, m.ay, m.az, 0) - 1.0) < 1e-12  # normvec(a0 = 1, kin = 0)
+    O.mhd_step(g, m, 1e-3, 1e-3, 5e-3)
+    # conducting walls: tangential A vanishes at both walls, gauge projection leaves div A ~ 0
+    a = m.ax.copy()
+    O.fftp1d_complex_to_real_z(g, a)
+    assert O.divergence(g, m.ax, m.ay, m.az) < 1e-8
+    assert np.isfinite(m.ph).all()
