@@ -117,6 +117,14 @@ int sx_cross(sx_plan* plan, const double* a, const double* b, const double* c, c
 int sx_hdcheck(sx_plan* plan, const double* a, const double* b, const double* c, const double* d,
                const double* e, const double* f, double* eng, double* ens, double* pot);                  /* ref: :943-1005 */
 
+/* ref: advect (pseudospec_phd.f90:23-113): e = A.grad(d) */
+int sx_advect(sx_plan* plan, const double* a, const double* b, const double* c, const double* d, double* e);
+/* ref: vector (pseudospec_mhd.f90:22-105): (x,y,z) = A x B, A = (a,b,c), B = (d,e,f) */
+int sx_vector(sx_plan* plan, const double* a, const double* b, const double* c, const double* d, const double* e,
+              const double* f, double* x, double* y, double* z);
+/* ref: variance (pseudospec_phd.f90:116-196) */
+int sx_variance(sx_plan* plan, const double* a, int kin, double* out);
+
 /* ---- boundary module -------------------------------------------------------- */
 /* ref: sol_project (boundary_mod.fpp:197-402); d returns the potential in the mixed domain */
 int sx_sol_project(sx_plan* plan, double* a, double* b, double* c, double* d, int bctarget, int bczsta, int bczend);
@@ -127,6 +135,13 @@ int sx_v_imposebc_and_project(sx_plan* plan, double* vx, double* vy, double* vz,
 int sx_bouncheck_z(sx_plan* plan, double* bot, double* top, const double* a, const double* b);
 /* ref: vdiagnostic (vboundary.f90:214-269): out[5] = div, vt0, vtL, vn0, vnL */
 int sx_vdiagnostic(sx_plan* plan, const double* a, const double* b, const double* c, double out[5]);
+
+/* ref: s_imposebc (sboundary.f90:67-119) with `constant' walls (s_constant_z :122-165) */
+int sx_s_imposebc(sx_plan* plan, double* th);
+/* ref: a_imposebc_and_project (bboundary.f90:100-189) with conducting walls at both ends: int_conducting_z,
+ * sol_project(...,0,0,0), conducting_z with neumann_reconstruct (fcgram_mod.f90:368-511); ph returns the gauge
+ * potential in the mixed domain */
+int sx_a_imposebc_and_project(sx_plan* plan, double* ax, double* ay, double* az, double* ph);
 
 /* ---- the RK substep (include/hd/hd_rkstep{1,2}.f90) --------------------------------- */
 /* Device-resident HD state owned by the plan.  put/get move whole fields in the reference
@@ -145,6 +160,36 @@ int sx_hd_rkstep2(sx_plan* plan, int o, double dt, double nu, const double v_zst
 int sx_hd_step_host(sx_plan* plan, double* vx_host, double* vy_host, double* vz_host, double* pr_host,
                     const double* fx_host, const double* fy_host, const double* fz_host, double dt, double nu,
                     const double v_zsta[2], const double v_zend[2]);
+
+/* ---- Boussinesq (include/bouss/bouss_rkstep{1,2}.f90) ------------------------------------ */
+/* plan-owned state: which = 0..2 v, 3 pr, 4..6 f, 7..9 C1..C3, 10 th, 11 fs, 12 C7 */
+int sx_bouss_put_state(sx_plan* plan, const double* vx_host, const double* vy_host, const double* vz_host,
+                       const double* pr_host, const double* th_host, const double* fx_host, const double* fy_host,
+                       const double* fz_host, const double* fs_host);
+int sx_bouss_get_state(sx_plan* plan, double* vx_host, double* vy_host, double* vz_host, double* pr_host,
+                       double* th_host);
+int sx_bouss_state_ptr(sx_plan* plan, int which, double** dptr);
+/* ref: bouss_rkstep1.f90:4-7 */
+int sx_bouss_rkstep1(sx_plan* plan);
+/* ref: bouss_rkstep2.f90:3-59 (gradre + advect, buoyancy / heat-current coupling, RK update, no-slip projection,
+ * s_imposebc, fc_filter and the theta 3-D round trip).  impl as in sx_hd_rkstep2. */
+int sx_bouss_rkstep2(sx_plan* plan, int o, double dt, double nu, double kappa, double xmom, double xtemp,
+                     const double v_zsta[2], const double v_zend[2], int impl);
+
+/* ---- vector-potential MHD (include/mhd/mhd_rkstep{1,2}.f90) ------------------------------- */
+/* plan-owned state: which = 0..2 v, 3 pr, 4..6 f, 7..9 C1..C3, 10..12 a, 13 ph, 14..16 m, 17..19 C9..C11 */
+int sx_mhd_put_state(sx_plan* plan, const double* vx_host, const double* vy_host, const double* vz_host,
+                     const double* pr_host, const double* ax_host, const double* ay_host, const double* az_host,
+                     const double* fx_host, const double* fy_host, const double* fz_host, const double* mx_host,
+                     const double* my_host, const double* mz_host);
+int sx_mhd_get_state(sx_plan* plan, double* vx_host, double* vy_host, double* vz_host, double* pr_host,
+                     double* ax_host, double* ay_host, double* az_host, double* ph_host);
+int sx_mhd_state_ptr(sx_plan* plan, int which, double** dptr);
+/* ref: mhd_rkstep1.f90:4-9 */
+int sx_mhd_rkstep1(sx_plan* plan);
+/* ref: mhd_rkstep2.f90:3-84 (B = curl A + b0, J = curl B, prodre - Lorentz force, EMF, RK update, no-slip
+ * projection, conducting-wall gauge projection).  b0 may be NULL (no uniform field). */
+int sx_mhd_rkstep2(sx_plan* plan, int o, double dt, double nu, double mu, const double b0[3], int impl);
 
 #ifdef __cplusplus
 }

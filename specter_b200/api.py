@@ -94,6 +94,21 @@ SIGNATURES = {
     "sx_hd_rkstep1": [_P],
     "sx_hd_rkstep2": [_P, _I, _F, _F, _PD, _PD, _I],
     "sx_hd_step_host": [_P, _D, _D, _D, _D, _D, _D, _D, _F, _F, _PD, _PD],
+    "sx_advect": [_P, _D, _D, _D, _D, _D],
+    "sx_vector": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _D],
+    "sx_variance": [_P, _D, _I, _PD],
+    "sx_s_imposebc": [_P, _D],
+    "sx_a_imposebc_and_project": [_P, _D, _D, _D, _D],
+    "sx_bouss_put_state": [_P, _D, _D, _D, _D, _D, _D, _D, _D, _D],
+    "sx_bouss_get_state": [_P, _D, _D, _D, _D, _D],
+    "sx_bouss_state_ptr": [_P, _I, C.POINTER(_D)],
+    "sx_bouss_rkstep1": [_P],
+    "sx_bouss_rkstep2": [_P, _I, _F, _F, _F, _F, _F, _PD, _PD, _I],
+    "sx_mhd_put_state": [_P] + [_D] * 13,
+    "sx_mhd_get_state": [_P] + [_D] * 8,
+    "sx_mhd_state_ptr": [_P, _I, C.POINTER(_D)],
+    "sx_mhd_rkstep1": [_P],
+    "sx_mhd_rkstep2": [_P, _I, _F, _F, _F, _PD, _I],
 }
 _RESTYPES = {"sx_stage_name": C.c_char_p, "sx_last_error": C.c_char_p, "sx_version": C.c_char_p,
              "sx_plan_launch_count": C.c_ulonglong, "sx_spectral_bytes": C.c_size_t,
@@ -439,3 +454,82 @@ class Plan:
                 raise SpecterError("hd_step_host needs C-contiguous complex128 arrays of the plan's spectral shape")
         self._call("sx_hd_step_host", vx.ctypes.data, vy.ctypes.data, vz.ctypes.data, pr.ctypes.data,
                    fx.ctypes.data, fy.ctypes.data, fz.ctypes.data, dt, nu, _vec2(v_zsta), _vec2(v_zend))
+
+    # ---- Boussinesq / MHD operators (pseudospec_phd.f90, pseudospec_mhd.f90, sboundary.f90, bboundary.f90) ----
+    def advect(self, a, b, c, d, e):
+        self._call("sx_advect", a.ptr, b.ptr, c.ptr, d.ptr, e.ptr)
+
+    def vector(self, a, b, c, d, e, f, x, y, z):
+        self._call("sx_vector", a.ptr, b.ptr, c.ptr, d.ptr, e.ptr, f.ptr, x.ptr, y.ptr, z.ptr)
+
+    def variance(self, a, kin) -> float:
+        out = C.c_double()
+        self._call("sx_variance", a.ptr, kin, C.byref(out))
+        return out.value
+
+    def s_imposebc(self, th):
+        self._call("sx_s_imposebc", th.ptr)
+
+    def a_imposebc_and_project(self, ax, ay, az, ph):
+        self._call("sx_a_imposebc_and_project", ax.ptr, ay.ptr, az.ptr, ph.ptr)
+
+    def _host_fields(self, arrs, what):
+        out = [None if a is None else np.ascontiguousarray(a, dtype=np.complex128) for a in arrs]
+        for a in out:
+            if a is not None and a.shape != tuple(self.cshape):
+                raise SpecterError(f"{what}: shape mismatch")
+        return out
+
+    # ---- Boussinesq substep on plan-owned state (include/bouss/bouss_rkstep{1,2}.f90) ----
+    def bouss_put_state(self, vx=None, vy=None, vz=None, pr=None, th=None, fx=None, fy=None, fz=None, fs=None):
+        arrs = self._host_fields((vx, vy, vz, pr, th, fx, fy, fz, fs), "bouss_put_state")
+        self._call("sx_bouss_put_state", *[None if a is None else a.ctypes.data for a in arrs])
+
+    def bouss_get_state(self):
+        out = [np.empty(self.cshape, dtype=np.complex128) for _ in range(5)]
+        self._call("sx_bouss_get_state", *[a.ctypes.data for a in out])
+        return out
+
+    def bouss_field(self, which: int) -> DeviceArray:
+        ptr = C.c_void_p()
+        self._call("sx_bouss_state_ptr", which, C.byref(ptr))
+        return DeviceArray.view(self, "spectral", ptr)
+
+    def bouss_rkstep1(self):
+        self._call("sx_bouss_rkstep1")
+
+    def bouss_rkstep2(self, o, dt, nu, kappa, xmom=1.0, xtemp=1.0, v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0), impl=0):
+        self._call("sx_bouss_rkstep2", o, dt, nu, kappa, xmom, xtemp, _vec2(v_zsta), _vec2(v_zend), impl)
+
+    def bouss_step(self, dt, nu, kappa, xmom=1.0, xtemp=1.0, v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0), impl=0):
+        self.bouss_rkstep1()
+        for o in range(self.ord, 0, -1):
+            self.bouss_rkstep2(o, dt, nu, kappa, xmom, xtemp, v_zsta, v_zend, impl)
+
+    # ---- MHD substep on plan-owned state (include/mhd/mhd_rkstep{1,2}.f90) ----
+    def mhd_put_state(self, vx=None, vy=None, vz=None, pr=None, ax=None, ay=None, az=None, fx=None, fy=None, fz=None,
+                      mx=None, my=None, mz=None):
+        arrs = self._host_fields((vx, vy, vz, pr, ax, ay, az, fx, fy, fz, mx, my, mz), "mhd_put_state")
+        self._call("sx_mhd_put_state", *[None if a is None else a.ctypes.data for a in arrs])
+
+    def mhd_get_state(self):
+        out = [np.empty(self.cshape, dtype=np.complex128) for _ in range(8)]
+        self._call("sx_mhd_get_state", *[a.ctypes.data for a in out])
+        return out
+
+    def mhd_field(self, which: int) -> DeviceArray:
+        ptr = C.c_void_p()
+        self._call("sx_mhd_state_ptr", which, C.byref(ptr))
+        return DeviceArray.view(self, "spectral", ptr)
+
+    def mhd_rkstep1(self):
+        self._call("sx_mhd_rkstep1")
+
+    def mhd_rkstep2(self, o, dt, nu, mu, b0=(0.0, 0.0, 0.0), impl=0):
+        b = (C.c_double * 3)(*[float(x) for x in b0])
+        self._call("sx_mhd_rkstep2", o, dt, nu, mu, b, impl)
+
+    def mhd_step(self, dt, nu, mu, b0=(0.0, 0.0, 0.0), impl=0):
+        self.mhd_rkstep1()
+        for o in range(self.ord, 0, -1):
+            self.mhd_rkstep2(o, dt, nu, mu, b0, impl)

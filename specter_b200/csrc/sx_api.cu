@@ -169,6 +169,7 @@ static int plan_init(Plan& p, const sx_config& c) {
   if (p.Cz > 0) {
     SX_REQUIRE(c.tdir != nullptr, "tdir is required when Cz > 0");
     if (load_dirichlet(p, c.tdir)) return 1;
+    p.tdir = c.tdir;
   } else {
     p.h_dir.assign(1, 0.0);
   }
@@ -198,6 +199,7 @@ static int plan_init(Plan& p, const sx_config& c) {
 
 static void plan_release(Plan& p) {
   hd_state_free(p);
+  solver_states_free(p);
   fused_free(p);
   comm_free(p);
   for (auto e : p.timer.ev) cudaEventDestroy(e);

@@ -31,7 +31,7 @@ struct Comm {
   sx_alltoallv_fn a2a = nullptr;
   sx_allreduce_fn allred = nullptr;
   void* user = nullptr;
-  cudaEvent_t ready[16] = {nullptr}, done[16] = {nullptr};
+  cudaEvent_t ready[32] = {nullptr}, done[32] = {nullptr};
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   double* d_scal = nullptr;
   double* h_scal = nullptr;
@@ -46,7 +46,7 @@ int comm_free(Plan& p) {
 #ifndef SX_EMU
   if (c->nccl) ncclCommDestroy(c->nccl);
 #endif
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < 32; ++i) {
     if (c->ready[i]) cudaEventDestroy(c->ready[i]);
     if (c->done[i]) cudaEventDestroy(c->done[i]);
   }
@@ -65,7 +65,7 @@ static int comm_get(Plan& p, Comm** out) {
     Comm* c = new Comm();
     p.comm = c;
     SX_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 32; ++i) {
       SX_CUDA_CHECK(cudaEventCreate(&c->ready[i]));
       SX_CUDA_CHECK(cudaEventCreate(&c->done[i]));
     }
@@ -94,7 +94,7 @@ int exchange_begin(Plan& p, int ev, const cplx* send, cplx* recv, const size_t* 
                    const size_t* rdispl, const size_t* rcount) {
   SX_REQUIRE(p.nprocs > 1, "exchange on a single-rank plan");
   SX_REQUIRE(comm_ready(p), "multi-rank plan without a communicator: call sx_plan_set_comm or sx_plan_set_comm_callbacks");
-  SX_REQUIRE(ev >= 0 && ev < 16, "exchange: bad event slot");
+  SX_REQUIRE(ev >= 0 && ev < 32, "exchange: bad event slot");
   Comm& c = *p.comm;
   if (stage_mark(p, ST_EXCHANGE)) return 1;
   double sent = 0.0;

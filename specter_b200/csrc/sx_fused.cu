@@ -41,12 +41,13 @@ struct Fused {
   size_t wsize = 0;  // complex elements of one exchange-layout slot: nxl * nph * ny
   size_t vsize = 0;  // complex elements of one [z][y][kx] slot: nzf * ny * nxp
   ZMap* d_zmap = nullptr;
-  cplx* W[6] = {nullptr};   // z-stage side, exchange layout (v_c, dz v_c)
-  cplx* R[6] = {nullptr};   // y-stage side [kx][zl][ky] (aliases W on one GPU)
-  cplx* V[9] = {nullptr};   // [zl][y][kx]: v, dy v, dz v
-  cplx* X[3] = {nullptr};   // [zl][y][kx]: nonlinear term after the x pass
-  cplx* U[3] = {nullptr};   // y-stage side of the way back [kx][zl][ky]
-  cplx* Uz[3] = {nullptr};  // z-stage side of the way back (aliases U on one GPU)
+  // work fields, grown on demand by fused_reserve (HD 6/9/3, BOUSS 8/12/4, MHD 12/12/6)
+  std::vector<cplx*> W;   // z-stage side, exchange layout (fields and their z derivatives)
+  std::vector<cplx*> R;   // y-stage side [kx][zl][ky] (aliases W on one GPU)
+  std::vector<cplx*> V;   // [zl][y][kx]: fields, dy, dz
+  std::vector<cplx*> X;   // [zl][y][kx]: nonlinear terms after the x pass
+  std::vector<cplx*> U;   // y-stage side of the way back [kx][zl][ky]
+  std::vector<cplx*> Uz;  // z-stage side of the way back (aliases U on one GPU)
   // all-to-all-v block tables in complex elements: z side [rank][kxl][zl_r][ky], xy side [kx][zl][ky]
   std::vector<size_t> z_displ, z_count, x_displ, x_count;
 };
@@ -257,8 +258,8 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tile(YfwdArgs a, cons
 // reference applies derivk before the transform).
 // ------------------------------------------------------------------------------------------
 struct XpassArgs {
-  const cplx* V[9];  // v(3), dy v(3), dz v(3)   [zl][y][kx]
-  cplx* X[3];
+  const cplx* V[12];  // q(NC), dy q(NC), dz q(NC) with q = (vx, vy, vz[, theta])   [zl][y][kx]
+  cplx* X[4];
   const double* kx;  // GLOBAL kx(1:nx/2+1)
   int ny, nxp, nzf;
   double tmp;        // 1/(nx ny nz)^2
@@ -269,7 +270,7 @@ struct XpassArgs {
 // transform m+1 are in flight as cp.async copies into thread-private slots.  The three velocity
 // lines are parked in thread-private shared memory, so the register file only holds one transform
 // and one accumulator.
-template <int N, int LP, bool PF, int MINB>
+template <int N, int LP, bool PF, int MINB, int NC>
 __global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_gradre(XpassArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8, NT = LP * T, XS = sidx_elem_stride<N>();
@@ -278,10 +279,11 @@ __global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_gradre(XpassArgs a, 
   cplx* park = smem + (size_t)LP * XS + threadIdx.x;            // park[(c*8+k)*NT]
   cplx* slot = smem + (size_t)LP * XS + (size_t)24 * NT + threadIdx.x;  // slot[(2k+h)*NT]
   const int groups_y = cdiv(a.ny, 2 * LP), ngroups = groups_y * a.nzf;
+  constexpr int NM = 3 + 3 * NC;  // inverse transforms per group: u(3), then d_x, d_y, d_z of each component
   auto field_of = [&](int m) -> const cplx* {
     if (m < 3) return a.V[m];
     const int c = (m - 3) / 3, d = (m - 3) % 3;
-    return a.V[d * 3 + c];
+    return a.V[d * NC + c];
   };
   auto issue = [&](int g, int m) {
     if (!PF) return;
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_gradre(XpassArgs a, 
     const size_t rowA = ((size_t)zl * a.ny + (active ? y0 : 0)) * a.nxp, rowB = rowA + a.nxp;
     cplx acc[8];
 #pragma unroll 1
-    for (int m = 0; m < 12; ++m) {
+    for (int m = 0; m < NM; ++m) {
       const bool deriv = m >= 3 && (m - 3) % 3 == 0;
       cplx v[8];
       if (PF) cp_async_wait_all();
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_gradre(XpassArgs a, 
         if (e > N / 2) { A.y = -A.y; B.y = -B.y; }
         v[k] = cmake(A.x - B.y, A.y + B.x);
       }
-      if (m < 11) issue(g, m + 1);
+      if (m < NM - 1) issue(g, m + 1);
       else if (g + (int)gridDim.x < ngroups) issue(g + gridDim.x, 0);
       fft_regs<N, 1>(v, t, smem, si, tw);
       if (m < 3) {
@@ -378,22 +380,161 @@ __global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_gradre(XpassArgs a, 
 }
 
 // ------------------------------------------------------------------------------------------
+// xpass (cross products): X = sum over pairs s * (P x Q) / N^2 on the physical rows.  Used for the MHD
+// nonlinear terms: omega x v - J x B = -(v x omega) + (B x J) (prodre pseudospec_hd.f90:357-399 and vector
+// pseudospec_mhd.f90:87-102 as called at mhd_rkstep2.f90:29-37) and the electromotive force v x B (:45).
+// The three lines of P are parked in thread-private shared memory, the lines of Q stream through the
+// registers one transform at a time and feed three accumulators.
+// ------------------------------------------------------------------------------------------
+struct XcrossArgs {
+  const cplx* P[2][3];
+  const cplx* Q[2][3];
+  double sgn[2];
+  int npairs;
+  cplx* X[3];
+  int ny, nxp, nzf;
+  double tmp;  // 1/(nx ny nz)^2
+};
+
+template <int N, int LP, int MINB>
+__global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_cross(XcrossArgs a, const cplx* __restrict__ tw) {
+  SX_DYN_SMEM(cplx, smem);
+  constexpr int T = N / 8, NT = LP * T, XS = sidx_elem_stride<N>();
+  const int lp = threadIdx.x / T, t = threadIdx.x % T;
+  const SIdxElem si{lp * XS};
+  cplx* park = smem + (size_t)LP * XS + threadIdx.x;                     // park[(c*8+k)*NT]
+  cplx* slot = smem + (size_t)LP * XS + (size_t)24 * NT + threadIdx.x;   // slot[(2k+h)*NT]
+  const int groups_y = cdiv(a.ny, 2 * LP), ngroups = groups_y * a.nzf;
+  const int nm = 6 * a.npairs;
+  auto field_of = [&](int m) -> const cplx* {
+    const int pr = m / 6, q = m % 6;
+    return q < 3 ? a.P[pr][q] : a.Q[pr][q - 3];
+  };
+  auto issue = [&](int g, int m) {
+    const int y0 = ((g % groups_y) * LP + lp) * 2, zl = g / groups_y;
+    if (y0 < a.ny) {
+      const cplx* rowA = field_of(m) + ((size_t)zl * a.ny + y0) * a.nxp;
+      const cplx* rowB = rowA + a.nxp;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = t + k * T;
+        const int kx = e <= N / 2 ? e : N - e;
+        cp_async16(slot + (2 * k) * NT, rowA + kx);
+        cp_async16(slot + (2 * k + 1) * NT, rowB + kx);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) slot[k * NT] = cmake(0.0, 0.0);
+    }
+    cp_async_commit();
+  };
+  int g = blockIdx.x;
+  if (g < ngroups) issue(g, 0);
+  for (; g < ngroups; g += gridDim.x) {
+    const int y0 = ((g % groups_y) * LP + lp) * 2, zl = g / groups_y;
+    const bool active = y0 < a.ny;
+    const size_t rowA = ((size_t)zl * a.ny + (active ? y0 : 0)) * a.nxp, rowB = rowA + a.nxp;
+    cplx ax[8], ay[8], az[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ax[k] = ay[k] = az[k] = cmake(0.0, 0.0);
+#pragma unroll 1
+    for (int m = 0; m < nm; ++m) {
+      const int q = m % 6;
+      const double sg = a.sgn[m / 6];
+      cplx v[8];
+      cp_async_wait_all();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = t + k * T;
+        const int kx = e <= N / 2 ? e : N - e;
+        cplx A = slot[(2 * k) * NT], B = slot[(2 * k + 1) * NT];
+        if (kx == 0 || kx == N / 2) { A.y = 0.0; B.y = 0.0; }
+        if (e > N / 2) { A.y = -A.y; B.y = -B.y; }
+        v[k] = cmake(A.x - B.y, A.y + B.x);
+      }
+      if (m < nm - 1) issue(g, m + 1);
+      else if (g + (int)gridDim.x < ngroups) issue(g + gridDim.x, 0);
+      fft_regs<N, 1>(v, t, smem, si, tw);
+      if (q < 3) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) park[(q * 8 + k) * NT] = v[k];
+      } else if (q == 3) {   // Q_x: y += P_z Q_x, z -= P_y Q_x
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const cplx py = park[(8 + k) * NT], pz = park[(16 + k) * NT];
+          ay[k] = cmake(fma(sg * pz.x, v[k].x, ay[k].x), fma(sg * pz.y, v[k].y, ay[k].y));
+          az[k] = cmake(fma(-sg * py.x, v[k].x, az[k].x), fma(-sg * py.y, v[k].y, az[k].y));
+        }
+      } else if (q == 4) {   // Q_y: x -= P_z Q_y, z += P_x Q_y
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const cplx px = park[k * NT], pz = park[(16 + k) * NT];
+          ax[k] = cmake(fma(-sg * pz.x, v[k].x, ax[k].x), fma(-sg * pz.y, v[k].y, ax[k].y));
+          az[k] = cmake(fma(sg * px.x, v[k].x, az[k].x), fma(sg * px.y, v[k].y, az[k].y));
+        }
+      } else {               // Q_z: x += P_y Q_z, y -= P_x Q_z
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const cplx px = park[k * NT], py = park[(8 + k) * NT];
+          ax[k] = cmake(fma(sg * py.x, v[k].x, ax[k].x), fma(sg * py.y, v[k].y, ax[k].y));
+          ay[k] = cmake(fma(-sg * px.x, v[k].x, ay[k].x), fma(-sg * px.y, v[k].y, ay[k].y));
+        }
+      }
+    }
+    // forward transforms of the three packed pairs and split into the half spectra
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      cplx acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const cplx s3 = c == 0 ? ax[k] : (c == 1 ? ay[k] : az[k]);
+        acc[k] = cmake(s3.x * a.tmp, s3.y * a.tmp);
+      }
+      fft_regs<N, -1>(acc, t, smem, si, tw);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) smem[si(t + k * T)] = acc[k];
+      __syncthreads();
+      cplx* out = a.X[c];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int kk = t + k * T;
+        if (kk <= N / 2 && active) {
+          const cplx Zk = acc[k];
+          const cplx Zn = smem[si((N - kk) & (N - 1))];
+          out[rowA + kk] = cmake(0.5 * (Zk.x + Zn.x), 0.5 * (Zk.y - Zn.y));
+          out[rowB + kk] = cmake(0.5 * (Zk.y + Zn.y), -0.5 * (Zk.x - Zn.x));
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // zfwd_rk: one CTA = NP adjacent ky pencils of one kx.  Reads the nonlinear term in the exchange
 // layout, continues it, transforms, filters and performs the RK update of one velocity component.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxDF = 10;
 
+// out = v0 + dt*( cL*(lap ? -k^2 v : v) + sNL*filter(NL^ + ccoef*couple) + f )*rmp
+//   HD/BOUSS velocity: cL = nu, lap, sNL = -1 (hd_rkstep2.f90:14-32); BOUSS adds the buoyancy / heat-current
+//   coupling before the filter (bouss_rkstep2.f90:9-24); MHD potential: v holds J, cL = -mu, no lap,
+//   sNL = +1 (mhd_rkstep2.f90:69-74)
 struct ZfwdArgs {
   const cplx* nl;     // exchange layout [rank][kxl][zl][ky], physical rows
-  cplx* v;            // spectral, in/out
+  const cplx* v;      // spectral field the linear term is taken from
+  cplx* vout;         // result (may alias v)
   const cplx* v0;     // RK base
   const cplx* f;      // forcing
+  const cplx* couple; // optional spectral field added to the nonlinear term before the filter
+  double ccoef, cL, sNL;
+  int lap;
   const ZMap* zmap;
   const double *kx, *ky, *kz;     // kx LOCAL
   const double *fx, *fy, *fz;     // filter factors (fx LOCAL)
   const double* dir;  // [C][d]
   int ny, nxl, nph, C, d;
-  double dt, nu, rmp;
+  double dt, rmp;
 };
 
 // continuation rows of a pencil-fastest tile from the stashed boundary values
@@ -493,11 +634,13 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
       for (int k = 0; k < 8; ++k) {
         const int e = j + k * T;
         const double z = __ldg(&a.kz[e]), f3 = __ldg(&a.fz[e]);
-        const double kk2 = kh2 + z * z;
-        const cplx NL = cscale(cscale(cscale(v[k], f1), f2), f3);
+        const double lm = a.lap ? -(kh2 + z * z) : 1.0;
+        cplx NL = v[k];
+        if (a.couple != nullptr) NL = caxpy(a.ccoef, a.couple[base + e], NL);
+        NL = cscale(cscale(cscale(NL, f1), f2), f3);
         const cplx Lk = HOIST ? L[k] : a.v[base + e], Bk = HOIST ? B[k] : a.v0[base + e], Fk = HOIST ? F[k] : a.f[base + e];
-        a.v[base + e] = cmake(Bk.x + a.dt * (a.nu * (-kk2 * Lk.x) - NL.x + Fk.x) * a.rmp,
-                              Bk.y + a.dt * (a.nu * (-kk2 * Lk.y) - NL.y + Fk.y) * a.rmp);
+        a.vout[base + e] = cmake(Bk.x + a.dt * (a.cL * (lm * Lk.x) + a.sNL * NL.x + Fk.x) * a.rmp,
+                                 Bk.y + a.dt * (a.cL * (lm * Lk.y) + a.sNL * NL.y + Fk.y) * a.rmp);
       }
     }
   }
@@ -731,21 +874,21 @@ static void range0(int n, int nprocs, int r, int* sta, int* cnt) {  // `range` o
   *cnt = w + (m > r ? 1 : 0);
 }
 
+static void release_fields(std::vector<cplx*>& a, const std::vector<cplx*>* alias = nullptr) {
+  for (size_t i = 0; i < a.size(); ++i)
+    if (a[i] && (!alias || i >= alias->size() || (*alias)[i] != a[i])) cudaFree(a[i]);
+  a.clear();
+}
+
 int fused_free(Plan& p) {
   Fused* f = p.fused;
   if (!f) return 0;
-  auto rel = [](cplx** a, int n, cplx** alias = nullptr) {
-    for (int i = 0; i < n; ++i) {
-      if (a[i] && (!alias || alias[i] != a[i])) cudaFree(a[i]);
-      a[i] = nullptr;
-    }
-  };
-  rel(f->R, 6, f->W);
-  rel(f->W, 6);
-  rel(f->V, 9);
-  rel(f->X, 3);
-  rel(f->Uz, 3, f->U);
-  rel(f->U, 3);
+  release_fields(f->R, &f->W);
+  release_fields(f->W);
+  release_fields(f->V);
+  release_fields(f->X);
+  release_fields(f->Uz, &f->U);
+  release_fields(f->U);
   if (f->d_zmap) cudaFree(f->d_zmap);
   delete f;
   p.fused = nullptr;
@@ -782,20 +925,37 @@ static int fused_init(Plan& p, Fused** out) {
   }
   SX_CUDA_CHECK(cudaMalloc((void**)&f->d_zmap, zm.size() * sizeof(ZMap)));
   SX_CUDA_CHECK(cudaMemcpy(f->d_zmap, zm.data(), zm.size() * sizeof(ZMap), cudaMemcpyHostToDevice));
-  const size_t rsize = (size_t)p.nxh * f->nzf * p.ny;  // y-stage side [kx][zl][ky]
-  for (int i = 0; i < 6; ++i) {
-    SX_CUDA_CHECK(cudaMalloc((void**)&f->W[i], (f->wsize > rsize ? f->wsize : rsize) * sizeof(cplx)));
-    if (p.nprocs == 1) f->R[i] = f->W[i];
-    else SX_CUDA_CHECK(cudaMalloc((void**)&f->R[i], rsize * sizeof(cplx)));
-  }
-  for (int i = 0; i < 9; ++i) SX_CUDA_CHECK(cudaMalloc((void**)&f->V[i], f->vsize * sizeof(cplx)));
-  for (int i = 0; i < 3; ++i) {
-    SX_CUDA_CHECK(cudaMalloc((void**)&f->X[i], f->vsize * sizeof(cplx)));
-    SX_CUDA_CHECK(cudaMalloc((void**)&f->U[i], (f->wsize > rsize ? f->wsize : rsize) * sizeof(cplx)));
-    if (p.nprocs == 1) f->Uz[i] = f->U[i];
-    else SX_CUDA_CHECK(cudaMalloc((void**)&f->Uz[i], f->wsize * sizeof(cplx)));
-  }
   *out = f;
+  return 0;
+}
+
+// grow the work-field pools: nw transposed inverse fields, nv real-side inputs of the x pass, nx nonlinear terms
+static int fused_reserve(Plan& p, Fused& f, int nw, int nv, int nx) {
+  const size_t rsize = (size_t)p.nxh * f.nzf * p.ny;  // y-stage side [kx][zl][ky]
+  const size_t both = f.wsize > rsize ? f.wsize : rsize;
+  while ((int)f.W.size() < nw) {
+    cplx *w = nullptr, *r = nullptr;
+    SX_CUDA_CHECK(cudaMalloc((void**)&w, both * sizeof(cplx)));
+    if (p.nprocs == 1) r = w;
+    else SX_CUDA_CHECK(cudaMalloc((void**)&r, rsize * sizeof(cplx)));
+    f.W.push_back(w);
+    f.R.push_back(r);
+  }
+  while ((int)f.V.size() < nv) {
+    cplx* v = nullptr;
+    SX_CUDA_CHECK(cudaMalloc((void**)&v, f.vsize * sizeof(cplx)));
+    f.V.push_back(v);
+  }
+  while ((int)f.X.size() < nx) {
+    cplx *x = nullptr, *u = nullptr, *uz = nullptr;
+    SX_CUDA_CHECK(cudaMalloc((void**)&x, f.vsize * sizeof(cplx)));
+    SX_CUDA_CHECK(cudaMalloc((void**)&u, both * sizeof(cplx)));
+    if (p.nprocs == 1) uz = u;
+    else SX_CUDA_CHECK(cudaMalloc((void**)&uz, f.wsize * sizeof(cplx)));
+    f.X.push_back(x);
+    f.U.push_back(u);
+    f.Uz.push_back(uz);
+  }
   return 0;
 }
 
@@ -857,12 +1017,12 @@ template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* ou
   SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   return 0;
 }
-template <int N, int LP, bool PF, int MINB> static int run_xpass_v(Plan& p, Fused& f, const double* d_kx_global) {
+template <int N, int LP, bool PF, int MINB, int NC> static int run_xpass_v(Plan& p, Fused& f, const double* d_kx_global) {
   constexpr int T = N / 8;
   if (f.nzf == 0) return 0;
   XpassArgs a;
-  for (int i = 0; i < 9; ++i) a.V[i] = f.V[i];
-  for (int i = 0; i < 3; ++i) a.X[i] = f.X[i];
+  for (int i = 0; i < 3 * NC; ++i) a.V[i] = f.V[i];
+  for (int i = 0; i < NC; ++i) a.X[i] = f.X[i];
   a.kx = d_kx_global;
   a.ny = p.ny;
   a.nxp = f.nxp;
@@ -870,32 +1030,65 @@ template <int N, int LP, bool PF, int MINB> static int run_xpass_v(Plan& p, Fuse
   const double Ntot = (double)p.nx * (double)p.ny * (double)p.nz;
   a.tmp = 1.0 / (Ntot * Ntot);
   const cplx* tw = p.tw_x;
-  auto kfn = k_xpass_gradre<N, LP, PF, MINB>;
+  auto kfn = k_xpass_gradre<N, LP, PF, MINB, NC>;
   const size_t smem = ((size_t)LP * sidx_elem_stride<N>() + (size_t)(PF ? 40 : 24) * LP * T) * sizeof(cplx);
   int grid;
   if (persistent_grid(p, kfn, LP * T, smem, cdiv(p.ny, 2 * LP) * f.nzf, &grid)) return 1;
   SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(grid), LP * T, smem, a, tw);
   return 0;
 }
-template <int N> static int run_xpass(Plan& p, Fused& f, const double* d_kx_global) {
+template <int N, int NC> static int run_xpass(Plan& p, Fused& f, const double* d_kx_global) {
   constexpr int T = N / 8;
   constexpr int LP = T >= 128 ? 1 : 128 / T;
-  if constexpr (N == 512) {
+  if constexpr (N == 512 && NC == 3) {
     switch (p.knob_xp) {
-      case 1: return run_xpass_v<N, 1, true, 4>(p, f, d_kx_global);
-      case 2: return run_xpass_v<N, 1, false, 6>(p, f, d_kx_global);
-      case 3: return run_xpass_v<N, 2, false, 3>(p, f, d_kx_global);
-      case 4: return run_xpass_v<N, 1, false, 4>(p, f, d_kx_global);
+      case 1: return run_xpass_v<N, 1, true, 4, NC>(p, f, d_kx_global);
+      case 2: return run_xpass_v<N, 1, false, 6, NC>(p, f, d_kx_global);
+      case 3: return run_xpass_v<N, 2, false, 3, NC>(p, f, d_kx_global);
+      case 4: return run_xpass_v<N, 1, false, 4, NC>(p, f, d_kx_global);
       default: break;
     }
   }
-  return run_xpass_v<N, LP, true, (N <= 1024 ? 2 : 1)>(p, f, d_kx_global);
+  return run_xpass_v<N, LP, true, (N <= 1024 ? 2 : 1), NC>(p, f, d_kx_global);
 }
-template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, cplx* v, const cplx* v0, const cplx* frc,
-                                        double dt, double nu, double rmp) {
+// X[xo..xo+2] = sum_pairs sgn * (V[P] x V[Q]) / N^2; Pi/Qi index the first of three consecutive V fields
+template <int N> static int run_xcross(Plan& p, Fused& f, int npairs, const int* Pi, const int* Qi, const double* sgn, int xo) {
+  constexpr int T = N / 8;
+  constexpr int LP = T >= 128 ? 1 : 128 / T;
+  if (f.nzf == 0) return 0;
+  XcrossArgs a;
+  for (int q = 0; q < 2; ++q)
+    for (int c = 0; c < 3; ++c) {
+      a.P[q][c] = f.V[Pi[q < npairs ? q : 0] + c];
+      a.Q[q][c] = f.V[Qi[q < npairs ? q : 0] + c];
+    }
+  a.sgn[0] = sgn[0];
+  a.sgn[1] = npairs > 1 ? sgn[1] : 0.0;
+  a.npairs = npairs;
+  for (int c = 0; c < 3; ++c) a.X[c] = f.X[xo + c];
+  a.ny = p.ny;
+  a.nxp = f.nxp;
+  a.nzf = f.nzf;
+  const double Ntot = (double)p.nx * (double)p.ny * (double)p.nz;
+  a.tmp = 1.0 / (Ntot * Ntot);
+  const cplx* tw = p.tw_x;
+  auto kfn = k_xpass_cross<N, LP, (N <= 1024 ? 2 : 1)>;
+  const size_t smem = ((size_t)LP * sidx_elem_stride<N>() + (size_t)40 * LP * T) * sizeof(cplx);
+  int grid;
+  if (persistent_grid(p, kfn, LP * T, smem, cdiv(p.ny, 2 * LP) * f.nzf, &grid)) return 1;
+  SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(grid), LP * T, smem, a, tw);
+  return 0;
+}
+struct RkTerm {   // see ZfwdArgs
+  const cplx* couple = nullptr;
+  double ccoef = 0.0, cL = 0.0, sNL = -1.0;
+  int lap = 1;
+};
+template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, const cplx* v, cplx* vout, const cplx* v0,
+                                        const cplx* frc, const RkTerm& rk, double dt, double rmp) {
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
-  ZfwdArgs a{nl, v, v0, frc, f.d_zmap, p.d_kx, p.d_ky, p.d_kz, p.d_fx, p.d_fy, p.d_fz, p.d_dir,
-             p.ny, p.nxl, f.nph, p.Cz, p.oz, dt, nu, rmp};
+  ZfwdArgs a{nl, v, vout, v0, frc, rk.couple, rk.ccoef, rk.cL, rk.sNL, rk.lap, f.d_zmap, p.d_kx, p.d_ky, p.d_kz,
+             p.d_fx, p.d_fy, p.d_fz, p.d_dir, p.ny, p.nxl, f.nph, p.Cz, p.oz, dt, rmp};
   const cplx* tw = p.tw_z;
   const size_t smem = ((size_t)2 * NP * N + (size_t)2 * kMaxDF * NP) * sizeof(cplx) + (size_t)N * sizeof(ZMap);
   int grid;
@@ -972,14 +1165,19 @@ static int yfwd(Plan& p, Fused& f, const cplx* in, cplx* out) {
   SX_SIZE_SWITCH(p.ny, C_);
 #undef C_
 }
-static int xpass(Plan& p, Fused& f, const double* kxg) {
-#define C_(N) run_xpass<N>(p, f, kxg)
+template <int NC> static int xpass(Plan& p, Fused& f, const double* kxg) {
+#define C_(N) run_xpass<N, NC>(p, f, kxg)
   SX_SIZE_SWITCH(p.nx, C_);
 #undef C_
 }
-static int zfwd_rk(Plan& p, Fused& f, const cplx* nl, cplx* v, const cplx* v0, const cplx* frc, double dt, double nu,
-                   double rmp) {
-#define C_(N) run_zfwd_rk<N>(p, f, nl, v, v0, frc, dt, nu, rmp)
+static int xcross(Plan& p, Fused& f, int npairs, const int* Pi, const int* Qi, const double* sgn, int xo) {
+#define C_(N) run_xcross<N>(p, f, npairs, Pi, Qi, sgn, xo)
+  SX_SIZE_SWITCH(p.nx, C_);
+#undef C_
+}
+static int zfwd_rk(Plan& p, Fused& f, const cplx* nl, const cplx* v, cplx* vout, const cplx* v0, const cplx* frc,
+                   const RkTerm& rk, double dt, double rmp) {
+#define C_(N) run_zfwd_rk<N>(p, f, nl, v, vout, v0, frc, rk, dt, rmp)
   SX_SIZE_SWITCH(p.nz, C_);
 #undef C_
 }
@@ -989,44 +1187,148 @@ static int project(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, in
 #undef C_
 }
 
-// W[slot] (z side, [rank][kxl][zl][ky]) -> R[slot] (xy side, [kx][zl][ky]); event slots 0..5
+// W[slot] (z side, [rank][kxl][zl][ky]) -> R[slot] (xy side, [kx][zl][ky]); event slots 0..15
 static int to_real_begin(Plan& p, Fused& f, int slot) {
   if (p.nprocs == 1) return 0;
   return exchange_begin(p, slot, f.W[slot], f.R[slot], f.z_displ.data(), f.z_count.data(), f.x_displ.data(), f.x_count.data());
 }
-// U[slot] (xy side) -> Uz[slot] (z side); event slots 6..8
+// U[slot] (xy side) -> Uz[slot] (z side); event slots 16..23
 static int to_spec_begin(Plan& p, Fused& f, int slot) {
   if (p.nprocs == 1) return 0;
-  return exchange_begin(p, 6 + slot, f.U[slot], f.Uz[slot], f.x_displ.data(), f.x_count.data(), f.z_displ.data(), f.z_count.data());
+  return exchange_begin(p, 16 + slot, f.U[slot], f.Uz[slot], f.x_displ.data(), f.x_count.data(), f.z_displ.data(), f.z_count.data());
 }
 static int ex_wait(Plan& p, int ev) { return p.nprocs == 1 ? 0 : exchange_wait(p, ev); }
+
+static int fused_begin(Plan& p, Fused** fp, int nw, int nv, int nx) {
+  if (fused_init(p, fp)) return 1;
+  SX_REQUIRE(comm_ready(p), "multi-rank plan without a communicator: call sx_plan_set_comm or sx_plan_set_comm_callbacks");
+  return fused_reserve(p, **fp, nw, nv, nx);
+}
+
+// inverse half shared by HD and BOUSS: q_c -> V[c], V[NC+c] (dy), V[2NC+c] (dz)
+template <int NC> static int gradient_fields_to_real(Plan& p, Fused& f, const cplx* const* q) {
+  for (int c = 0; c < NC; ++c) {
+    if (zinv(p, f, q[c], f.W[2 * c], f.W[2 * c + 1])) return 1;
+    if (to_real_begin(p, f, 2 * c) || to_real_begin(p, f, 2 * c + 1)) return 1;
+  }
+  for (int c = 0; c < NC; ++c) {
+    if (ex_wait(p, 2 * c) || ex_wait(p, 2 * c + 1)) return 1;
+    if (yinv(p, f, f.R[2 * c], f.V[c], f.V[NC + c])) return 1;
+    if (yinv(p, f, f.R[2 * c + 1], f.V[2 * NC + c], nullptr)) return 1;
+  }
+  return 0;
+}
+static int nonlinear_to_spectral_begin(Plan& p, Fused& f, int nx) {
+  for (int c = 0; c < nx; ++c) {
+    if (yfwd(p, f, f.X[c], f.U[c])) return 1;
+    if (to_spec_begin(p, f, c)) return 1;
+  }
+  return 0;
+}
 
 // hd_rkstep2.f90:3-36.  st[0..2] v, st[3] pr, st[4..6] f, st[7..9] RK base.
 int hd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, const double* zs, const double* ze) {
   Fused* fp;
-  if (fused_init(p, &fp)) return 1;
+  if (fused_begin(p, &fp, 6, 9, 3)) return 1;
   Fused& f = *fp;
-  SX_REQUIRE(comm_ready(p), "multi-rank plan without a communicator: call sx_plan_set_comm or sx_plan_set_comm_callbacks");
   const double rmp = 1.0 / (double)o;
+  if (gradient_fields_to_real<3>(p, f, st)) return 1;
+  if (xpass<3>(p, f, p.d_kxg)) return 1;
+  if (nonlinear_to_spectral_begin(p, f, 3)) return 1;
+  RkTerm rk;
+  rk.cL = nu;
   for (int c = 0; c < 3; ++c) {
-    if (zinv(p, f, st[c], f.W[2 * c], f.W[2 * c + 1])) return 1;
-    if (to_real_begin(p, f, 2 * c) || to_real_begin(p, f, 2 * c + 1)) return 1;
-  }
-  for (int c = 0; c < 3; ++c) {
-    if (ex_wait(p, 2 * c) || ex_wait(p, 2 * c + 1)) return 1;
-    if (yinv(p, f, f.R[2 * c], f.V[c], f.V[3 + c])) return 1;
-    if (yinv(p, f, f.R[2 * c + 1], f.V[6 + c], nullptr)) return 1;
-  }
-  if (xpass(p, f, p.d_kxg)) return 1;
-  for (int c = 0; c < 3; ++c) {
-    if (yfwd(p, f, f.X[c], f.U[c])) return 1;
-    if (to_spec_begin(p, f, c)) return 1;
-  }
-  for (int c = 0; c < 3; ++c) {
-    if (ex_wait(p, 6 + c)) return 1;
-    if (zfwd_rk(p, f, f.Uz[c], st[c], st[7 + c], st[4 + c], dt, nu, rmp)) return 1;
+    if (ex_wait(p, 16 + c)) return 1;
+    if (zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk, dt, rmp)) return 1;
   }
   return project(p, f, st[0], st[1], st[2], st[3], o, zs, ze);
+}
+
+int s_imposebc(Plan& p, cplx* th);
+int theta_roundtrip(Plan& p, cplx* th, cplx* out);
+int a_imposebc_and_project(Plan& p, cplx* ax, cplx* ay, cplx* az, cplx* ph);
+
+// bouss_rkstep2.f90:3-59.  st[0..2] v, 3 pr, 4..6 f, 7..9 C1..C3, 10 th, 11 fs, 12 C7, 13 scratch.
+int bouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double kappa, double xmom, double xtemp,
+                        const double* zs, const double* ze) {
+  Fused* fp;
+  if (fused_begin(p, &fp, 8, 12, 4)) return 1;
+  Fused& f = *fp;
+  const double rmp = 1.0 / (double)o;
+  const cplx* q[4] = {st[0], st[1], st[2], st[10]};
+  if (gradient_fields_to_real<4>(p, f, q)) return 1;
+  if (xpass<4>(p, f, p.d_kxg)) return 1;          // gradre (3) and advect (1) in one pass
+  if (nonlinear_to_spectral_begin(p, f, 4)) return 1;
+  // theta first, into the scratch field: it reads the not yet updated v_z (heat current), and v_z below reads
+  // the not yet updated theta (buoyancy)
+  RkTerm rt;
+  rt.cL = kappa; rt.couple = st[2]; rt.ccoef = -xtemp;
+  if (ex_wait(p, 16 + 3)) return 1;
+  if (zfwd_rk(p, f, f.Uz[3], st[10], st[13], st[12], st[11], rt, dt, rmp)) return 1;
+  for (int c = 0; c < 3; ++c) {
+    RkTerm rk;
+    rk.cL = nu;
+    if (c == 2) { rk.couple = st[10]; rk.ccoef = -xmom; }
+    if (ex_wait(p, 16 + c)) return 1;
+    if (zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk, dt, rmp)) return 1;
+  }
+  if (project(p, f, st[0], st[1], st[2], st[3], o, zs, ze)) return 1;
+  // s_imposebc, fc_filter and the theta round trip (bouss_rkstep2.f90:53-59); all pencil-local
+  return s_imposebc(p, st[13]) || op_fc_filter(p, st[13]) || theta_roundtrip(p, st[13], st[10]);
+}
+
+// mhd_rkstep2.f90:3-84.  st[0..2] v, 3 pr, 4..6 f, 7..9 C1..C3, 10..12 a, 13 ph, 14..16 m, 17..19 C9..C11.
+int mhd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double mu, const double* b0) {
+  Fused* fp;
+  if (fused_begin(p, &fp, 12, 12, 6)) return 1;
+  Fused& f = *fp;
+  const double rmp = 1.0 / (double)o;
+  const double N = (double)p.nx * (double)p.ny * (double)p.nz;
+  cplx *B[3], *Wv[3];
+  for (int c = 0; c < 3; ++c)
+    if (plan_cwork(p, 9 + c, &B[c]) || plan_cwork(p, 12 + c, &Wv[c])) return 1;
+  cplx *ax = st[10], *ay = st[11], *az = st[12];
+  // B = curl A (+ uniform field at the mean mode), J = curl B written over A, omega = curl v   (:6-20, prodre)
+  if (op_curlk(p, ay, az, B[0], 1) || op_curlk(p, ax, az, B[1], 2) || op_curlk(p, ax, ay, B[2], 3)) return 1;
+  if (p.ista == 1)
+    for (int c = 0; c < 3; ++c)
+      if (op_set_elem(p, B[c], 0, (b0 ? b0[c] : 0.0) * N, 0.0)) return 1;
+  if (op_curlk(p, B[1], B[2], ax, 1) || op_curlk(p, B[0], B[2], ay, 2) || op_curlk(p, B[0], B[1], az, 3)) return 1;
+  if (op_curlk(p, st[1], st[2], Wv[0], 1) || op_curlk(p, st[0], st[2], Wv[1], 2) || op_curlk(p, st[0], st[1], Wv[2], 3)) return 1;
+  // twelve plain fields to real space: v -> V[0..2], omega -> V[3..5], B -> V[6..8], J -> V[9..11]
+  const cplx* q[12] = {st[0], st[1], st[2], Wv[0], Wv[1], Wv[2], B[0], B[1], B[2], ax, ay, az};
+  for (int c = 0; c < 12; ++c) {
+    if (zinv(p, f, q[c], f.W[c], nullptr)) return 1;
+    if (to_real_begin(p, f, c)) return 1;
+  }
+  for (int c = 0; c < 12; ++c) {
+    if (ex_wait(p, c)) return 1;
+    if (yinv(p, f, f.R[c], f.V[c], nullptr)) return 1;
+  }
+  // X[0..2] = omega x v - J x B = -(v x omega) + (B x J);  X[3..5] = v x B
+  {
+    const int Pi[2] = {0, 6}, Qi[2] = {3, 9};
+    const double sg[2] = {-1.0, 1.0};
+    if (xcross(p, f, 2, Pi, Qi, sg, 0)) return 1;
+    const int Pe[1] = {0}, Qe[1] = {6};
+    const double se[1] = {1.0};
+    if (xcross(p, f, 1, Pe, Qe, se, 3)) return 1;
+  }
+  if (nonlinear_to_spectral_begin(p, f, 6)) return 1;
+  for (int c = 0; c < 3; ++c) {
+    RkTerm rk;
+    rk.cL = nu;
+    if (ex_wait(p, 16 + c)) return 1;
+    if (zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk, dt, rmp)) return 1;
+  }
+  for (int c = 0; c < 3; ++c) {
+    RkTerm rk;
+    rk.cL = -mu; rk.lap = 0; rk.sNL = 1.0;
+    if (ex_wait(p, 16 + 3 + c)) return 1;
+    if (zfwd_rk(p, f, f.Uz[3 + c], st[10 + c], st[10 + c], st[17 + c], st[14 + c], rk, dt, rmp)) return 1;
+  }
+  if (project(p, f, st[0], st[1], st[2], st[3], o, nullptr, nullptr)) return 1;
+  return a_imposebc_and_project(p, ax, ay, az, st[13]);
 }
 
 }  // namespace sx

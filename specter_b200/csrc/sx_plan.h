@@ -9,6 +9,7 @@ namespace sx {
 struct HdState;  // fused-path device state (sx_rkstep.cu)
 struct Fused;    // fused-path work buffers and slab maps (sx_fused.cu)
 struct Comm;     // NCCL communicator / transport callbacks (sx_comm.cu)
+struct SolverState;  // BOUSS / MHD device state (sx_solvers.cu)
 
 // Per-stage CUDA-event timers (the reference's ffttime/tratime/comtime/conttime counters,
 // fftp_mod.fpp:32-37, re-cast per kernel family).
@@ -51,7 +52,10 @@ struct Plan {
   double* d_red = nullptr;   // reduction partials
   double* h_red = nullptr;   // pinned host landing zone
   int red_blocks = 0;
+  std::string tdir;          // FC-Gram table directory (Neumann tables are loaded on first use)
   HdState* hd = nullptr;
+  SolverState* bouss = nullptr;
+  SolverState* mhd = nullptr;
   Fused* fused = nullptr;
   Comm* comm = nullptr;
   StageTimer timer;
@@ -114,9 +118,14 @@ int fft1d_z_bwd(Plan& p, const cplx* in, cplx* out, double scale_phys);
 int fft3d_r2c(Plan& p, const double* r, cplx* out);
 int fft3d_c2r(Plan& p, const cplx* in, double* r);
 int gradre(Plan& p, const cplx* a, const cplx* b, const cplx* c, cplx* d, cplx* e, cplx* f);
+int prodre(Plan& p, const cplx* a, const cplx* b, const cplx* c, cplx* d, cplx* e, cplx* f);
+int sol_project(Plan& p, cplx* a, cplx* b, cplx* c, cplx* d, int bctarget, int bczsta, int bczend);
 int v_imposebc_and_project(Plan& p, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int rki, const double* zs,
                            const double* ze);
 int hd_state_free(Plan& p);
+int solver_states_free(Plan& p);
+int op_set_elem(Plan& p, cplx* a, size_t idx, double re, double im);
+int load_neumann(Plan& p);
 int fused_free(Plan& p);
 int comm_free(Plan& p);
 bool comm_ready(const Plan& p);

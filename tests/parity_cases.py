@@ -253,3 +253,111 @@ def case_hd_diagnostics_100(lib, tables, shape, nsteps=100, ord=2, impl=0, dt=1e
     assert np.abs(rows[:, 4] - ref[:, 4]).max() <= TOL_DIAG * np.abs(ref[:, 1]).max()
     p.close()
     return rows
+
+
+# ---- Boussinesq / MHD operators and substeps -------------------------------------------------------
+def fields_close(got, ref, tol=TOL_FIELD, rows=None):
+    scale = max(np.abs(r).max() for r in ref)
+    for q, r in zip(got, ref):
+        if rows is not None:
+            q, r = q[:, :, :rows], r[:, :, :rows]
+        err = np.abs(q - r).max() / (scale if scale > 0 else 1.0)
+        assert err < tol, err
+
+
+def phys_close(g, got, ref, tol=TOL_FIELD):
+    """Compare in the mixed (z,ky,kx) domain on the physical rows -- the well-conditioned representation.
+    The spectral coefficients of a twice re-continued field (BOUSS theta: s_imposebc, fc_filter, then the 3-D
+    round trip of bouss_rkstep2.f90:53-59) carry FC-Gram continuation noise amplified by |dir| ~ 3.5e3 per
+    continuation: perturbing the ORACLE's own input by 1e-16 relative moves its spectral theta by 1.0e-10
+    (measured, 32x16x64) while the physical rows move by < 1e-13."""
+    nph = g.nz - g.Cz
+    scale = max(np.abs(O.fftp1d_complex_to_real_z(g, r.copy())[:, :, :nph]).max() for r in ref)
+    for q, r in zip(got, ref):
+        a = O.fftp1d_complex_to_real_z(g, np.array(q, dtype=np.complex128))[:, :, :nph]
+        b = O.fftp1d_complex_to_real_z(g, r.copy())[:, :, :nph]
+        err = np.abs(a - b).max() / scale
+        assert err < tol, err
+
+
+TOL_RECONTINUED = 2e-9   # spectral coefficients of a twice re-continued field, see phys_close
+
+
+def case_advect_vector(lib, tables, shape):
+    """advect (pseudospec_phd.f90:23-113) and vector (pseudospec_mhd.f90:22-105)."""
+    g, p = make(lib, tables, *shape)
+    v = smooth_velocity(g, 11)
+    b = smooth_velocity(g, 12)
+    dv = [p.spectral(q) for q in v]
+    db = [p.spectral(q) for q in b]
+    out = [p.spectral() for _ in range(3)]
+    p.advect(*dv, db[0], out[0])
+    fields_close([out[0].get()], [O.advect(g, *v, b[0])])
+    p.vector(*dv, *db, *out)
+    fields_close([q.get() for q in out], O.vector(g, *v, *b))
+    a = smooth_velocity(g, 13)[0]
+    da = p.spectral(a)
+    for kin in (0, 1):
+        assert abs(p.variance(da, kin) / O.variance(g, a, kin) - 1) < TOL_DIAG
+    p.close()
+
+
+def case_scalar_vecpot_bc(lib, tables, shape):
+    """s_imposebc (sboundary.f90:67-119) and a_imposebc_and_project (bboundary.f90:100-189, conducting)."""
+    g, p = make(lib, tables, *shape)
+    g.load_neumann()
+    th = smooth_velocity(g, 14)[0]
+    dth = p.spectral(th)
+    p.s_imposebc(dth)
+    r = th.copy(); O.s_imposebc(g, r)
+    fields_close([dth.get()], [r])
+    a = smooth_velocity(g, 15)
+    da = [p.spectral(q) for q in a]
+    dph = p.spectral()
+    p.a_imposebc_and_project(*da, dph)
+    ra = [q.copy() for q in a]
+    rph = O.a_imposebc_and_project(g, *ra)
+    fields_close([q.get() for q in da], ra)
+    nph = g.nz - g.Cz
+    fields_close([dph.get()], [rph], rows=nph)
+    p.close()
+
+
+def case_bouss_substeps(lib, tables, shape, ord=2, nsteps=1, impl=0, dt=1e-3, nu=1e-3, kappa=1e-3, xmom=1.0, xtemp=1.0):
+    """Per-substep spectral fields against the oracle (bouss_rkstep2.f90:3-59)."""
+    g, p = make(lib, tables, *shape, ord=ord)
+    s = O.make_bouss_state(g)
+    p.bouss_put_state(s.vx, s.vy, s.vz, s.pr, s.th, s.fx, s.fy, s.fz, s.fs)
+    nph = g.nz - g.Cz
+    for _ in range(nsteps):
+        p.bouss_rkstep1()
+        C = [s.vx.copy(), s.vy.copy(), s.vz.copy(), s.th.copy()]
+        for o in range(ord, 0, -1):
+            p.bouss_rkstep2(o, dt, nu, kappa, xmom, xtemp, impl=impl)
+            O.bouss_rkstep2(g, s, *C, o, dt, nu, kappa, xmom, xtemp)
+            got = p.bouss_get_state()
+            fields_close(got[:3], (s.vx, s.vy, s.vz))
+            phys_close(g, [got[4]], [s.th])
+            fields_close([got[4]], [s.th], tol=TOL_RECONTINUED)
+            assert rel(got[3][:, :, :nph], s.pr[:, :, :nph]) < 100 * TOL_FIELD
+    p.close()
+
+
+def case_mhd_substeps(lib, tables, shape, ord=2, nsteps=1, impl=0, dt=1e-3, nu=1e-3, mu=5e-3, b0=(0.0, 0.0, 0.0)):
+    """Per-substep spectral fields against the oracle (mhd_rkstep2.f90:3-84), conducting walls."""
+    g, p = make(lib, tables, *shape, ord=ord)
+    s = O.make_mhd_state(g)
+    p.mhd_put_state(s.vx, s.vy, s.vz, s.pr, s.ax, s.ay, s.az, s.fx, s.fy, s.fz, s.mx, s.my, s.mz)
+    nph = g.nz - g.Cz
+    for _ in range(nsteps):
+        p.mhd_rkstep1()
+        C = [q.copy() for q in (s.vx, s.vy, s.vz, s.ax, s.ay, s.az)]
+        for o in range(ord, 0, -1):
+            p.mhd_rkstep2(o, dt, nu, mu, b0, impl)
+            O.mhd_rkstep2(g, s, *C, o, dt, nu, mu, b0)
+            got = p.mhd_get_state()
+            fields_close(got[:3], (s.vx, s.vy, s.vz))
+            fields_close(got[4:7], (s.ax, s.ay, s.az))
+            assert rel(got[3][:, :, :nph], s.pr[:, :, :nph]) < 100 * TOL_FIELD
+            fields_close([got[7]], [s.ph], rows=nph, tol=100 * TOL_FIELD)
+    p.close()

@@ -51,3 +51,21 @@ def test_hd_substeps_rk4_moving_walls(emu_lib, tables):
 
 def test_hd_step_host(emu_lib, tables):
     P.case_hd_step_host(emu_lib, tables, SMALL)
+
+
+def test_advect_vector(emu_lib, tables):
+    P.case_advect_vector(emu_lib, tables, SMALL)
+
+
+def test_scalar_vecpot_bc(emu_lib, tables):
+    P.case_scalar_vecpot_bc(emu_lib, tables, SMALL)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_bouss_substeps(emu_lib, tables, impl):
+    P.case_bouss_substeps(emu_lib, tables, SMALL, ord=2, nsteps=1, impl=impl)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_mhd_substeps(emu_lib, tables, impl):
+    P.case_mhd_substeps(emu_lib, tables, SMALL, ord=2, nsteps=1, impl=impl)

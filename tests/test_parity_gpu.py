@@ -65,3 +65,29 @@ def test_hd_diagnostics_100_steps_cfg1(cuda_lib, tables):
         gold = json.load(f)
     rows = P.case_hd_diagnostics_100(cuda_lib, tables, CFG1, nsteps=100, ord=2, impl=0, golden=gold["rows"])
     assert rows.shape[0] == 10
+
+
+def test_advect_vector(cuda_lib, tables):
+    P.case_advect_vector(cuda_lib, tables, CFG1)
+
+
+def test_scalar_vecpot_bc(cuda_lib, tables):
+    P.case_scalar_vecpot_bc(cuda_lib, tables, CFG1)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_bouss_substeps_cfg1(cuda_lib, tables, impl):
+    P.case_bouss_substeps(cuda_lib, tables, CFG1, ord=2, nsteps=2, impl=impl)
+
+
+def test_bouss_substeps_rk4(cuda_lib, tables):
+    P.case_bouss_substeps(cuda_lib, tables, (128, 64, 128), ord=4, nsteps=1, impl=0)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_mhd_substeps_cfg1(cuda_lib, tables, impl):
+    P.case_mhd_substeps(cuda_lib, tables, CFG1, ord=2, nsteps=2, impl=impl)
+
+
+def test_mhd_substeps_rk4_uniform_field(cuda_lib, tables):
+    P.case_mhd_substeps(cuda_lib, tables, (64, 128, 128), ord=4, nsteps=1, impl=0, b0=(0.1, 0.0, 0.2))
