@@ -27,9 +27,17 @@ WORKLOADS = {
     "hd512": (512, 512, 512, 4, 2e-4, "HD channel flow 512x512x512 FP64 RK4, no-slip walls, FC-Gram C=25 d=5"),
     "hd256": (256, 256, 256, 4, 5e-4, "HD channel flow 256^3 FP64 RK4 (reduced; not the headline config)"),
     "hd64": (64, 64, 64, 2, 1e-3, "HD 64^3 RK2 (BASELINE configs[0], parity config)"),
+    "hd1024": (1024, 1024, 512, 4, 1e-4, "HD 1024x1024x512 FP64 RK4 (multi-GPU sizes; needs >= 4 GPUs)"),
+    "hd2048": (2048, 2048, 1024, 4, 5e-5, "HD 2048x2048x1024 FP64 RK4 (BASELINE configs[4]; needs 8 GPUs)"),
+    "bouss512": (512, 512, 512, 4, 2e-4, "BOUSS Rayleigh-Benard 512x512x512 FP64 RK4, no-slip + constant-temperature walls"),
+    "bouss1024": (1024, 1024, 512, 4, 1e-4, "BOUSS Rayleigh-Benard 1024x1024x512 FP64 RK4 (BASELINE configs[2]; needs 8 GPUs)"),
+    "mhd512": (512, 512, 512, 4, 2e-4, "MHD vector potential 512x512x512 FP64 RK4, no-slip + conducting walls (BASELINE configs[3])"),
 }
 CZ, OZ, NU = 25, 5, 1e-3
-B_ALG = 440.0  # algorithmic HBM bytes per grid-point-substep of the HD path (55 F, F = 8 B/pt)
+KAPPA, MU = 1e-3, 5e-3
+# algorithmic HBM bytes per grid-point-substep (55 F / 73 F / 98 F, F = 8 B/pt)
+B_ALG_BY_SOLVER = {"hd": 440.0, "bouss": 584.0, "mhd": 784.0}
+B_ALG = 440.0
 # algorithmic bytes per grid point of each pass (DESIGN.md "Kernels"): F = 8 B per point per full-field read or write
 def stage_bytes_per_pt(r):
     """r = physical rows / nz: only physical rows cross the transposition."""
@@ -139,6 +147,61 @@ def synthetic_state(plan, seed=1234):
     return host + [np.zeros((nxl, ny, nz), dtype=np.complex128)] + f
 
 
+def _low_modes(plan, seed, ncomp):
+    import numpy as np
+    nxl, ny, nz = plan.cshape
+    nph = nz - plan.Cz
+    rng = np.random.default_rng(seed + plan.ista)
+    z = np.arange(nph) / (nph - 1.0)
+    env = np.sin(np.pi * z) ** 2
+    N = float(plan.nx) * plan.ny * plan.nz
+    kmax = 4
+    out = []
+    for c in range(ncomp):
+        a = np.zeros((nxl, ny, nz), dtype=np.complex128)
+        for i in range(nxl):
+            kx = plan.ista - 1 + i
+            if kx > kmax:
+                break
+            for j in list(range(0, kmax + 1)) + list(range(ny - kmax, ny)):
+                if kx == 0 and j > ny // 2:
+                    continue
+                amp = (rng.standard_normal() + 1j * rng.standard_normal()) * (N / plan.nz) * 0.05
+                prof = env * np.cos(np.pi * (1 + (i + j + c) % 3) * z)
+                a[i, j, :nph] = amp * prof
+                if kx == 0:
+                    if j == 0:
+                        a[i, j, :nph] = (amp.real * prof)
+                    else:
+                        a[i, ny - j, :nph] = np.conj(a[i, j, :nph])
+        out.append(a)
+    return out
+
+
+def synthetic_scalar(plan, seed=4321):
+    """Temperature fluctuation with constant (zero) walls: low modes -> continued z-FFT -> sx_s_imposebc."""
+    d = plan.spectral(_low_modes(plan, seed, 1)[0])
+    plan.fftp1d_real_to_complex_z(d)
+    plan.s_imposebc(d)
+    h = d.get()
+    d.free()
+    return h
+
+
+def synthetic_potential(plan, seed=9876):
+    """Vector potential satisfying the conducting-wall conditions: low modes -> continued z-FFT ->
+    sx_a_imposebc_and_project."""
+    dev = [plan.spectral(a) for a in _low_modes(plan, seed, 3)]
+    for d in dev:
+        plan.fftp1d_real_to_complex_z(d)
+    ph = plan.spectral()
+    plan.a_imposebc_and_project(dev[0], dev[1], dev[2], ph)
+    host = [d.get() for d in dev]
+    for d in dev + [ph]:
+        d.free()
+    return host
+
+
 def cpu_oracle_substep_rate(nx, ny, nz, ord_, dt, reps=1, workers=None):
     """The oracle (numpy/scipy restatement of the reference's pass structure) timed on the host cores."""
     from oracle import specter_oracle as O
@@ -196,6 +259,25 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def emit(text):
+    """The one JSON line goes to the process's original stdout; everything else a library prints on fd 1
+    (e.g. NCCL's version banner) was redirected to stderr by quiet_stdout()."""
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -210,6 +292,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    quiet_stdout()
     if args.impl == "reference":
         return reference_arm(args, rank, world)
     args.warmup = max(args.warmup, 3)
@@ -224,11 +307,27 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx, ny, nz, ord_, dt, desc = WORKLOADS[args.workload]
+    solver = "bouss" if args.workload.startswith("bouss") else ("mhd" if args.workload.startswith("mhd") else "hd")
+    b_alg = B_ALG_BY_SOLVER[solver]
     plan = api.Plan(nx, ny, nz, CZ, OZ, ord=ord_, tdir=TABLES, nprocs=world, myrank=rank, device=local)
     if world > 1:
         plan.init_comm_torch(dist)
     st = synthetic_state(plan)
-    plan.hd_put_state(*st)
+    zero = np.zeros_like(st[0])
+    if solver == "hd":
+        plan.hd_put_state(*st)
+        step = lambda: plan.hd_step(dt, NU, impl=args.path)
+    elif solver == "bouss":
+        th = synthetic_scalar(plan)
+        plan.bouss_put_state(st[0], st[1], st[2], st[3], th, st[4], st[5], st[6], zero)
+        step = lambda: plan.bouss_step(dt, NU, KAPPA, impl=args.path)
+    else:
+        a = synthetic_potential(plan)
+        plan.mhd_put_state(st[0], st[1], st[2], st[3], a[0], a[1], a[2], zero, zero, zero, zero, zero, zero)
+        step = lambda: plan.mhd_step(dt, NU, MU, impl=args.path)
+    if solver != "hd":
+        args.no_e2e = True          # the host-buffer entry exists for the headline (HD) path
+        args.no_cpu_baseline = True
 
     def barrier():
         if world > 1:
@@ -237,7 +336,7 @@ def main():
         plan.synchronize()
 
     for _ in range(args.warmup):
-        plan.hd_step(dt, NU, impl=args.path)
+        step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -246,7 +345,7 @@ def main():
     barrier()
     plan.time_begin()
     for _ in range(args.steps):
-        plan.hd_step(dt, NU, impl=args.path)
+        step()
     ms = plan.time_end()
     barrier()
     launches = plan.launch_count - n0
@@ -260,17 +359,20 @@ def main():
     peak, peak_src = peaks()
 
     # ---- per-kernel device times (a separate, untimed-for-the-headline pass with stage events) ----
+    if world > 1:
+        plan.comm_stats(reset=True)
     plan.stage_timing(True)
     for _ in range(2):
-        plan.hd_step(dt, NU, impl=args.path)
+        step()
     stages = plan.stage_times()
     plan.stage_timing(False)
+    comm = plan.comm_stats() if world > 1 else None
     stage_report, dominant = {}, None
     tot_ms = sum(v[0] for v in stages.values()) or 1.0
     for name, (sms, cnt) in stages.items():
         per_launch = sms / cnt
         launches_per_substep = cnt / (2.0 * ord_)
-        bpp = stage_bytes_per_pt((nz - CZ) / nz).get(name)
+        bpp = stage_bytes_per_pt((nz - CZ) / nz).get(name) if solver == "hd" else None
         entry = {"ms_per_launch": per_launch, "launches_per_substep": launches_per_substep, "share": sms / tot_ms}
         if bpp:
             alg_bytes = bpp * npts / world / launches_per_substep
@@ -285,8 +387,12 @@ def main():
                 "frac": dom.get("frac_of_hbm_peak"), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom.get("algorithmic_bytes_per_launch"),
                 "avg_launch_ms": dom.get("ms_per_launch"),
-                "whole_substep": {"algorithmic_bytes_per_point": B_ALG,
-                                  "achieved": B_ALG * value / world / 1e9, "frac": B_ALG * value / world / 1e9 / peak}}
+                "whole_substep": {"algorithmic_bytes_per_point": b_alg,
+                                  "achieved": b_alg * value / world / 1e9, "frac": b_alg * value / world / 1e9 / peak}}
+    if solver != "hd":   # per-kernel byte model exists for the HD kernels only: report the whole substep
+        roofline.update(kernel="whole substep", achieved=roofline["whole_substep"]["achieved"],
+                        frac=roofline["whole_substep"]["frac"], algorithmic_bytes_per_launch=b_alg * npts / world,
+                        avg_launch_ms=ms / args.steps / ord_)
 
     # ---- end to end through the host-buffer C-ABI entry (H2D + ord substeps + D2H per step) ----
     e2e = None
@@ -330,7 +436,16 @@ def main():
                            "parallelism": f"slab x{world}"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "stages": stage_report}
-        print(json.dumps(line), flush=True)
+        if comm and comm["exchanges"] and comm["ms"] > 0:
+            # NVLink roofline: bytes this rank sent per exchange / device time of the exchange on the comm
+            # stream, measured un-overlapped in the stage-timing pass (sx_plan_comm_stats)
+            per_ex = comm["bytes_sent"] / comm["exchanges"]
+            ms_ex = comm["ms"] / comm["exchanges"]
+            line["nvlink"] = {"bytes_sent_per_exchange": per_ex, "ms_per_exchange": ms_ex,
+                              "exchanges_per_substep": comm["exchanges"] / (2.0 * ord_),
+                              "achieved_gbs_per_direction": per_ex / (ms_ex * 1e-3) / 1e9,
+                              "peak_gbs_per_direction": 900.0, "frac": per_ex / (ms_ex * 1e-3) / 1e9 / 900.0}
+        emit(json.dumps(line))
     plan.close()
     if world > 1:
         dist.destroy_process_group()
