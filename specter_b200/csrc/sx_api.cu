@@ -189,6 +189,7 @@ static int plan_init(Plan& p, const sx_config& c) {
   if (const char* e = getenv("SX_ZF")) p.knob_zf = atoi(e);
   if (const char* e = getenv("SX_XP")) p.knob_xp = atoi(e);
   if (const char* e = getenv("SX_PJ")) p.knob_pj = atoi(e);
+  if (const char* e = getenv("SX_TILE_PF")) p.knob_pf = atoi(e);
   if (const char* e = getenv("SX_TILE_NP")) p.knob_np = atoi(e);
   if (const char* e = getenv("SX_TILE_MINB")) p.knob_minb = atoi(e);
   p.red_blocks = 148 * 4;

@@ -79,7 +79,7 @@ struct ZinvArgs {
   int ny, nxl, nph;
 };
 
-template <int N, int NP, int MINB>
+template <int N, int NP, int MINB, bool PF>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zinv_tile(ZinvArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8, NT = NP * T;
@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zinv_tile(ZinvArgs a, cons
   const SIdxPencil si{p, NP};
   const int tiles_y = cdiv(a.ny, NP), ntiles = tiles_y * a.nxl;
   auto issue = [&](int t) {
+    if (!PF) return;
     const int ky = (t % tiles_y) * NP + p, kxl = t / tiles_y;
     if (ky < a.ny) {
       const cplx* src = a.in + ((size_t)kxl * a.ny + ky) * N + j;
@@ -107,13 +108,14 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zinv_tile(ZinvArgs a, cons
   for (; t < ntiles; t += gridDim.x) {
     const int ky = (t % tiles_y) * NP + p, kxl = t / tiles_y;
     const bool active = ky < a.ny;
+    const cplx* src = a.in + ((size_t)kxl * a.ny + (active ? ky : 0)) * N + j;
     cplx v[8];
-    cp_async_wait_all();
+    if (PF) cp_async_wait_all();
     if (a.out1 != nullptr) {
-      // derivative first: the slots still hold this tile
+      // derivative first: the slots (or L1) still hold this tile
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const cplx q = slot[k * NT];
+        const cplx q = PF ? slot[k * NT] : (active ? src[k * T] : cmake(0.0, 0.0));
         const double kk = __ldg(&a.kz[j + k * T]);
         v[k] = cmake(-kk * q.y, kk * q.x);
       }
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zinv_tile(ZinvArgs a, cons
       }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+    for (int k = 0; k < 8; ++k) v[k] = PF ? slot[k * NT] : (active ? src[k * T] : cmake(0.0, 0.0));
     if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
     fft_regs<N, 1>(v, j, smem, si, tw);
 #pragma unroll
@@ -153,7 +155,7 @@ struct YinvArgs {
   int nxh, nxp, nzf;
 };
 
-template <int N, int NP, int MINB>
+template <int N, int NP, int MINB, bool PF>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yinv_tile(YinvArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8, NT = NP * T;
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yinv_tile(YinvArgs a, cons
   const SIdxPencil si{p, NP};
   const int tiles_x = cdiv(a.nxp, NP), ntiles = tiles_x * a.nzf;
   auto issue = [&](int t) {
+    if (!PF) return;
     const int kx = (t % tiles_x) * NP + p, zl = t / tiles_x;
     if (kx < a.nxh) {
       const cplx* src = a.in + ((size_t)kx * a.nzf + zl) * N + j;
@@ -177,14 +180,15 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yinv_tile(YinvArgs a, cons
   if (t < ntiles) issue(t);
   for (; t < ntiles; t += gridDim.x) {
     const int kx = (t % tiles_x) * NP + p, zl = t / tiles_x;
-    const bool store = kx < a.nxp;
+    const bool store = kx < a.nxp, load = kx < a.nxh;
     const size_t dst = (size_t)zl * N * a.nxp + kx;
+    const cplx* src = a.in + ((size_t)(load ? kx : 0) * a.nzf + zl) * N + j;
     cplx v[8];
-    cp_async_wait_all();
+    if (PF) cp_async_wait_all();
     if (a.out1 != nullptr) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const cplx q = slot[k * NT];
+        const cplx q = PF ? slot[k * NT] : (load ? src[k * T] : cmake(0.0, 0.0));
         const double kk = __ldg(&a.ky[j + k * T]);
         v[k] = cmake(-kk * q.y, kk * q.x);
       }
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yinv_tile(YinvArgs a, cons
       }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+    for (int k = 0; k < 8; ++k) v[k] = PF ? slot[k * NT] : (load ? src[k * T] : cmake(0.0, 0.0));
     if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
     fft_regs<N, 1>(v, j, smem, si, tw);
     if (store) {
@@ -214,7 +218,7 @@ struct YfwdArgs {
   int nxh, nxp, nzf;
 };
 
-template <int N, int NP, int MINB>
+template <int N, int NP, int MINB, bool PF>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tile(YfwdArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8, NT = NP * T;
@@ -222,6 +226,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tile(YfwdArgs a, cons
   cplx* slot = smem + (size_t)NP * N + threadIdx.x;
   const int tiles_x = cdiv(a.nxh, NP), ntiles = tiles_x * a.nzf;
   auto issue = [&](int t) {
+    if (!PF) return;
     const int kx = (t % tiles_x) * NP + p, zl = t / tiles_x;
     if (kx < a.nxh) {
       const cplx* src = a.in + ((size_t)zl * N + j) * a.nxp + kx;
@@ -238,9 +243,15 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tile(YfwdArgs a, cons
   for (; t < ntiles; t += gridDim.x) {
     const int kx = (t % tiles_x) * NP + p, zl = t / tiles_x;
     cplx v[8];
-    cp_async_wait_all();
+    if (PF) {
+      cp_async_wait_all();
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+      for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+    } else {
+      const cplx* src = a.in + ((size_t)zl * N + j) * a.nxp + (kx < a.nxh ? kx : 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = kx < a.nxh ? src[(size_t)k * T * a.nxp] : cmake(0.0, 0.0);
+    }
     if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
     fft_regs<N, -1>(v, j, smem, SIdxPencil{p, NP}, tw);
     if (kx < a.nxh) {
@@ -573,7 +584,7 @@ __device__ __forceinline__ void stash_boundary_tile(const cplx (&v)[8], int j, i
   }
 }
 
-template <int N, int NP, int MINB, bool HOIST>
+template <int N, int NP, int MINB, bool HOIST, bool PF>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8, NT = NP * T;
@@ -585,6 +596,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
   __syncthreads();
   const int tiles_y = cdiv(a.ny, NP), ntiles = tiles_y * a.nxl;
   auto issue = [&](int t) {
+    if (!PF) return;
     const int ky = (t % tiles_y) * NP + p, kxl = t / tiles_y;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -604,9 +616,21 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
     const int ky = (t % tiles_y) * NP + p, kxl = t / tiles_y;
     const bool active = ky < a.ny;
     cplx v[8];
-    cp_async_wait_all();
+    if (PF) {
+      cp_async_wait_all();
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+      for (int k = 0; k < 8; ++k) v[k] = slot[k * NT];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int z = j + k * T;
+        v[k] = cmake(0.0, 0.0);
+        if (active && z < a.nph) {
+          const ZMap m = zm[z];
+          v[k] = a.nl[m.base + ((long long)kxl * m.nzl + m.zl) * a.ny + ky];
+        }
+      }
+    }
     if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
     // the three spectral pencils of the RK update: issued before the transform so that their latency
     // is covered by it (HOIST), or loaded at the point of use
@@ -986,11 +1010,17 @@ template <int N> static int run_zinv(Plan& p, Fused& f, const cplx* in, cplx* ou
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
   ZinvArgs a{in, out0, out1, p.d_kz, f.d_zmap, p.ny, p.nxl, f.nph};
   const cplx* tw = p.tw_z;
-  auto kfn = k_zinv_tile<N, NP, MINB>;
   const size_t smem = (size_t)2 * NP * N * sizeof(cplx) + (size_t)N * sizeof(ZMap);
   int grid;
-  if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
-  SX_FUSED_LAUNCH(p, ST_ZINV, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  if (p.knob_pf & 1) {
+    auto kfn = k_zinv_tile<N, NP, MINB, true>;
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
+    SX_FUSED_LAUNCH(p, ST_ZINV, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  } else {
+    auto kfn = k_zinv_tile<N, NP, MINB, false>;
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
+    SX_FUSED_LAUNCH(p, ST_ZINV, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  }
   return 0;
 }
 template <int N> static int run_yinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
@@ -998,11 +1028,18 @@ template <int N> static int run_yinv(Plan& p, Fused& f, const cplx* in, cplx* ou
   if (f.nzf == 0) return 0;
   YinvArgs a{in, out0, out1, p.d_ky, p.nxh, f.nxp, f.nzf};
   const cplx* tw = p.tw_y;
-  auto kfn = k_yinv_tile<N, NP, MINB>;
-  const size_t smem = (size_t)2 * NP * N * sizeof(cplx);
   int grid;
-  if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(f.nxp, NP) * f.nzf, &grid)) return 1;
-  SX_FUSED_LAUNCH(p, ST_YINV, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  if (p.knob_pf & 2) {
+    auto kfn = k_yinv_tile<N, NP, MINB, true>;
+    const size_t smem = (size_t)2 * NP * N * sizeof(cplx);
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(f.nxp, NP) * f.nzf, &grid)) return 1;
+    SX_FUSED_LAUNCH(p, ST_YINV, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  } else {
+    auto kfn = k_yinv_tile<N, NP, MINB, false>;
+    const size_t smem = (size_t)NP * N * sizeof(cplx);
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(f.nxp, NP) * f.nzf, &grid)) return 1;
+    SX_FUSED_LAUNCH(p, ST_YINV, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  }
   return 0;
 }
 template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* out) {
@@ -1010,11 +1047,18 @@ template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* ou
   if (f.nzf == 0) return 0;
   YfwdArgs a{in, out, p.nxh, f.nxp, f.nzf};
   const cplx* tw = p.tw_y;
-  auto kfn = k_yfwd_tile<N, NP, MINB>;
-  const size_t smem = (size_t)2 * NP * N * sizeof(cplx);
   int grid;
-  if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.nxh, NP) * f.nzf, &grid)) return 1;
-  SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  if (p.knob_pf & 4) {
+    auto kfn = k_yfwd_tile<N, NP, MINB, true>;
+    const size_t smem = (size_t)2 * NP * N * sizeof(cplx);
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.nxh, NP) * f.nzf, &grid)) return 1;
+    SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  } else {
+    auto kfn = k_yfwd_tile<N, NP, MINB, false>;
+    const size_t smem = (size_t)NP * N * sizeof(cplx);
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.nxh, NP) * f.nzf, &grid)) return 1;
+    SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  }
   return 0;
 }
 template <int N, int LP, bool PF, int MINB, int NC> static int run_xpass_v(Plan& p, Fused& f, const double* d_kx_global) {
@@ -1043,11 +1087,14 @@ template <int N, int NC> static int run_xpass(Plan& p, Fused& f, const double* d
   if constexpr (N == 512 && NC == 3) {
     switch (p.knob_xp) {
       case 1: return run_xpass_v<N, 1, true, 4, NC>(p, f, d_kx_global);
-      case 2: return run_xpass_v<N, 1, false, 6, NC>(p, f, d_kx_global);
+      case 2: return run_xpass_v<N, 2, true, 2, NC>(p, f, d_kx_global);
       case 3: return run_xpass_v<N, 2, false, 3, NC>(p, f, d_kx_global);
       case 4: return run_xpass_v<N, 1, false, 4, NC>(p, f, d_kx_global);
       default: break;
     }
+  }
+  if constexpr (N == 512) {   // measured best on B200 (profiles/r1h_knobs.md): one pair per CTA, direct loads
+    if (p.knob_xp == 0) return run_xpass_v<N, 1, false, 6, NC>(p, f, d_kx_global);
   }
   return run_xpass_v<N, LP, true, (N <= 1024 ? 2 : 1), NC>(p, f, d_kx_global);
 }
@@ -1093,14 +1140,20 @@ template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, const
   const size_t smem = ((size_t)2 * NP * N + (size_t)2 * kMaxDF * NP) * sizeof(cplx) + (size_t)N * sizeof(ZMap);
   int grid;
   if (N == 512 && p.knob_zf == 1) {
-    auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), true>;
+    auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), true, true>;
     if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
     SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
     return 0;
   }
-  auto kfn = k_zfwd_rk<N, NP, MINB, false>;
-  if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
-  SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  if (p.knob_pf & 8) {
+    auto kfn = k_zfwd_rk<N, NP, MINB, false, true>;
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
+    SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  } else {
+    auto kfn = k_zfwd_rk<N, NP, MINB, false, false>;
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
+    SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+  }
   return 0;
 }
 template <int N, int NPB, bool PF, int MINB> static int run_project_v(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
@@ -1127,12 +1180,15 @@ template <int N> static int run_project(Plan& p, Fused& f, cplx* vx, cplx* vy, c
   constexpr int NPB = T >= 128 ? 1 : 128 / T;
   if constexpr (N == 512) {
     switch (p.knob_pj) {
-      case 1: return run_project_v<N, 1, true, 6>(p, f, vx, vy, vz, pr, o, zs, ze);
+      case 1: return run_project_v<N, 2, true, 3>(p, f, vx, vy, vz, pr, o, zs, ze);
       case 2: return run_project_v<N, 1, false, 8>(p, f, vx, vy, vz, pr, o, zs, ze);
       case 3: return run_project_v<N, 2, false, 4>(p, f, vx, vy, vz, pr, o, zs, ze);
       case 4: return run_project_v<N, 1, true, 8>(p, f, vx, vy, vz, pr, o, zs, ze);
       default: break;
     }
+  }
+  if constexpr (N == 512) {   // measured best on B200 (profiles/r1h_knobs.md): one pencil per CTA
+    if (p.knob_pj == 0) return run_project_v<N, 1, true, 6>(p, f, vx, vy, vz, pr, o, zs, ze);
   }
   return run_project_v<N, NPB, true, (N <= 512 ? 3 : 1)>(p, f, vx, vy, vz, pr, o, zs, ze);
 }

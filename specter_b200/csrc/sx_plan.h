@@ -62,6 +62,7 @@ struct Plan {
   int num_sms = 148;                // multiProcessorCount of the device
   int knob_zf = 0;
   int knob_xp = 0, knob_pj = 0;     // kernel-variant experiments (env SX_XP, SX_PJ)
+  int knob_pf = 13;                 // cp.async prefetch per tile kernel: bit 0 zinv, 1 yinv, 2 yfwd, 3 zfwd (env SX_TILE_PF)
   int knob_np = 0, knob_minb = 1;   // tuning experiments (env SX_TILE_NP, SX_TILE_MINB)
   unsigned long long launches = 0;  // kernels launched by this plan (bench "gpu_launches")
 
