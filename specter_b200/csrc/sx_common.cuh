@@ -35,6 +35,58 @@ inline void cp_async_commit() {}
 inline void cp_async_wait_all() {}
 #endif
 
+// ---- bulk asynchronous copies (TMA, cp.async.bulk) global -> shared, completion on an mbarrier ------------
+// One elected thread issues a copy of a whole contiguous row block; the data lands in shared memory without
+// passing through the SM's load/store pipe or the register file, so a ring of stages keeps tens of KB per SM
+// in flight at two warps per CTA.  bytes: multiple of 16; both addresses 16-byte aligned.
+#ifndef SX_EMU
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+// several copies completing on one barrier: expect the total first, then issue the pieces
+__device__ __forceinline__ void mbar_expect(unsigned long long* bar, unsigned bytes) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load_piece(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+// pull a contiguous range into L2 ahead of the loads that will use it (no shared memory, no registers)
+__device__ __forceinline__ void l2_prefetch(const void* gsrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SX_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SX_DONE_%=;\n"
+      "bra SX_WAIT_%=;\n"
+      "SX_DONE_%=:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+#else
+inline void mbar_init(unsigned long long*, unsigned) {}
+inline void mbar_init_fence() {}
+inline void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long*) { memcpy(smem_dst, gsrc, bytes); }
+inline void mbar_expect(unsigned long long*, unsigned) {}
+inline void bulk_load_piece(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long*) { memcpy(smem_dst, gsrc, bytes); }
+inline void mbar_wait(unsigned long long*, unsigned) {}
+inline void l2_prefetch(const void*, unsigned) {}
+#endif
+
 __host__ __device__ __forceinline__ cplx cmake(double x, double y) { return make_double2(x, y); }
 __host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }

@@ -35,9 +35,18 @@ struct SIdxElem {
 };
 template <int N> constexpr int sidx_elem_stride() { return N + N / 8; }
 // pencil-fastest: NP pencils interleaved (conflict free when NP % 8 == 0)
+// With np == 4 a quarter-warp covers two butterflies whose first-pass scatter addresses differ by a multiple
+// of 128 B (2-way conflict); flipping the low element bit with bit 3 separates them and leaves the gathers and
+// the second scatter conflict free -- but costs address arithmetic in the 80-register tile kernels and measured
+// 3-15 % SLOWER on B200 (profiles/r1i_session4.md), so it is off unless built with -DSX_SWIZZLE.
 struct SIdxPencil {
   int p, np;
-  __device__ __forceinline__ int operator()(int e) const { return e * np + p; }
+  __device__ __forceinline__ int operator()(int e) const {
+#ifdef SX_SWIZZLE
+    if (np == 4) e ^= (e >> 3) & 1;
+#endif
+    return e * np + p;
+  }
 };
 
 // ---- small in-register DFTs (natural order in/out) ---------------------------------
@@ -94,9 +103,48 @@ template <int R, int DIR> __device__ __forceinline__ void butterflies(cplx (&v)[
   }
 }
 
-template <int N, int DIR, int P, class SI>
+// ---- twiddles ------------------------------------------------------------------------------
+// The twiddle of (pass P, butterfly b, leg m) is w1^m with w1 = exp(-2 pi i q /(Ns*r)), and q only
+// depends on the thread (q = (j + b*T) mod Ns).  TwRegs keeps the w1 of every pass in registers
+// (loaded once per kernel, N=512: two complex values) and the passes generate the powers with
+// 21 flops instead of loading r-1 table entries: the table loads were ~17 % of the L1/shared
+// pipe traffic of every kernel (profiles/r1h_knobs.md), the FP64 pipe has the headroom.
+template <int N> struct TwSlots {
+  typedef Fft1D<N> F;
+  static constexpr int nb(int p) { return 8 / F::radix(p); }
+  static constexpr int off(int p) { int o = 0; for (int q = 1; q < p; ++q) o += nb(q); return o; }
+  static constexpr int count = off(F::npass) > 0 ? off(F::npass) : 1;
+};
+template <int N> struct TwRegs {
+  cplx w[TwSlots<N>::count];
+  const cplx* table;
+  template <int P> __device__ __forceinline__ void load_pass(const cplx* __restrict__ tw, int j) {
+    typedef Fft1D<N> F;
+    if constexpr (P < F::npass) {
+      constexpr int r = F::radix(P), nb = 8 / r, Ns = F::ns(P);
+#pragma unroll
+      for (int b = 0; b < nb; ++b) w[TwSlots<N>::off(P) + b] = __ldg(&tw[F::twoff(P) + ((j + b * F::T) & (Ns - 1))]);
+      load_pass<P + 1>(tw, j);
+    }
+  }
+  __device__ __forceinline__ void load(const cplx* __restrict__ tw, int j) {
+    table = tw;
+    load_pass<1>(tw, j);
+  }
+};
+__device__ __forceinline__ cplx csqr(cplx a) { return cmake(fma(a.x, a.x, -(a.y * a.y)), (a.x + a.x) * a.y); }
+
+// Hook: code run by every thread right before / after the first barrier of a transform (the point where the
+// inputs of all threads have been consumed and the exchange buffer is about to be overwritten); the bulk-copy
+// kernels use it to wait for an asynchronous store that still reads the buffer and to start the next load.
+struct NoHook {
+  __device__ __forceinline__ void before_sync() const {}
+  __device__ __forceinline__ void after_sync() const {}
+};
+
+template <int N, int DIR, int P, class SI, class Hook>
 __device__ __forceinline__ void fft_pass(cplx (&v)[8], const int j, cplx* s, const SI& si,
-                                         const cplx* __restrict__ tw) {
+                                         const cplx* __restrict__ tw, const TwRegs<N>* twr, const Hook& hook) {
   typedef Fft1D<N> F;
   constexpr int r = F::radix(P), nb = 8 / r, Ns = F::ns(P), T = F::T;
   constexpr bool first = (P == 0), last = (P == F::npass - 1);
@@ -109,18 +157,38 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[8], const int j, cplx* s, con
     }
 #pragma unroll
     for (int b = 0; b < nb; ++b) {
-      const int q = (j + b * T) & (Ns - 1);
+      if (twr != nullptr) {
+        cplx w1 = twr->w[TwSlots<N>::off(P) + b];
+        if (DIR > 0) w1.y = -w1.y;
+        v[b + nb] = cmul(v[b + nb], w1);
+        if constexpr (r >= 4) {
+          const cplx w2 = csqr(w1), w3 = cmul(w2, w1);
+          v[b + 2 * nb] = cmul(v[b + 2 * nb], w2);
+          v[b + 3 * nb] = cmul(v[b + 3 * nb], w3);
+          if constexpr (r == 8) {
+            const cplx w4 = csqr(w2), w5 = cmul(w4, w1), w6 = csqr(w3), w7 = cmul(w4, w3);
+            v[b + 4 * nb] = cmul(v[b + 4 * nb], w4);
+            v[b + 5 * nb] = cmul(v[b + 5 * nb], w5);
+            v[b + 6 * nb] = cmul(v[b + 6 * nb], w6);
+            v[b + 7 * nb] = cmul(v[b + 7 * nb], w7);
+          }
+        }
+      } else {
+        const int q = (j + b * T) & (Ns - 1);
 #pragma unroll
-      for (int m = 1; m < r; ++m) {
-        cplx w = __ldg(&tw[toff + (m - 1) * Ns + q]);
-        if (DIR > 0) w.y = -w.y;
-        v[b + m * nb] = cmul(v[b + m * nb], w);
+        for (int m = 1; m < r; ++m) {
+          cplx w = __ldg(&tw[toff + (m - 1) * Ns + q]);
+          if (DIR > 0) w.y = -w.y;
+          v[b + m * nb] = cmul(v[b + m * nb], w);
+        }
       }
     }
   }
   butterflies<r, DIR>(v);
   if (!last) {
+    if (first) hook.before_sync();
     __syncthreads();  // WAR: everybody has finished reading this buffer
+    if (first) hook.after_sync();
 #pragma unroll
     for (int b = 0; b < nb; ++b) {
       const int jb = j + b * T;
@@ -132,11 +200,11 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[8], const int j, cplx* s, con
   }
 }
 
-template <int N, int DIR, int P, class SI>
+template <int N, int DIR, int P, class SI, class Hook>
 __device__ __forceinline__ void fft_run(cplx (&v)[8], int j, cplx* s, const SI& si,
-                                        const cplx* __restrict__ tw) {
-  fft_pass<N, DIR, P, SI>(v, j, s, si, tw);
-  if constexpr (P + 1 < Fft1D<N>::npass) fft_run<N, DIR, P + 1, SI>(v, j, s, si, tw);
+                                        const cplx* __restrict__ tw, const TwRegs<N>* twr, const Hook& hook) {
+  fft_pass<N, DIR, P, SI, Hook>(v, j, s, si, tw, twr, hook);
+  if constexpr (P + 1 < Fft1D<N>::npass) fft_run<N, DIR, P + 1, SI, Hook>(v, j, s, si, tw, twr, hook);
 }
 
 // v[k] <-> element j + k*T on entry and exit.  `s` is this CTA's exchange buffer; every
@@ -147,7 +215,22 @@ __device__ __forceinline__ void fft_regs(cplx (&v)[8], int j, cplx* s, const SI&
 #ifdef SX_NOFFT  // timing experiment only (tools/gpu_nofft.sh): data movement without the transforms
   (void)v; (void)j; (void)s; (void)si; (void)tw;
 #else
-  fft_run<N, DIR, 0, SI>(v, j, s, si, tw);
+  fft_run<N, DIR, 0, SI, NoHook>(v, j, s, si, tw, nullptr, NoHook());
+#endif
+}
+// same, twiddles from registers (SX_TW_TABLE: build-time switch back to the table, for A/B timing)
+template <int N, int DIR, class SI, class Hook = NoHook>
+__device__ __forceinline__ void fft_regs(cplx (&v)[8], int j, cplx* s, const SI& si, const TwRegs<N>& twr,
+                                         const Hook& hook = Hook()) {
+#ifdef SX_NOFFT
+  (void)v; (void)j; (void)s; (void)si; (void)twr;
+  hook.before_sync();
+  __syncthreads();
+  hook.after_sync();
+#elif defined(SX_TW_TABLE)
+  fft_run<N, DIR, 0, SI, Hook>(v, j, s, si, twr.table, nullptr, hook);
+#else
+  fft_run<N, DIR, 0, SI, Hook>(v, j, s, si, twr.table, &twr, hook);
 #endif
 }
 

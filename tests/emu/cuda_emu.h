@@ -155,6 +155,10 @@ static inline void __syncthreads() { emu::yield(); }
 #define SX_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::t_worker->smem)
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline void sincospi(double x, double* s, double* c) {
+  *s = std::sin(3.14159265358979323846 * x);
+  *c = std::cos(3.14159265358979323846 * x);
+}
 static inline double atomicAdd(double* addr, double v) {
   std::atomic_ref<double> r(*addr);
   double old = r.load();

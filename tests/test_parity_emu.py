@@ -69,3 +69,26 @@ def test_bouss_substeps(emu_lib, tables, impl):
 @pytest.mark.parametrize("impl", [1, 0])
 def test_mhd_substeps(emu_lib, tables, impl):
     P.case_mhd_substeps(emu_lib, tables, SMALL, ord=2, nsteps=1, impl=impl)
+
+
+def test_hd_substeps_bulk_xpass(emu_lib, tables, monkeypatch):
+    # the bulk-copy (TMA ring) x pass is the default from nx = 256; force it on a small grid
+    monkeypatch.setenv("SX_XP", "10")
+    P.case_hd_substeps(emu_lib, tables, (64, 16, 64), ord=2, nsteps=1, impl=1)
+
+
+def test_bouss_substeps_bulk_xpass(emu_lib, tables, monkeypatch):
+    monkeypatch.setenv("SX_XP", "10")
+    P.case_bouss_substeps(emu_lib, tables, (64, 16, 64), ord=2, nsteps=1, impl=1)
+
+
+def test_hd_substeps_bulk_tiles(emu_lib, tables, monkeypatch):
+    # the bulk-copy (TMA) tile kernels are the default from length 256; force them on a small grid
+    monkeypatch.setenv("SX_TMA_MIN", "16")
+    P.case_hd_substeps(emu_lib, tables, (16, 128, 128), ord=2, nsteps=1, impl=0)
+
+
+def test_hd_substeps_bulk_project(emu_lib, tables, monkeypatch):
+    # bulk-copy projection kernel (default from nz = 256): wall rows by reduction, exponentials by recurrence
+    monkeypatch.setenv("SX_PJ", "10")
+    P.case_hd_substeps(emu_lib, tables, (16, 16, 256), ord=2, nsteps=2, impl=0, walls=((0.2, -0.1), (-0.3, 0.1)))

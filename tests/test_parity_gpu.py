@@ -91,3 +91,18 @@ def test_mhd_substeps_cfg1(cuda_lib, tables, impl):
 
 def test_mhd_substeps_rk4_uniform_field(cuda_lib, tables):
     P.case_mhd_substeps(cuda_lib, tables, (64, 128, 128), ord=4, nsteps=1, impl=0, b0=(0.1, 0.0, 0.2))
+
+
+def test_hd_substeps_length_512_kernels(cuda_lib, tables):
+    """The kernel instantiations the 512^3 bench runs (length-512 transforms along each axis in turn, bulk-copy
+    x pass from nx = 256), on grids small enough for the oracle."""
+    P.case_hd_substeps(cuda_lib, tables, (512, 16, 64), ord=2, nsteps=1, impl=0)
+    P.case_hd_substeps(cuda_lib, tables, (16, 512, 64), ord=2, nsteps=1, impl=0)
+    P.case_hd_substeps(cuda_lib, tables, (16, 16, 512), ord=2, nsteps=1, impl=0)
+    P.case_hd_substeps(cuda_lib, tables, (256, 32, 128), ord=4, nsteps=1, impl=0)
+
+
+def test_bouss_mhd_substeps_long_x(cuda_lib, tables):
+    P.case_bouss_substeps(cuda_lib, tables, (256, 32, 64), ord=2, nsteps=1, impl=0)
+    P.case_bouss_substeps(cuda_lib, tables, (512, 16, 64), ord=2, nsteps=1, impl=0)
+    P.case_mhd_substeps(cuda_lib, tables, (256, 32, 64), ord=2, nsteps=1, impl=0)
