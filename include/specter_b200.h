@@ -65,6 +65,16 @@ int sx_plan_stage_times(sx_plan* plan, double* ms, long long* counts, int n);
  * (MPI_BCAST in the Fortran driver, torch.distributed in the Python harness) */
 int sx_nccl_unique_id(void* id128);
 int sx_plan_set_comm(sx_plan* plan, const void* id128);
+/* Peer-to-peer slab exchange for one process per GPU on an NVLink / NVSwitch node.  The receive buffers of the
+ * fused substep (n_inverse fields on the way to real space, n_forward on the way back; HD 6/3, BOUSS 8/4,
+ * MHD 12/6) live in one device allocation per rank.  sx_plan_p2p_export creates it and writes its 64-byte CUDA
+ * IPC handle; the caller gathers the handles of all ranks (MPI_ALLGATHER in the Fortran driver,
+ * torch.distributed in the Python harness) and passes the nprocs x 64 bytes to sx_plan_p2p_import.  From then on
+ * every block of the all-to-all-v is written straight into the destination GPU's buffer by the copy engines and
+ * NCCL only carries the completion barrier; without these calls the blocks travel as ncclSend/ncclRecv.
+ * Replaces the MPI_ISEND/MPI_IRECV ring of fftp/fftp.fpp:478-499, 887-907. */
+int sx_plan_p2p_export(sx_plan* plan, int n_inverse, int n_forward, void* handle64);
+int sx_plan_p2p_import(sx_plan* plan, const void* handles);
 /* Alternative transport (e.g. CUDA-aware MPI_Alltoallv / MPI_Allreduce from the Fortran driver, or
  * torch.distributed in the test-suite).  Buffers are device pointers, displacements and counts are in
  * BYTES per peer rank; the all-reduce sums n doubles in a host array in place.  Return 0 on success. */

@@ -58,6 +58,8 @@ SIGNATURES = {
     "sx_plan_stage_times": [_P, _PD, C.POINTER(C.c_longlong), _I],
     "sx_nccl_unique_id": [_D],
     "sx_plan_set_comm": [_P, _D],
+    "sx_plan_p2p_export": [_P, _I, _I, _D],
+    "sx_plan_p2p_import": [_P, _D],
     "sx_plan_set_comm_callbacks": [_P, _D, _D, _D],
     "sx_plan_comm_stats": [_P, _PD, _PD, C.POINTER(C.c_longlong), _I],
     "sx_malloc": [_P, C.c_size_t, C.POINTER(_D)],
@@ -211,6 +213,7 @@ class Plan:
     def __init__(self, nx, ny, nz, Cz, oz, ord=2, Lx=1.0, Ly=1.0, Lz=1.0, tdir="", nprocs=1, myrank=0,
                  device=-1, lib: Optional[Library] = None):
         self.lib = lib or load_library()
+        self.p2p = False
         self.cfg = sx_config(nx, ny, nz, Cz, oz, ord, Lx, Ly, Lz, tdir.encode(), nprocs, myrank, device)
         self.handle = C.c_void_p()
         self.lib.check(self.lib.dll.sx_plan_create(C.byref(self.cfg), C.byref(self.handle)))
@@ -247,7 +250,7 @@ class Plan:
         return out
 
     # ---- multi-GPU ----
-    def init_comm_torch(self, dist):
+    def init_comm_torch(self, dist, p2p=True, p2p_fields=(12, 6)):
         """Create the plan's own NCCL communicator; the 128-byte unique id travels over the caller's
         torch.distributed group (the Fortran driver would MPI_BCAST it)."""
         import torch
@@ -260,6 +263,21 @@ class Plan:
         dist.broadcast(t, src=0)
         raw = bytes(t.cpu().tolist())
         self._call("sx_plan_set_comm", C.c_char_p(raw))
+        if p2p and dist.get_backend() == "nccl" and os.environ.get("SX_P2P", "1") != "0":
+            self.init_p2p_torch(dist, *p2p_fields)
+
+    def init_p2p_torch(self, dist, n_inverse=6, n_forward=3):
+        """Peer-to-peer exchange buffers: export this rank's receive arena, all-gather the 64-byte CUDA IPC
+        handles over the caller's group, map the peers' arenas (sx_plan_p2p_export / sx_plan_p2p_import)."""
+        import torch
+        buf = (C.c_char * 64)()
+        self._call("sx_plan_p2p_export", n_inverse, n_forward, buf)
+        mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8).cuda()
+        allh = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(allh, mine)
+        raw = b"".join(bytes(h.cpu().tolist()) for h in allh)
+        self._call("sx_plan_p2p_import", C.c_char_p(raw))
+        self.p2p = True
 
     def set_comm_callbacks(self, alltoallv, allreduce):
         """Route the slab exchange through caller code: alltoallv(send_ptr, sdispl, scount, recv_ptr,

@@ -12,6 +12,7 @@
 // A caller may instead install callbacks (sx_plan_set_comm_callbacks): the Fortran/MPI driver can
 // route the blocks through CUDA-aware MPI_Alltoallv, and the CPU test-suite routes them through
 // torch.distributed/gloo under the kernel emulation.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -35,6 +36,10 @@ struct Comm {
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   double* d_scal = nullptr;
   double* h_scal = nullptr;
+  float* d_bar = nullptr;   // payload of the completion barrier of the peer-to-peer exchange
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // extra copy streams: one copy engine does not fill NVLink
+  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+  int nsplit = 2;
   // accounting for the NVLink roofline
   double bytes_sent = 0.0, ms = 0.0;
   long long exchanges = 0;
@@ -54,6 +59,12 @@ int comm_free(Plan& p) {
   if (c->t1) cudaEventDestroy(c->t1);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->d_scal) cudaFree(c->d_scal);
+  if (c->d_bar) cudaFree(c->d_bar);
+  for (int i = 0; i < 3; ++i) {
+    if (c->side[i]) cudaStreamDestroy(c->side[i]);
+    if (c->join[i]) cudaEventDestroy(c->join[i]);
+  }
+  if (c->fork) cudaEventDestroy(c->fork);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   delete c;
   p.comm = nullptr;
@@ -72,6 +83,14 @@ static int comm_get(Plan& p, Comm** out) {
     SX_CUDA_CHECK(cudaEventCreate(&c->t0));
     SX_CUDA_CHECK(cudaEventCreate(&c->t1));
     SX_CUDA_CHECK(cudaMalloc((void**)&c->d_scal, 64 * sizeof(double)));
+    SX_CUDA_CHECK(cudaMalloc((void**)&c->d_bar, 64));
+    SX_CUDA_CHECK(cudaMemset(c->d_bar, 0, 64));
+    for (int i = 0; i < 3; ++i) {
+      SX_CUDA_CHECK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+      SX_CUDA_CHECK(cudaEventCreate(&c->join[i]));
+    }
+    SX_CUDA_CHECK(cudaEventCreate(&c->fork));
+    if (const char* e = getenv("SX_P2P_SPLIT")) c->nsplit = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
     SX_CUDA_CHECK(cudaMallocHost((void**)&c->h_scal, 64 * sizeof(double)));
   }
   *out = p.comm;
@@ -141,6 +160,67 @@ int exchange_begin(Plan& p, int ev, const cplx* send, cplx* recv, const size_t* 
   return 0;
 #else
   SX_REQUIRE(false, "the emulated build has no NCCL: install callbacks with sx_plan_set_comm_callbacks");
+#endif
+}
+
+// The same all-to-all-v with the payload moved by the copy engines: block r of `send` goes straight into rank r's
+// receive buffer (peer_dst[r], an IPC-mapped pointer that already includes this rank's displacement there).  The
+// copies use no SM and run at NVLink speed next to the transforms of the next field; a one-word NCCL all-reduce
+// behind them on the same stream is the completion barrier: when it returns on this rank, every rank has
+// finished the copies it enqueued before it, so everything addressed to this rank has landed.  The same chain of
+// barriers orders the reuse of a receive buffer in the next substep after its readers of this one.
+int exchange_begin_p2p(Plan& p, int ev, const cplx* send, const size_t* sdispl, const size_t* scount, cplx* const* peer_dst) {
+#ifndef SX_EMU
+  SX_REQUIRE(p.nprocs > 1 && p.comm && p.comm->nccl, "peer-to-peer exchange needs the NCCL communicator (sx_plan_set_comm)");
+  SX_REQUIRE(ev >= 0 && ev < 32, "exchange: bad event slot");
+  Comm& c = *p.comm;
+  if (stage_mark(p, ST_EXCHANGE)) return 1;
+  double sent = 0.0;
+  for (int r = 0; r < p.nprocs; ++r)
+    if (r != p.myrank) sent += (double)scount[r] * sizeof(cplx);
+  c.bytes_sent += sent;
+  c.exchanges++;
+  SX_CUDA_CHECK(cudaEventRecord(c.ready[ev], p.stream));
+  SX_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ready[ev], 0));
+  const bool timing = p.timer.on;
+  if (timing) SX_CUDA_CHECK(cudaEventRecord(c.t0, c.stream));
+  // every block is cut into nsplit pieces that travel on different streams (= different copy engines)
+  const int ns = c.nsplit;
+  if (ns > 1) {
+    SX_CUDA_CHECK(cudaEventRecord(c.fork, c.stream));
+    for (int i = 0; i < ns - 1; ++i) SX_CUDA_CHECK(cudaStreamWaitEvent(c.side[i], c.fork, 0));
+  }
+  for (int q = 1; q <= p.nprocs; ++q) {   // neighbours first, the local block last
+    const int r = (p.myrank + q) % p.nprocs;
+    if (!scount[r]) continue;
+    const size_t piece = (scount[r] + ns - 1) / ns;
+    for (int i = 0; i < ns; ++i) {
+      const size_t o = (size_t)i * piece;
+      if (o >= scount[r]) break;
+      const size_t n = scount[r] - o < piece ? scount[r] - o : piece;
+      SX_CUDA_CHECK(cudaMemcpyAsync(peer_dst[r] + o, send + sdispl[r] + o, n * sizeof(cplx), cudaMemcpyDeviceToDevice,
+                                    i == 0 ? c.stream : c.side[i - 1]));
+    }
+  }
+  for (int i = 0; i < ns - 1; ++i) {
+    SX_CUDA_CHECK(cudaEventRecord(c.join[i], c.side[i]));
+    SX_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.join[i], 0));
+  }
+  ncclResult_t st = ncclAllReduce(c.d_bar, c.d_bar, 1, ncclFloat, ncclSum, c.nccl, c.stream);
+  SX_REQUIRE(st == ncclSuccess, std::string("NCCL barrier failed: ") + ncclGetErrorString(st));
+  if (timing) {
+    SX_CUDA_CHECK(cudaEventRecord(c.t1, c.stream));
+    SX_CUDA_CHECK(cudaEventSynchronize(c.t1));
+    float f = 0.f;
+    SX_CUDA_CHECK(cudaEventElapsedTime(&f, c.t0, c.t1));
+    c.ms += f;
+  }
+  SX_CUDA_CHECK(cudaEventRecord(c.done[ev], c.stream));
+  p.launches++;
+  return 0;
+#else
+  (void)p; (void)ev; (void)send; (void)sdispl; (void)scount; (void)peer_dst;
+  SX_REQUIRE(false, "the emulated build has no peer-to-peer exchange");
 #endif
 }
 
@@ -227,6 +307,18 @@ int sx_plan_set_comm_callbacks(sx_plan* plan, sx_alltoallv_fn alltoallv, sx_allr
   c->allred = allreduce;
   c->user = user;
   return 0;
+}
+
+int sx_plan_p2p_export(sx_plan* plan, int n_inverse, int n_forward, void* handle64) {
+  SX_PLAN(plan);
+  SX_REQUIRE(handle64 != nullptr && n_inverse > 0 && n_forward > 0, "sx_plan_p2p_export: bad arguments");
+  return fused_p2p_export(p, n_inverse, n_forward, handle64);
+}
+
+int sx_plan_p2p_import(sx_plan* plan, const void* handles) {
+  SX_PLAN(plan);
+  SX_REQUIRE(handles != nullptr, "sx_plan_p2p_import: null handles");
+  return fused_p2p_import(p, handles);
 }
 
 int sx_plan_comm_stats(sx_plan* plan, double* bytes_sent, double* ms, long long* exchanges, int reset) {

@@ -21,6 +21,7 @@
 // (p = tid % NP, j = tid / NP, T = N/8 threads per line).  One side of the kernel then moves
 // NP*16 B = 128 B full lines per quarter-warp and the other side 64 B pieces of NP different lines,
 // which is the transposition.
+#include <cstring>
 #include "sx_fused.h"
 
 namespace sx {
@@ -43,6 +44,15 @@ static void release_fields(std::vector<cplx*>& a, const std::vector<cplx*>* alia
 int fused_free(Plan& p) {
   Fused* f = p.fused;
   if (!f) return 0;
+  if (f->arena) {   // R and Uz live inside the arena
+    f->R.assign(f->R.size(), nullptr);
+    f->Uz.assign(f->Uz.size(), nullptr);
+#ifndef SX_EMU
+    for (size_t r = 0; r < f->peer_arena.size(); ++r)
+      if ((int)r != p.myrank && f->peer_arena[r]) cudaIpcCloseMemHandle(f->peer_arena[r]);
+#endif
+    cudaFree(f->arena);
+  }
   release_fields(f->R, &f->W);
   release_fields(f->W);
   release_fields(f->V);
@@ -89,14 +99,28 @@ static int fused_init(Plan& p, Fused** out) {
   return 0;
 }
 
+// element counts (rounded to 256 B) of one receive buffer of rank r: xy side [kx][zl_r][ky], z side [rank][kxl_r][zl][ky]
+static size_t arena_rs(const Plan& p, int r) {
+  int s, c;
+  range0(p.nz - p.Cz, p.nprocs, r, &s, &c);
+  return ((size_t)p.nxh * c * p.ny + 15) / 16 * 16;
+}
+static size_t arena_ws(const Plan& p, int r) {
+  int s, c;
+  range0(p.nxh, p.nprocs, r, &s, &c);
+  return ((size_t)c * (p.nz - p.Cz) * p.ny + 15) / 16 * 16;
+}
+
 // grow the work-field pools: nw transposed inverse fields, nv real-side inputs of the x pass, nx nonlinear terms
 static int fused_reserve(Plan& p, Fused& f, int nw, int nv, int nx) {
   const size_t rsize = (size_t)p.nxh * f.nzf * p.ny;  // y-stage side [kx][zl][ky]
   const size_t both = f.wsize > rsize ? f.wsize : rsize;
+  if (f.arena) SX_REQUIRE(nw <= f.arena_nw && nx <= f.arena_nx, "the peer-to-peer arena was exported for fewer fields than this solver transposes");
   while ((int)f.W.size() < nw) {
     cplx *w = nullptr, *r = nullptr;
     SX_CUDA_CHECK(cudaMalloc((void**)&w, both * sizeof(cplx)));
     if (p.nprocs == 1) r = w;
+    else if (f.arena) r = f.arena + f.W.size() * arena_rs(p, p.myrank);
     else SX_CUDA_CHECK(cudaMalloc((void**)&r, rsize * sizeof(cplx)));
     f.W.push_back(w);
     f.R.push_back(r);
@@ -111,6 +135,7 @@ static int fused_reserve(Plan& p, Fused& f, int nw, int nv, int nx) {
     SX_CUDA_CHECK(cudaMalloc((void**)&x, f.vsize * sizeof(cplx)));
     SX_CUDA_CHECK(cudaMalloc((void**)&u, both * sizeof(cplx)));
     if (p.nprocs == 1) uz = u;
+    else if (f.arena) uz = f.arena + f.arena_nw * arena_rs(p, p.myrank) + f.X.size() * arena_ws(p, p.myrank);
     else SX_CUDA_CHECK(cudaMalloc((void**)&uz, f.wsize * sizeof(cplx)));
     f.X.push_back(x);
     f.U.push_back(u);
@@ -122,11 +147,37 @@ static int fused_reserve(Plan& p, Fused& f, int nw, int nv, int nx) {
 // W[slot] (z side, [rank][kxl][zl][ky]) -> R[slot] (xy side, [kx][zl][ky]); event slots 0..15
 static int to_real_begin(Plan& p, Fused& f, int slot) {
   if (p.nprocs == 1) return 0;
+  if (f.p2p) {   // my kx slab goes to rows [xs_me, xs_me + nxl) of every rank's [kx][zl_r][ky]
+    std::vector<cplx*> dst(p.nprocs);
+    int xs, xc;
+    range0(p.nxh, p.nprocs, p.myrank, &xs, &xc);
+    for (int r = 0; r < p.nprocs; ++r) {
+      int zs, zc;
+      range0(f.nph, p.nprocs, r, &zs, &zc);
+      dst[r] = f.peer_arena[r] + slot * arena_rs(p, r) + (size_t)xs * zc * p.ny;
+    }
+    return exchange_begin_p2p(p, slot, f.W[slot], f.z_displ.data(), f.z_count.data(), dst.data());
+  }
   return exchange_begin(p, slot, f.W[slot], f.R[slot], f.z_displ.data(), f.z_count.data(), f.x_displ.data(), f.x_count.data());
 }
 // U[slot] (xy side) -> Uz[slot] (z side); event slots 16..23
 static int to_spec_begin(Plan& p, Fused& f, int slot) {
   if (p.nprocs == 1) return 0;
+  if (f.p2p) {   // my z slab goes behind the slabs of the lower ranks in every rank's [rank][kxl_r][zl][ky]
+    std::vector<cplx*> dst(p.nprocs);
+    for (int r = 0; r < p.nprocs; ++r) {
+      int xs, xc;
+      range0(p.nxh, p.nprocs, r, &xs, &xc);
+      size_t before = 0;
+      for (int q = 0; q < p.myrank; ++q) {
+        int zs, zc;
+        range0(f.nph, p.nprocs, q, &zs, &zc);
+        before += (size_t)xc * zc * p.ny;
+      }
+      dst[r] = f.peer_arena[r] + f.arena_nw * arena_rs(p, r) + slot * arena_ws(p, r) + before;
+    }
+    return exchange_begin_p2p(p, 16 + slot, f.U[slot], f.x_displ.data(), f.x_count.data(), dst.data());
+  }
   return exchange_begin(p, 16 + slot, f.U[slot], f.Uz[slot], f.x_displ.data(), f.x_count.data(), f.z_displ.data(), f.z_count.data());
 }
 static int ex_wait(Plan& p, int ev) { return p.nprocs == 1 ? 0 : exchange_wait(p, ev); }
@@ -156,6 +207,49 @@ static int nonlinear_to_spectral_begin(Plan& p, Fused& f, int nx) {
     if (to_spec_begin(p, f, c)) return 1;
   }
   return 0;
+}
+
+int fused_p2p_export(Plan& p, int nw, int nx, void* handle64) {
+#ifndef SX_EMU
+  SX_REQUIRE(p.nprocs > 1, "sx_plan_p2p_export: single-rank plan");
+  Fused* fp;
+  if (fused_init(p, &fp)) return 1;
+  Fused& f = *fp;
+  SX_REQUIRE(f.arena == nullptr && f.W.empty() && f.X.empty(), "sx_plan_p2p_export: call once, before the first substep");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are expected to be 64 bytes");
+  const size_t elems = (size_t)nw * arena_rs(p, p.myrank) + (size_t)nx * arena_ws(p, p.myrank);
+  SX_CUDA_CHECK(cudaMalloc((void**)&f.arena, elems * sizeof(cplx)));
+  f.arena_nw = nw;
+  f.arena_nx = nx;
+  cudaIpcMemHandle_t h;
+  SX_CUDA_CHECK(cudaIpcGetMemHandle(&h, f.arena));
+  memcpy(handle64, &h, sizeof(h));
+  return 0;
+#else
+  (void)p; (void)nw; (void)nx; (void)handle64;
+  SX_REQUIRE(false, "the emulated build has no peer-to-peer exchange");
+#endif
+}
+
+int fused_p2p_import(Plan& p, const void* handles) {
+#ifndef SX_EMU
+  Fused* f = p.fused;
+  SX_REQUIRE(f != nullptr && f->arena != nullptr, "sx_plan_p2p_import: call sx_plan_p2p_export first");
+  f->peer_arena.assign(p.nprocs, nullptr);
+  for (int r = 0; r < p.nprocs; ++r) {
+    if (r == p.myrank) { f->peer_arena[r] = f->arena; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    SX_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    f->peer_arena[r] = (cplx*)ptr;
+  }
+  f->p2p = true;
+  return 0;
+#else
+  (void)p; (void)handles;
+  SX_REQUIRE(false, "the emulated build has no peer-to-peer exchange");
+#endif
 }
 
 // hd_rkstep2.f90:3-36.  st[0..2] v, st[3] pr, st[4..6] f, st[7..9] RK base.

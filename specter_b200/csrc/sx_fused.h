@@ -30,6 +30,11 @@ struct Fused {
   std::vector<cplx*> Uz;  // z-stage side of the way back (aliases U on one GPU)
   // all-to-all-v block tables in complex elements: z side [rank][kxl][zl_r][ky], xy side [kx][zl][ky]
   std::vector<size_t> z_displ, z_count, x_displ, x_count;
+  // peer-to-peer exchange (sx_plan_p2p_export / _import): R and Uz are carved from one IPC-exported arena per rank
+  cplx* arena = nullptr;
+  int arena_nw = 0, arena_nx = 0;
+  std::vector<cplx*> peer_arena;   // IPC-mapped arenas of the other ranks (own entry = arena)
+  bool p2p = false;
 };
 
 // lines per CTA of the tile kernels: 256 threads up to N = 512 (64 B pieces on the strided side --

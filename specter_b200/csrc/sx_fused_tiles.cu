@@ -229,8 +229,15 @@ template <class B, class A> struct Hook2 {
   __device__ __forceinline__ void after_sync() const { a(); }
 };
 template <class B, class A> __device__ __forceinline__ Hook2<B, A> make_hook(B b, A a) { return Hook2<B, A>{b, a}; }
-__device__ __forceinline__ cplx* smem_align128(cplx* s) {
-  return reinterpret_cast<cplx*>((reinterpret_cast<uintptr_t>(s) + 127) & ~(uintptr_t)127);
+// 128-byte aligned start inside the dynamic shared memory, computed as an element offset so that the compiler
+// keeps the shared address space (a pointer round trip through uintptr_t turns every access into a generic LD/ST)
+__device__ __forceinline__ int smem_align128_offset(const cplx* s) {
+#ifndef SX_EMU
+  const unsigned a = (unsigned)__cvta_generic_to_shared(s);
+#else
+  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+#endif
+  return (int)(((128u - (unsigned)(a & 127u)) & 127u) / sizeof(cplx));
 }
 
 // inverse transform of NP adjacent lines of one plane, optional derivative, results to the strided side.
@@ -251,7 +258,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_inv_tma(InvTmaArgs a, cons
   SX_DYN_SMEM(cplx, smem_raw);
   typedef TileGeo<N, NP> G;
   constexpr int T = G::T;
-  cplx* exch = smem_align128(smem_raw);          // [row][NP]: exchange buffer and store tile
+  cplx* exch = smem_raw + smem_align128_offset(smem_raw);          // [row][NP]: exchange buffer and store tile
   cplx* in = exch + (size_t)N * NP;              // [NP][PITCH]
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(in + (size_t)NP * G::PITCH);
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tma(YfwdArgs a, const
   SX_DYN_SMEM(cplx, smem_raw);
   typedef TileGeo<N, NP> G;
   constexpr int T = G::T;
-  cplx* exch = smem_align128(smem_raw);
+  cplx* exch = smem_raw + smem_align128_offset(smem_raw);
   cplx* in = exch + (size_t)N * NP;              // [row][NP]
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(in + (size_t)N * NP);
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;

@@ -134,7 +134,10 @@ int comm_free(Plan& p);
 bool comm_ready(const Plan& p);
 int exchange_begin(Plan& p, int ev, const cplx* send, cplx* recv, const size_t* sdispl, const size_t* scount,
                    const size_t* rdispl, const size_t* rcount);
+int exchange_begin_p2p(Plan& p, int ev, const cplx* send, const size_t* sdispl, const size_t* scount, cplx* const* peer_dst);
 int exchange_wait(Plan& p, int ev);
+int fused_p2p_export(Plan& p, int nw, int nx, void* handle64);
+int fused_p2p_import(Plan& p, const void* handles);
 int allreduce_sum(Plan& p, double* v, int n);
 
 }  // namespace sx
