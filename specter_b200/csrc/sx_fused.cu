@@ -21,6 +21,7 @@
 // (p = tid % NP, j = tid / NP, T = N/8 threads per line).  One side of the kernel then moves
 // NP*16 B = 128 B full lines per quarter-warp and the other side 64 B pieces of NP different lines,
 // which is the transposition.
+#include <cstdlib>
 #include <cstring>
 #include "sx_fused.h"
 
@@ -29,12 +30,6 @@ namespace sx {
 // ==========================================================================================
 // host side
 // ==========================================================================================
-static void range0(int n, int nprocs, int r, int* sta, int* cnt) {  // `range` on [0,n)
-  const int w = n / nprocs, m = n % nprocs;
-  *sta = r * w + (r < m ? r : m);
-  *cnt = w + (m > r ? 1 : 0);
-}
-
 static void release_fields(std::vector<cplx*>& a, const std::vector<cplx*>* alias = nullptr) {
   for (size_t i = 0; i < a.size(); ++i)
     if (a[i] && (!alias || i >= alias->size() || (*alias)[i] != a[i])) cudaFree(a[i]);
@@ -71,7 +66,7 @@ static int fused_init(Plan& p, Fused** out) {
   Fused* f = new Fused();
   p.fused = f;
   f->nph = p.nz - p.Cz;
-  range0(f->nph, p.nprocs, p.myrank, &f->zf0, &f->nzf);
+  zrange(f->nph, p.nprocs, p.myrank, &f->zf0, &f->nzf);
   f->nxp = (p.nxh + 7) / 8 * 8;
   f->wsize = (size_t)p.nxl * f->nph * p.ny;
   f->vsize = (size_t)f->nzf * p.ny * f->nxp;
@@ -79,14 +74,14 @@ static int fused_init(Plan& p, Fused** out) {
   long long base = 0;
   for (int r = 0; r < p.nprocs; ++r) {
     int s, c;
-    range0(f->nph, p.nprocs, r, &s, &c);
+    zrange(f->nph, p.nprocs, r, &s, &c);
     for (int q = 0; q < c; ++q) zm[s + q] = ZMap{base, c, q};
     base += (long long)p.nxl * c * p.ny;
   }
   f->z_displ.resize(p.nprocs); f->z_count.resize(p.nprocs); f->x_displ.resize(p.nprocs); f->x_count.resize(p.nprocs);
   for (int r = 0; r < p.nprocs; ++r) {
     int s, c, xs, xc;
-    range0(f->nph, p.nprocs, r, &s, &c);
+    zrange(f->nph, p.nprocs, r, &s, &c);
     range0(p.nxh, p.nprocs, r, &xs, &xc);
     f->z_displ[r] = c ? (size_t)zm[s].base : 0;
     f->z_count[r] = (size_t)p.nxl * c * p.ny;
@@ -97,18 +92,6 @@ static int fused_init(Plan& p, Fused** out) {
   SX_CUDA_CHECK(cudaMemcpy(f->d_zmap, zm.data(), zm.size() * sizeof(ZMap), cudaMemcpyHostToDevice));
   *out = f;
   return 0;
-}
-
-// element counts (rounded to 256 B) of one receive buffer of rank r: xy side [kx][zl_r][ky], z side [rank][kxl_r][zl][ky]
-static size_t arena_rs(const Plan& p, int r) {
-  int s, c;
-  range0(p.nz - p.Cz, p.nprocs, r, &s, &c);
-  return ((size_t)p.nxh * c * p.ny + 15) / 16 * 16;
-}
-static size_t arena_ws(const Plan& p, int r) {
-  int s, c;
-  range0(p.nxh, p.nprocs, r, &s, &c);
-  return ((size_t)c * (p.nz - p.Cz) * p.ny + 15) / 16 * 16;
 }
 
 // grow the work-field pools: nw transposed inverse fields, nv real-side inputs of the x pass, nx nonlinear terms
@@ -147,36 +130,29 @@ static int fused_reserve(Plan& p, Fused& f, int nw, int nv, int nx) {
 // W[slot] (z side, [rank][kxl][zl][ky]) -> R[slot] (xy side, [kx][zl][ky]); event slots 0..15
 static int to_real_begin(Plan& p, Fused& f, int slot) {
   if (p.nprocs == 1) return 0;
-  if (f.p2p) {   // my kx slab goes to rows [xs_me, xs_me + nxl) of every rank's [kx][zl_r][ky]
+  if (f.p2p) {
     std::vector<cplx*> dst(p.nprocs);
-    int xs, xc;
-    range0(p.nxh, p.nprocs, p.myrank, &xs, &xc);
+    std::vector<size_t> cnt(f.z_count);
     for (int r = 0; r < p.nprocs; ++r) {
-      int zs, zc;
-      range0(f.nph, p.nprocs, r, &zs, &zc);
-      dst[r] = f.peer_arena[r] + slot * arena_rs(p, r) + (size_t)xs * zc * p.ny;
+      dst[r] = peer_r_dst(p, f, slot, r);
+      // blocks the z-inverse kernel already stored into their destination (sx_fused_tiles.cu) are not copied
+      if (f.zinv_direct && (f.direct >= 2 || (f.direct == 1 && r == p.myrank))) cnt[r] = 0;
     }
-    return exchange_begin_p2p(p, slot, f.W[slot], f.z_displ.data(), f.z_count.data(), dst.data());
+    return exchange_begin_p2p(p, slot, f.W[slot], f.z_displ.data(), cnt.data(), dst.data());
   }
   return exchange_begin(p, slot, f.W[slot], f.R[slot], f.z_displ.data(), f.z_count.data(), f.x_displ.data(), f.x_count.data());
 }
 // U[slot] (xy side) -> Uz[slot] (z side); event slots 16..23
 static int to_spec_begin(Plan& p, Fused& f, int slot) {
   if (p.nprocs == 1) return 0;
-  if (f.p2p) {   // my z slab goes behind the slabs of the lower ranks in every rank's [rank][kxl_r][zl][ky]
+  if (f.p2p) {
     std::vector<cplx*> dst(p.nprocs);
+    std::vector<size_t> cnt(f.x_count);
     for (int r = 0; r < p.nprocs; ++r) {
-      int xs, xc;
-      range0(p.nxh, p.nprocs, r, &xs, &xc);
-      size_t before = 0;
-      for (int q = 0; q < p.myrank; ++q) {
-        int zs, zc;
-        range0(f.nph, p.nprocs, q, &zs, &zc);
-        before += (size_t)xc * zc * p.ny;
-      }
-      dst[r] = f.peer_arena[r] + f.arena_nw * arena_rs(p, r) + slot * arena_ws(p, r) + before;
+      dst[r] = peer_uz_dst(p, f, slot, r);
+      if (f.yfwd_direct && (f.direct >= 2 || (f.direct == 1 && r == p.myrank))) cnt[r] = 0;
     }
-    return exchange_begin_p2p(p, 16 + slot, f.U[slot], f.x_displ.data(), f.x_count.data(), dst.data());
+    return exchange_begin_p2p(p, 16 + slot, f.U[slot], f.x_displ.data(), cnt.data(), dst.data());
   }
   return exchange_begin(p, 16 + slot, f.U[slot], f.Uz[slot], f.x_displ.data(), f.x_count.data(), f.z_displ.data(), f.z_count.data());
 }
@@ -245,6 +221,7 @@ int fused_p2p_import(Plan& p, const void* handles) {
     f->peer_arena[r] = (cplx*)ptr;
   }
   f->p2p = true;
+  if (const char* e = getenv("SX_P2P_DIRECT")) f->direct = atoi(e);
   return 0;
 #else
   (void)p; (void)handles;

@@ -35,7 +35,64 @@ struct Fused {
   int arena_nw = 0, arena_nx = 0;
   std::vector<cplx*> peer_arena;   // IPC-mapped arenas of the other ranks (own entry = arena)
   bool p2p = false;
+  // which blocks the producing kernels store straight into the destination rank's buffer instead of the send
+  // buffer: 0 none (all blocks travel by copy engine), 1 the local block, 2 every block (stores over NVLink)
+  int direct = 1;
+  bool zinv_direct = false, yfwd_direct = false;   // set by the launchers when the kernel variant in use does so
 };
+
+inline void range0(int n, int nprocs, int r, int* sta, int* cnt) {  // `range` on [0,n)
+  const int w = n / nprocs, m = n % nprocs;
+  *sta = r * w + (r < m ? r : m);
+  *cnt = w + (m > r ? 1 : 0);
+}
+// The real-space z partition of the fused substep is internal (the ABI only exposes the reference's ksta:kend for
+// the per-operator entries): rows are dealt in pairs so that every rank's first row is even and its rows start
+// 128-byte aligned in the [row][4 lines] tiles the tensor-map stores read.
+inline void zrange(int nph, int nprocs, int r, int* sta, int* cnt) {
+  int us, uc;
+  range0((nph + 1) / 2, nprocs, r, &us, &uc);
+  *sta = 2 * us < nph ? 2 * us : nph;
+  const int end = 2 * (us + uc) < nph ? 2 * (us + uc) : nph;
+  *cnt = end - *sta;
+}
+
+// element counts (rounded to 256 B) of one receive buffer of rank r: xy side [kx][zl_r][ky], z side [rank][kxl_r][zl][ky]
+inline size_t arena_rs(const Plan& p, int r) {
+  int s, c;
+  zrange(p.nz - p.Cz, p.nprocs, r, &s, &c);
+  return ((size_t)p.nxh * c * p.ny + 15) / 16 * 16;
+}
+inline size_t arena_ws(const Plan& p, int r) {
+  int s, c;
+  range0(p.nxh, p.nprocs, r, &s, &c);
+  return ((size_t)c * (p.nz - p.Cz) * p.ny + 15) / 16 * 16;
+}
+
+// where this rank's block starts inside rank r's receive buffer `slot` of the way to real space ([kx][zl_r][ky]:
+// my kx slab) and of the way back ([rank][kxl_r][zl][ky]: behind the z slabs of the lower ranks)
+inline cplx* peer_r_dst(const Plan& p, const Fused& f, int slot, int r) {
+  int xs, xc, zs, zc;
+  range0(p.nxh, p.nprocs, p.myrank, &xs, &xc);
+  zrange(f.nph, p.nprocs, r, &zs, &zc);
+  return f.peer_arena[r] + slot * arena_rs(p, r) + (size_t)xs * zc * p.ny;
+}
+inline cplx* peer_uz_dst(const Plan& p, const Fused& f, int slot, int r) {
+  int xs, xc;
+  range0(p.nxh, p.nprocs, r, &xs, &xc);
+  size_t before = 0;
+  for (int q = 0; q < p.myrank; ++q) {
+    int zs, zc;
+    zrange(f.nph, p.nprocs, q, &zs, &zc);
+    before += (size_t)xc * zc * p.ny;
+  }
+  return f.peer_arena[r] + f.arena_nw * arena_rs(p, r) + slot * arena_ws(p, r) + before;
+}
+inline int slot_of(const std::vector<cplx*>& pool, const cplx* ptr) {
+  for (size_t i = 0; i < pool.size(); ++i)
+    if (pool[i] == ptr) return (int)i;
+  return -1;
+}
 
 // lines per CTA of the tile kernels: 256 threads up to N = 512 (64 B pieces on the strided side --
 // measured FASTER on B200 than 128 B pieces with twice the CTA footprint), 4 lines beyond

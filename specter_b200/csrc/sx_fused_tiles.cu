@@ -157,7 +157,16 @@ struct YfwdArgs {
   const cplx* in;
   cplx* out;
   int nxh, nxp, nzf;
+  // peer-to-peer: lines of the kx slab [xs[d], xs[d+1]) go straight into rank d's buffer when peer[d] != nullptr
+  cplx* peer[8];
+  int xs[9];
+  int npeer;
 };
+__device__ __forceinline__ cplx* yfwd_line(const YfwdArgs& a, int kx, int zl, int n) {
+  for (int d = 0; d < a.npeer; ++d)
+    if (kx >= a.xs[d] && kx < a.xs[d + 1] && a.peer[d] != nullptr) return a.peer[d] + ((size_t)(kx - a.xs[d]) * a.nzf + zl) * n;
+  return a.out + ((size_t)kx * a.nzf + zl) * n;
+}
 
 template <int N, int NP, int MINB, bool PF>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tile(YfwdArgs a, const cplx* __restrict__ tw) {
@@ -198,7 +207,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tile(YfwdArgs a, cons
     if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
     fft_regs<N, -1>(v, j, smem, SIdxPencil{p, NP}, twr);
     if (kx < a.nxh) {
-      cplx* dst = a.out + ((size_t)kx * a.nzf + zl) * N;
+      cplx* dst = yfwd_line(a, kx, zl, N);
 #pragma unroll
       for (int k = 0; k < 8; ++k) dst[j + k * T] = v[k];
     }
@@ -252,9 +261,18 @@ struct InvTmaArgs {
   int has1;
 };
 
+// destination blocks of the strided side: one tensor map per block (one per rank in the exchange layout),
+// block r holds rows [row0[r], row0[r] + rows) of every tile, stored as nbox[r] boxes of brows[r] rows
+constexpr int kMaxBlocks = 8;
+struct InvTmaMaps {
+  TmaMap m[kMaxBlocks];
+  int row0[kMaxBlocks], nbox[kMaxBlocks], brows[kMaxBlocks];
+  int nblocks;
+};
+
 template <int N, int NP, int MINB>
-__global__ void __launch_bounds__(NP*(N / 8), MINB) k_inv_tma(InvTmaArgs a, const SX_GRID_CONSTANT TmaMap m0,
-                                                              const SX_GRID_CONSTANT TmaMap m1, const cplx* __restrict__ tw) {
+__global__ void __launch_bounds__(NP*(N / 8), MINB) k_inv_tma(InvTmaArgs a, const SX_GRID_CONSTANT InvTmaMaps m0,
+                                                              const SX_GRID_CONSTANT InvTmaMaps m1, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem_raw);
   typedef TileGeo<N, NP> G;
   constexpr int T = G::T;
@@ -290,15 +308,16 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_inv_tma(InvTmaArgs a, cons
     mbar_wait(bar, phase);
     phase ^= 1;
     const cplx* mine = in + (size_t)p * G::PITCH + j;
-    auto store_tile = [&](const TmaMap* m, cplx (&v)[8]) {
+    auto store_tile = [&](const InvTmaMaps* m, cplx (&v)[8]) {
       __syncthreads();   // the last gather of the transform is done: the buffer becomes the store tile
 #pragma unroll
       for (int k = 0; k < 8; ++k) exch[(size_t)(j + k * T) * NP + p] = v[k];
       fence_proxy_async();
       __syncthreads();
       if (lead) {
-#pragma unroll
-        for (int b = 0; b < G::NBOX; ++b) tma_store_3d(m, exch + (size_t)b * G::ROWS * NP, 2 * l0, b * G::ROWS, pl);
+        for (int r = 0; r < m->nblocks; ++r)
+          for (int b = 0; b < m->nbox[r]; ++b)
+            tma_store_3d(&m->m[r], exch + (size_t)(m->row0[r] + b * m->brows[r]) * NP, 2 * l0, b * m->brows[r], pl);
         tma_store_commit();
       }
     };
@@ -362,7 +381,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tma(YfwdArgs a, const
     for (int k = 0; k < 8; ++k) v[k] = kx < a.nxh ? in[(size_t)(j + k * T) * NP + p] : cmake(0.0, 0.0);
     fft_regs<N, -1>(v, j, exch, SIdxPencil{p, NP}, twr, make_hook([] {}, [&] { if (lead && tn < ntiles) issue(tn); }));
     if (kx < a.nxh) {
-      cplx* dst = a.out + ((size_t)kx * a.nzf + zl) * N;
+      cplx* dst = yfwd_line(a, kx, zl, N);
 #pragma unroll
       for (int k = 0; k < 8; ++k) dst[j + k * T] = v[k];
     }
@@ -373,7 +392,7 @@ template <int N, int NP> static size_t inv_tma_smem() {
   return ((size_t)N * NP + (size_t)NP * TileGeo<N, NP>::PITCH) * sizeof(cplx) + 8 + TileGeo<N, NP>::ALIGN;
 }
 // returns -1 when the bulk-copy path does not apply (caller falls back to the register-path kernels)
-template <int N> static int run_inv_tma(Plan& p, Fused& f, int stage, const InvTmaArgs& a, const TmaMap& m0, const TmaMap& m1) {
+template <int N> static int run_inv_tma(Plan& p, Fused& f, int stage, const InvTmaArgs& a, const InvTmaMaps& m0, const InvTmaMaps& m1) {
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
   auto kfn = k_inv_tma<N, NP, MINB>;
   const size_t smem = inv_tma_smem<N, NP>();
@@ -383,27 +402,64 @@ template <int N> static int run_inv_tma(Plan& p, Fused& f, int stage, const InvT
   SX_FUSED_LAUNCH(p, stage, kfn, dim3(grid), NP * (N / 8), smem, a, m0, m1, tw);
   return 0;
 }
+// one destination block: rows [row0, row0 + rows) of the tiles -> tensor (n0 lines, rows, n2 planes) at `base`
+static int add_block(InvTmaMaps& m, const void* base, size_t n0, int row0, int rows, size_t n2, size_t pitch1, size_t pitch2, int np) {
+  const int r = m.nblocks++;
+  m.row0[r] = row0;
+  m.nbox[r] = (rows + 255) / 256;
+  m.brows[r] = m.nbox[r] > 1 ? 256 : rows;
+  return tma_encode(&m.m[r], base, n0, rows, n2, pitch1, pitch2, np, m.brows[r]);
+}
 template <int N> static int run_zinv_tma(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
   constexpr int NP = TileNP<N>::value;
-  typedef TileGeo<N, NP> G;
-  if (N < p.knob_tma_min || p.nprocs != 1 || p.ny % NP != 0 || !(p.knob_tma & 1)) return -1;
-  TmaMap m0, m1;
-  // exchange layout on one rank: [kxl][z][ky], physical rows only: the boxes are clipped at nph
-  if (tma_encode(&m0, out0, p.ny, f.nph, p.nxl, p.ny, (size_t)f.nph * p.ny, NP, G::ROWS)) return 1;
-  if (tma_encode(&m1, out1 ? out1 : out0, p.ny, f.nph, p.nxl, p.ny, (size_t)f.nph * p.ny, NP, G::ROWS)) return 1;
+  if (N < p.knob_tma_min || p.nprocs > kMaxBlocks || p.ny % NP != 0 || !(p.knob_tma & 1)) return -1;
+  // exchange layout [rank][kxl][zl_r][ky], physical rows only; a block's tile rows must start 128-byte aligned
+  std::vector<int> z0(p.nprocs), zc(p.nprocs);
+  for (int r = 0; r < p.nprocs; ++r) {
+    zc[r] = (int)(f.z_count[r] / ((size_t)p.nxl * p.ny));
+    z0[r] = r == 0 ? 0 : z0[r - 1] + zc[r - 1];
+    if (zc[r] > 0 && ((size_t)z0[r] * NP * sizeof(cplx)) % 128 != 0) return -1;
+  }
+  InvTmaMaps m0, m1;
+  m0.nblocks = m1.nblocks = 0;
+  // peer-to-peer: a block may be stored straight into the destination rank's receive buffer (same geometry there)
+  const int s0 = slot_of(f.W, out0), s1 = out1 ? slot_of(f.W, out1) : s0;
+  f.zinv_direct = f.p2p && s0 >= 0 && s1 >= 0;
+  for (int r = 0; r < p.nprocs; ++r) {
+    if (zc[r] == 0) continue;
+    const bool direct = f.zinv_direct && (f.direct >= 2 || (f.direct == 1 && r == p.myrank));
+    cplx* b0 = direct ? peer_r_dst(p, f, s0, r) : out0 + f.z_displ[r];
+    cplx* b1 = direct ? peer_r_dst(p, f, s1, r) : (out1 ? out1 : out0) + f.z_displ[r];
+    if (add_block(m0, b0, p.ny, z0[r], zc[r], p.nxl, p.ny, (size_t)zc[r] * p.ny, NP)) return 1;
+    if (add_block(m1, b1, p.ny, z0[r], zc[r], p.nxl, p.ny, (size_t)zc[r] * p.ny, NP)) return 1;
+  }
   InvTmaArgs a{in, p.d_kz, p.ny, p.nxl, 1, p.ny, out1 != nullptr};
   return run_inv_tma<N>(p, f, ST_ZINV, a, m0, m1);
 }
 template <int N> static int run_yinv_tma(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
   constexpr int NP = TileNP<N>::value;
-  typedef TileGeo<N, NP> G;
   if (N < p.knob_tma_min || f.nxp % NP != 0 || !(p.knob_tma & 2)) return -1;
   if (f.nzf == 0) return 0;
-  TmaMap m0, m1;
-  if (tma_encode(&m0, out0, f.nxp, p.ny, f.nzf, f.nxp, (size_t)p.ny * f.nxp, NP, G::ROWS)) return 1;
-  if (tma_encode(&m1, out1 ? out1 : out0, f.nxp, p.ny, f.nzf, f.nxp, (size_t)p.ny * f.nxp, NP, G::ROWS)) return 1;
+  InvTmaMaps m0, m1;
+  m0.nblocks = m1.nblocks = 0;
+  if (add_block(m0, out0, f.nxp, 0, N, f.nzf, f.nxp, (size_t)p.ny * f.nxp, NP)) return 1;
+  if (add_block(m1, out1 ? out1 : out0, f.nxp, 0, N, f.nzf, f.nxp, (size_t)p.ny * f.nxp, NP)) return 1;
   InvTmaArgs a{in, p.d_ky, p.nxh, f.nzf, f.nzf, 1, out1 != nullptr};
   return run_inv_tma<N>(p, f, ST_YINV, a, m0, m1);
+}
+static int yfwd_peers(Plan& p, Fused& f, const cplx* out, YfwdArgs& a) {
+  const int slot = slot_of(f.U, out);
+  f.yfwd_direct = f.p2p && slot >= 0 && p.nprocs <= 8 && f.direct >= 1;
+  if (!f.yfwd_direct) return 0;
+  a.npeer = p.nprocs;
+  for (int d = 0; d < p.nprocs; ++d) {
+    int xs, xc;
+    range0(p.nxh, p.nprocs, d, &xs, &xc);
+    a.xs[d] = xs;
+    a.xs[d + 1] = xs + xc;
+    a.peer[d] = (f.direct >= 2 || d == p.myrank) ? peer_uz_dst(p, f, slot, d) : nullptr;
+  }
+  return 0;
 }
 template <int N> static int run_yfwd_tma(Plan& p, Fused& f, const cplx* in, cplx* out) {
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
@@ -412,7 +468,8 @@ template <int N> static int run_yfwd_tma(Plan& p, Fused& f, const cplx* in, cplx
   if (f.nzf == 0) return 0;
   TmaMap min;
   if (tma_encode(&min, in, f.nxp, p.ny, f.nzf, f.nxp, (size_t)p.ny * f.nxp, NP, G::ROWS)) return 1;
-  YfwdArgs a{in, out, p.nxh, f.nxp, f.nzf};
+  YfwdArgs a{in, out, p.nxh, f.nxp, f.nzf, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, {0}, 0};
+  if (yfwd_peers(p, f, out, a)) return 1;
   auto kfn = k_yfwd_tma<N, NP, MINB>;
   const size_t smem = (size_t)2 * N * NP * sizeof(cplx) + 8 + G::ALIGN;
   int grid;
@@ -425,6 +482,7 @@ template <int N> static int run_yfwd_tma(Plan& p, Fused& f, const cplx* in, cplx
 template <int N> static int run_zinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
   if (const int rc = run_zinv_tma<N>(p, f, in, out0, out1); rc >= 0) return rc;
+  f.zinv_direct = false;
   ZinvArgs a{in, out0, out1, p.d_kz, f.d_zmap, p.ny, p.nxl, f.nph};
   const cplx* tw = p.tw_z;
   const size_t smem = (size_t)2 * NP * N * sizeof(cplx) + (size_t)N * sizeof(ZMap);
@@ -464,7 +522,8 @@ template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* ou
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
   if (const int rc = run_yfwd_tma<N>(p, f, in, out); rc >= 0) return rc;
   if (f.nzf == 0) return 0;
-  YfwdArgs a{in, out, p.nxh, f.nxp, f.nzf};
+  YfwdArgs a{in, out, p.nxh, f.nxp, f.nzf, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, {0}, 0};
+  if (yfwd_peers(p, f, out, a)) return 1;
   const cplx* tw = p.tw_y;
   int grid;
   if (p.knob_pf & 4) {

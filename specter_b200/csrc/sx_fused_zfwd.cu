@@ -66,7 +66,7 @@ __device__ __forceinline__ void stash_boundary_tile(const cplx (&v)[8], int j, i
   }
 }
 
-template <int N, int NP, int MINB, bool HOIST, bool PF, bool L2PF = false>
+template <int N, int NP, int MINB, bool HOIST, bool PF, bool L2PF = false, bool BATCH = false>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8, NT = NP * T;
@@ -147,6 +147,37 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
       const double x = __ldg(&a.kx[kxl]), y = __ldg(&a.ky[ky]);
       const double f1 = __ldg(&a.fx[kxl]), f2 = __ldg(&a.fy[ky]);
       const double kh2 = x * x + y * y;
+      if (BATCH) {
+        // one field at a time, eight independent loads in flight per thread: at 80 registers the fused form
+        // below only keeps three loads in flight and pays the memory latency once per element instead
+        // of once per field (the arithmetic is associated exactly as below)
+        if (a.couple != nullptr) {
+          cplx Q[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) Q[k] = a.couple[base + j + k * T];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = caxpy(a.ccoef, Q[k], v[k]);
+        }
+        cplx Q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) Q[k] = a.v[base + j + k * T];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          const double z = __ldg(&a.kz[e]), f3 = __ldg(&a.fz[e]);
+          const double lm = a.lap ? -(kh2 + z * z) : 1.0;
+          const cplx NL = cscale(cscale(cscale(v[k], f1), f2), f3);
+          v[k] = cmake(a.cL * (lm * Q[k].x) + a.sNL * NL.x, a.cL * (lm * Q[k].y) + a.sNL * NL.y);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) Q[k] = a.f[base + j + k * T];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = cmake((v[k].x + Q[k].x) * a.dt * a.rmp, (v[k].y + Q[k].y) * a.dt * a.rmp);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) Q[k] = a.v0[base + j + k * T];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.vout[base + j + k * T] = cmake(Q[k].x + v[k].x, Q[k].y + v[k].y);
+      } else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int e = j + k * T;
@@ -158,6 +189,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
         const cplx Lk = HOIST ? L[k] : a.v[base + e], Bk = HOIST ? B[k] : a.v0[base + e], Fk = HOIST ? F[k] : a.f[base + e];
         a.vout[base + e] = cmake(Bk.x + a.dt * (a.cL * (lm * Lk.x) + a.sNL * NL.x + Fk.x) * a.rmp,
                                  Bk.y + a.dt * (a.cL * (lm * Lk.y) + a.sNL * NL.y + Fk.y) * a.rmp);
+      }
       }
     }
   }
@@ -263,7 +295,22 @@ template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, const
     SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
     return 0;
   }
-  if ((p.knob_pf & 8) && p.knob_zf == 3) {   // L2 prefetch of the RK pencils: measured slower (1.20 -> 1.38 ms), kept as an experiment
+  // default for length 512 (profiles/r1i_session4.md): the RK fields one at a time, 128 registers, two CTAs per SM
+  if ((p.knob_pf & 8) && N == 512 && (p.knob_zf == 0 || (p.knob_zf >= 4 && p.knob_zf <= 6))) {
+    if (p.knob_zf == 4) {
+      auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), false, true>;
+      if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
+      SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+    } else if (p.knob_zf == 5) {
+      auto kfn = k_zfwd_rk<N, NP, MINB, false, true, false, true>;
+      if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
+      SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+    } else {
+      auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), false, true, false, true>;
+      if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
+      SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+    }
+  } else if ((p.knob_pf & 8) && p.knob_zf == 3) {   // L2 prefetch of the RK pencils: measured slower (1.20 -> 1.38 ms), kept as an experiment
     auto kfn = k_zfwd_rk<N, NP, MINB, false, true, true>;
     if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
     SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);

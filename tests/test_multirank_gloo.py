@@ -76,8 +76,11 @@ def _gloo_a2a(dist, outs, ins, rank, world):
         q.wait()
 
 
-@pytest.mark.parametrize("world,shape,ord_", [(2, (32, 16, 64), 2), (3, (16, 16, 64), 2)])
-def test_fused_substep_multirank(world, shape, ord_, emu_lib, tables):
+@pytest.mark.parametrize("world,shape,ord_,tma_min", [(2, (32, 16, 64), 2, None), (3, (16, 16, 64), 2, None),
+                                                      (2, (16, 128, 128), 2, "16")])
+def test_fused_substep_multirank(world, shape, ord_, tma_min, emu_lib, tables, monkeypatch):
+    if tma_min:   # bulk-copy tile kernels with one tensor-map block per destination rank (default from length 256)
+        monkeypatch.setenv("SX_TMA_MIN", tma_min)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000) + world

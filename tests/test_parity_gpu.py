@@ -106,3 +106,12 @@ def test_bouss_mhd_substeps_long_x(cuda_lib, tables):
     P.case_bouss_substeps(cuda_lib, tables, (256, 32, 64), ord=2, nsteps=1, impl=0)
     P.case_bouss_substeps(cuda_lib, tables, (512, 16, 64), ord=2, nsteps=1, impl=0)
     P.case_mhd_substeps(cuda_lib, tables, (256, 32, 64), ord=2, nsteps=1, impl=0)
+
+
+def test_hd_substeps_length_1024_2048_kernels(cuda_lib, tables):
+    """Transform lengths of the multi-GPU configurations (1024x1024x512, 2048x2048x1024) along each axis in turn."""
+    P.case_hd_substeps(cuda_lib, tables, (1024, 16, 64), ord=2, nsteps=1, impl=0)
+    P.case_hd_substeps(cuda_lib, tables, (2048, 16, 64), ord=2, nsteps=1, impl=0)
+    P.case_hd_substeps(cuda_lib, tables, (16, 1024, 64), ord=2, nsteps=1, impl=0)
+    P.case_hd_substeps(cuda_lib, tables, (16, 2048, 64), ord=2, nsteps=1, impl=0)
+    P.case_hd_substeps(cuda_lib, tables, (16, 16, 1024), ord=2, nsteps=1, impl=0)
