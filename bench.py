@@ -389,8 +389,18 @@ def main():
         if dominant is None or sms > stages[dominant][0]:
             dominant = name
     dom = stage_report.get(dominant, {})
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this same command
+    # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/ncu_traffic.json, written by tools/ncu_summary.py)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tj = json.load(fh)
+        if tj.get("workload") == args.workload and world == 1:
+            traffic = tj["stages"].get(dominant, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError, KeyError):
+        traffic = None
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": dom.get("achieved_gbs"), "peak": peak, "unit": "GB/s",
-                "frac": dom.get("frac_of_hbm_peak"), "traffic": None, "peak_source": peak_src,
+                "frac": dom.get("frac_of_hbm_peak"), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom.get("algorithmic_bytes_per_launch"),
                 "avg_launch_ms": dom.get("ms_per_launch"),
                 "whole_substep": {"algorithmic_bytes_per_point": b_alg,

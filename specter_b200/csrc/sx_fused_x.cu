@@ -440,7 +440,7 @@ template <int N, int NC> static int run_xpass(Plan& p, Fused& f, const double* d
   constexpr int T = N / 8;
   constexpr int LP = T >= 128 ? 1 : 128 / T;
   // bulk-copy ring (TMA) + register accumulators: default from one warp per line pair upwards (SX_XP=9: previous kernels)
-  if constexpr (N >= 64 && N <= 1024) {
+  if constexpr (N >= 64 && N <= 2048) {
     const bool want = p.knob_xp == 0 ? N >= 256 : (p.knob_xp >= 10 && p.knob_xp < 20);
     if (want) {
       // 255 registers: accumulators, velocity line and one transform live in the register file, so four
@@ -453,7 +453,7 @@ template <int N, int NC> static int run_xpass(Plan& p, Fused& f, const double* d
           default: break;
         }
       }
-      return run_xpass_bulk<N, NC, 3, (N <= 512 ? 4 : 2)>(p, f, d_kx_global);
+      return run_xpass_bulk<N, NC, 3, (N <= 512 ? 4 : (N == 1024 ? 2 : 1))>(p, f, d_kx_global);
     }
   }
   if constexpr (N == 512) {   // measured best on B200 (profiles/r1h_knobs.md): one pair per CTA, direct loads
