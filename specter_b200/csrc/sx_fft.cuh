@@ -32,6 +32,8 @@ template <int N> struct Fft1D {
 struct SIdxElem {
   int base;
   __device__ __forceinline__ int operator()(int e) const { return base + e + (e >> 3); }
+  // index distance of two elements n apart: n a multiple of 8, or both inside one group of 8
+  __device__ __forceinline__ constexpr int stride(int n) const { return n + (n >> 3); }
 };
 template <int N> constexpr int sidx_elem_stride() { return N + N / 8; }
 // pencil-fastest: NP pencils interleaved (conflict free when NP % 8 == 0)
@@ -47,6 +49,7 @@ struct SIdxPencil {
 #endif
     return e * np + p;
   }
+  __device__ __forceinline__ constexpr int stride(int n) const { return n * np; }
 };
 
 // ---- small in-register DFTs (natural order in/out) ---------------------------------
@@ -149,11 +152,28 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[8], const int j, cplx* s, con
   constexpr int r = F::radix(P), nb = 8 / r, Ns = F::ns(P), T = F::T;
   constexpr bool first = (P == 0), last = (P == F::npass - 1);
   constexpr int toff = F::twoff(P);
+  // For T a multiple of 8 every element offset inside a pass is a multiple of 8 (or stays inside one group of 8),
+  // so the shared-memory index is ONE per-thread base plus compile-time strides: the accesses become
+  // [base + immediate] instead of one address register per butterfly leg.
+#ifdef SX_SWIZZLE
+  constexpr bool linear = false;
+#else
+  constexpr bool linear = (T % 8 == 0);
+#endif
   if (!first) {
+    if constexpr (linear) {
+      const int g0 = si(j);
 #pragma unroll
-    for (int b = 0; b < nb; ++b) {
+      for (int b = 0; b < nb; ++b) {
 #pragma unroll
-      for (int m = 0; m < r; ++m) v[b + m * nb] = s[si(j + b * T + m * (N / r))];
+        for (int m = 0; m < r; ++m) v[b + m * nb] = s[g0 + si.stride(b * T + m * (N / r))];
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < nb; ++b) {
+#pragma unroll
+        for (int m = 0; m < r; ++m) v[b + m * nb] = s[si(j + b * T + m * (N / r))];
+      }
     }
 #pragma unroll
     for (int b = 0; b < nb; ++b) {
@@ -193,8 +213,14 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[8], const int j, cplx* s, con
     for (int b = 0; b < nb; ++b) {
       const int jb = j + b * T;
       const int j0 = (jb / Ns) * (Ns * r) + (jb & (Ns - 1));
+      if constexpr (linear) {
+        const int s0 = si(j0);
 #pragma unroll
-      for (int m = 0; m < r; ++m) s[si(j0 + m * Ns)] = v[b + m * nb];
+        for (int m = 0; m < r; ++m) s[s0 + si.stride(m * Ns)] = v[b + m * nb];
+      } else {
+#pragma unroll
+        for (int m = 0; m < r; ++m) s[si(j0 + m * Ns)] = v[b + m * nb];
+      }
     }
     __syncthreads();
   }

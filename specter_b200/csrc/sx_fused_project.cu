@@ -271,16 +271,17 @@ __global__ void __launch_bounds__(N / 8, MINB) k_project_bulk(ProjBulkArgs pa, c
     mbar_init_fence();
   }
   __syncthreads();
-  long g = blockIdx.x;
-  if (lead && g < a.npencils) {
+  int g = blockIdx.x;   // pencil index: ny * nxl < 2^31
+  const int npencils = (int)a.npencils;
+  if (lead && g < npencils) {
     bulk_load(sx, a.vx + (size_t)g * N, PBYTES, bar);
     bulk_load(sy, a.vy + (size_t)g * N, PBYTES, bar + 1);
     bulk_load(sz, a.vz + (size_t)g * N, PBYTES, bar + 2);
   }
   unsigned phase = 0;
-  for (; g < a.npencils; g += gridDim.x) {
-    const long gn = g + gridDim.x;
-    const int ky_i = (int)(g % a.ny), kx_i = (int)(g / a.ny);
+  for (; g < npencils; g += gridDim.x) {
+    const int gn = g + gridDim.x;
+    const int kx_i = g / a.ny, ky_i = g - kx_i * a.ny;
     const size_t base = (size_t)g * N;
     const double x = __ldg(&a.kx[kx_i]), y = __ldg(&a.ky[ky_i]);
     const bool mean = a.has_mean && g == 0;
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(N / 8, MINB) k_project_bulk(ProjBulkArgs pa, c
       a.vy[base + e] = cmake(B.x + y * h.y, B.y - y * h.x);
     }
     __syncthreads();   // every thread is done with the vx / vy slots: refill them under the last transform
-    if (lead && gn < a.npencils) {
+    if (lead && gn < npencils) {
       bulk_load(sx, a.vx + (size_t)gn * N, PBYTES, bar);
       bulk_load(sy, a.vy + (size_t)gn * N, PBYTES, bar + 1);
     }
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(N / 8, MINB) k_project_bulk(ProjBulkArgs pa, c
       a.vz[base + j + k * T] = cmake(Cc.x - v[k].x, Cc.y - v[k].y);
     }
     __syncthreads();   // the v_z slot is free; its refill lands during the four transforms that precede its use
-    if (lead && gn < a.npencils) bulk_load(sz, a.vz + (size_t)gn * N, PBYTES, bar + 2);
+    if (lead && gn < npencils) bulk_load(sz, a.vz + (size_t)gn * N, PBYTES, bar + 2);
   }
 }
 

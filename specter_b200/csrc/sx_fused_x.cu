@@ -171,16 +171,26 @@ __global__ void __launch_bounds__(N / 8, MINB) k_xpass_gradre_bulk(XpassArgs a, 
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(stage + (size_t)S * 2 * NXP);
   const int groups_y = a.ny / 2, ngroups = groups_y * a.nzf;
   const int mine = ((int)blockIdx.x < ngroups) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const long total = (long)mine * NM;
   auto row_of = [&](int gi) -> size_t {
     const int g = blockIdx.x + gi * gridDim.x;
     return ((size_t)(g / groups_y) * a.ny + (size_t)(g % groups_y) * 2) * NXP;
   };
-  auto issue = [&](long L) {
-    const int gi = (int)(L / NM), m = (int)(L % NM), d = m / (NC + 1), i = m % (NC + 1);
-    const cplx* field = i == 0 ? a.V[d] : a.V[d * NC + i - 1];
-    const int s = (int)(L % S);
-    bulk_load(stage + (size_t)s * 2 * NXP, field + row_of(gi), BYTES, bar + s);
+  // producer state (only meaningful in the lead thread): next load = transform (pd, pi) of group pg into stage ps.
+  // All counters are advanced incrementally: no divisions in the per-transform path.
+  int pg = 0, pd = 0, pi = 0, ps = 0;
+  size_t prow = mine > 0 ? row_of(0) : 0;
+  auto issue_next = [&]() {
+    if (pg >= mine) return;
+    const cplx* field = pi == 0 ? a.V[pd] : a.V[pd * NC + pi - 1];
+    bulk_load(stage + (size_t)ps * 2 * NXP, field + prow, BYTES, bar + ps);
+    if (++ps == S) ps = 0;
+    if (++pi == NC + 1) {
+      pi = 0;
+      if (++pd == 3) {
+        pd = 0;
+        if (++pg < mine) prow = row_of(pg);
+      }
+    }
   };
   if (t == 0) {
     for (int s = 0; s < S; ++s) mbar_init(bar + s, 1);
@@ -188,45 +198,52 @@ __global__ void __launch_bounds__(N / 8, MINB) k_xpass_gradre_bulk(XpassArgs a, 
   }
   __syncthreads();
   if (t == 0)
-    for (long L = 0; L < S - 1 && L < total; ++L) issue(L);
-  long L = 0;
+    for (int q = 0; q < S - 1; ++q) issue_next();
+  int cs = 0;            // consumer stage
+  unsigned cph = 0;      // and its mbarrier parity
   for (int gi = 0; gi < mine; ++gi) {
     const size_t rowA = row_of(gi), rowB = rowA + NXP;
     cplx acc0[8], acc1[8], acc2[8], acc3[NC > 3 ? 8 : 1], u[8];
 #pragma unroll 1
-    for (int m = 0; m < NM; ++m, ++L) {
-      const int d = m / (NC + 1), i = m % (NC + 1);
-      // stage (L-1) % S was read before the barriers of the previous transform: refill it
-      if (t == 0 && L + S - 1 < total) issue(L + S - 1);
-      mbar_wait(bar + (int)(L % S), (unsigned)((L / S) & 1));
-      const cplx* sA = stage + (size_t)(L % S) * 2 * NXP;
-      const cplx* sB = sA + NXP;
-      const bool deriv = d == 0 && i > 0;
-      cplx v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int e = t + k * T;
-        const int kx = e <= N / 2 ? e : N - e;
-        cplx A = sA[kx], B = sB[kx];
-        if (deriv) {
-          const double kk = __ldg(&a.kx[kx]);
-          A = cmake(-kk * A.y, kk * A.x);
-          B = cmake(-kk * B.y, kk * B.x);
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll 1
+      for (int i = 0; i <= NC; ++i) {
+        // the stage consumed by the previous transform was read before that transform's barriers: refill it
+        if (t == 0) issue_next();
+        mbar_wait(bar + cs, cph);
+        const cplx* sA = stage + (size_t)cs * 2 * NXP;
+        const cplx* sB = sA + NXP;
+        if (++cs == S) {
+          cs = 0;
+          cph ^= 1;
         }
-        if (kx == 0 || kx == N / 2) { A.y = 0.0; B.y = 0.0; }
-        if (e > N / 2) { A.y = -A.y; B.y = -B.y; }
-        v[k] = cmake(A.x - B.y, A.y + B.x);
-      }
-      fft_regs<N, 1>(v, t, smem, si, twr);
-      if (i == 0) {
+        const bool deriv = d == 0 && i > 0;
+        cplx v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) u[k] = v[k];
-      } else {
-        const bool f0 = d == 0;
-        if (i == 1) accum(acc0, u, v, f0);
-        else if (i == 2) accum(acc1, u, v, f0);
-        else if (i == 3) accum(acc2, u, v, f0);
-        else if (NC > 3) accum(acc3, u, v, f0);
+        for (int k = 0; k < 8; ++k) {
+          const int e = t + k * T;
+          const int kx = e <= N / 2 ? e : N - e;
+          cplx A = sA[kx], B = sB[kx];
+          if (deriv) {
+            const double kk = __ldg(&a.kx[kx]);
+            A = cmake(-kk * A.y, kk * A.x);
+            B = cmake(-kk * B.y, kk * B.x);
+          }
+          if (kx == 0 || kx == N / 2) { A.y = 0.0; B.y = 0.0; }
+          if (e > N / 2) { A.y = -A.y; B.y = -B.y; }
+          v[k] = cmake(A.x - B.y, A.y + B.x);
+        }
+        fft_regs<N, 1>(v, t, smem, si, twr);
+        if (i == 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) u[k] = v[k];
+        } else {
+          const bool f0 = d == 0;
+          if (i == 1) accum(acc0, u, v, f0);
+          else if (i == 2) accum(acc1, u, v, f0);
+          else if (i == 3) accum(acc2, u, v, f0);
+          else if (NC > 3) accum(acc3, u, v, f0);
+        }
       }
     }
     // forward transforms of the packed pairs and split into the two half spectra
