@@ -15,6 +15,7 @@ struct XpassArgs {
   const double* kx;  // GLOBAL kx(1:nx/2+1)
   int ny, nxp, nzf;
   double tmp;        // 1/(nx ny nz)^2
+  double dkx;        // kx(i) = (i-1) dkx for i <= nx/2, kx(nx/2+1) = -(nx/2) dkx (specter.fpp:772-789)
 };
 
 // One CTA = LP pairs of adjacent y lines; persistent over (z row, y group).  The 12 inverse
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(N / 8, MINB) k_xpass_gradre_bulk(XpassArgs a, 
           const int kx = e <= N / 2 ? e : N - e;
           cplx A = sA[kx], B = sB[kx];
           if (deriv) {
-            const double kk = __ldg(&a.kx[kx]);
+            const double kk = (double)(kx == N / 2 ? -kx : kx) * a.dkx;   // the product the host table holds
             A = cmake(-kk * A.y, kk * A.x);
             B = cmake(-kk * B.y, kk * B.x);
           }
@@ -424,6 +425,7 @@ template <int N, int LP, bool PF, int MINB, int NC> static int run_xpass_v(Plan&
   a.nzf = f.nzf;
   const double Ntot = (double)p.nx * (double)p.ny * (double)p.nz;
   a.tmp = 1.0 / (Ntot * Ntot);
+  a.dkx = p.Dkx;
   const cplx* tw = p.tw_x;
   auto kfn = k_xpass_gradre<N, LP, PF, MINB, NC>;
   const size_t smem = ((size_t)LP * sidx_elem_stride<N>() + (size_t)(PF ? 40 : 24) * LP * T) * sizeof(cplx);
@@ -445,6 +447,7 @@ template <int N, int NC, int S, int MINB> static int run_xpass_bulk(Plan& p, Fus
   a.nzf = f.nzf;
   const double Ntot = (double)p.nx * (double)p.ny * (double)p.nz;
   a.tmp = 1.0 / (Ntot * Ntot);
+  a.dkx = p.Dkx;
   const cplx* tw = p.tw_x;
   auto kfn = k_xpass_gradre_bulk<N, NC, S, MINB>;
   const size_t smem = XpassBulk<N>::smem_bytes(S);
