@@ -190,6 +190,7 @@ static int plan_init(Plan& p, const sx_config& c) {
   if (const char* e = getenv("SX_XP")) p.knob_xp = atoi(e);
   if (const char* e = getenv("SX_PJ")) p.knob_pj = atoi(e);
   if (const char* e = getenv("SX_TILE_PF")) p.knob_pf = atoi(e);
+  if (const char* e = getenv("SX_ZCHUNKS")) p.knob_zchunks = atoi(e);
   if (const char* e = getenv("SX_TMA")) p.knob_tma = atoi(e);
   if (const char* e = getenv("SX_TMA_MIN")) p.knob_tma_min = atoi(e);
   if (const char* e = getenv("SX_TILE_NP")) p.knob_np = atoi(e);

@@ -224,6 +224,61 @@ int exchange_begin_p2p(Plan& p, int ev, const cplx* send, const size_t* sdispl, 
 #endif
 }
 
+// Chunked form of the same transport (the z-chunk pipeline of sx_fused.cu): a round is a list of 2-D block copies
+// (rows of one z chunk of every transposed field), optionally closed by the barrier.
+int p2p_mark(Plan& p, int slot) {
+  SX_REQUIRE(p.comm && slot >= 0 && slot < 32, "p2p_mark: bad slot");
+  SX_CUDA_CHECK(cudaEventRecord(p.comm->ready[slot], p.stream));
+  return 0;
+}
+
+int p2p_round(Plan& p, const int* wait_slots, int nwait, const P2PCopy* cp, int n, bool barrier, int done_slot) {
+#ifndef SX_EMU
+  SX_REQUIRE(p.nprocs > 1 && p.comm && p.comm->nccl, "peer-to-peer exchange needs the NCCL communicator (sx_plan_set_comm)");
+  Comm& c = *p.comm;
+  if (stage_mark(p, ST_EXCHANGE)) return 1;
+  for (int i = 0; i < nwait; ++i) SX_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ready[wait_slots[i]], 0));
+  const bool timing = p.timer.on;
+  if (timing) SX_CUDA_CHECK(cudaEventRecord(c.t0, c.stream));
+  const int ns = c.nsplit;
+  if (ns > 1 && n > 0) {
+    SX_CUDA_CHECK(cudaEventRecord(c.fork, c.stream));
+    for (int i = 0; i < ns - 1; ++i) SX_CUDA_CHECK(cudaStreamWaitEvent(c.side[i], c.fork, 0));
+  }
+  for (int i = 0; i < n; ++i) {   // whole blocks round-robin over the copy streams (= copy engines)
+    const P2PCopy& q = cp[i];
+    if (q.width == 0 || q.height == 0) continue;
+    if (q.remote) c.bytes_sent += (double)q.width * q.height * sizeof(cplx);
+    cudaStream_t st = (ns > 1 && i % ns) ? c.side[i % ns - 1] : c.stream;
+    SX_CUDA_CHECK(cudaMemcpy2DAsync(q.dst, q.dpitch * sizeof(cplx), q.src, q.spitch * sizeof(cplx), q.width * sizeof(cplx),
+                                    q.height, cudaMemcpyDeviceToDevice, st));
+  }
+  if (ns > 1 && n > 0)
+    for (int i = 0; i < ns - 1; ++i) {
+      SX_CUDA_CHECK(cudaEventRecord(c.join[i], c.side[i]));
+      SX_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.join[i], 0));
+    }
+  if (barrier) {
+    ncclResult_t st = ncclAllReduce(c.d_bar, c.d_bar, 1, ncclFloat, ncclSum, c.nccl, c.stream);
+    SX_REQUIRE(st == ncclSuccess, std::string("NCCL barrier failed: ") + ncclGetErrorString(st));
+    c.exchanges++;
+  }
+  if (timing) {
+    SX_CUDA_CHECK(cudaEventRecord(c.t1, c.stream));
+    SX_CUDA_CHECK(cudaEventSynchronize(c.t1));
+    float f = 0.f;
+    SX_CUDA_CHECK(cudaEventElapsedTime(&f, c.t0, c.t1));
+    c.ms += f;
+  }
+  if (done_slot >= 0) SX_CUDA_CHECK(cudaEventRecord(c.done[done_slot], c.stream));
+  p.launches++;
+  return 0;
+#else
+  (void)p; (void)wait_slots; (void)nwait; (void)cp; (void)n; (void)barrier; (void)done_slot;
+  SX_REQUIRE(false, "the emulated build has no peer-to-peer exchange");
+#endif
+}
+
 int exchange_wait(Plan& p, int ev) {
   Comm& c = *p.comm;
   if (c.a2a) return 0;

@@ -156,7 +156,7 @@ static int to_spec_begin(Plan& p, Fused& f, int slot) {
   }
   return exchange_begin(p, 16 + slot, f.U[slot], f.Uz[slot], f.x_displ.data(), f.x_count.data(), f.z_displ.data(), f.z_count.data());
 }
-static int ex_wait(Plan& p, int ev) { return p.nprocs == 1 ? 0 : exchange_wait(p, ev); }
+static int ex_wait(Plan& p, int ev) { return (p.nprocs == 1 || (p.fused && p.fused->chunked_now)) ? 0 : exchange_wait(p, ev); }
 
 static int fused_begin(Plan& p, Fused** fp, int nw, int nv, int nx) {
   if (fused_init(p, fp)) return 1;
@@ -177,6 +177,85 @@ template <int NC> static int gradient_fields_to_real(Plan& p, Fused& f, const cp
   }
   return 0;
 }
+// ------------------------------------------------------------------------------------------
+// Multi-rank xy stage as a pipeline over z chunks (peer-to-peer transport only).  The exchanges of the 2*NC
+// inverse fields and of the NC nonlinear terms sit on the critical path on both sides of the x pass; cut into
+// NCH z chunks, chunk k of every field travels while chunk k-1 is in the y-inverse / x pass / y-forward
+// kernels, and the way back of chunk k travels under the kernels of chunk k+1:
+//   zinv(all fields) -> [in-round k: rows of chunk k of every field into every rank's R, barrier] k = 0..NCH-1
+//   for k: wait in-round k; yinv, xpass, yfwd on the z window of chunk k; out-round k (rows of chunk k of U -> Uz)
+// All rounds run on the communication stream in issue order; the chain of barriers orders buffer reuse as before.
+// ------------------------------------------------------------------------------------------
+static bool chunked(const Plan& p, const Fused& f) {
+  return p.nprocs > 1 && f.p2p && p.knob_zchunks > 1 && p.knob_zchunks <= 8;
+}
+
+template <int NC> static int xy_stage_chunked(Plan& p, Fused& f, const cplx* const* q) {
+  const int nch = p.knob_zchunks;
+  int xs_me, xc_me;
+  range0(p.nxh, p.nprocs, p.myrank, &xs_me, &xc_me);
+  std::vector<int> zc(p.nprocs);
+  for (int r = 0; r < p.nprocs; ++r) {
+    int s;
+    zrange(f.nph, p.nprocs, r, &s, &zc[r]);
+  }
+  // z stage: all inverse fields (the local block goes straight into R when the tensor-map kernel runs)
+  for (int c = 0; c < NC; ++c) {
+    if (fused_zinv(p, f, q[c], f.W[2 * c], f.W[2 * c + 1])) return 1;
+    if (p2p_mark(p, c)) return 1;
+  }
+  const bool zdirect = f.zinv_direct && f.direct >= 1;
+  std::vector<P2PCopy> cp;
+  for (int k = 0; k < nch; ++k) {
+    for (int c = 0; c < NC; ++c) {   // sub-round per component: starts as soon as that component's zinv is done
+      cp.clear();
+      for (int h = 0; h < 2; ++h)
+        for (int qd = 1; qd <= p.nprocs; ++qd) {
+          const int r = (p.myrank + qd) % p.nprocs;
+          if (r == p.myrank && zdirect) continue;
+          int c0, cc;
+          range0(zc[r], nch, k, &c0, &cc);
+          cp.push_back(P2PCopy{peer_r_dst(p, f, 2 * c + h, r) + (size_t)c0 * p.ny, f.W[2 * c + h] + f.z_displ[r] + (size_t)c0 * p.ny,
+                               (size_t)cc * p.ny, (size_t)p.nxl, (size_t)zc[r] * p.ny, (size_t)zc[r] * p.ny, r != p.myrank});
+        }
+      const int w = c;
+      if (p2p_round(p, &w, k == 0 ? 1 : 0, cp.data(), (int)cp.size(), c == NC - 1, c == NC - 1 ? k : -1)) return 1;
+    }
+  }
+  f.chunked_now = true;
+  for (int k = 0; k < nch; ++k) {
+    int c0, cc;
+    range0(f.nzf, nch, k, &c0, &cc);
+    if (exchange_wait(p, k)) return 1;
+    f.zw0 = c0;
+    f.zwc = cc;
+    for (int c = 0; c < NC; ++c) {
+      if (fused_yinv(p, f, f.R[2 * c], f.V[c], f.V[NC + c])) return 1;
+      if (fused_yinv(p, f, f.R[2 * c + 1], f.V[2 * NC + c], nullptr)) return 1;
+    }
+    if (fused_xpass(p, f, NC, p.d_kxg)) return 1;
+    for (int c = 0; c < NC; ++c)
+      if (fused_yfwd(p, f, f.X[c], f.U[c])) return 1;
+    if (p2p_mark(p, 16 + k)) return 1;
+    const bool ydirect = f.yfwd_direct && f.direct >= 1;
+    cp.clear();
+    for (int c = 0; c < NC; ++c)
+      for (int qd = 1; qd <= p.nprocs; ++qd) {
+        const int r = (p.myrank + qd) % p.nprocs;
+        if (r == p.myrank && ydirect) continue;
+        int xs, xc;
+        range0(p.nxh, p.nprocs, r, &xs, &xc);
+        cp.push_back(P2PCopy{peer_uz_dst(p, f, c, r) + (size_t)c0 * p.ny, f.U[c] + f.x_displ[r] + (size_t)c0 * p.ny,
+                             (size_t)cc * p.ny, (size_t)xc, (size_t)f.nzf * p.ny, (size_t)f.nzf * p.ny, r != p.myrank});
+      }
+    const int w = 16 + k;
+    if (p2p_round(p, &w, 1, cp.data(), (int)cp.size(), true, 16 + k)) return 1;
+  }
+  f.zwc = -1;
+  f.zw0 = 0;
+  return exchange_wait(p, 16 + nch - 1);   // the rounds complete in order: the last one covers them all
+}
+
 static int nonlinear_to_spectral_begin(Plan& p, Fused& f, int nx) {
   for (int c = 0; c < nx; ++c) {
     if (fused_yfwd(p, f, f.X[c], f.U[c])) return 1;
@@ -235,9 +314,14 @@ int hd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, cons
   if (fused_begin(p, &fp, 6, 9, 3)) return 1;
   Fused& f = *fp;
   const double rmp = 1.0 / (double)o;
-  if (gradient_fields_to_real<3>(p, f, st)) return 1;
-  if (fused_xpass(p, f, 3, p.d_kxg)) return 1;
-  if (nonlinear_to_spectral_begin(p, f, 3)) return 1;
+  f.chunked_now = false;
+  if (chunked(p, f)) {
+    if (xy_stage_chunked<3>(p, f, st)) return 1;
+  } else {
+    if (gradient_fields_to_real<3>(p, f, st)) return 1;
+    if (fused_xpass(p, f, 3, p.d_kxg)) return 1;
+    if (nonlinear_to_spectral_begin(p, f, 3)) return 1;
+  }
   RkTerm rk;
   rk.cL = nu;
   for (int c = 0; c < 3; ++c) {
@@ -259,9 +343,14 @@ int bouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, d
   Fused& f = *fp;
   const double rmp = 1.0 / (double)o;
   const cplx* q[4] = {st[0], st[1], st[2], st[10]};
-  if (gradient_fields_to_real<4>(p, f, q)) return 1;
-  if (fused_xpass(p, f, 4, p.d_kxg)) return 1;          // gradre (3) and advect (1) in one pass
-  if (nonlinear_to_spectral_begin(p, f, 4)) return 1;
+  f.chunked_now = false;
+  if (chunked(p, f)) {
+    if (xy_stage_chunked<4>(p, f, q)) return 1;
+  } else {
+    if (gradient_fields_to_real<4>(p, f, q)) return 1;
+    if (fused_xpass(p, f, 4, p.d_kxg)) return 1;          // gradre (3) and advect (1) in one pass
+    if (nonlinear_to_spectral_begin(p, f, 4)) return 1;
+  }
   // theta first, into the scratch field: it reads the not yet updated v_z (heat current), and v_z below reads
   // the not yet updated theta (buoyancy)
   RkTerm rt;
@@ -285,6 +374,7 @@ int mhd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, dou
   Fused* fp;
   if (fused_begin(p, &fp, 12, 12, 6)) return 1;
   Fused& f = *fp;
+  f.chunked_now = false;
   const double rmp = 1.0 / (double)o;
   const double N = (double)p.nx * (double)p.ny * (double)p.nz;
   cplx *B[3], *Wv[3];

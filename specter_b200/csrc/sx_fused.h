@@ -39,6 +39,12 @@ struct Fused {
   // buffer: 0 none (all blocks travel by copy engine), 1 the local block, 2 every block (stores over NVLink)
   int direct = 1;
   bool zinv_direct = false, yfwd_direct = false;   // set by the launchers when the kernel variant in use does so
+  // z window of the xy stage (y-inverse, x pass, y-forward launchers): rows [zw0, zw0 + zwc) of the local slab;
+  // zwc < 0 = the whole slab.  The chunked multi-rank pipeline (sx_fused.cu) moves it from chunk to chunk.
+  int zw0 = 0, zwc = -1;
+  bool chunked_now = false;   // the current substep ran the chunked pipeline (its exchanges are already waited for)
+  int z0() const { return zwc < 0 ? 0 : zw0; }
+  int zc() const { return zwc < 0 ? nzf : zwc; }
 };
 
 inline void range0(int n, int nprocs, int r, int* sta, int* cnt) {  // `range` on [0,n)

@@ -91,7 +91,8 @@ struct YinvArgs {
   cplx* out0;       // IFFT_y(in)          [zl][y][kx]
   cplx* out1;       // IFFT_y(i ky in) or nullptr
   const double* ky;
-  int nxh, nxp, nzf;
+  int nxh, nxp, nzf;   // nzf: z rows of the slab (line stride of `in`)
+  int nzc;             // z rows to process (in / out already point at the first one)
 };
 
 template <int N, int NP, int MINB, bool PF>
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yinv_tile(YinvArgs a, cons
   twr.load(tw, j);
   cplx* slot = smem + (size_t)NP * N + threadIdx.x;
   const SIdxPencil si{p, NP};
-  const int tiles_x = cdiv(a.nxp, NP), ntiles = tiles_x * a.nzf;
+  const int tiles_x = cdiv(a.nxp, NP), ntiles = tiles_x * a.nzc;
   auto issue = [&](int t) {
     if (!PF) return;
     const int kx = (t % tiles_x) * NP + p, zl = t / tiles_x;
@@ -156,7 +157,8 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yinv_tile(YinvArgs a, cons
 struct YfwdArgs {
   const cplx* in;
   cplx* out;
-  int nxh, nxp, nzf;
+  int nxh, nxp, nzf;   // nzf: z rows of the slab (line stride of `out` and of the peers)
+  int nzc;             // z rows to process (in / out / peers already point at the first one)
   // peer-to-peer: lines of the kx slab [xs[d], xs[d+1]) go straight into rank d's buffer when peer[d] != nullptr
   cplx* peer[8];
   int xs[9];
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tile(YfwdArgs a, cons
   TwRegs<N> twr;
   twr.load(tw, j);
   cplx* slot = smem + (size_t)NP * N + threadIdx.x;
-  const int tiles_x = cdiv(a.nxh, NP), ntiles = tiles_x * a.nzf;
+  const int tiles_x = cdiv(a.nxh, NP), ntiles = tiles_x * a.nzc;
   auto issue = [&](int t) {
     if (!PF) return;
     const int kx = (t % tiles_x) * NP + p, zl = t / tiles_x;
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tma(YfwdArgs a, const
   const bool lead = threadIdx.x == 0;
   TwRegs<N> twr;
   twr.load(tw, j);
-  const int tiles_x = cdiv(a.nxh, NP), ntiles = tiles_x * a.nzf;
+  const int tiles_x = cdiv(a.nxh, NP), ntiles = tiles_x * a.nzc;
   auto issue = [&](int t) {
     const int kx0 = (t % tiles_x) * NP, zl = t / tiles_x;
     mbar_expect(bar, (unsigned)((size_t)N * NP * sizeof(cplx)));
@@ -442,9 +444,11 @@ template <int N> static int run_yinv_tma(Plan& p, Fused& f, const cplx* in, cplx
   if (f.nzf == 0) return 0;
   InvTmaMaps m0, m1;
   m0.nblocks = m1.nblocks = 0;
-  if (add_block(m0, out0, f.nxp, 0, N, f.nzf, f.nxp, (size_t)p.ny * f.nxp, NP)) return 1;
-  if (add_block(m1, out1 ? out1 : out0, f.nxp, 0, N, f.nzf, f.nxp, (size_t)p.ny * f.nxp, NP)) return 1;
-  InvTmaArgs a{in, p.d_ky, p.nxh, f.nzf, f.nzf, 1, out1 != nullptr};
+  const size_t zo = (size_t)f.z0() * p.ny * f.nxp;   // z window of the [zl][y][kx] outputs
+  if (f.zc() == 0) return 0;
+  if (add_block(m0, out0 + zo, f.nxp, 0, N, f.zc(), f.nxp, (size_t)p.ny * f.nxp, NP)) return 1;
+  if (add_block(m1, (out1 ? out1 : out0) + zo, f.nxp, 0, N, f.zc(), f.nxp, (size_t)p.ny * f.nxp, NP)) return 1;
+  InvTmaArgs a{in + (size_t)f.z0() * N, p.d_ky, p.nxh, f.zc(), f.nzf, 1, out1 != nullptr};
   return run_inv_tma<N>(p, f, ST_YINV, a, m0, m1);
 }
 static int yfwd_peers(Plan& p, Fused& f, const cplx* out, YfwdArgs& a) {
@@ -457,7 +461,7 @@ static int yfwd_peers(Plan& p, Fused& f, const cplx* out, YfwdArgs& a) {
     range0(p.nxh, p.nprocs, d, &xs, &xc);
     a.xs[d] = xs;
     a.xs[d + 1] = xs + xc;
-    a.peer[d] = (f.direct >= 2 || d == p.myrank) ? peer_uz_dst(p, f, slot, d) : nullptr;
+    a.peer[d] = (f.direct >= 2 || d == p.myrank) ? peer_uz_dst(p, f, slot, d) + (size_t)f.z0() * p.ny : nullptr;
   }
   return 0;
 }
@@ -467,13 +471,15 @@ template <int N> static int run_yfwd_tma(Plan& p, Fused& f, const cplx* in, cplx
   if (N < p.knob_tma_min || f.nxp % NP != 0 || !(p.knob_tma & 4)) return -1;
   if (f.nzf == 0) return 0;
   TmaMap min;
-  if (tma_encode(&min, in, f.nxp, p.ny, f.nzf, f.nxp, (size_t)p.ny * f.nxp, NP, G::ROWS)) return 1;
-  YfwdArgs a{in, out, p.nxh, f.nxp, f.nzf, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, {0}, 0};
+  if (f.zc() == 0) return 0;
+  if (tma_encode(&min, in + (size_t)f.z0() * p.ny * f.nxp, f.nxp, p.ny, f.zc(), f.nxp, (size_t)p.ny * f.nxp, NP, G::ROWS)) return 1;
+  YfwdArgs a{in + (size_t)f.z0() * p.ny * f.nxp, out + (size_t)f.z0() * N, p.nxh, f.nxp, f.nzf, f.zc(),
+             {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, {0}, 0};
   if (yfwd_peers(p, f, out, a)) return 1;
   auto kfn = k_yfwd_tma<N, NP, MINB>;
   const size_t smem = (size_t)2 * N * NP * sizeof(cplx) + 8 + G::ALIGN;
   int grid;
-  if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.nxh, NP) * f.nzf, &grid)) return 1;
+  if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.nxh, NP) * f.zc(), &grid)) return 1;
   const cplx* tw = p.tw_y;
   SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(grid), NP * (N / 8), smem, a, min, tw);
   return 0;
@@ -501,19 +507,20 @@ template <int N> static int run_zinv(Plan& p, Fused& f, const cplx* in, cplx* ou
 template <int N> static int run_yinv(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
   if (const int rc = run_yinv_tma<N>(p, f, in, out0, out1); rc >= 0) return rc;
-  if (f.nzf == 0) return 0;
-  YinvArgs a{in, out0, out1, p.d_ky, p.nxh, f.nxp, f.nzf};
+  if (f.zc() == 0) return 0;
+  const size_t zo = (size_t)f.z0() * N * f.nxp;
+  YinvArgs a{in + (size_t)f.z0() * N, out0 + zo, out1 ? out1 + zo : nullptr, p.d_ky, p.nxh, f.nxp, f.nzf, f.zc()};
   const cplx* tw = p.tw_y;
   int grid;
   if (p.knob_pf & 2) {
     auto kfn = k_yinv_tile<N, NP, MINB, true>;
     const size_t smem = (size_t)2 * NP * N * sizeof(cplx);
-    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(f.nxp, NP) * f.nzf, &grid)) return 1;
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(f.nxp, NP) * f.zc(), &grid)) return 1;
     SX_FUSED_LAUNCH(p, ST_YINV, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   } else {
     auto kfn = k_yinv_tile<N, NP, MINB, false>;
     const size_t smem = (size_t)NP * N * sizeof(cplx);
-    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(f.nxp, NP) * f.nzf, &grid)) return 1;
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(f.nxp, NP) * f.zc(), &grid)) return 1;
     SX_FUSED_LAUNCH(p, ST_YINV, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   }
   return 0;
@@ -521,20 +528,21 @@ template <int N> static int run_yinv(Plan& p, Fused& f, const cplx* in, cplx* ou
 template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* out) {
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
   if (const int rc = run_yfwd_tma<N>(p, f, in, out); rc >= 0) return rc;
-  if (f.nzf == 0) return 0;
-  YfwdArgs a{in, out, p.nxh, f.nxp, f.nzf, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, {0}, 0};
+  if (f.zc() == 0) return 0;
+  YfwdArgs a{in + (size_t)f.z0() * p.ny * f.nxp, out + (size_t)f.z0() * N, p.nxh, f.nxp, f.nzf, f.zc(),
+             {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, {0}, 0};
   if (yfwd_peers(p, f, out, a)) return 1;
   const cplx* tw = p.tw_y;
   int grid;
   if (p.knob_pf & 4) {
     auto kfn = k_yfwd_tile<N, NP, MINB, true>;
     const size_t smem = (size_t)2 * NP * N * sizeof(cplx);
-    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.nxh, NP) * f.nzf, &grid)) return 1;
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.nxh, NP) * f.zc(), &grid)) return 1;
     SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   } else {
     auto kfn = k_yfwd_tile<N, NP, MINB, false>;
     const size_t smem = (size_t)NP * N * sizeof(cplx);
-    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.nxh, NP) * f.nzf, &grid)) return 1;
+    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.nxh, NP) * f.zc(), &grid)) return 1;
     SX_FUSED_LAUNCH(p, ST_YFWD, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   }
   return 0;

@@ -415,14 +415,15 @@ __global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_cross(XcrossArgs a, 
 
 template <int N, int LP, bool PF, int MINB, int NC> static int run_xpass_v(Plan& p, Fused& f, const double* d_kx_global) {
   constexpr int T = N / 8;
-  if (f.nzf == 0) return 0;
+  if (f.zc() == 0) return 0;
   XpassArgs a;
-  for (int i = 0; i < 3 * NC; ++i) a.V[i] = f.V[i];
-  for (int i = 0; i < NC; ++i) a.X[i] = f.X[i];
+  const size_t zo = (size_t)f.z0() * p.ny * f.nxp;   // z window of the [zl][y][kx] arrays
+  for (int i = 0; i < 3 * NC; ++i) a.V[i] = f.V[i] + zo;
+  for (int i = 0; i < NC; ++i) a.X[i] = f.X[i] + zo;
   a.kx = d_kx_global;
   a.ny = p.ny;
   a.nxp = f.nxp;
-  a.nzf = f.nzf;
+  a.nzf = f.zc();
   const double Ntot = (double)p.nx * (double)p.ny * (double)p.nz;
   a.tmp = 1.0 / (Ntot * Ntot);
   a.dkx = p.Dkx;
@@ -430,21 +431,22 @@ template <int N, int LP, bool PF, int MINB, int NC> static int run_xpass_v(Plan&
   auto kfn = k_xpass_gradre<N, LP, PF, MINB, NC>;
   const size_t smem = ((size_t)LP * sidx_elem_stride<N>() + (size_t)(PF ? 40 : 24) * LP * T) * sizeof(cplx);
   int grid;
-  if (persistent_grid(p, kfn, LP * T, smem, cdiv(p.ny, 2 * LP) * f.nzf, &grid)) return 1;
+  if (persistent_grid(p, kfn, LP * T, smem, cdiv(p.ny, 2 * LP) * f.zc(), &grid)) return 1;
   SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(grid), LP * T, smem, a, tw);
   return 0;
 }
 template <int N, int NC, int S, int MINB> static int run_xpass_bulk(Plan& p, Fused& f, const double* d_kx_global) {
   constexpr int T = N / 8;
-  if (f.nzf == 0) return 0;
+  if (f.zc() == 0) return 0;
   SX_REQUIRE(f.nxp == XpassBulk<N>::NXP && p.ny % 2 == 0, "xpass (bulk): unexpected row padding");
   XpassArgs a;
-  for (int i = 0; i < 3 * NC; ++i) a.V[i] = f.V[i];
-  for (int i = 0; i < NC; ++i) a.X[i] = f.X[i];
+  const size_t zo = (size_t)f.z0() * p.ny * f.nxp;   // z window of the [zl][y][kx] arrays
+  for (int i = 0; i < 3 * NC; ++i) a.V[i] = f.V[i] + zo;
+  for (int i = 0; i < NC; ++i) a.X[i] = f.X[i] + zo;
   a.kx = d_kx_global;
   a.ny = p.ny;
   a.nxp = f.nxp;
-  a.nzf = f.nzf;
+  a.nzf = f.zc();
   const double Ntot = (double)p.nx * (double)p.ny * (double)p.nz;
   a.tmp = 1.0 / (Ntot * Ntot);
   a.dkx = p.Dkx;
@@ -452,7 +454,7 @@ template <int N, int NC, int S, int MINB> static int run_xpass_bulk(Plan& p, Fus
   auto kfn = k_xpass_gradre_bulk<N, NC, S, MINB>;
   const size_t smem = XpassBulk<N>::smem_bytes(S);
   int grid;
-  if (persistent_grid(p, kfn, T, smem, (p.ny / 2) * f.nzf, &grid)) return 1;
+  if (persistent_grid(p, kfn, T, smem, (p.ny / 2) * f.zc(), &grid)) return 1;
   SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(grid), T, smem, a, tw);
   return 0;
 }
@@ -485,27 +487,27 @@ template <int N, int NC> static int run_xpass(Plan& p, Fused& f, const double* d
 template <int N> static int run_xcross(Plan& p, Fused& f, int npairs, const int* Pi, const int* Qi, const double* sgn, int xo) {
   constexpr int T = N / 8;
   constexpr int LP = T >= 128 ? 1 : 128 / T;
-  if (f.nzf == 0) return 0;
+  if (f.zc() == 0) return 0;
   XcrossArgs a;
   for (int q = 0; q < 2; ++q)
     for (int c = 0; c < 3; ++c) {
-      a.P[q][c] = f.V[Pi[q < npairs ? q : 0] + c];
-      a.Q[q][c] = f.V[Qi[q < npairs ? q : 0] + c];
+      a.P[q][c] = f.V[Pi[q < npairs ? q : 0] + c] + (size_t)f.z0() * p.ny * f.nxp;
+      a.Q[q][c] = f.V[Qi[q < npairs ? q : 0] + c] + (size_t)f.z0() * p.ny * f.nxp;
     }
   a.sgn[0] = sgn[0];
   a.sgn[1] = npairs > 1 ? sgn[1] : 0.0;
   a.npairs = npairs;
-  for (int c = 0; c < 3; ++c) a.X[c] = f.X[xo + c];
+  for (int c = 0; c < 3; ++c) a.X[c] = f.X[xo + c] + (size_t)f.z0() * p.ny * f.nxp;
   a.ny = p.ny;
   a.nxp = f.nxp;
-  a.nzf = f.nzf;
+  a.nzf = f.zc();
   const double Ntot = (double)p.nx * (double)p.ny * (double)p.nz;
   a.tmp = 1.0 / (Ntot * Ntot);
   const cplx* tw = p.tw_x;
   auto kfn = k_xpass_cross<N, LP, (N <= 1024 ? 2 : 1)>;
   const size_t smem = ((size_t)LP * sidx_elem_stride<N>() + (size_t)40 * LP * T) * sizeof(cplx);
   int grid;
-  if (persistent_grid(p, kfn, LP * T, smem, cdiv(p.ny, 2 * LP) * f.nzf, &grid)) return 1;
+  if (persistent_grid(p, kfn, LP * T, smem, cdiv(p.ny, 2 * LP) * f.zc(), &grid)) return 1;
   SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(grid), LP * T, smem, a, tw);
   return 0;
 }

@@ -65,6 +65,7 @@ struct Plan {
   int knob_pf = 13;                 // cp.async prefetch per tile kernel: bit 0 zinv, 1 yinv, 2 yfwd, 3 zfwd (env SX_TILE_PF)
   int knob_tma = 3;                 // bulk-copy (TMA) tile kernels: bit 0 zinv, 1 yinv, 2 yfwd, 3 zfwd (env SX_TMA)
   int knob_tma_min = 256;           // smallest transform length the bulk-copy tile kernels are used for (env SX_TMA_MIN)
+  int knob_zchunks = 4;             // z chunks of the multi-rank xy stage pipeline (env SX_ZCHUNKS; 1 = unchunked)
   int knob_np = 0, knob_minb = 1;   // tuning experiments (env SX_TILE_NP, SX_TILE_MINB)
   unsigned long long launches = 0;  // kernels launched by this plan (bench "gpu_launches")
 
@@ -136,6 +137,14 @@ int exchange_begin(Plan& p, int ev, const cplx* send, cplx* recv, const size_t* 
                    const size_t* rdispl, const size_t* rcount);
 int exchange_begin_p2p(Plan& p, int ev, const cplx* send, const size_t* sdispl, const size_t* scount, cplx* const* peer_dst);
 int exchange_wait(Plan& p, int ev);
+struct P2PCopy {   // 2-D block copy in complex elements
+  cplx* dst;
+  const cplx* src;
+  size_t width, height, spitch, dpitch;
+  int remote;
+};
+int p2p_mark(Plan& p, int slot);
+int p2p_round(Plan& p, const int* wait_slots, int nwait, const P2PCopy* cp, int n, bool barrier, int done_slot);
 int fused_p2p_export(Plan& p, int nw, int nx, void* handle64);
 int fused_p2p_import(Plan& p, const void* handles);
 int allreduce_sum(Plan& p, double* v, int n);
