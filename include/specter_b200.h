@@ -171,6 +171,18 @@ int sx_hd_step_host(sx_plan* plan, double* vx_host, double* vy_host, double* vz_
                     const double* fx_host, const double* fy_host, const double* fz_host, double dt, double nu,
                     const double v_zsta[2], const double v_zend[2]);
 
+/* ---- field files and the output / restart blocks of the driver --------------------------------- */
+/* ref: io_write / io_read, mpiio/binary_io.f90:165-223, 89-160: `<dir>/<fname>.<nmb>.out`, raw native reals,
+ * Fortran order, global extent (nx, ny, nz-Cz); this rank moves its planes ksta..min(kend, nz-Cz) of the DEVICE
+ * real array real_dev(nx, ny, ksta:kend).  io_read zeroes the planes that are not in the file. */
+int sx_io_write(sx_plan* plan, const double* real_dev, const char* dir, const char* fname, const char* nmb);
+int sx_io_read(sx_plan* plan, double* real_dev, const char* dir, const char* fname, const char* nmb);
+/* ref: the BIN block of specter.fpp:1005-1053 on the plan-owned HD state: vx, vy, vz (and wx, wy, wz when
+ * outs >= 1) through C = v/N and the 3-D c2r, pr through p = p'/(nx ny dt) and the xy c2r, each to
+ * `<odir>/<name>.<ext>.out`.  sx_hd_restart is the stat != 0 branch of specter.fpp:886-912 (files -> state). */
+int sx_hd_output(sx_plan* plan, const char* odir, const char* ext, double dt, int outs);
+int sx_hd_restart(sx_plan* plan, const char* idir, const char* ext, double dt);
+
 /* ---- Boussinesq (include/bouss/bouss_rkstep{1,2}.f90) ------------------------------------ */
 /* plan-owned state: which = 0..2 v, 3 pr, 4..6 f, 7..9 C1..C3, 10 th, 11 fs, 12 C7 */
 int sx_bouss_put_state(sx_plan* plan, const double* vx_host, const double* vy_host, const double* vz_host,

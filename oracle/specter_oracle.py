@@ -735,6 +735,60 @@ def make_hd_state(g: Grid, **ic) -> HDState:
     return HDState(vx, vy, vz, pr, fx, fy, fz)
 
 
+# ----------------------------------------------------------------------------
+# field files and the output / restart blocks of the driver
+# ----------------------------------------------------------------------------
+def io_path(dir, fname, nmb):
+    """binary_io.f90:202-204."""
+    import os
+    return os.path.join(str(dir), f"{fname}.{nmb}.out")
+
+
+def io_write(g: Grid, dir, fname, nmb, var: np.ndarray):
+    """io_write, mpiio/binary_io.f90:165-223 with the view of io_init (:15-86): raw native reals, Fortran order,
+    global extent (nx, ny, nz-Cz); this rank's planes ksta..min(kend, nz-Cz) at the offset of its first plane."""
+    nk = max(0, min(g.kend, g.nz - g.Cz) - g.ksta + 1)
+    data = np.ascontiguousarray(var[:nk], dtype=np.float64)
+    path = io_path(dir, fname, nmb)
+    mode = "r+b" if __import__("os").path.exists(path) else "w+b"
+    with open(path, mode) as f:
+        f.seek((g.ksta - 1) * g.nx * g.ny * 8)
+        f.write(data.tobytes())
+
+
+def io_read(g: Grid, dir, fname, nmb) -> np.ndarray:
+    """io_read, mpiio/binary_io.f90:89-160; planes that are not in the file stay zero."""
+    nk = max(0, min(g.kend, g.nz - g.Cz) - g.ksta + 1)
+    out = np.zeros(g.rshape())
+    with open(io_path(dir, fname, nmb), "rb") as f:
+        f.seek((g.ksta - 1) * g.nx * g.ny * 8)
+        out[:nk] = np.frombuffer(f.read(nk * g.nx * g.ny * 8), dtype=np.float64).reshape(nk, g.ny, g.nx)
+    return out
+
+
+def hd_output(g: Grid, s: "HDState", odir, ext, dt, outs=0):
+    """The BIN block of specter.fpp:1005-1053 (HD fields)."""
+    rmp = 1.0 / (float(g.nx) * float(g.ny) * float(g.nz))
+    C1, C2, C3 = s.vx * rmp, s.vy * rmp, s.vz * rmp
+    if outs >= 1:
+        io_write(g, odir, "wx", ext, fftp3d_complex_to_real(g, curlk(g, C2, C3, 1)))
+        io_write(g, odir, "wy", ext, fftp3d_complex_to_real(g, curlk(g, C1, C3, 2)))
+        io_write(g, odir, "wz", ext, fftp3d_complex_to_real(g, curlk(g, C1, C2, 3)))
+    io_write(g, odir, "vx", ext, fftp3d_complex_to_real(g, C1))
+    io_write(g, odir, "vy", ext, fftp3d_complex_to_real(g, C2))
+    io_write(g, odir, "vz", ext, fftp3d_complex_to_real(g, C3))
+    rmp = 1.0 / (float(g.nx) * float(g.ny) * dt)
+    io_write(g, odir, "pr", ext, fftp2d_complex_to_real_xy(g, s.pr * rmp))
+
+
+def hd_restart(g: Grid, idir, ext, dt):
+    """The stat != 0 branch of specter.fpp:886-912: returns (vx, vy, vz, pr) with pr back in p' units."""
+    v = [fftp3d_real_to_complex(g, io_read(g, idir, n, ext)) for n in ("vx", "vy", "vz")]
+    pr = fftp2d_real_to_complex_xy(g, io_read(g, idir, "pr", ext))
+    pr[:, :, : g.nz - g.Cz] *= dt
+    return v[0], v[1], v[2], pr
+
+
 def analytic_field(g: Grid, kind="sin"):
     """The src/tests fields: sin4x cos8y sin6z (fc_dirichlet.f90:14, energy.f90:13)
     or sin4x cos8y exp(.4 z/Lz) (poisson.f90:21) on the local real slab."""

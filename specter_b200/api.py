@@ -58,6 +58,10 @@ SIGNATURES = {
     "sx_plan_stage_times": [_P, _PD, C.POINTER(C.c_longlong), _I],
     "sx_nccl_unique_id": [_D],
     "sx_plan_set_comm": [_P, _D],
+    "sx_io_write": [_P, _D, C.c_char_p, C.c_char_p, C.c_char_p],
+    "sx_io_read": [_P, _D, C.c_char_p, C.c_char_p, C.c_char_p],
+    "sx_hd_output": [_P, C.c_char_p, C.c_char_p, C.c_double, _I],
+    "sx_hd_restart": [_P, C.c_char_p, C.c_char_p, C.c_double],
     "sx_plan_p2p_export": [_P, _I, _I, _D],
     "sx_plan_p2p_import": [_P, _D],
     "sx_plan_set_comm_callbacks": [_P, _D, _D, _D],
@@ -117,6 +121,25 @@ _RESTYPES = {"sx_stage_name": C.c_char_p, "sx_last_error": C.c_char_p, "sx_versi
              "sx_real_bytes": C.c_size_t}
 
 
+def _preload_nccl():
+    """The library links libnccl.so.2; PyTorch ships its own (newer) copy.  Whichever is mapped first serves both,
+    and torch's CUDA library needs symbols of its own version: map that copy first when it is installed, so that
+    the import order of torch and specter_b200 does not matter."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for d in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(d, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 class Library:
     """ctypes binding of one build of the C ABI."""
 
@@ -126,6 +149,7 @@ class Library:
                 f"{path} not found: build the CUDA extension first (python -m specter_b200.build); "
                 "specter_b200 has no CPU fallback")
         self.path = path
+        _preload_nccl()
         self.dll = C.CDLL(path)
         for name, args in SIGNATURES.items():
             fn = getattr(self.dll, name)  # AttributeError if the ABI is incomplete
@@ -464,6 +488,18 @@ class Plan:
         self.hd_rkstep1()
         for o in range(self.ord, 0, -1):
             self.hd_rkstep2(o, dt, nu, v_zsta, v_zend, impl)
+
+    def io_write(self, r: DeviceArray, dir, fname, nmb):
+        self._call("sx_io_write", r.ptr, str(dir).encode(), fname.encode(), nmb.encode())
+
+    def io_read(self, r: DeviceArray, dir, fname, nmb):
+        self._call("sx_io_read", r.ptr, str(dir).encode(), fname.encode(), nmb.encode())
+
+    def hd_output(self, odir, ext, dt, outs=0):
+        self._call("sx_hd_output", str(odir).encode(), ext.encode(), float(dt), int(outs))
+
+    def hd_restart(self, idir, ext, dt):
+        self._call("sx_hd_restart", str(idir).encode(), ext.encode(), float(dt))
 
     def hd_step_host(self, vx, vy, vz, pr, fx, fy, fz, dt, nu, v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0)):
         """One full step on HOST arrays (in place): H2D, rkstep1 + ord substeps, D2H."""

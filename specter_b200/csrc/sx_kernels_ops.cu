@@ -84,6 +84,9 @@ __global__ void k_copy(size_t n, const cplx* __restrict__ a, cplx* __restrict__ 
   SX_GRID_STRIDE(idx, n) b[idx] = a[idx];
 }
 
+__global__ void k_scale_copy(size_t n, const cplx* __restrict__ a, cplx* __restrict__ b, double s) {
+  SX_GRID_STRIDE(idx, n) b[idx] = cscale(a[idx], s);
+}
 __global__ void k_add(size_t n, cplx* __restrict__ a, const cplx* __restrict__ b) {
   SX_GRID_STRIDE(idx, n) a[idx] = cadd(a[idx], b[idx]);
 }
@@ -355,6 +358,11 @@ int op_copy(Plan& p, const cplx* a, cplx* b) {
 int op_add(Plan& p, cplx* a, const cplx* b) {
   const size_t n = p.csize();
   SX_EW_LAUNCH(p, k_add, n, n, a, b);
+  return 0;
+}
+int op_scale_copy(Plan& p, const cplx* a, cplx* b, double s) {   // b = s a on all nz rows (specter.fpp:1010-1020)
+  const size_t n = p.csize();
+  SX_EW_LAUNCH(p, k_scale_copy, n, n, a, b, s);
   return 0;
 }
 int op_scale_phys(Plan& p, cplx* a, double s) {

@@ -100,6 +100,9 @@ int op_fc_filter(Plan& p, cplx* a);
 int op_copy(Plan& p, const cplx* a, cplx* b);
 int op_add(Plan& p, cplx* a, const cplx* b);
 int op_scale_phys(Plan& p, cplx* a, double s);
+int op_scale_copy(Plan& p, const cplx* a, cplx* b, double s);
+int fft2d_xy_r2c(Plan& p, const double* r, cplx* out, int nz_active);
+int fft2d_xy_c2r(Plan& p, cplx* mixed_destroyed, double* r, int nz_active);
 int op_rk_axpy(Plan& p, cplx* v, const cplx* v0, const cplx* nl, const cplx* f, double dt,
                double nu, double rmp);
 int op_gradre_products(Plan& p, double* const r[12], double* rx, double* ry, double* rz);

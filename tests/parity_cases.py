@@ -361,3 +361,43 @@ def case_mhd_substeps(lib, tables, shape, ord=2, nsteps=1, impl=0, dt=1e-3, nu=1
             assert rel(got[3][:, :, :nph], s.pr[:, :, :nph]) < 100 * TOL_FIELD
             fields_close([got[7]], [s.ph], rows=nph, tol=100 * TOL_FIELD)
     p.close()
+
+
+# ---- field files, output and restart (binary_io.f90, specter.fpp:1005-1053 / 886-912) ----------------------------
+def case_io_output_restart(lib, tables, shape, tmpdir, ord=2, dt=1e-3, nu=1e-3):
+    import os
+    g, p = make(lib, tables, *shape, ord=ord)
+    s = O.make_hd_state(g)
+    p.hd_put_state(s.vx, s.vy, s.vz, s.pr, s.fx, s.fy, s.fz)
+    p.hd_step(dt, nu)
+    O.hd_step(g, s, dt, nu)
+    ours, ref = os.path.join(str(tmpdir), "ours"), os.path.join(str(tmpdir), "ref")
+    os.makedirs(ours), os.makedirs(ref)
+    p.hd_output(ours, "0001", dt, outs=1)
+    O.hd_output(g, s, ref, "0001", dt, outs=1)
+    nph = g.nz - g.Cz
+    for name in ("vx", "vy", "vz", "wx", "wy", "wz", "pr"):
+        a = np.fromfile(O.io_path(ours, name, "0001"))
+        b = np.fromfile(O.io_path(ref, name, "0001"))
+        assert a.size == b.size == g.nx * g.ny * nph, (name, a.size)       # the physical box, nothing else
+        tol = 100 * TOL_FIELD if name == "pr" else TOL_FIELD                  # p = p'/dt: see hd_fields_close
+        assert rel(a, b) < tol, (name, rel(a, b))
+    # the raw io entry points: a device real array round-trips through a file bit for bit on the physical planes
+    rng = np.random.default_rng(5)
+    r = rng.standard_normal(g.rshape())
+    d = p.real(r)
+    p.io_write(d, ours, "rt", "0007")
+    assert np.array_equal(np.fromfile(O.io_path(ours, "rt", "0007")).reshape(nph, g.ny, g.nx), r[:nph])
+    d2 = p.real()
+    p.io_read(d2, ours, "rt", "0007")
+    back = d2.get()
+    assert np.array_equal(back[:nph], r[:nph]) and not back[nph:].any()
+    # restart from the REFERENCE-format files written by the oracle: state equals the oracle's restart
+    p.hd_restart(ref, "0001", dt)
+    got = p.hd_get_state()
+    want = O.hd_restart(g, ref, "0001", dt)
+    scale = max(np.abs(q).max() for q in want[:3])
+    for q, w in zip(got[:3], want[:3]):
+        assert np.abs(q - w).max() / scale < TOL_FIELD
+    assert rel(got[3][:, :, :nph], want[3][:, :, :nph]) < 100 * TOL_FIELD
+    p.close()

@@ -92,3 +92,7 @@ def test_hd_substeps_bulk_project(emu_lib, tables, monkeypatch):
     # bulk-copy projection kernel (default from nz = 256): wall rows by reduction, exponentials by recurrence
     monkeypatch.setenv("SX_PJ", "10")
     P.case_hd_substeps(emu_lib, tables, (16, 16, 256), ord=2, nsteps=2, impl=0, walls=((0.2, -0.1), (-0.3, 0.1)))
+
+
+def test_io_output_restart(emu_lib, tables, tmp_path):
+    P.case_io_output_restart(emu_lib, tables, SMALL, tmp_path)

@@ -115,3 +115,7 @@ def test_hd_substeps_length_1024_2048_kernels(cuda_lib, tables):
     P.case_hd_substeps(cuda_lib, tables, (16, 1024, 64), ord=2, nsteps=1, impl=0)
     P.case_hd_substeps(cuda_lib, tables, (16, 2048, 64), ord=2, nsteps=1, impl=0)
     P.case_hd_substeps(cuda_lib, tables, (16, 16, 1024), ord=2, nsteps=1, impl=0)
+
+
+def test_io_output_restart(cuda_lib, tables, tmp_path):
+    P.case_io_output_restart(cuda_lib, tables, CFG1, tmp_path)
