@@ -148,10 +148,41 @@ int sx_vdiagnostic(sx_plan* plan, const double* a, const double* b, const double
 
 /* ref: s_imposebc (sboundary.f90:67-119) with `constant' walls (s_constant_z :122-165) */
 int sx_s_imposebc(sx_plan* plan, double* th);
-/* ref: a_imposebc_and_project (bboundary.f90:100-189) with conducting walls at both ends: int_conducting_z,
+/* ref: a_imposebc_and_project (bboundary.f90:100-189); wall kinds from sx_setup_bc(plan, "b", ...) (default
+ * conducting at both ends; vacuum walls use insulating_z :294-344 with robin_reconstruct): int_conducting_z,
  * sol_project(...,0,0,0), conducting_z with neumann_reconstruct (fcgram_mod.f90:368-511); ph returns the gauge
  * potential in the mixed domain */
 int sx_a_imposebc_and_project(sx_plan* plan, double* ax, double* ay, double* az, double* ph);
+
+/* ---- wall BC kinds, stand-alone reconstructions, remaining diagnostics -------- */
+/* ref: setup_bc (boundary_mod.fpp:30-68) -> v_setup / s_setup / b_setup.  field = "v" | "s" | "b"; bckind[6] = the
+ * strings of parameter.inp for x=0, x=Lx, y=0, y=Ly, z=0, z=Lz: "periodic", "noslip" (v), "constant" (s),
+ * "conducting" | "vacuum" (b).  x and y must be periodic.  Defaults without a call: noslip / constant / conducting. */
+int sx_setup_bc(sx_plan* plan, const char* field, const char* const bckind[6]);
+/* ref: neumann_reconstruct (fcgram_mod.f90:368-511), z branches: f in the mixed domain with the prescribed normal
+ * derivative in the wall row; boun 5 (z=0) | 6 (z=Lz); order 1 | 2 */
+int sx_neumann_reconstruct(sx_plan* plan, double* f, int boun, int order);
+/* ref: robin_reconstruct (fcgram_mod.f90:514-644), z branches: wall value from f' + a f = g; a = device array
+ * (ny, ista:iend) of real coefficients, or NULL for khom = sqrt(kx^2+ky^2) (what every caller passes) */
+int sx_robin_reconstruct(sx_plan* plan, double* f, int boun, const double* a);
+int sx_helicity(sx_plan* plan, const double* a, const double* b, const double* c, double* out); /* ref: pseudospec_hd.f90:638-775 */
+int sx_product(sx_plan* plan, const double* a, const double* b, double* out);                   /* ref: pseudospec_phd.f90:199-272 */
+/* ref: pscheck (pseudospec_phd.f90:275-321): out = the scalar.txt columns <th^2>, <|k^2 th|^2>, injection */
+int sx_pscheck(sx_plan* plan, const double* a, const double* b, double out[3]);
+/* ref: maxabs (pseudospec_hd.f90:1008-1079): kin 0 curl, 1 laplacian, 2 the field */
+int sx_maxabs(sx_plan* plan, const double* a, const double* b, const double* c, int kin, double* out);
+/* ref: mhdcheck (pseudospec_mhd.f90:109-212): out = eng, ens, cur (balance.txt), engk, engm (energy.txt),
+ * helk, helm (helicity.txt, hel=1), crh, asq (cross.txt, crs=1) */
+int sx_mhdcheck(sx_plan* plan, const double* a, const double* b, const double* c, const double* ma, const double* mb,
+                const double* mc, int hel, int crs, double out[9]);
+/* ref: robcheck (bboundary.f90:434-602): out = d, e, f, g */
+int sx_robcheck(sx_plan* plan, const double* a, const double* b, const double* c, double out[4]);
+/* ref: bdiagnostic (bboundary.f90:348-430): the six columns after the time of conducting_diagnostic.txt and / or
+ * vacuum_diagnostic.txt, chosen by the wall kinds of sx_setup_bc(plan, "b", ...); *which bit 0 / bit 1 says which */
+int sx_bdiagnostic(sx_plan* plan, const double* a, const double* b, const double* c, double conducting[6],
+                   double vacuum[6], int* which);
+/* ref: sdiagnostic (sboundary.f90:168-210): out = <|th|^2> at z=0 and z=Lz */
+int sx_sdiagnostic(sx_plan* plan, const double* a, double out[2]);
 
 /* ---- the RK substep (include/hd/hd_rkstep{1,2}.f90) --------------------------------- */
 /* Device-resident HD state owned by the plan.  put/get move whole fields in the reference
@@ -199,6 +230,11 @@ int sx_bouss_rkstep2(sx_plan* plan, int o, double dt, double nu, double kappa, d
                      const double v_zsta[2], const double v_zend[2], int impl);
 
 /* ---- vector-potential MHD (include/mhd/mhd_rkstep{1,2}.f90) ------------------------------- */
+/* ref: include/rotbouss/rotbouss_rkstep2.f90:3-56 on the BOUSS state (rotbouss_rkstep1 = bouss_rkstep1):
+ * omega[3] = the rotation vector of the `rotation' namelist; no theta filter / round trip at the end */
+int sx_rotbouss_rkstep2(sx_plan* plan, int o, double dt, double nu, double kappa, double xmom, double xtemp,
+                        const double omega[3], const double v_zsta[2], const double v_zend[2], int impl);
+
 /* plan-owned state: which = 0..2 v, 3 pr, 4..6 f, 7..9 C1..C3, 10..12 a, 13 ph, 14..16 m, 17..19 C9..C11 */
 int sx_mhd_put_state(sx_plan* plan, const double* vx_host, const double* vy_host, const double* vz_host,
                      const double* pr_host, const double* ax_host, const double* ay_host, const double* az_host,
@@ -212,6 +248,20 @@ int sx_mhd_rkstep1(sx_plan* plan);
 /* ref: mhd_rkstep2.f90:3-84 (B = curl A + b0, J = curl B, prodre - Lorentz force, EMF, RK update, no-slip
  * projection, conducting-wall gauge projection).  b0 may be NULL (no uniform field). */
 int sx_mhd_rkstep2(sx_plan* plan, int o, double dt, double nu, double mu, const double b0[3], int impl);
+
+/* ---- MHDBOUSS (include/mhdbouss/mhdbouss_rkstep{1,2}.f90) ------------------------------------------
+ * state slots: the MHD ones (0..2 v, 3 pr, 4..6 f, 7..9 C1..C3, 10..12 a, 13 ph, 14..16 m, 17..19 C9..C11),
+ * 20 th, 21 fs, 22 C7.  Only the per-operator composition (impl = 1) exists for this solver. */
+int sx_mhdbouss_put_state(sx_plan* plan, const double* vx_host, const double* vy_host, const double* vz_host,
+                          const double* pr_host, const double* ax_host, const double* ay_host, const double* az_host,
+                          const double* th_host, const double* fx_host, const double* fy_host, const double* fz_host,
+                          const double* mx_host, const double* my_host, const double* mz_host, const double* fs_host);
+int sx_mhdbouss_get_state(sx_plan* plan, double* vx_host, double* vy_host, double* vz_host, double* pr_host,
+                          double* ax_host, double* ay_host, double* az_host, double* ph_host, double* th_host);
+int sx_mhdbouss_state_ptr(sx_plan* plan, int which, double** dptr);
+int sx_mhdbouss_rkstep1(sx_plan* plan);
+int sx_mhdbouss_rkstep2(sx_plan* plan, int o, double dt, double nu, double mu, double kappa, double xmom,
+                        double xtemp, const double b0[3], int impl);
 
 #ifdef __cplusplus
 }

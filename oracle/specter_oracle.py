@@ -1051,3 +1051,258 @@ def make_mhd_state(g: Grid, seed=1000, **ic) -> MhdState:
     ax, ay, az = initialb(g, rnd)
     z = np.zeros(g.cshape(), dtype=np.complex128)
     return MhdState(vx, vy, vz, z.copy(), z.copy(), z.copy(), z.copy(), ax, ay, az, z.copy(), z.copy(), z.copy(), z.copy())
+
+
+# ----------------------------------------------------------------------------
+# vacuum (Robin) walls, ROTBOUSS / MHDBOUSS substeps, the remaining diagnostics
+# ----------------------------------------------------------------------------
+def robin_reconstruct(g: Grid, f, boun: int, a: np.ndarray):
+    """fcgram_mod.f90:514-644, z branches (:612-635): wall value from f' + a f = g_wall stored in the wall row;
+    a[i,j] is the (real) coefficient per (kx,ky) (the callers pass khom)."""
+    if g.neu is None:
+        raise ValueError("[ERROR] Neumann table not loaded in robin_reconstruct. Aborting...")
+    neu = g.neu
+    d = g.oz
+    if boun == 5:
+        acc = neu[d - 1] * f[:, :, 0]
+        for k in range(1, d):
+            acc = acc + neu[k - 1] * f[:, :, d - k]
+        f[:, :, 0] = acc / (a * neu[d - 1] + 1)
+    elif boun == 6:
+        top = g.nz - g.Cz - 1
+        acc = neu[d - 1] * f[:, :, top]
+        for k in range(1, d):
+            acc = acc + neu[k - 1] * f[:, :, top - d + k]
+        f[:, :, top] = acc / (a * neu[d - 1] + 1)
+    else:
+        raise ValueError("[ERROR] Robin reconstruction not performed. Wrong boundary specified. Aborting...")
+
+
+B_CONDUCTING, B_VACUUM = 0, 1   # b_parsebc, bboundary.f90:15-40
+
+
+def a_imposebc_and_project_bc(g: Grid, ax, ay, az, bczsta: int, bczend: int):
+    """bboundary.f90:100-189 for every wall combination it accepts (0 conducting, 1 vacuum).  Returns ph."""
+    if bczsta not in (0, 1) or bczend not in (0, 1):
+        raise ValueError("[ERROR] Unsupported boundary conditions in Z direction. Aborting...")
+    if g.neu is None:
+        g.load_neumann()
+    if g.ista == 1:
+        az[0, 0, 0] = 0.0
+    top = g.nz - g.Cz - 1
+    walls = ((0, 0, bczsta), (1, top, bczend))
+    if bczsta == 0 or bczend == 0:
+        goto_domain_w_boundaries(g, ax, ay)
+        for pos, ind, kind in walls:                       # int_conducting_z :192-236
+            if kind == 0:
+                ax[:, :, ind] = 0.0
+                ay[:, :, ind] = 0.0
+        goto_3d_fourier(g, ax, ay)
+    ph = sol_project(g, ax, ay, az, 0, 2 * bczsta, 2 * bczend)
+    goto_domain_w_boundaries(g, ax, ay, az)
+    for pos, ind, kind in walls:
+        ax[:, :, ind] = 0.0
+        ay[:, :, ind] = 0.0
+        az[:, :, ind] = 0.0
+        if kind == 0:                                      # conducting_z :239-290
+            neumann_reconstruct(g, ax, 5 + pos, 2)
+            neumann_reconstruct(g, ay, 5 + pos, 2)
+            neumann_reconstruct(g, az, 5 + pos, 1)
+        else:                                              # insulating_z :294-344
+            robin_reconstruct(g, ax, 5 + pos, g.khom)
+            robin_reconstruct(g, ay, 5 + pos, g.khom)
+            robin_reconstruct(g, az, 5 + pos, g.khom)
+    goto_3d_fourier(g, ax, ay, az)
+    return ph
+
+
+def helicity(g: Grid, a, b, c) -> float:
+    """pseudospec_hd.f90:638-775: <A . curl A> over the physical rows."""
+    tmp = 1.0 / g.N ** 2 / float(g.nz - g.Cz)
+
+    def prod(p, q):
+        c1 = p.copy(); c2 = q.copy()
+        fftp1d_complex_to_real_z(g, c1); fftp1d_complex_to_real_z(g, c2)
+        return (c1 * np.conj(c2)).real
+
+    r1 = prod(a, curlk(g, b, c, 1))
+    r1 = r1 + prod(b, curlk(g, a, c, 2))
+    r1 = r1 + prod(c, curlk(g, a, b, 3))
+    return _mean_phys(g, r1, tmp)
+
+
+def product(g: Grid, a, b) -> float:
+    """pseudospec_phd.f90:199-272."""
+    tmp = 1.0 / g.N ** 2 / float(g.nz - g.Cz)
+    at = a.copy(); bt = b.copy()
+    fftp1d_complex_to_real_z(g, at); fftp1d_complex_to_real_z(g, bt)
+    return _mean_phys(g, (at * np.conj(bt)).real, tmp)
+
+
+def pscheck(g: Grid, a, b):
+    """pseudospec_phd.f90:275-321 -> the scalar.txt columns (eng, ens, pot)."""
+    return variance(g, a, 1), variance(g, a, 0), product(g, a, b)
+
+
+def maxabs(g: Grid, a, b, c, kin: int) -> float:
+    """pseudospec_hd.f90:1008-1079 (one rank): max |curl|, |laplacian| or |field| over the physical rows."""
+    if kin == 0:
+        c1, c2, c3 = curlk(g, b, c, 1), curlk(g, a, c, 2), curlk(g, a, b, 3)
+    elif kin == 1:
+        c1, c2, c3 = laplak(g, a), laplak(g, b), laplak(g, c)
+    else:
+        c1, c2, c3 = a, b, c
+    r1 = fftp3d_complex_to_real(g, c1); r2 = fftp3d_complex_to_real(g, c2); r3 = fftp3d_complex_to_real(g, c3)
+    ph = _phys(g)
+    dloc = float(np.max(r1[ph] ** 2 + r2[ph] ** 2 + r3[ph] ** 2))
+    return np.sqrt(dloc) / g.N
+
+
+def mhdcheck(g: Grid, a, b, c, ma, mb, mc):
+    """pseudospec_mhd.f90:109-212 with hel=1, crs=1 -> (eng, ens, cur, engk, engm, helk, helm, crh, asq):
+    the columns of balance.txt, energy.txt, helicity.txt and cross.txt."""
+    engk = energy(g, a, b, c, 1)
+    ens = energy(g, a, b, c, 0)
+    engm = energy(g, ma, mb, mc, 0)
+    cur = energy(g, ma, mb, mc, 2)
+    helk = helicity(g, a, b, c)
+    helm = helicity(g, ma, mb, mc)
+    asq = energy(g, ma, mb, mc, 1)
+    crh = cross(g, a, b, c, derivk(g, ma, 1), derivk(g, mb, 2), derivk(g, mc, 3), 1)
+    return engk + engm, ens, cur, engk, engm, helk, helm, crh, asq
+
+
+def robcheck(g: Grid, a, b, c):
+    """bboundary.f90:434-602: mean squared residual of the vacuum condition da/dn + khom a at both walls,
+    tangential (a,b) and normal (c) parts."""
+    tmp = 1.0 / g.N ** 2
+    top = g.nz - g.Cz - 1
+    w = _weights(g)[:, None]
+
+    def resid(q):
+        C1 = q.copy()
+        C2 = derivk(g, C1, 3)
+        fftp1d_complex_to_real_z(g, C1); fftp1d_complex_to_real_z(g, C2)
+        r0 = -C2[:, :, 0] + g.khom * C1[:, :, 0]
+        r1 = C2[:, :, top] + g.khom * C1[:, :, top]
+        return r0.real ** 2 + r0.imag ** 2, r1.real ** 2 + r1.imag ** 2
+
+    a0, a1 = resid(a); b0, b1 = resid(b); c0, c1 = resid(c)
+    return (float(np.sum(w * (a0 + b0) * tmp)), float(np.sum(w * (a1 + b1) * tmp)),
+            float(np.sum(w * c0 * tmp)), float(np.sum(w * c1 * tmp)))
+
+
+def bdiagnostic(g: Grid, a, b, c, bczsta: int = 0, bczend: int = 0):
+    """bboundary.f90:348-430 -> {'conducting': 6 columns, 'vacuum': 6 columns} of the two diagnostic files."""
+    c1 = curlk(g, b, c, 1); c2 = curlk(g, a, c, 2); c3 = curlk(g, a, b, 3)
+    tm1 = divergence(g, a, b, c)
+    tm2 = divergence(g, c1, c2, c3)
+    out = {}
+    if bczsta == 0 or bczend == 0:
+        tmr, tms = bouncheck_z(g, c3)
+        c4 = curlk(g, c2, c3, 1)
+        c2b = curlk(g, c1, c3, 2)
+        tmp, tmq = bouncheck_z(g, c4, c2b)
+        out["conducting"] = (tm1, tm2, tmp, tmq, tmr, tms)
+    if bczsta == 1 or bczend == 1:
+        out["vacuum"] = (tm1, tm2) + robcheck(g, a, b, c)
+    return out
+
+
+def sdiagnostic(g: Grid, a):
+    """sboundary.f90:168-210 -> scalar_constant_diagnostic.txt columns."""
+    return bouncheck_z(g, a)
+
+
+def rotbouss_rkstep2(g: Grid, s: BoussState, C1, C2, C3, C7, o: int, dt: float, nu: float, kappa: float,
+                     xmom: float = 1.0, xtemp: float = 1.0, omega=(0.0, 0.0, 0.0),
+                     v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0)):
+    """include/rotbouss/rotbouss_rkstep2.f90:3-56 (no theta filter / round trip at the end, unlike BOUSS)."""
+    rmp = 1.0 / float(o)
+    ox, oy, oz_ = omega
+    C4, C5, C6 = gradre(g, s.vx, s.vy, s.vz)
+    C8 = advect(g, s.vx, s.vy, s.vz, s.th)
+    C4 = C4 + 2 * (oy * s.vz - oz_ * s.vy)
+    C5 = C5 + 2 * (oz_ * s.vx - ox * s.vz)
+    C6 = C6 + 2 * (ox * s.vy - oy * s.vx) - xmom * s.th
+    C8 = C8 - xtemp * s.vz
+    for q in (C4, C5, C6, C8):
+        fc_filter(g, q)
+    s.vx = laplak(g, s.vx); s.vy = laplak(g, s.vy); s.vz = laplak(g, s.vz); s.th = laplak(g, s.th)
+    s.vx = C1 + dt * (nu * s.vx - C4 + s.fx) * rmp
+    s.vy = C2 + dt * (nu * s.vy - C5 + s.fy) * rmp
+    s.vz = C3 + dt * (nu * s.vz - C6 + s.fz) * rmp
+    s.th = C7 + dt * (kappa * s.th - C8 + s.fs) * rmp
+    s.pr = v_imposebc_and_project(g, s.vx, s.vy, s.vz, s.pr, o, v_zsta, v_zend)
+    s_imposebc(g, s.th)
+
+
+def rotbouss_step(g: Grid, s: BoussState, dt, nu, kappa, on_substep=None, **kw):
+    C1 = s.vx.copy(); C2 = s.vy.copy(); C3 = s.vz.copy(); C7 = s.th.copy()
+    for o in range(g.ord, 0, -1):
+        rotbouss_rkstep2(g, s, C1, C2, C3, C7, o, dt, nu, kappa, **kw)
+        if on_substep is not None:
+            on_substep(o, s)
+
+
+@dataclass
+class MhdBoussState(MhdState):
+    th: np.ndarray = None
+    fs: np.ndarray = None
+
+
+def mhdbouss_rkstep2(g: Grid, s: MhdBoussState, C1, C2, C3, C7, C9, C10, C11, o: int, dt: float, nu: float,
+                     mu: float, kappa: float, xmom: float = 1.0, xtemp: float = 1.0, b0=(0.0, 0.0, 0.0),
+                     bczsta: int = 0, bczend: int = 0):
+    """include/mhdbouss/mhdbouss_rkstep2.f90:3-106 (theta round trip without the filter; static walls)."""
+    rmp = 1.0 / float(o)
+    C12 = curlk(g, s.ay, s.az, 1); C13 = curlk(g, s.ax, s.az, 2); C14 = curlk(g, s.ax, s.ay, 3)
+    if g.ista == 1:
+        C12[0, 0, 0] = b0[0] * g.N; C13[0, 0, 0] = b0[1] * g.N; C14[0, 0, 0] = b0[2] * g.N
+    s.ax = curlk(g, C13, C14, 1); s.ay = curlk(g, C12, C14, 2); s.az = curlk(g, C12, C13, 3)
+    C4, C5, C6 = prodre(g, s.vx, s.vy, s.vz)
+    C8 = advect(g, s.vx, s.vy, s.vz, s.th)
+    C15, C16, C17 = vector(g, s.ax, s.ay, s.az, C12, C13, C14)
+    C4 = C4 - C15; C5 = C5 - C16; C6 = C6 - C17
+    C6 = C6 - xmom * s.th
+    C8 = C8 - xtemp * s.vz
+    for q in (C4, C5, C6, C8):
+        fc_filter(g, q)
+    C15, C16, C17 = vector(g, s.vx, s.vy, s.vz, C12, C13, C14)
+    for q in (C15, C16, C17):
+        fc_filter(g, q)
+    s.vx = laplak(g, s.vx); s.vy = laplak(g, s.vy); s.vz = laplak(g, s.vz); s.th = laplak(g, s.th)
+    s.vx = C1 + dt * (nu * s.vx - C4 + s.fx) * rmp
+    s.vy = C2 + dt * (nu * s.vy - C5 + s.fy) * rmp
+    s.vz = C3 + dt * (nu * s.vz - C6 + s.fz) * rmp
+    s.ax = C9 + dt * (-mu * s.ax + C15 + s.mx) * rmp
+    s.ay = C10 + dt * (-mu * s.ay + C16 + s.my) * rmp
+    s.az = C11 + dt * (-mu * s.az + C17 + s.mz) * rmp
+    s.th = C7 + dt * (kappa * s.th - C8 + s.fs) * rmp
+    s.pr = v_imposebc_and_project(g, s.vx, s.vy, s.vz, s.pr, o)
+    s.ph = a_imposebc_and_project_bc(g, s.ax, s.ay, s.az, bczsta, bczend)
+    s_imposebc(g, s.th)
+    R1 = fftp3d_complex_to_real(g, s.th)
+    R1 = R1 / g.nx / g.ny / g.nz
+    s.th = fftp3d_real_to_complex(g, R1)
+
+
+def mhdbouss_step(g: Grid, s: MhdBoussState, dt, nu, mu, kappa, on_substep=None, **kw):
+    C = [q.copy() for q in (s.vx, s.vy, s.vz, s.th, s.ax, s.ay, s.az)]
+    for o in range(g.ord, 0, -1):
+        mhdbouss_rkstep2(g, s, *C, o, dt, nu, mu, kappa, **kw)
+        if on_substep is not None:
+            on_substep(o, s)
+
+
+def make_mhdbouss_state(g: Grid, seed=1000, **ic) -> MhdBoussState:
+    """initialv + initials + initialb drawn from one randu stream in the driver's order (specter.fpp:861-874:
+    velocity, then scalar, then vector potential)."""
+    rnd = Randu(seed)
+    vx, vy, vz = initialv(g, rnd=rnd, **ic)
+    th = initials(g, rnd)
+    ax, ay, az = initialb(g, rnd)
+    fx, fy, fz = initialfv(g)
+    z = np.zeros(g.cshape(), dtype=np.complex128)
+    return MhdBoussState(vx, vy, vz, z.copy(), fx, fy, fz, ax, ay, az, z.copy(), z.copy(), z.copy(), z.copy(),
+                         th, z.copy())

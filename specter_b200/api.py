@@ -115,6 +115,23 @@ SIGNATURES = {
     "sx_mhd_state_ptr": [_P, _I, C.POINTER(_D)],
     "sx_mhd_rkstep1": [_P],
     "sx_mhd_rkstep2": [_P, _I, _F, _F, _F, _PD, _I],
+    "sx_setup_bc": [_P, C.c_char_p, C.POINTER(C.c_char_p)],
+    "sx_neumann_reconstruct": [_P, _D, _I, _I],
+    "sx_robin_reconstruct": [_P, _D, _I, _D],
+    "sx_helicity": [_P, _D, _D, _D, _PD],
+    "sx_product": [_P, _D, _D, _PD],
+    "sx_pscheck": [_P, _D, _D, _PD],
+    "sx_maxabs": [_P, _D, _D, _D, _I, _PD],
+    "sx_mhdcheck": [_P, _D, _D, _D, _D, _D, _D, _I, _I, _PD],
+    "sx_robcheck": [_P, _D, _D, _D, _PD],
+    "sx_bdiagnostic": [_P, _D, _D, _D, _PD, _PD, _PI],
+    "sx_sdiagnostic": [_P, _D, _PD],
+    "sx_rotbouss_rkstep2": [_P, _I, _F, _F, _F, _F, _F, _PD, _PD, _PD, _I],
+    "sx_mhdbouss_put_state": [_P] + [_D] * 15,
+    "sx_mhdbouss_get_state": [_P] + [_D] * 9,
+    "sx_mhdbouss_state_ptr": [_P, _I, C.POINTER(_D)],
+    "sx_mhdbouss_rkstep1": [_P],
+    "sx_mhdbouss_rkstep2": [_P, _I, _F, _F, _F, _F, _F, _F, _PD, _I],
 }
 _RESTYPES = {"sx_stage_name": C.c_char_p, "sx_last_error": C.c_char_p, "sx_version": C.c_char_p,
              "sx_plan_launch_count": C.c_ulonglong, "sx_spectral_bytes": C.c_size_t,
@@ -587,3 +604,102 @@ class Plan:
         self.mhd_rkstep1()
         for o in range(self.ord, 0, -1):
             self.mhd_rkstep2(o, dt, nu, mu, b0, impl)
+
+    # ---- wall BC kinds, stand-alone reconstructions, remaining diagnostics ----
+    def setup_bc(self, field, bckind):
+        """``setup_bc`` (boundary_mod.fpp:30-68): field 'v' | 's' | 'b', bckind = six strings as in parameter.inp."""
+        if len(bckind) != 6:
+            raise SpecterError("setup_bc: bckind takes six strings (x0, xL, y0, yL, z0, zL)")
+        arr = (C.c_char_p * 6)(*[str(b).encode() for b in bckind])
+        self._call("sx_setup_bc", field.encode(), arr)
+
+    def neumann_reconstruct(self, f, boun, order):
+        self._call("sx_neumann_reconstruct", f.ptr, boun, order)
+
+    def robin_reconstruct(self, f, boun, a=None):
+        """a: None for khom (what the reference's callers pass), or a device pointer of (nxl, ny) real coefficients."""
+        self._call("sx_robin_reconstruct", f.ptr, boun, a)
+
+    def _scalar_out(self, name, *args):
+        out = C.c_double()
+        self._call(name, *args, C.byref(out))
+        return out.value
+
+    def helicity(self, a, b, c) -> float:
+        return self._scalar_out("sx_helicity", a.ptr, b.ptr, c.ptr)
+
+    def product(self, a, b) -> float:
+        return self._scalar_out("sx_product", a.ptr, b.ptr)
+
+    def pscheck(self, a, b):
+        out = (C.c_double * 3)()
+        self._call("sx_pscheck", a.ptr, b.ptr, out)
+        return tuple(out)
+
+    def maxabs(self, a, b, c, kin) -> float:
+        return self._scalar_out("sx_maxabs", a.ptr, b.ptr, c.ptr, kin)
+
+    def mhdcheck(self, a, b, c, ma, mb, mc, hel=1, crs=1):
+        out = (C.c_double * 9)()
+        self._call("sx_mhdcheck", a.ptr, b.ptr, c.ptr, ma.ptr, mb.ptr, mc.ptr, hel, crs, out)
+        return tuple(out)
+
+    def robcheck(self, a, b, c):
+        out = (C.c_double * 4)()
+        self._call("sx_robcheck", a.ptr, b.ptr, c.ptr, out)
+        return tuple(out)
+
+    def bdiagnostic(self, a, b, c) -> dict:
+        cond, vac, which = (C.c_double * 6)(), (C.c_double * 6)(), C.c_int()
+        self._call("sx_bdiagnostic", a.ptr, b.ptr, c.ptr, cond, vac, C.byref(which))
+        out = {}
+        if which.value & 1:
+            out["conducting"] = tuple(cond)
+        if which.value & 2:
+            out["vacuum"] = tuple(vac)
+        return out
+
+    def sdiagnostic(self, a):
+        out = (C.c_double * 2)()
+        self._call("sx_sdiagnostic", a.ptr, out)
+        return tuple(out)
+
+    # ---- ROTBOUSS on the BOUSS state (include/rotbouss/rotbouss_rkstep{1,2}.f90) ----
+    def rotbouss_rkstep2(self, o, dt, nu, kappa, xmom=1.0, xtemp=1.0, omega=(0.0, 0.0, 0.0), v_zsta=(0.0, 0.0),
+                         v_zend=(0.0, 0.0), impl=0):
+        om = (C.c_double * 3)(*[float(x) for x in omega])
+        self._call("sx_rotbouss_rkstep2", o, dt, nu, kappa, xmom, xtemp, om, _vec2(v_zsta), _vec2(v_zend), impl)
+
+    def rotbouss_step(self, dt, nu, kappa, xmom=1.0, xtemp=1.0, omega=(0.0, 0.0, 0.0), v_zsta=(0.0, 0.0),
+                      v_zend=(0.0, 0.0), impl=0):
+        self.bouss_rkstep1()
+        for o in range(self.ord, 0, -1):
+            self.rotbouss_rkstep2(o, dt, nu, kappa, xmom, xtemp, omega, v_zsta, v_zend, impl)
+
+    # ---- MHDBOUSS on plan-owned state (include/mhdbouss/mhdbouss_rkstep{1,2}.f90) ----
+    def mhdbouss_put_state(self, vx=None, vy=None, vz=None, pr=None, ax=None, ay=None, az=None, th=None, fx=None,
+                           fy=None, fz=None, mx=None, my=None, mz=None, fs=None):
+        arrs = self._host_fields((vx, vy, vz, pr, ax, ay, az, th, fx, fy, fz, mx, my, mz, fs), "mhdbouss_put_state")
+        self._call("sx_mhdbouss_put_state", *[None if a is None else a.ctypes.data for a in arrs])
+
+    def mhdbouss_get_state(self):
+        out = [np.empty(self.cshape, dtype=np.complex128) for _ in range(9)]
+        self._call("sx_mhdbouss_get_state", *[a.ctypes.data for a in out])
+        return out
+
+    def mhdbouss_field(self, which: int) -> DeviceArray:
+        ptr = C.c_void_p()
+        self._call("sx_mhdbouss_state_ptr", which, C.byref(ptr))
+        return DeviceArray.view(self, "spectral", ptr)
+
+    def mhdbouss_rkstep1(self):
+        self._call("sx_mhdbouss_rkstep1")
+
+    def mhdbouss_rkstep2(self, o, dt, nu, mu, kappa, xmom=1.0, xtemp=1.0, b0=(0.0, 0.0, 0.0), impl=1):
+        b = (C.c_double * 3)(*[float(x) for x in b0])
+        self._call("sx_mhdbouss_rkstep2", o, dt, nu, mu, kappa, xmom, xtemp, b, impl)
+
+    def mhdbouss_step(self, dt, nu, mu, kappa, xmom=1.0, xtemp=1.0, b0=(0.0, 0.0, 0.0), impl=1):
+        self.mhdbouss_rkstep1()
+        for o in range(self.ord, 0, -1):
+            self.mhdbouss_rkstep2(o, dt, nu, mu, kappa, xmom, xtemp, b0, impl)

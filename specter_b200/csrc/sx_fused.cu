@@ -369,6 +369,43 @@ int bouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, d
   return s_imposebc(p, st[13]) || op_fc_filter(p, st[13]) || theta_roundtrip(p, st[13], st[10]);
 }
 
+int rot_couple(Plan& p, cplx* const* f, const double* om, double xmom, cplx* cx, cplx* cy, cplx* cz);
+
+// rotbouss_rkstep2.f90:3-56 on the BOUSS state: the fused BOUSS passes with the Coriolis (+ buoyancy) terms handed
+// to the z-forward / RK kernel as one precomputed coupling field per component (they read the not yet updated v, th),
+// and theta updated in place (no filter / round trip at the end).
+int rotbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double kappa, double xmom,
+                           double xtemp, const double* om, const double* zs, const double* ze) {
+  Fused* fp;
+  if (fused_begin(p, &fp, 8, 12, 4)) return 1;
+  Fused& f = *fp;
+  const double rmp = 1.0 / (double)o;
+  cplx* cpl[3];
+  for (int c = 0; c < 3; ++c) if (plan_cwork(p, 9 + c, &cpl[c])) return 1;
+  if (rot_couple(p, st, om, xmom, cpl[0], cpl[1], cpl[2])) return 1;
+  const cplx* q[4] = {st[0], st[1], st[2], st[10]};
+  f.chunked_now = false;
+  if (chunked(p, f)) {
+    if (xy_stage_chunked<4>(p, f, q)) return 1;
+  } else {
+    if (gradient_fields_to_real<4>(p, f, q)) return 1;
+    if (fused_xpass(p, f, 4, p.d_kxg)) return 1;
+    if (nonlinear_to_spectral_begin(p, f, 4)) return 1;
+  }
+  RkTerm rt;   // theta first: the heat current reads the not yet updated v_z
+  rt.cL = kappa; rt.couple = st[2]; rt.ccoef = -xtemp;
+  if (ex_wait(p, 16 + 3)) return 1;
+  if (fused_zfwd_rk(p, f, f.Uz[3], st[10], st[10], st[12], st[11], rt, dt, rmp)) return 1;
+  for (int c = 0; c < 3; ++c) {
+    RkTerm rk;
+    rk.cL = nu; rk.couple = cpl[c]; rk.ccoef = 1.0;
+    if (ex_wait(p, 16 + c)) return 1;
+    if (fused_zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk, dt, rmp)) return 1;
+  }
+  if (fused_project(p, f, st[0], st[1], st[2], st[3], o, zs, ze)) return 1;
+  return s_imposebc(p, st[10]);
+}
+
 // mhd_rkstep2.f90:3-84.  st[0..2] v, 3 pr, 4..6 f, 7..9 C1..C3, 10..12 a, 13 ph, 14..16 m, 17..19 C9..C11.
 int mhd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double mu, const double* b0) {
   Fused* fp;

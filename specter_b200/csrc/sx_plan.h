@@ -53,9 +53,13 @@ struct Plan {
   double* h_red = nullptr;   // pinned host landing zone
   int red_blocks = 0;
   std::string tdir;          // FC-Gram table directory (Neumann tables are loaded on first use)
+  // BCPLAN of the three fields at the z walls (setup_bc, boundary_mod.fpp:30-68): v 0 noslip; s 0 constant;
+  // b 0 conducting / 1 vacuum
+  int v_bczsta = 0, v_bczend = 0, s_bczsta = 0, s_bczend = 0, b_bczsta = 0, b_bczend = 0;
   HdState* hd = nullptr;
   SolverState* bouss = nullptr;
   SolverState* mhd = nullptr;
+  SolverState* mhdbouss = nullptr;
   Fused* fused = nullptr;
   Comm* comm = nullptr;
   StageTimer timer;
@@ -129,6 +133,17 @@ int prodre(Plan& p, const cplx* a, const cplx* b, const cplx* c, cplx* d, cplx* 
 int sol_project(Plan& p, cplx* a, cplx* b, cplx* c, cplx* d, int bctarget, int bczsta, int bczend);
 int v_imposebc_and_project(Plan& p, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int rki, const double* zs,
                            const double* ze);
+int energy(Plan& p, const cplx* a, const cplx* b, const cplx* c, int kin, double* out);
+int divergence(Plan& p, const cplx* a, const cplx* b, const cplx* c, double* out);
+int cross(Plan& p, const cplx* a, const cplx* b, const cplx* c, const cplx* d, const cplx* e, const cplx* f,
+          int kin, double* out);
+int bouncheck_z(Plan& p, double* bot, double* top, const cplx* a, const cplx* b);
+int variance(Plan& p, const cplx* a, int kin, double* out);
+int advect(Plan& p, const cplx* a, const cplx* b, const cplx* c, const cplx* d, cplx* e);
+int vector(Plan& p, const cplx* a, const cplx* b, const cplx* c, const cplx* d, const cplx* e, const cplx* f,
+           cplx* x, cplx* y, cplx* z);
+int s_imposebc(Plan& p, cplx* th);
+int a_imposebc_and_project(Plan& p, cplx* ax, cplx* ay, cplx* az, cplx* ph);
 int hd_state_free(Plan& p);
 int solver_states_free(Plan& p);
 int op_set_elem(Plan& p, cplx* a, size_t idx, double re, double im);

@@ -62,28 +62,50 @@ __global__ void k_zero_walls(Dims d, cplx* __restrict__ a, cplx* __restrict__ b,
   }
 }
 
-// conducting_z (bboundary.f90:239-290): wall rows <- 0, then neumann_reconstruct
-// (fcgram_mod.f90:456-499) with the 2nd-order weights for a,b and the 1st-order weights for c
+// conducting_z (bboundary.f90:239-290) and insulating_z (:294-344): wall rows <- 0, then, per wall,
+// neumann_reconstruct (fcgram_mod.f90:456-499) with the 2nd-order weights for a,b and the 1st-order weights for c
+// (conducting, kind 0), or robin_reconstruct (fcgram_mod.f90:612-635) with the 1st-order weights and the
+// coefficient khom = sqrt(kx^2+ky^2) for all three components (vacuum, kind 1)
 struct NeuW { double w1[10], w2[10]; };
-__global__ void k_conducting_walls(Dims d, cplx* __restrict__ a, cplx* __restrict__ b, cplx* __restrict__ c,
-                                   int top, int dd, NeuW nw) {
+__global__ void k_magnetic_walls(Dims d, cplx* __restrict__ a, cplx* __restrict__ b, cplx* __restrict__ c,
+                                 int top, int dd, NeuW nw, int kind_sta, int kind_end,
+                                 const double* __restrict__ kx, const double* __restrict__ ky) {
   const size_t npen = (size_t)d.ny * d.nxl;
   SX_GRID_STRIDE(t, 2 * npen) {
     const bool upper = t / npen;
-    const size_t base = (t % npen) * d.nz;
+    const size_t pen = t % npen;
+    const size_t base = pen * d.nz;
+    const int kind = upper ? kind_end : kind_sta;
+    double inv = 1.0;
+    if (kind == 1) {
+      const double x = kx[pen / d.ny], y = ky[pen % d.ny];
+      inv = 1.0 / (sqrt(x * x + y * y) * nw.w1[dd - 1] + 1.0);
+    }
     cplx* f[3] = {a, b, c};
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      const double* w = q < 2 ? nw.w2 : nw.w1;
-      // the prescribed normal derivative (wall row) is zero: neu(d)*0 + sum_k neu(k) f(.)
+      const double* w = (q < 2 && kind == 0) ? nw.w2 : nw.w1;
+      // the prescribed wall datum (wall row) is zero: neu(d)*0 + sum_k neu(k) f(.)
       double sx_ = 0.0, sy_ = 0.0;
       for (int k = 1; k < dd; ++k) {
         const cplx v = upper ? f[q][base + top - dd + k] : f[q][base + dd - k];
         sx_ += w[k - 1] * v.x;
         sy_ += w[k - 1] * v.y;
       }
-      f[q][base + (upper ? top : 0)] = cmake(sx_, sy_);
+      f[q][base + (upper ? top : 0)] = kind == 1 ? cmake(sx_ * inv, sy_ * inv) : cmake(sx_, sy_);
     }
+  }
+}
+
+// wall rows of one or both walls of up to three fields set to zero (int_conducting_z only acts on conducting walls)
+__global__ void k_zero_wall_sel(Dims d, cplx* __restrict__ a, cplx* __restrict__ b, int top, int do_sta, int do_end) {
+  const size_t npen = (size_t)d.ny * d.nxl;
+  SX_GRID_STRIDE(t, 2 * npen) {
+    const bool upper = t / npen;
+    if (upper ? !do_end : !do_sta) continue;
+    const size_t idx = (t % npen) * d.nz + (upper ? top : 0);
+    a[idx] = cmake(0.0, 0.0);
+    b[idx] = cmake(0.0, 0.0);
   }
 }
 
@@ -97,6 +119,19 @@ __global__ void k_bouss_couple(size_t n, cplx* __restrict__ c6, cplx* __restrict
   SX_GRID_STRIDE(idx, n) {
     c6[idx] = caxpy(-xmom, th[idx], c6[idx]);
     c8[idx] = caxpy(-xtemp, vz[idx], c8[idx]);
+  }
+}
+
+// rotbouss_rkstep2.f90:14-18: the Coriolis (+ buoyancy) terms added to the nonlinear term before the filter,
+// as three stand-alone fields:  cx = 2(oy vz - oz vy), cy = 2(oz vx - ox vz), cz = 2(ox vy - oy vx) - xmom th
+__global__ void k_rot_couple(size_t n, const cplx* __restrict__ vx, const cplx* __restrict__ vy,
+                             const cplx* __restrict__ vz, const cplx* __restrict__ th, double ox, double oy, double oz,
+                             double xmom, cplx* __restrict__ cx, cplx* __restrict__ cy, cplx* __restrict__ cz) {
+  SX_GRID_STRIDE(idx, n) {
+    const cplx X = vx[idx], Y = vy[idx], Z = vz[idx], T = th[idx];
+    cx[idx] = cmake(2 * (oy * Z.x - oz * Y.x), 2 * (oy * Z.y - oz * Y.y));
+    cy[idx] = cmake(2 * (oz * X.x - ox * Z.x), 2 * (oz * X.y - ox * Z.y));
+    cz[idx] = cmake(2 * (ox * Y.x - oy * X.x) - xmom * T.x, 2 * (ox * Y.y - oy * X.y) - xmom * T.y);
   }
 }
 
@@ -227,25 +262,33 @@ int theta_roundtrip(Plan& p, cplx* th, cplx* out) {
   return launch_zfft(p, th, out, (long)p.ny * p.nxl, -1, true, 1.0, 1.0);
 }
 
-// a_imposebc_and_project (bboundary.f90:100-189), conducting walls at both ends
+// a_imposebc_and_project (bboundary.f90:100-189); wall kinds from sx_setup_bc(plan, "b", ...): 0 conducting
+// (default), 1 vacuum.  The combinations laplace_z refuses (vacuum bottom under a conducting top) fail as there.
 int a_imposebc_and_project(Plan& p, cplx* ax, cplx* ay, cplx* az, cplx* ph) {
   SX_REQUIRE(p.Cz > 0, "vector-potential wall BCs need a non-periodic z direction (Cz > 0)");
+  const int ks = p.b_bczsta, ke = p.b_bczend;
+  SX_REQUIRE((ks == 0 || ks == 1) && (ke == 0 || ke == 1), "Unsupported boundary conditions in Z direction. Aborting...");
+  SX_REQUIRE(!(ks == 1 && ke == 0), "Unsupported BC combination in call to laplace_z. Aborting...");
   if (load_neumann(p)) return 1;
   const double inv_nz = 1.0 / (double)p.nz;
+  const Dims d = dims_of(p);
+  const size_t n = 2 * (size_t)p.ny * p.nxl;
+  const int top = p.nphys() - 1;
   if (p.ista == 1 && op_set_elem(p, az, 0, 0.0, 0.0)) return 1;           // bboundary.f90:147-149
-  if (fft1d_z_bwd(p, ax, ax, inv_nz) || fft1d_z_bwd(p, ay, ay, inv_nz)) return 1;
-  if (op_zero_walls(p, ax, ay, nullptr)) return 1;                          // int_conducting_z
-  if (fft1d_z_fwd(p, ax) || fft1d_z_fwd(p, ay)) return 1;
-  if (sol_project(p, ax, ay, az, ph, 0, 0, 0)) return 1;
+  if (ks == 0 || ke == 0) {
+    if (fft1d_z_bwd(p, ax, ax, inv_nz) || fft1d_z_bwd(p, ay, ay, inv_nz)) return 1;
+    SX_EW_LAUNCH(p, k_zero_wall_sel, n, d, ax, ay, top, ks == 0, ke == 0);  // int_conducting_z
+    if (fft1d_z_fwd(p, ax) || fft1d_z_fwd(p, ay)) return 1;
+  }
+  if (sol_project(p, ax, ay, az, ph, 0, 2 * ks, 2 * ke)) return 1;
   if (fft1d_z_bwd(p, ax, ax, inv_nz) || fft1d_z_bwd(p, ay, ay, inv_nz) || fft1d_z_bwd(p, az, az, inv_nz)) return 1;
   NeuW nw;
   for (int k = 0; k < 10; ++k) {
     nw.w1[k] = k < p.oz ? p.h_neu[k] : 0.0;
     nw.w2[k] = k < p.oz ? p.h_neu2[k] : 0.0;
   }
-  const Dims d = dims_of(p);
-  const size_t n = 2 * (size_t)p.ny * p.nxl;
-  SX_EW_LAUNCH(p, k_conducting_walls, n, d, ax, ay, az, p.nphys() - 1, p.oz, nw);  // conducting_z
+  const double *kx = p.d_kx, *ky = p.d_ky;
+  SX_EW_LAUNCH(p, k_magnetic_walls, n, d, ax, ay, az, top, p.oz, nw, ks, ke, kx, ky);  // conducting_z / insulating_z
   return fft1d_z_fwd(p, ax) || fft1d_z_fwd(p, ay) || fft1d_z_fwd(p, az);
 }
 
@@ -294,9 +337,11 @@ static void state_free(SolverState** slot) {
 int solver_states_free(Plan& p) {
   state_free(&p.bouss);
   state_free(&p.mhd);
+  state_free(&p.mhdbouss);
   return 0;
 }
-constexpr int kBoussFields = 14, kMhdFields = 20;
+// MHDBOUSS: the MHD slots, then 20 th, 21 fs, 22 C7
+constexpr int kBoussFields = 14, kMhdFields = 20, kMhdBoussFields = 23;
 
 static int put_fields(Plan& p, SolverState& s, const double* const* h, const int* which, int n) {
   const size_t bytes = p.csize() * sizeof(cplx);
@@ -375,8 +420,81 @@ static int mhd_rkstep2_modular(Plan& p, SolverState& s, int o, double dt, double
   return a_imposebc_and_project(p, ax, ay, az, f[13]);
 }
 
+// rotbouss_rkstep2.f90:3-56 (ends with s_imposebc: no theta filter / round trip)
+int rot_couple(Plan& p, cplx* const* f, const double* om, double xmom, cplx* cx, cplx* cy, cplx* cz) {
+  const size_t n = p.csize();
+  SX_EW_LAUNCH(p, k_rot_couple, n, n, f[0], f[1], f[2], f[10], om[0], om[1], om[2], xmom, cx, cy, cz);
+  return 0;
+}
+static int rotbouss_rkstep2_modular(Plan& p, SolverState& s, int o, double dt, double nu, double kappa, double xmom,
+                                    double xtemp, const double* om, const double* zs, const double* ze) {
+  cplx *c4, *c5, *c6, *c8, *r[3];
+  if (plan_cwork(p, 6, &c4) || plan_cwork(p, 7, &c5) || plan_cwork(p, 8, &c6) || plan_cwork(p, 9, &c8)) return 1;
+  for (int q = 0; q < 3; ++q) if (plan_cwork(p, 10 + q, &r[q])) return 1;
+  const double rmp = 1.0 / (double)o;
+  cplx** f = s.f.data();
+  if (gradre(p, f[0], f[1], f[2], c4, c5, c6)) return 1;
+  if (advect(p, f[0], f[1], f[2], f[10], c8)) return 1;
+  const size_t n = p.csize();
+  if (rot_couple(p, f, om, xmom, r[0], r[1], r[2])) return 1;
+  cplx* nl[3] = {c4, c5, c6};
+  for (int q = 0; q < 3; ++q) if (op_add(p, nl[q], r[q])) return 1;
+  SX_EW_LAUNCH(p, k_bouss_couple, n, n, c6, c8, f[10], f[2], 0.0, xtemp);   // heat current only
+  if (op_fc_filter(p, c4) || op_fc_filter(p, c5) || op_fc_filter(p, c6) || op_fc_filter(p, c8)) return 1;
+  for (int q = 0; q < 3; ++q) {
+    if (op_laplak(p, f[q], f[q])) return 1;
+    if (op_rk_axpy(p, f[q], f[7 + q], nl[q], f[4 + q], dt, nu, rmp)) return 1;
+  }
+  if (op_laplak(p, f[10], f[10]) || op_rk_axpy(p, f[10], f[12], c8, f[11], dt, kappa, rmp)) return 1;
+  if (v_imposebc_and_project(p, f[0], f[1], f[2], f[3], o, zs, ze)) return 1;
+  return s_imposebc(p, f[10]);
+}
+
+// mhdbouss_rkstep2.f90:3-106, composed from the stand-alone operators in the reference's order.
+// State: the MHD slots (0..19), 20 th, 21 fs, 22 C7.
+static int mhdbouss_rkstep2_modular(Plan& p, SolverState& s, int o, double dt, double nu, double mu, double kappa,
+                                    double xmom, double xtemp, const double* b0) {
+  cplx *c4, *c5, *c6, *c8, *c12, *c13, *c14, *c15, *c16, *c17;
+  if (plan_cwork(p, 6, &c4) || plan_cwork(p, 7, &c5) || plan_cwork(p, 8, &c6)) return 1;
+  if (plan_cwork(p, 9, &c12) || plan_cwork(p, 10, &c13) || plan_cwork(p, 11, &c14)) return 1;
+  if (plan_cwork(p, 12, &c15) || plan_cwork(p, 13, &c16) || plan_cwork(p, 14, &c17) || plan_cwork(p, 15, &c8)) return 1;
+  const double rmp = 1.0 / (double)o;
+  const double N = (double)p.nx * (double)p.ny * (double)p.nz;
+  cplx** f = s.f.data();
+  cplx *ax = f[10], *ay = f[11], *az = f[12], *th = f[20];
+  if (op_curlk(p, ay, az, c12, 1) || op_curlk(p, ax, az, c13, 2) || op_curlk(p, ax, ay, c14, 3)) return 1;
+  if (p.ista == 1) {
+    if (op_set_elem(p, c12, 0, (b0 ? b0[0] : 0.0) * N, 0.0) || op_set_elem(p, c13, 0, (b0 ? b0[1] : 0.0) * N, 0.0) ||
+        op_set_elem(p, c14, 0, (b0 ? b0[2] : 0.0) * N, 0.0)) return 1;
+  }
+  if (op_curlk(p, c13, c14, ax, 1) || op_curlk(p, c12, c14, ay, 2) || op_curlk(p, c12, c13, az, 3)) return 1;
+  if (prodre(p, f[0], f[1], f[2], c4, c5, c6)) return 1;
+  if (advect(p, f[0], f[1], f[2], th, c8)) return 1;
+  if (vector(p, ax, ay, az, c12, c13, c14, c15, c16, c17)) return 1;
+  if (op_sub(p, c4, c15) || op_sub(p, c5, c16) || op_sub(p, c6, c17)) return 1;
+  const size_t n = p.csize();
+  SX_EW_LAUNCH(p, k_bouss_couple, n, n, c6, c8, th, f[2], xmom, xtemp);
+  if (op_fc_filter(p, c4) || op_fc_filter(p, c5) || op_fc_filter(p, c6) || op_fc_filter(p, c8)) return 1;
+  if (vector(p, f[0], f[1], f[2], c12, c13, c14, c15, c16, c17)) return 1;
+  if (op_fc_filter(p, c15) || op_fc_filter(p, c16) || op_fc_filter(p, c17)) return 1;
+  cplx* nl[3] = {c4, c5, c6};
+  cplx* emf[3] = {c15, c16, c17};
+  for (int q = 0; q < 3; ++q) {
+    if (op_laplak(p, f[q], f[q])) return 1;
+    if (op_rk_axpy(p, f[q], f[7 + q], nl[q], f[4 + q], dt, nu, rmp)) return 1;
+    SX_EW_LAUNCH(p, k_rk_axpy_a, n, n, f[10 + q], f[17 + q], emf[q], f[14 + q], dt, mu, rmp);
+  }
+  if (op_laplak(p, th, th) || op_rk_axpy(p, th, f[22], c8, f[21], dt, kappa, rmp)) return 1;
+  if (v_imposebc_and_project(p, f[0], f[1], f[2], f[3], o, nullptr, nullptr)) return 1;
+  if (a_imposebc_and_project(p, ax, ay, az, f[13])) return 1;
+  if (s_imposebc(p, th)) return 1;
+  return theta_roundtrip(p, th, th);
+}
+
 int bouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double kappa, double xmom, double xtemp,
                         const double* zs, const double* ze);
+int rotbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double kappa, double xmom,
+                           double xtemp, const double* om, const double* zs, const double* ze);
 int mhd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double mu, const double* b0);
 
 }  // namespace sx
@@ -452,6 +570,20 @@ int sx_bouss_rkstep2(sx_plan* plan, int o, double dt, double nu, double kappa, d
   return bouss_rkstep2_fused(p, s->f.data(), o, dt, nu, kappa, xmom, xtemp, v_zsta, v_zend);
 }
 
+/* rotbouss_rkstep2.f90:3-56 on the BOUSS state (rotbouss_rkstep1.f90 = bouss_rkstep1.f90) */
+int sx_rotbouss_rkstep2(sx_plan* plan, int o, double dt, double nu, double kappa, double xmom, double xtemp,
+                        const double omega[3], const double v_zsta[2], const double v_zend[2], int impl) {
+  SX_PLAN(plan);
+  SX_REQUIRE(o >= 1 && o <= p.ord, "sx_rotbouss_rkstep2: substep index o must be in 1..ord");
+  SX_REQUIRE(p.Cz > 0, "wall BCs need a non-periodic z direction (Cz > 0)");
+  SX_REQUIRE(omega != nullptr, "sx_rotbouss_rkstep2: omega[3] is required");
+  SolverState* s;
+  if (state_get(p, &p.bouss, kBoussFields, &s)) return 1;
+  if (impl == 1) return rotbouss_rkstep2_modular(p, *s, o, dt, nu, kappa, xmom, xtemp, omega, v_zsta, v_zend);
+  SX_REQUIRE(impl == 0, "sx_rotbouss_rkstep2: impl must be 0 (fused) or 1 (per-operator)");
+  return rotbouss_rkstep2_fused(p, s->f.data(), o, dt, nu, kappa, xmom, xtemp, omega, v_zsta, v_zend);
+}
+
 // ---- MHD -----------------------------------------------------------------------------------------
 int sx_mhd_put_state(sx_plan* plan, const double* vx, const double* vy, const double* vz, const double* pr,
                      const double* ax, const double* ay, const double* az, const double* fx, const double* fy,
@@ -498,6 +630,56 @@ int sx_mhd_rkstep2(sx_plan* plan, int o, double dt, double nu, double mu, const 
   if (impl == 1) return mhd_rkstep2_modular(p, *s, o, dt, nu, mu, b0);
   SX_REQUIRE(impl == 0, "sx_mhd_rkstep2: impl must be 0 (fused) or 1 (per-operator)");
   return mhd_rkstep2_fused(p, s->f.data(), o, dt, nu, mu, b0);
+}
+
+// ---- MHDBOUSS ------------------------------------------------------------------------------------
+int sx_mhdbouss_put_state(sx_plan* plan, const double* vx, const double* vy, const double* vz, const double* pr,
+                          const double* ax, const double* ay, const double* az, const double* th, const double* fx,
+                          const double* fy, const double* fz, const double* mx, const double* my, const double* mz,
+                          const double* fs) {
+  SX_PLAN(plan);
+  SolverState* s;
+  if (state_get(p, &p.mhdbouss, kMhdBoussFields, &s)) return 1;
+  const double* h[15] = {vx, vy, vz, pr, ax, ay, az, th, fx, fy, fz, mx, my, mz, fs};
+  const int which[15] = {0, 1, 2, 3, 10, 11, 12, 20, 4, 5, 6, 14, 15, 16, 21};
+  return put_fields(p, *s, h, which, 15);
+}
+int sx_mhdbouss_get_state(sx_plan* plan, double* vx, double* vy, double* vz, double* pr, double* ax, double* ay,
+                          double* az, double* ph, double* th) {
+  SX_PLAN(plan);
+  SolverState* s;
+  if (state_get(p, &p.mhdbouss, kMhdBoussFields, &s)) return 1;
+  double* h[9] = {vx, vy, vz, pr, ax, ay, az, ph, th};
+  const int which[9] = {0, 1, 2, 3, 10, 11, 12, 13, 20};
+  return get_fields(p, *s, h, which, 9);
+}
+int sx_mhdbouss_state_ptr(sx_plan* plan, int which, double** dptr) {
+  SX_PLAN(plan);
+  SX_REQUIRE(which >= 0 && which < kMhdBoussFields && dptr, "sx_mhdbouss_state_ptr: which must be 0..22");
+  SolverState* s;
+  if (state_get(p, &p.mhdbouss, kMhdBoussFields, &s)) return 1;
+  *dptr = reinterpret_cast<double*>(s->f[which]);
+  return 0;
+}
+/* mhdbouss_rkstep1.f90:6-12 */
+int sx_mhdbouss_rkstep1(sx_plan* plan) {
+  SX_PLAN(plan);
+  SolverState* s;
+  if (state_get(p, &p.mhdbouss, kMhdBoussFields, &s)) return 1;
+  for (int q = 0; q < 3; ++q)
+    if (copy_field(p, s->f[7 + q], s->f[q]) || copy_field(p, s->f[17 + q], s->f[10 + q])) return 1;
+  return copy_field(p, s->f[22], s->f[20]);
+}
+/* mhdbouss_rkstep2.f90:3-106; impl must be 1: this solver only has the per-operator composition so far */
+int sx_mhdbouss_rkstep2(sx_plan* plan, int o, double dt, double nu, double mu, double kappa, double xmom,
+                        double xtemp, const double b0[3], int impl) {
+  SX_PLAN(plan);
+  SX_REQUIRE(o >= 1 && o <= p.ord, "sx_mhdbouss_rkstep2: substep index o must be in 1..ord");
+  SX_REQUIRE(p.Cz > 0, "wall BCs need a non-periodic z direction (Cz > 0)");
+  SX_REQUIRE(impl == 1, "sx_mhdbouss_rkstep2: only impl = 1 (per-operator composition) exists for MHDBOUSS");
+  SolverState* s;
+  if (state_get(p, &p.mhdbouss, kMhdBoussFields, &s)) return 1;
+  return mhdbouss_rkstep2_modular(p, *s, o, dt, nu, mu, kappa, xmom, xtemp, b0);
 }
 
 }  // extern "C"

@@ -203,3 +203,88 @@ def test_bouss_and_mhd_substep_invariants(tables):
     O.fftp1d_complex_to_real_z(g, a)
     assert O.divergence(g, m.ax, m.ay, m.az) < 1e-8
     assert np.isfinite(m.ph).all()
+
+
+def test_fc_robin_reconstruction(g):
+    # tests/fc_robin.f90 (z branches; y is periodic here): wall values recovered from the Robin datum
+    # dn f + khom f, with khom = sqrt(kx^2 + ky^2); thresholds from a first CPU run (FC(5) accuracy at 39 points)
+    if g.neu is None:
+        g.load_neumann()
+    nph = g.nz - g.Cz
+    x, y, z = g.x[None, None, :], g.y[None, :, None], g.z[:, None, None]
+    r1 = np.sin(4 * x) * np.cos(8 * y) * np.sin(6 * z)
+    r3 = 6 * np.sin(4 * x) * np.cos(8 * y) * np.cos(6 * z)
+    c1 = O.fftp2d_real_to_complex_xy(g, r1)
+    c3 = O.fftp2d_real_to_complex_xy(g, r3)
+    c1[:, :, 0] = -c3[:, :, 0] + g.khom * c1[:, :, 0]                    # d/dz = -d/dn   (fc_robin.f90:66)
+    c1[:, :, nph - 1] = c3[:, :, nph - 1] + g.khom * c1[:, :, nph - 1]    # (:67)
+    O.robin_reconstruct(g, c1, 5, g.khom)
+    O.robin_reconstruct(g, c1, 6, g.khom)
+    back = O.fftp2d_complex_to_real_xy(g, c1.copy()) / g.nx / g.ny
+    e0 = np.abs(back[0] - r1[0]).max()
+    eL = np.abs(back[nph - 1] - r1[nph - 1]).max()
+    print("robin", e0, eL)
+    assert e0 < 5e-5 and eL < 5e-5, (e0, eL)
+    # z derivative of the reconstructed field through the continuation (fc_robin.f90:146-160)
+    O.fftp1d_real_to_complex_z(g, c1)
+    d = O.fftp3d_complex_to_real(g, O.derivk(g, c1, 3)) / g.N
+    err = np.abs(d[:nph] - r3[:nph]).max()
+    print("robin dz", err)
+    assert err < 2e-3
+
+
+def test_vacuum_walls_and_new_diagnostics(tables):
+    g = O.Grid(32, 32, 64, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, ord=2)
+    m = O.make_mhd_state(g)
+    # helicity / product are bilinear and symmetric where they should be
+    assert abs(O.product(g, m.ax, m.ay) - O.product(g, m.ay, m.ax)) < 1e-14
+    assert abs(O.product(g, m.ax, m.ax) - O.variance(g, m.ax, 1)) < 1e-14
+    h = O.helicity(g, m.vx, m.vy, m.vz)
+    assert abs(O.helicity(g, 2 * m.vx, 2 * m.vy, 2 * m.vz) - 4 * h) < 1e-12 * max(1.0, abs(h))
+    assert O.maxabs(g, m.vx, m.vy, m.vz, 2) > 0
+    for (bs, be) in ((1, 1), (0, 1)):
+        ax, ay, az = m.ax.copy(), m.ay.copy(), m.az.copy()
+        before = O.robcheck(g, ax, ay, az)
+        ph = O.a_imposebc_and_project_bc(g, ax, ay, az, bs, be)
+        assert np.isfinite(ph).all()
+        after = O.robcheck(g, ax, ay, az)
+        diag = O.bdiagnostic(g, ax, ay, az, bs, be)
+        print("vacuum", bs, be, before, after, diag)
+        # the vacuum condition dn a + khom a = 0 holds at the vacuum walls after the step (to FC accuracy),
+        # and it did not before
+        if bs == 1:
+            assert after[0] < 1e-4 * before[0] and after[2] < 1e-8
+        if be == 1:
+            assert after[1] < 1e-4 * before[1] and after[3] < 1e-8
+        assert "vacuum" in diag and (("conducting" in diag) == (bs == 0 or be == 0))
+    # vacuum bottom / conducting top is refused by laplace_z, as in the reference (boundary_mod.fpp:625-630)
+    with pytest.raises(ValueError, match="Unsupported BC combination"):
+        O.a_imposebc_and_project_bc(g, m.ax.copy(), m.ay.copy(), m.az.copy(), 1, 0)
+    # both walls conducting: identical to the conducting-only restatement
+    a1 = [q.copy() for q in (m.ax, m.ay, m.az)]
+    a2 = [q.copy() for q in (m.ax, m.ay, m.az)]
+    p1 = O.a_imposebc_and_project(g, *a1)
+    p2 = O.a_imposebc_and_project_bc(g, *a2, 0, 0)
+    assert all(np.array_equal(u, v) for u, v in zip(a1 + [p1], a2 + [p2]))
+
+
+def test_rotbouss_and_mhdbouss_substep_invariants(tables):
+    g = O.Grid(32, 32, 64, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, ord=2)
+    s = O.make_bouss_state(g)
+    s0 = O.make_bouss_state(g)
+    # without rotation ROTBOUSS differs from BOUSS only in the missing theta filter / round trip
+    O.rotbouss_step(g, s, 1e-3, 1e-3, 1e-3, omega=(0.0, 0.0, 0.0))
+    O.bouss_step(g, s0, 1e-3, 1e-3, 1e-3)
+    assert np.abs(s.vx - s0.vx).max() < 1e-6 * np.abs(s0.vx).max()
+    r = O.make_bouss_state(g)
+    O.rotbouss_step(g, r, 1e-3, 1e-3, 1e-3, omega=(0.3, -0.2, 1.5))
+    assert np.abs(r.vx - s.vx).max() > 1e-6 * np.abs(s.vx).max()      # the Coriolis term acts
+    assert O.vdiagnostic(g, r.vx, r.vy, r.vz)[0] < 1e-8
+    assert max(O.sdiagnostic(g, r.th)) < 1e-20                           # walls exactly constant
+    mb = O.make_mhdbouss_state(g)
+    O.mhdbouss_step(g, mb, 1e-3, 1e-3, 5e-3, 1e-3)
+    assert O.vdiagnostic(g, mb.vx, mb.vy, mb.vz)[0] < 1e-8
+    assert O.divergence(g, mb.ax, mb.ay, mb.az) < 1e-8
+    out = O.mhdcheck(g, mb.vx, mb.vy, mb.vz, mb.ax, mb.ay, mb.az)
+    assert np.isfinite(out).all() and out[0] > 0
+    assert np.isfinite(O.pscheck(g, mb.th, mb.fs)).all()

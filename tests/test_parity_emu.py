@@ -96,3 +96,25 @@ def test_hd_substeps_bulk_project(emu_lib, tables, monkeypatch):
 
 def test_io_output_restart(emu_lib, tables, tmp_path):
     P.case_io_output_restart(emu_lib, tables, SMALL, tmp_path)
+
+
+def test_wall_reconstructions(emu_lib, tables):
+    P.case_wall_reconstructions(emu_lib, tables, SMALL)
+
+
+def test_vacuum_walls(emu_lib, tables):
+    P.case_vacuum_walls(emu_lib, tables, SMALL)
+
+
+def test_more_diagnostics(emu_lib, tables):
+    P.case_more_diagnostics(emu_lib, tables, SMALL)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_rotbouss_substeps(emu_lib, tables, impl):
+    P.case_rotbouss_substeps(emu_lib, tables, SMALL, ord=2, nsteps=1, impl=impl)
+
+
+def test_mhdbouss_substeps(emu_lib, tables):
+    P.case_mhdbouss_substeps(emu_lib, tables, SMALL, ord=2, nsteps=1)
+    P.case_mhdbouss_substeps(emu_lib, tables, (16, 16, 64), ord=2, nsteps=1, bc=(0, 1))

@@ -119,3 +119,29 @@ def test_hd_substeps_length_1024_2048_kernels(cuda_lib, tables):
 
 def test_io_output_restart(cuda_lib, tables, tmp_path):
     P.case_io_output_restart(cuda_lib, tables, CFG1, tmp_path)
+
+
+def test_wall_reconstructions(cuda_lib, tables):
+    P.case_wall_reconstructions(cuda_lib, tables, CFG1)
+
+
+def test_vacuum_walls(cuda_lib, tables):
+    P.case_vacuum_walls(cuda_lib, tables, CFG1)
+
+
+def test_more_diagnostics(cuda_lib, tables):
+    P.case_more_diagnostics(cuda_lib, tables, CFG1)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_rotbouss_substeps_cfg1(cuda_lib, tables, impl):
+    P.case_rotbouss_substeps(cuda_lib, tables, CFG1, ord=2, nsteps=2, impl=impl)
+
+
+def test_rotbouss_substeps_rk4_moving_walls(cuda_lib, tables):
+    P.case_rotbouss_substeps(cuda_lib, tables, (128, 64, 128), ord=4, nsteps=1, impl=0, walls=((0.2, -0.1), (-0.3, 0.1)))
+
+
+def test_mhdbouss_substeps_cfg1(cuda_lib, tables):
+    P.case_mhdbouss_substeps(cuda_lib, tables, CFG1, ord=2, nsteps=2)
+    P.case_mhdbouss_substeps(cuda_lib, tables, (32, 32, 64), ord=2, nsteps=1, bc=(1, 1))
