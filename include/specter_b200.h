@@ -213,6 +213,17 @@ int sx_io_read(sx_plan* plan, double* real_dev, const char* dir, const char* fna
  * `<odir>/<name>.<ext>.out`.  sx_hd_restart is the stat != 0 branch of specter.fpp:886-912 (files -> state). */
 int sx_hd_output(sx_plan* plan, const char* odir, const char* ext, double dt, int outs);
 int sx_hd_restart(sx_plan* plan, const char* idir, const char* ext, double dt);
+/* The same two blocks for any solver (specter.fpp:1005-1128 and 886-957): solver = "HD" | "BOUSS" | "ROTBOUSS" |
+ * "MHD" | "MHDBOUSS" picks the plan-owned state; SCALAR_ adds th, MAGFIELD_ adds ax,ay,az (bx,by,bz for outs >= 1,
+ * jx,jy,jz for outs == 2) and ph = ph'/dt */
+int sx_output(sx_plan* plan, const char* solver, const char* odir, const char* ext, double dt, int outs);
+int sx_restart(sx_plan* plan, const char* solver, const char* idir, const char* ext, double dt);
+/* ref: the benchmark.txt row of specter.fpp:1182-1228 (non-CUDA column set: nx ny nz nsteps nprocs nth TCPU TOMP
+ * TWTIME TFFT TTRA TCOM TCONT TNEU TROB TTOT, seconds per step), appended by rank 0, header when the file is new.
+ * TCPU/TOMP/TWTIME are the caller's totals; the T* columns come from the stage timers (sx_plan_stage_timing): the
+ * transposition, continuation and wall reconstructions are fused into the transform kernels, so TTRA, TCONT, TNEU,
+ * TROB are zero and their time is inside TFFT; TCOM = slab exchanges. */
+int sx_benchmark_write(sx_plan* plan, const char* path, int nsteps, int nth, double tcpu, double tomp, double twtime);
 
 /* ---- Boussinesq (include/bouss/bouss_rkstep{1,2}.f90) ------------------------------------ */
 /* plan-owned state: which = 0..2 v, 3 pr, 4..6 f, 7..9 C1..C3, 10 th, 11 fs, 12 C7 */

@@ -1306,3 +1306,38 @@ def make_mhdbouss_state(g: Grid, seed=1000, **ic) -> MhdBoussState:
     z = np.zeros(g.cshape(), dtype=np.complex128)
     return MhdBoussState(vx, vy, vz, z.copy(), fx, fy, fz, ax, ay, az, z.copy(), z.copy(), z.copy(), z.copy(),
                          th, z.copy())
+
+
+def solver_output(g: Grid, s, odir, ext, dt, outs=0):
+    """The whole BIN block of specter.fpp:1005-1128: HD fields, then th (SCALAR_), then a, b, j, ph (MAGFIELD_)."""
+    hd_output(g, s, odir, ext, dt, outs)
+    rmp = 1.0 / (float(g.nx) * float(g.ny) * float(g.nz))
+    if getattr(s, "th", None) is not None:
+        io_write(g, odir, "th", ext, fftp3d_complex_to_real(g, s.th * rmp))
+    if getattr(s, "ax", None) is not None:
+        C1, C2, C3 = s.ax * rmp, s.ay * rmp, s.az * rmp
+        if outs >= 1:
+            io_write(g, odir, "bx", ext, fftp3d_complex_to_real(g, curlk(g, C2, C3, 1)))
+            io_write(g, odir, "by", ext, fftp3d_complex_to_real(g, curlk(g, C1, C3, 2)))
+            io_write(g, odir, "bz", ext, fftp3d_complex_to_real(g, curlk(g, C1, C2, 3)))
+        if outs == 2:
+            for n, c in (("jx", C1), ("jy", C2), ("jz", C3)):
+                io_write(g, odir, n, ext, fftp3d_complex_to_real(g, laplak(g, c)))
+        for n, c in (("ax", C1), ("ay", C2), ("az", C3)):
+            io_write(g, odir, n, ext, fftp3d_complex_to_real(g, c))
+        io_write(g, odir, "ph", ext, fftp2d_complex_to_real_xy(g, s.ph * (1.0 / (float(g.nx) * float(g.ny) * dt))))
+
+
+def solver_restart(g: Grid, idir, ext, dt, scalar=False, magnetic=False):
+    """The stat != 0 branch of specter.fpp:886-957 -> dict of spectral fields (pr, ph back in primed units)."""
+    vx, vy, vz, pr = hd_restart(g, idir, ext, dt)
+    out = {"vx": vx, "vy": vy, "vz": vz, "pr": pr}
+    if scalar:
+        out["th"] = fftp3d_real_to_complex(g, io_read(g, idir, "th", ext))
+    if magnetic:
+        for n in ("ax", "ay", "az"):
+            out[n] = fftp3d_real_to_complex(g, io_read(g, idir, n, ext))
+        ph = fftp2d_real_to_complex_xy(g, io_read(g, idir, "ph", ext))
+        ph[:, :, : g.nz - g.Cz] *= dt
+        out["ph"] = ph
+    return out

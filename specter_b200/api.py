@@ -62,6 +62,9 @@ SIGNATURES = {
     "sx_io_read": [_P, _D, C.c_char_p, C.c_char_p, C.c_char_p],
     "sx_hd_output": [_P, C.c_char_p, C.c_char_p, C.c_double, _I],
     "sx_hd_restart": [_P, C.c_char_p, C.c_char_p, C.c_double],
+    "sx_output": [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, _I],
+    "sx_restart": [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double],
+    "sx_benchmark_write": [_P, C.c_char_p, _I, _I, _F, _F, _F],
     "sx_plan_p2p_export": [_P, _I, _I, _D],
     "sx_plan_p2p_import": [_P, _D],
     "sx_plan_set_comm_callbacks": [_P, _D, _D, _D],
@@ -703,3 +706,13 @@ class Plan:
         self.mhdbouss_rkstep1()
         for o in range(self.ord, 0, -1):
             self.mhdbouss_rkstep2(o, dt, nu, mu, kappa, xmom, xtemp, b0, impl)
+
+    # ---- output / restart blocks for any solver, benchmark.txt ----
+    def output(self, solver, odir, ext, dt, outs=0):
+        self._call("sx_output", solver.encode(), str(odir).encode(), ext.encode(), float(dt), int(outs))
+
+    def restart(self, solver, idir, ext, dt):
+        self._call("sx_restart", solver.encode(), str(idir).encode(), ext.encode(), float(dt))
+
+    def benchmark_write(self, path, nsteps, nth=1, tcpu=0.0, tomp=0.0, twtime=0.0):
+        self._call("sx_benchmark_write", str(path).encode(), int(nsteps), int(nth), float(tcpu), float(tomp), float(twtime))

@@ -113,6 +113,89 @@ int hd_restart(Plan& p, cplx* const* st, const char* idir, const char* ext, doub
   return op_scale_phys(p, st[3], dt);
 }
 
+// the SCALAR_ block of the BIN output (specter.fpp:1055-1069): th/N -> c2r -> io_write
+int scalar_output(Plan& p, const cplx* th, const char* odir, const char* ext) {
+  cplx* c1;
+  double* r1;
+  if (plan_cwork(p, 2, &c1) || plan_rwork(p, 0, &r1)) return 1;
+  const double rmp = 1.0 / ((double)p.nx * (double)p.ny * (double)p.nz);
+  return op_scale_copy(p, th, c1, rmp) || fft3d_c2r(p, c1, r1) || io_write(p, r1, odir, "th", ext);
+}
+
+// the MAGFIELD_ block (specter.fpp:1071-1128): a/N; outs >= 1: b = curl a; outs == 2: j = laplak(a) as written
+// there (the sign convention of the reference); a; ph = ph'/(nx ny dt) -> c2r_xy
+int magnetic_output(Plan& p, cplx* const a[3], const cplx* ph, const char* odir, const char* ext, double dt, int outs) {
+  cplx *c1, *c2, *c3, *c4;
+  double* r1;
+  if (plan_cwork(p, 2, &c1) || plan_cwork(p, 3, &c2) || plan_cwork(p, 4, &c3) || plan_cwork(p, 5, &c4)) return 1;
+  if (plan_rwork(p, 0, &r1)) return 1;
+  const double rmp = 1.0 / ((double)p.nx * (double)p.ny * (double)p.nz);
+  if (op_scale_copy(p, a[0], c1, rmp) || op_scale_copy(p, a[1], c2, rmp) || op_scale_copy(p, a[2], c3, rmp)) return 1;
+  cplx* c[3] = {c1, c2, c3};
+  if (outs >= 1) {
+    const char* bn[3] = {"bx", "by", "bz"};
+    for (int d = 1; d <= 3; ++d) {
+      const cplx* u = d == 1 ? c2 : c1;
+      const cplx* v = d == 3 ? c2 : c3;
+      if (op_curlk(p, u, v, c4, d) || fft3d_c2r(p, c4, r1) || io_write(p, r1, odir, bn[d - 1], ext)) return 1;
+    }
+  }
+  if (outs == 2) {
+    const char* jn[3] = {"jx", "jy", "jz"};
+    for (int q = 0; q < 3; ++q)
+      if (op_laplak(p, c[q], c4) || fft3d_c2r(p, c4, r1) || io_write(p, r1, odir, jn[q], ext)) return 1;
+  }
+  const char* an[3] = {"ax", "ay", "az"};
+  for (int q = 0; q < 3; ++q)
+    if (fft3d_c2r(p, c[q], r1) || io_write(p, r1, odir, an[q], ext)) return 1;
+  if (op_scale_copy(p, ph, c1, 1.0 / ((double)p.nx * (double)p.ny * dt))) return 1;
+  return fft2d_xy_c2r(p, c1, r1, p.nz) || io_write(p, r1, odir, "ph", ext);
+}
+
+// specter.fpp:935-938 and :941-957 (dyna = 0): th; a and ph (physical rows x dt, back to ph')
+int scalar_restart(Plan& p, cplx* th, const char* idir, const char* ext) {
+  double* r1;
+  if (plan_rwork(p, 0, &r1)) return 1;
+  return io_read(p, r1, idir, "th", ext) || fft3d_r2c(p, r1, th);
+}
+int magnetic_restart(Plan& p, cplx* const a[3], cplx* ph, const char* idir, const char* ext, double dt) {
+  double* r1;
+  if (plan_rwork(p, 0, &r1)) return 1;
+  const char* an[3] = {"ax", "ay", "az"};
+  for (int q = 0; q < 3; ++q)
+    if (io_read(p, r1, idir, an[q], ext) || fft3d_r2c(p, r1, a[q])) return 1;
+  if (io_read(p, r1, idir, "ph", ext) || fft2d_xy_r2c(p, r1, ph, p.nz)) return 1;
+  return op_scale_phys(p, ph, dt);
+}
+
+// benchmark.txt (specter.fpp:1182-1228, the non-CUDA column set): appended by rank 0, header on creation.
+// TFFT / TTRA / TCOM / TCONT / TNEU / TROB / TTOT come from the stage timers (seconds per step): every transform
+// kernel carries its transposition, continuation and wall reconstructions fused in, so TTRA, TCONT, TNEU and TROB
+// are part of TFFT and reported as zero; TCOM is the device time of the slab exchanges.
+int benchmark_write(Plan& p, const char* path, int nsteps, int nth, double tcpu, double tomp, double twtime) {
+  SX_REQUIRE(path && nsteps > 0, "sx_benchmark_write: bad arguments");
+  if (stage_flush(p)) return 1;
+  double fft = 0.0, com = 0.0, tot = 0.0;
+  for (int i = 0; i < ST_COUNT; ++i) {
+    const double s = p.timer.ms[i] * 1e-3;
+    tot += s;
+    if (i == ST_EXCHANGE) com += s;
+    else if (i != ST_EW && i != ST_REDUCE && i != ST_OTHER) fft += s;
+  }
+  if (p.myrank != 0) return 0;
+  struct stat sb;
+  const bool exists = stat(path, &sb) == 0;
+  FILE* f = fopen(path, "a");
+  SX_REQUIRE(f != nullptr, std::string("sx_benchmark_write: cannot open ") + path);
+  if (!exists) fprintf(f, " # nx ny nz nsteps nprocs nth TCPU TOMP TWTIME TFFT TTRA TCOMTCONT TNEU TROB TTOT\n");
+  const double n = (double)nsteps;
+  fprintf(f, " %11d %11d %11d %11d %11d %11d %24.16E %24.16E %24.16E %24.16E %24.16E %24.16E %24.16E %24.16E %24.16E %24.16E\n",
+          p.nx, p.ny, p.nz, nsteps, p.nprocs, nth, tcpu / n, tomp / n, twtime / n, fft / n, 0.0, com / n, 0.0, 0.0, 0.0,
+          tot / n);
+  fclose(f);
+  return 0;
+}
+
 }  // namespace sx
 
 using namespace sx;
@@ -152,6 +235,63 @@ int sx_hd_restart(sx_plan* plan, const char* idir, const char* ext, double dt) {
     if (sx_hd_state_ptr(plan, i, &d[i])) return 1;
   cplx* st[4] = {(cplx*)d[0], (cplx*)d[1], (cplx*)d[2], (cplx*)d[3]};
   return hd_restart(p, st, idir, ext, dt);
+}
+
+/* The BIN output block and the restart branch for any solver of the reference (specter.fpp:1005-1128, 886-957):
+ * solver = "HD" | "BOUSS" | "ROTBOUSS" | "MHD" | "MHDBOUSS", acting on that solver's plan-owned state. */
+static int solver_fields(sx_plan* plan, const char* solver, cplx* v[4], cplx** th, cplx* a[3], cplx** ph) {
+  sx::Plan& p = plan->p;
+  (void)p;
+  const std::string s = solver ? solver : "";
+  *th = *ph = nullptr;
+  a[0] = a[1] = a[2] = nullptr;
+  double* d = nullptr;
+  auto get = [&](int (*fn)(sx_plan*, int, double**), int which, cplx** out) -> int {
+    if (fn(plan, which, &d)) return 1;
+    *out = (cplx*)d;
+    return 0;
+  };
+  int (*fn)(sx_plan*, int, double**) = nullptr;
+  int ith = -1, ia = -1;
+  if (s == "HD") fn = sx_hd_state_ptr;
+  else if (s == "BOUSS" || s == "ROTBOUSS") { fn = sx_bouss_state_ptr; ith = 10; }
+  else if (s == "MHD") { fn = sx_mhd_state_ptr; ia = 10; }
+  else if (s == "MHDBOUSS") { fn = sx_mhdbouss_state_ptr; ia = 10; ith = 20; }
+  else SX_REQUIRE(false, "unknown solver '" + s + "' (HD, BOUSS, ROTBOUSS, MHD, MHDBOUSS)");
+  for (int i = 0; i < 4; ++i) if (get(fn, i, &v[i])) return 1;
+  if (ith >= 0 && get(fn, ith, th)) return 1;
+  if (ia >= 0) {
+    for (int q = 0; q < 3; ++q) if (get(fn, ia + q, &a[q])) return 1;
+    if (get(fn, ia + 3, ph)) return 1;
+  }
+  return 0;
+}
+
+int sx_output(sx_plan* plan, const char* solver, const char* odir, const char* ext, double dt, int outs) {
+  SX_PLAN(plan);
+  SX_REQUIRE(odir && ext && dt > 0.0, "sx_output: bad arguments");
+  cplx *v[4], *th, *a[3], *ph;
+  if (solver_fields(plan, solver, v, &th, a, &ph)) return 1;
+  if (hd_output(p, v, odir, ext, dt, outs)) return 1;
+  if (th && scalar_output(p, th, odir, ext)) return 1;
+  if (ph && magnetic_output(p, a, ph, odir, ext, dt, outs)) return 1;
+  return 0;
+}
+
+int sx_restart(sx_plan* plan, const char* solver, const char* idir, const char* ext, double dt) {
+  SX_PLAN(plan);
+  SX_REQUIRE(idir && ext && dt > 0.0, "sx_restart: bad arguments");
+  cplx *v[4], *th, *a[3], *ph;
+  if (solver_fields(plan, solver, v, &th, a, &ph)) return 1;
+  if (hd_restart(p, v, idir, ext, dt)) return 1;
+  if (th && scalar_restart(p, th, idir, ext)) return 1;
+  if (ph && magnetic_restart(p, a, ph, idir, ext, dt)) return 1;
+  return 0;
+}
+
+int sx_benchmark_write(sx_plan* plan, const char* path, int nsteps, int nth, double tcpu, double tomp, double twtime) {
+  SX_PLAN(plan);
+  return benchmark_write(p, path, nsteps, nth, tcpu, tomp, twtime);
 }
 
 }  // extern "C"

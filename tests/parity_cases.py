@@ -549,3 +549,55 @@ def case_mhdbouss_substeps(lib, tables, shape, ord=2, nsteps=1, dt=1e-3, nu=1e-3
     except api.SpecterError as e:
         assert "per-operator" in str(e)
     p.close()
+
+
+def case_solver_output_restart(lib, tables, shape, tmpdir, dt=1e-3):
+    """sx_output / sx_restart for the MHDBOUSS state (every field family at once) and benchmark.txt."""
+    import os
+    g, p = make(lib, tables, *shape)
+    g.load_neumann()
+    s = O.make_mhdbouss_state(g)
+    p.stage_timing(True)
+    p.mhdbouss_put_state(s.vx, s.vy, s.vz, s.pr, s.ax, s.ay, s.az, s.th, s.fx, s.fy, s.fz, s.mx, s.my, s.mz, s.fs)
+    p.mhdbouss_step(dt, 1e-3, 5e-3, 1e-3)
+    O.mhdbouss_step(g, s, dt, 1e-3, 5e-3, 1e-3)
+    ours, ref = os.path.join(str(tmpdir), "ours"), os.path.join(str(tmpdir), "ref")
+    os.makedirs(ours), os.makedirs(ref)
+    p.output("MHDBOUSS", ours, "0003", dt, outs=2)
+    O.solver_output(g, s, ref, "0003", dt, outs=2)
+    nph = g.nz - g.Cz
+    names = ["vx", "vy", "vz", "wx", "wy", "wz", "pr", "th", "ax", "ay", "az", "bx", "by", "bz", "jx", "jy", "jz", "ph"]
+    assert sorted(os.listdir(ours)) == sorted(os.listdir(ref)) == sorted(f"{n}.0003.out" for n in names)
+    for name in names:
+        a = np.fromfile(O.io_path(ours, name, "0003"))
+        b = np.fromfile(O.io_path(ref, name, "0003"))
+        assert a.size == b.size == g.nx * g.ny * nph, (name, a.size)
+        tol = 100 * TOL_FIELD if name in ("pr", "ph") else (TOL_RECONTINUED if name == "th" else 10 * TOL_FIELD)
+        assert rel(a, b) < tol, (name, rel(a, b))
+    p.restart("MHDBOUSS", ref, "0003", dt)
+    got = p.mhdbouss_get_state()
+    want = O.solver_restart(g, ref, "0003", dt, scalar=True, magnetic=True)
+    for q, n in zip(got, ("vx", "vy", "vz", "pr", "ax", "ay", "az", "ph", "th")):
+        w = want[n]
+        if n in ("pr", "ph"):
+            assert rel(q[:, :, :nph], w[:, :, :nph]) < 100 * TOL_FIELD, n
+        else:
+            assert rel(q, w) < TOL_FIELD, (n, rel(q, w))
+    try:
+        p.output("GHOST", ours, "0003", dt)
+        raise AssertionError("unknown solver must be refused")
+    except api.SpecterError as e:
+        assert "unknown solver" in str(e)
+    # benchmark.txt: header once, one row per call, the reference's column count (specter.fpp:1207-1218)
+    bench = os.path.join(str(tmpdir), "benchmark.txt")
+    p.benchmark_write(bench, 1, nth=1, tcpu=2.0, tomp=2.0, twtime=2.0)
+    p.benchmark_write(bench, 2, nth=1, tcpu=2.0, tomp=2.0, twtime=2.0)
+    lines = open(bench).read().splitlines()
+    assert len(lines) == 3 and lines[0].split()[:7] == ["#", "nx", "ny", "nz", "nsteps", "nprocs", "nth"]
+    row = lines[2].split()
+    assert len(row) == 16 and [int(x) for x in row[:6]] == [g.nx, g.ny, g.nz, 2, 1, 1]
+    vals = [float(x) for x in row[6:]]
+    assert vals[0] == vals[1] == vals[2] == 1.0                # totals / nsteps
+    tfft, ttra, tcom, tcont, tneu, trob, ttot = vals[3:]
+    assert tfft > 0 and ttot >= tfft and ttra == tcont == tneu == trob == 0.0 and tcom == 0.0
+    p.close()

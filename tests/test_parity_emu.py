@@ -118,3 +118,7 @@ def test_rotbouss_substeps(emu_lib, tables, impl):
 def test_mhdbouss_substeps(emu_lib, tables):
     P.case_mhdbouss_substeps(emu_lib, tables, SMALL, ord=2, nsteps=1)
     P.case_mhdbouss_substeps(emu_lib, tables, (16, 16, 64), ord=2, nsteps=1, bc=(0, 1))
+
+
+def test_solver_output_restart(emu_lib, tables, tmp_path):
+    P.case_solver_output_restart(emu_lib, tables, (16, 16, 64), tmp_path)

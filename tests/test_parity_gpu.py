@@ -145,3 +145,7 @@ def test_rotbouss_substeps_rk4_moving_walls(cuda_lib, tables):
 def test_mhdbouss_substeps_cfg1(cuda_lib, tables):
     P.case_mhdbouss_substeps(cuda_lib, tables, CFG1, ord=2, nsteps=2)
     P.case_mhdbouss_substeps(cuda_lib, tables, (32, 32, 64), ord=2, nsteps=1, bc=(1, 1))
+
+
+def test_solver_output_restart(cuda_lib, tables, tmp_path):
+    P.case_solver_output_restart(cuda_lib, tables, (32, 32, 64), tmp_path)
