@@ -1,6 +1,7 @@
 // C ABI (include/specter_b200.h): plan construction and the per-operator entry points that
 // mirror the reference's fftp / pseudo / boundary modules, composed from the kernels in
 // sx_kernels_fft.cu and sx_kernels_ops.cu.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -209,6 +210,8 @@ static void plan_release(Plan& p) {
   for (auto e : p.timer.ev) cudaEventDestroy(e);
   for (auto* q : p.cwork) if (q) cudaFree(q);
   for (auto* q : p.rwork) if (q) cudaFree(q);
+  if (p.xy_T) cudaFree(p.xy_T);
+  if (p.xy_S) cudaFree(p.xy_S);
   void* tabs[] = {p.d_kxg, p.d_kx, p.d_ky, p.d_kz, p.d_fx, p.d_fy, p.d_fz, p.d_z, p.d_dir, p.tw_x, p.tw_y, p.tw_z, p.d_red};
   for (void* q : tabs) if (q) cudaFree(q);
   if (p.h_red) cudaFreeHost(p.h_red);
@@ -216,6 +219,18 @@ static void plan_release(Plan& p) {
   if (p.ev_t1) cudaEventDestroy(p.ev_t1);
   if (p.stream) cudaStreamDestroy(p.stream);
 }
+
+#define SX_EW_LAUNCH_API(p, kernel, n, ...)                                                     \
+  do {                                                                                          \
+    auto kfn = kernel;                                                                          \
+    cudaStream_t st_ = (p).stream;                                                              \
+    size_t g_ = ((size_t)(n) + 255) / 256;                                                      \
+    if (g_ > 148u * 16u) g_ = 148u * 16u;                                                       \
+    if (stage_mark((p), ST_EW)) return 1;                                                       \
+    SX_LAUNCH(kfn, dim3((unsigned)(g_ ? g_ : 1)), dim3(256), 0, st_, __VA_ARGS__);              \
+    (p).launches++;                                                                             \
+    SX_KERNEL_CHECK();                                                                          \
+  } while (0)
 
 // ---- composite transforms -------------------------------------------------------------
 static inline cplx* C(double* a) { return reinterpret_cast<cplx*>(a); }
@@ -227,17 +242,110 @@ int fft1d_z_fwd(Plan& p, cplx* a) {  // fftp1d_real_to_complex_z
 int fft1d_z_bwd(Plan& p, const cplx* in, cplx* out, double scale_phys) {  // fftp1d_complex_to_real_z
   return launch_zfft(p, in, out, (long)p.ny * p.nxl, +1, false, scale_phys, 1.0);
 }
-#define SX_SINGLE_RANK(p, what) \
-  SX_REQUIRE((p).nprocs == 1, what ": the per-operator xy transforms are single-rank in this version (the fused substep is slab-parallel)")
+// ---- slab-parallel xy transforms (fftp.fpp:428-524, 824-919) ------------------------------------------
+// On P ranks a real field is split by z planes (ksta:kend) and a mixed / spectral field by kx (ista:iend).  The x
+// and y transforms of the local planes work on T[kx = 1..nxh][ky][zl] (z fastest, local planes only), whose block
+// for rank d -- kx in d's slab, every ky, the local planes -- is contiguous: it is the send block of the all-to-all-v
+// as it stands.  The received blocks [kxl][ky][planes of rank s] are interleaved into the z-fastest layout
+// (nz,ny,ista:iend) by one small kernel per source rank (the reference's csize-blocked local transpose, :503-522).
+__global__ void k_xy_unpack(cplx* __restrict__ out, const cplx* __restrict__ blk, size_t npen, int nz, int z0, int nzs) {
+  const size_t n = npen * (size_t)nzs;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t pen = t / nzs;
+    const int k = (int)(t - pen * nzs);
+    out[pen * nz + z0 + k] = blk[t];
+  }
+}
+__global__ void k_xy_pack(cplx* __restrict__ blk, const cplx* __restrict__ in, size_t npen, int nz, int z0, int nzs) {
+  const size_t n = npen * (size_t)nzs;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t pen = t / nzs;
+    const int k = (int)(t - pen * nzs);
+    blk[t] = in[pen * nz + z0 + k];
+  }
+}
+struct XyTables {
+  std::vector<size_t> xd, xc, zd, zc;   // displacements / counts (complex elements) of the kx-side and z-side blocks
+  std::vector<int> z0, nzs;
+};
+static void xy_tables(const Plan& p, XyTables& t) {
+  const int P = p.nprocs;
+  t.xd.assign(P, 0); t.xc.assign(P, 0); t.zd.assign(P, 0); t.zc.assign(P, 0); t.z0.assign(P, 0); t.nzs.assign(P, 0);
+  size_t zoff = 0;
+  for (int r = 0; r < P; ++r) {
+    int is, ie, ks, ke;
+    range_(1, p.nxh, P, r, &is, &ie);
+    range_(1, p.nz, P, r, &ks, &ke);
+    t.xd[r] = (size_t)(is - 1) * p.ny * p.nzl;            // block of T for rank r
+    t.xc[r] = (size_t)(ie - is + 1) * p.ny * p.nzl;
+    t.z0[r] = ks - 1;
+    t.nzs[r] = ke - ks + 1;
+    t.zd[r] = zoff;                                        // block [kxl][ky][planes of r] in the staging buffer
+    t.zc[r] = (size_t)p.nxl * p.ny * t.nzs[r];
+    zoff += t.zc[r];
+  }
+}
+static int xy_buffers(Plan& p, cplx** T, cplx** S) {
+  if (!p.xy_T) {
+    const size_t nT = std::max((size_t)p.nxh * p.ny * p.nzl, p.csize());
+    SX_CUDA_CHECK(cudaMalloc((void**)&p.xy_T, nT * sizeof(cplx)));
+    SX_CUDA_CHECK(cudaMalloc((void**)&p.xy_S, p.csize() * sizeof(cplx)));
+  }
+  *T = p.xy_T;
+  *S = p.xy_S;
+  return 0;
+}
+static inline int local_active(const Plan& p, int nz_active) {   // leading local planes among the first nz_active
+  const int n = std::min(p.kend, nz_active) - p.ksta + 1;
+  return n < 0 ? 0 : n;
+}
+constexpr int kXyEvent = 31;   // event slot of the stand-alone exchanges (the fused substep uses 0..27)
+
 int fft2d_xy_r2c(Plan& p, const double* r, cplx* out, int nz_active) {
-  SX_SINGLE_RANK(p, "fftp2d_real_to_complex_xy");
-  if (launch_x_r2c(p, r, out, p.nz, nz_active, 1.0)) return 1;
-  return launch_yfft(p, out, out, p.nz, p.nxh, nz_active, -1, 1.0);
+  if (p.nprocs == 1) {
+    if (launch_x_r2c(p, r, out, p.nz, nz_active, 1.0)) return 1;
+    return launch_yfft(p, out, out, p.nz, p.nxh, nz_active, -1, 1.0);
+  }
+  cplx *T, *S;
+  if (xy_buffers(p, &T, &S)) return 1;
+  XyTables t;
+  xy_tables(p, t);
+  const int act = local_active(p, nz_active);
+  if (act < p.nzl) SX_CUDA_CHECK(cudaMemsetAsync(T, 0, (size_t)p.nxh * p.ny * p.nzl * sizeof(cplx), p.stream));
+  if (launch_x_r2c(p, r, T, p.nzl, act, 1.0)) return 1;
+  if (launch_yfft(p, T, T, p.nzl, p.nxh, act, -1, 1.0)) return 1;
+  if (exchange_begin(p, kXyEvent, T, S, t.xd.data(), t.xc.data(), t.zd.data(), t.zc.data())) return 1;
+  if (exchange_wait(p, kXyEvent)) return 1;
+  const size_t npen = (size_t)p.nxl * p.ny;
+  for (int s = 0; s < p.nprocs; ++s) {
+    if (t.zc[s] == 0) continue;
+    const cplx* blk = S + t.zd[s];
+    const int nz = p.nz, z0 = t.z0[s], nzs = t.nzs[s];
+    SX_EW_LAUNCH_API(p, k_xy_unpack, t.zc[s], out, blk, npen, nz, z0, nzs);
+  }
+  return 0;
 }
 int fft2d_xy_c2r(Plan& p, cplx* mixed_destroyed, double* r, int nz_active) {
-  SX_SINGLE_RANK(p, "fftp2d_complex_to_real_xy");
-  if (launch_yfft(p, mixed_destroyed, mixed_destroyed, p.nz, p.nxh, nz_active, +1, 1.0)) return 1;
-  return launch_x_c2r(p, mixed_destroyed, r, p.nz, nz_active, 1.0);
+  if (p.nprocs == 1) {
+    if (launch_yfft(p, mixed_destroyed, mixed_destroyed, p.nz, p.nxh, nz_active, +1, 1.0)) return 1;
+    return launch_x_c2r(p, mixed_destroyed, r, p.nz, nz_active, 1.0);
+  }
+  cplx *T, *S;
+  if (xy_buffers(p, &T, &S)) return 1;
+  XyTables t;
+  xy_tables(p, t);
+  const size_t npen = (size_t)p.nxl * p.ny;
+  for (int d = 0; d < p.nprocs; ++d) {
+    if (t.zc[d] == 0) continue;
+    cplx* blk = S + t.zd[d];
+    const int nz = p.nz, z0 = t.z0[d], nzs = t.nzs[d];
+    SX_EW_LAUNCH_API(p, k_xy_pack, t.zc[d], blk, mixed_destroyed, npen, nz, z0, nzs);
+  }
+  if (exchange_begin(p, kXyEvent, S, T, t.zd.data(), t.zc.data(), t.xd.data(), t.xc.data())) return 1;
+  if (exchange_wait(p, kXyEvent)) return 1;
+  const int act = local_active(p, nz_active);
+  if (launch_yfft(p, T, T, p.nzl, p.nxh, act, +1, 1.0)) return 1;
+  return launch_x_c2r(p, T, r, p.nzl, act, 1.0);
 }
 int fft3d_r2c(Plan& p, const double* r, cplx* out) {
   // planes above the physical region are overwritten by the continuation (fftp.fpp:761)

@@ -256,7 +256,8 @@ __device__ __forceinline__ int smem_align128_offset(const cplx* s) {
 //   zinv: lines = ky, plane = kxl: src = in + (kxl*ny + line)*N          out box at (ky0, z, kxl) of [kxl][z][ky]
 struct InvTmaArgs {
   const cplx* in;
-  const double* kd;      // wavenumbers of the transformed direction (derivative output)
+  double dk;             // wavenumber spacing of the transformed direction: k(e) = (e < N/2 ? e : e - N) * dk, the
+                         // product the host tables hold (specter.fpp:772-789); no table loads in the tile loop
   int nlines;            // lines per plane that hold data (nxh / ny)
   int nplanes;
   long line_stride, plane_stride;   // in lines (units of N elements)
@@ -328,7 +329,8 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_inv_tma(InvTmaArgs a, cons
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const cplx q = load ? mine[k * T] : cmake(0.0, 0.0);
-        const double kk = __ldg(&a.kd[j + k * T]);
+        const int e = j + k * T;
+        const double kk = (double)(e < N / 2 ? e : e - N) * a.dk;
         v[k] = cmake(-kk * q.y, kk * q.x);
       }
       fft_regs<N, 1>(v, j, exch, si, twr, make_hook([&] { if (lead) tma_store_wait_read(); }, [] {}));
@@ -435,7 +437,7 @@ template <int N> static int run_zinv_tma(Plan& p, Fused& f, const cplx* in, cplx
     if (add_block(m0, b0, p.ny, z0[r], zc[r], p.nxl, p.ny, (size_t)zc[r] * p.ny, NP)) return 1;
     if (add_block(m1, b1, p.ny, z0[r], zc[r], p.nxl, p.ny, (size_t)zc[r] * p.ny, NP)) return 1;
   }
-  InvTmaArgs a{in, p.d_kz, p.ny, p.nxl, 1, p.ny, out1 != nullptr};
+  InvTmaArgs a{in, p.Dkz, p.ny, p.nxl, 1, p.ny, out1 != nullptr};
   return run_inv_tma<N>(p, f, ST_ZINV, a, m0, m1);
 }
 template <int N> static int run_yinv_tma(Plan& p, Fused& f, const cplx* in, cplx* out0, cplx* out1) {
@@ -448,7 +450,7 @@ template <int N> static int run_yinv_tma(Plan& p, Fused& f, const cplx* in, cplx
   if (f.zc() == 0) return 0;
   if (add_block(m0, out0 + zo, f.nxp, 0, N, f.zc(), f.nxp, (size_t)p.ny * f.nxp, NP)) return 1;
   if (add_block(m1, (out1 ? out1 : out0) + zo, f.nxp, 0, N, f.zc(), f.nxp, (size_t)p.ny * f.nxp, NP)) return 1;
-  InvTmaArgs a{in + (size_t)f.z0() * N, p.d_ky, p.nxh, f.zc(), f.nzf, 1, out1 != nullptr};
+  InvTmaArgs a{in + (size_t)f.z0() * N, p.Dky, p.nxh, f.zc(), f.nzf, 1, out1 != nullptr};
   return run_inv_tma<N>(p, f, ST_YINV, a, m0, m1);
 }
 static int yfwd_peers(Plan& p, Fused& f, const cplx* out, YfwdArgs& a) {

@@ -49,6 +49,7 @@ struct Plan {
   // scratch pool (lazily grown): complex spectral-sized and real-sized work arrays
   std::vector<cplx*> cwork;
   std::vector<double*> rwork;
+  cplx *xy_T = nullptr, *xy_S = nullptr;   // slab-parallel stand-alone xy transforms: local-plane array and block staging
   double* d_red = nullptr;   // reduction partials
   double* h_red = nullptr;   // pinned host landing zone
   int red_blocks = 0;

@@ -48,6 +48,31 @@ def _worker(rank, world, port, solver, shape, ord_, tables, q):
             b = np.fft.ifft(s.th, axis=2)[:, :, :nph]
             got = st[:3] + [a]
             ref = (s.vx, s.vy, s.vz, b)
+        elif solver == "ops":
+            # slab-parallel stand-alone transforms + the per-operator substep, then the ROTBOUSS fused substep
+            rng = np.random.default_rng(3)
+            r = rng.standard_normal(g.rshape())
+            zs = slice(p.ksta - 1, p.kend)
+            dr, dc = p.real(np.ascontiguousarray(r[zs])), p.spectral()
+            p.fftp3d_real_to_complex(dr, dc)
+            spec = O.fftp3d_real_to_complex(g, r.copy())
+            e1 = np.abs(dc.get() - spec[sl]).max() / np.abs(spec).max()
+            p.fftp3d_complex_to_real(dc, dr)
+            back = O.fftp3d_complex_to_real(g, spec)
+            e2 = np.abs(dr.get() - back[zs]).max() / np.abs(back).max()
+            assert e1 < 1e-12 and e2 < 1e-12, (e1, e2)
+            s = O.make_bouss_state(g)
+            p.hd_put_state(*cut((s.vx, s.vy, s.vz, s.pr, s.fx, s.fy, s.fz)))
+            p.hd_step(1e-3, 1e-3, impl=1)
+            h = O.make_hd_state(g)
+            O.hd_step(g, h, 1e-3, 1e-3)
+            p.bouss_put_state(*cut((s.vx, s.vy, s.vz, s.pr, s.th, s.fx, s.fy, s.fz, s.fs)))
+            om = (0.3, -0.2, 1.5)
+            p.rotbouss_step(1e-3, 1e-3, 1e-3, omega=om)
+            O.rotbouss_step(g, s, 1e-3, 1e-3, 1e-3, omega=om)
+            st = p.bouss_get_state()
+            got = p.hd_get_state()[:3] + st[:3] + [st[4]]
+            ref = (h.vx, h.vy, h.vz, s.vx, s.vy, s.vz, s.th)
         else:
             s = O.make_mhd_state(g)
             p.mhd_put_state(*cut((s.vx, s.vy, s.vz, s.pr, s.ax, s.ay, s.az, s.fx, s.fy, s.fz, s.mx, s.my, s.mz)))
@@ -70,7 +95,7 @@ def _worker(rank, world, port, solver, shape, ord_, tables, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("solver", ["hd", "bouss", "mhd"])
+@pytest.mark.parametrize("solver", ["hd", "bouss", "mhd", "ops"])
 def test_fused_substep_nccl(solver, tables):
     import torch
     import torch.multiprocessing as mp

@@ -98,3 +98,127 @@ def test_fused_substep_multirank(world, shape, ord_, tma_min, emu_lib, tables, m
         assert abs(div - div_ref) < 1e-9 * eng_ref
         covered += iend - ista + 1
     assert covered == shape[0] // 2 + 1
+
+
+def _install_gloo_callbacks(p, dist, rank, world):
+    import torch
+
+    def alltoallv(send, sd, sc, recv, rd, rc):
+        ins = [torch.from_numpy(np.frombuffer((C.c_char * sc[r]).from_address(send + sd[r]), dtype=np.uint8).copy())
+               if sc[r] else torch.empty(0, dtype=torch.uint8) for r in range(world)]
+        outs = [torch.empty(rc[r], dtype=torch.uint8) for r in range(world)]
+        _gloo_a2a(dist, outs, ins, rank, world)
+        for r in range(world):
+            if rc[r]:
+                C.memmove(recv + rd[r], outs[r].numpy().ctypes.data, rc[r])
+
+    def allreduce(ptr, n):
+        t = torch.tensor([ptr[i] for i in range(n)], dtype=torch.float64)
+        dist.all_reduce(t)
+        for i in range(n):
+            ptr[i] = float(t[i])
+
+    p.set_comm_callbacks(alltoallv, allreduce)
+
+
+def _worker_operators(rank, world, port, shape, emu_path, tables, tmpdir, q):
+    """Slab-parallel stand-alone transforms (fftp.fpp:388-524, 789-919), the per-operator substep, the ROTBOUSS fused
+    substep, diagnostics with MPI_MAX / MPI_SUM reductions and the field files written by several ranks."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import specter_oracle as O
+    from specter_b200 import api
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        lib = api.Library(emu_path)
+        nx, ny, nz = shape
+        p = api.Plan(nx, ny, nz, 25, 5, ord=2, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, nprocs=world, myrank=rank, lib=lib)
+        _install_gloo_callbacks(p, dist, rank, world)
+        g = O.Grid(nx, ny, nz, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, ord=2)
+        xs, zs = slice(p.ista - 1, p.iend), slice(p.ksta - 1, p.kend)
+        nph = nz - 25
+        errs = {}
+
+        def rel(a, b):
+            return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+        rng = np.random.default_rng(3)
+        r = rng.standard_normal(g.rshape())
+        dr, dc = p.real(np.ascontiguousarray(r[zs])), p.spectral()
+        p.fftp3d_real_to_complex(dr, dc)
+        spec = O.fftp3d_real_to_complex(g, r.copy())
+        errs["r2c3"] = rel(dc.get(), spec[xs])
+        p.fftp2d_real_to_complex_xy(dr, dc)
+        errs["r2c2"] = rel(dc.get(), O.fftp2d_real_to_complex_xy(g, r)[xs])
+        dc.put(np.ascontiguousarray(spec[xs]))
+        p.fftp3d_complex_to_real(dc, dr)
+        errs["c2r3"] = rel(dr.get(), O.fftp3d_complex_to_real(g, spec)[zs])
+        p.fftp2d_complex_to_real_xy(dc, dr)
+        errs["c2r2"] = rel(dr.get(), O.fftp2d_complex_to_real_xy(g, spec)[zs])
+        # per-operator HD substep (gradre with 12 + 3 slab-parallel 3-D transforms), then output / restart files
+        s = O.make_hd_state(g)
+        p.hd_put_state(*[np.ascontiguousarray(a[xs]) for a in (s.vx, s.vy, s.vz, s.pr, s.fx, s.fy, s.fz)])
+        p.hd_step(1e-3, 1e-3, impl=1)
+        O.hd_step(g, s, 1e-3, 1e-3)
+        got = p.hd_get_state()
+        scale = max(np.abs(a).max() for a in (s.vx, s.vy, s.vz))
+        errs["hd_modular"] = max(float(np.abs(a - b[xs]).max()) for a, b in zip(got[:3], (s.vx, s.vy, s.vz))) / scale
+        v = [p.hd_field(i) for i in range(3)]
+        errs["maxabs"] = abs(p.maxabs(*v, 0) / O.maxabs(g, s.vx, s.vy, s.vz, 0) - 1)
+        hs = (O.energy(g, s.vx, s.vy, s.vz, 1) * O.energy(g, s.vx, s.vy, s.vz, 0)) ** 0.5
+        errs["helicity"] = abs(p.helicity(*v) - O.helicity(g, s.vx, s.vy, s.vz)) / hs
+        ours = os.path.join(tmpdir, "ours")
+        ref = os.path.join(tmpdir, "ref")
+        if rank == 0:
+            os.makedirs(ours, exist_ok=True)
+            os.makedirs(ref, exist_ok=True)
+            O.hd_output(g, s, ref, "0001", 1e-3, outs=1)
+        dist.barrier()
+        p.output("HD", ours, "0001", 1e-3, outs=1)
+        dist.barrier()
+        worst = 0.0
+        for name in ("vx", "vy", "vz", "wx", "wy", "wz", "pr"):
+            a = np.fromfile(O.io_path(ours, name, "0001"))
+            b = np.fromfile(O.io_path(ref, name, "0001"))
+            assert a.size == b.size == nx * ny * nph, (name, a.size, b.size)
+            worst = max(worst, rel(a, b) / (100 if name == "pr" else 1))
+        errs["output"] = worst
+        p.restart("HD", ref, "0001", 1e-3)
+        want = O.hd_restart(g, ref, "0001", 1e-3)
+        got = p.hd_get_state()
+        scale = max(np.abs(a).max() for a in want[:3])     # global scale: the high-kx slab of a band-limited field is ~0
+        errs["restart"] = max(float(np.abs(a - b[xs]).max()) for a, b in zip(got[:3], want[:3])) / scale
+        # ROTBOUSS fused substep on several ranks
+        b = O.make_bouss_state(g)
+        p.bouss_put_state(*[np.ascontiguousarray(a[xs]) for a in (b.vx, b.vy, b.vz, b.pr, b.th, b.fx, b.fy, b.fz, b.fs)])
+        om = (0.3, -0.2, 1.5)
+        p.rotbouss_step(1e-3, 1e-3, 1e-3, omega=om)
+        O.rotbouss_step(g, b, 1e-3, 1e-3, 1e-3, omega=om)
+        got = p.bouss_get_state()
+        scale = max(np.abs(a).max() for a in (b.vx, b.vy, b.vz, b.th))
+        errs["rotbouss"] = max(float(np.abs(a - c[xs]).max()) for a, c in
+                               zip(got[:3] + [got[4]], (b.vx, b.vy, b.vz, b.th))) / scale
+        q.put((rank, errs))
+        p.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(2, (32, 16, 64)), (3, (16, 16, 64))])
+def test_operators_multirank(world, shape, emu_lib, tables, tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_operators, args=(r, world, port, shape, emu_lib.path, tables, str(tmp_path), q))
+             for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(timeout=900)
+    assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
+    for rank, errs in sorted(q.get(timeout=10) for _ in range(world)):
+        for k in ("r2c3", "r2c2", "c2r3", "c2r2"):
+            assert errs[k] < 1e-12, (rank, k, errs[k])
+        for k in ("hd_modular", "output", "restart", "rotbouss"):
+            assert errs[k] < 1e-11, (rank, k, errs[k])
+        assert errs["maxabs"] < 1e-9 and errs["helicity"] < 1e-9, (rank, errs)
