@@ -31,3 +31,39 @@ for t in range(100):
 with open(os.path.join(HERE, "hd64_diag100.json"), "w") as f:
     json.dump({"config": "HD 64^3 Cz=25 oz=5 RK2 dt=1e-3 nu=1e-3 Lx=1 Ly=0.5 Lz=1 seed=1000 f0=1",
                "columns": ["step", "energy", "enstrophy_ref_quirk", "injection", "divergence"], "rows": rows}, f, indent=1)
+
+
+# ---- solvers32_step1.npz: one RK2 step of every other solver on 32x32x64 (same box, seed, dt, nu; kappa=1e-3, mu=5e-3,
+# omega=(0.3,-0.2,1.5), b0=(0,0,0.1)), spectral fields sub-sampled, plus the global-output columns of that state
+def solver_goldens():
+    gs = O.Grid(32, 32, 64, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=os.path.join(HERE, "tables"), ord=2)
+    gs.load_neumann()
+    out = {}
+    sub = (slice(None, None, 4), slice(None, None, 4), slice(None, None, 4))
+
+    def put(tag, s, names):
+        for n in names:
+            out[f"{tag}_{n}"] = getattr(s, n)[sub]
+
+    b = O.make_bouss_state(gs)
+    O.bouss_step(gs, b, 1e-3, 1e-3, 1e-3)
+    put("bouss", b, ("vx", "vy", "vz", "th"))
+    out["bouss_pscheck"] = np.array(O.pscheck(gs, b.th, b.vz))
+    r = O.make_bouss_state(gs)
+    O.rotbouss_step(gs, r, 1e-3, 1e-3, 1e-3, omega=(0.3, -0.2, 1.5))
+    put("rotbouss", r, ("vx", "vy", "vz", "th"))
+    for tag, bc in (("mhd", (0, 0)), ("mhdvac", (1, 1))):
+        m = O.make_mhdbouss_state(gs)
+        O.mhdbouss_step(gs, m, 1e-3, 1e-3, 5e-3, 1e-3, b0=(0.0, 0.0, 0.1), bczsta=bc[0], bczend=bc[1])
+        put(tag + "bouss", m, ("vx", "vy", "vz", "ax", "ay", "az", "th"))
+        out[tag + "bouss_mhdcheck"] = np.array(O.mhdcheck(gs, m.vx, m.vy, m.vz, m.ax, m.ay, m.az))
+        d = O.bdiagnostic(gs, m.ax, m.ay, m.az, *bc)
+        out[tag + "bouss_bdiag"] = np.array(d["conducting" if bc == (0, 0) else "vacuum"])
+    m = O.make_mhd_state(gs)
+    O.mhd_step(gs, m, 1e-3, 1e-3, 5e-3)
+    put("mhd", m, ("vx", "vy", "vz", "ax", "ay", "az"))
+    np.savez_compressed(os.path.join(HERE, "solvers32_step1.npz"), **out)
+    print("solvers32_step1.npz:", sorted(out))
+
+
+solver_goldens()

@@ -601,3 +601,95 @@ def case_solver_output_restart(lib, tables, shape, tmpdir, dt=1e-3):
     tfft, ttra, tcom, tcont, tneu, trob, ttot = vals[3:]
     assert tfft > 0 and ttot >= tfft and ttra == tcont == tneu == trob == 0.0 and tcom == 0.0
     p.close()
+
+
+# ---- committed golden fixtures (tests/golden/make_golden.py) -----------------------------------------------------
+def golden_solver_runs(step_fns):
+    """Shared by the CPU pin of the oracle and the GPU parity test: step_fns maps a tag of solvers32_step1.npz to a
+    callable returning {field name: array (nxl, ny, nz)} and optional diagnostics after one RK2 step."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solvers32_step1.npz"))
+    sub = (slice(None, None, 4), slice(None, None, 4), slice(None, None, 4))
+    for tag, fn in step_fns.items():
+        fields, diags = fn()
+        names = sorted(fields)
+        scale_v = max(np.abs(gold[f"{tag}_{n}"]).max() for n in names if n.startswith("v"))
+        scale_a = max([np.abs(gold[f"{tag}_{n}"]).max() for n in names if n.startswith("a")] or [1.0])
+        for n in names:
+            want = gold[f"{tag}_{n}"]
+            scale = scale_a if n.startswith("a") else (np.abs(want).max() if n == "th" else scale_v)
+            tol = TOL_RECONTINUED if n == "th" else TOL_FIELD
+            err = np.abs(fields[n][sub] - want).max() / scale
+            assert err < tol, (tag, n, err)
+        for key, val in (diags or {}).items():
+            want = gold[f"{tag}_{key}"]
+            ref = np.abs(want).max()
+            assert np.abs(np.asarray(val) - want).max() < 10 * TOL_DIAG * ref, (tag, key, val, want)
+
+
+def case_golden_solvers(lib, tables):
+    """The CUDA path against the committed goldens (one RK2 step of BOUSS, ROTBOUSS, MHD, MHDBOUSS with conducting
+    and with vacuum walls on 32x32x64)."""
+    shape, om, b0 = (32, 32, 64), (0.3, -0.2, 1.5), (0.0, 0.0, 0.1)
+
+    def bouss(rot):
+        def run():
+            g, p = make(lib, tables, *shape)
+            s = O.make_bouss_state(g)
+            p.bouss_put_state(s.vx, s.vy, s.vz, s.pr, s.th, s.fx, s.fy, s.fz, s.fs)
+            if rot:
+                p.rotbouss_step(1e-3, 1e-3, 1e-3, omega=om)
+            else:
+                p.bouss_step(1e-3, 1e-3, 1e-3)
+            got = p.bouss_get_state()
+            d = None if rot else {"pscheck": p.pscheck(p.bouss_field(10), p.bouss_field(2))}
+            p.close()
+            return dict(vx=got[0], vy=got[1], vz=got[2], th=got[4]), d
+        return run
+
+    def mhdbouss(bc):
+        def run():
+            g, p = make(lib, tables, *shape)
+            g.load_neumann()
+            p.setup_bc("b", PERIODIC4 + [B_KIND[bc[0]], B_KIND[bc[1]]])
+            s = O.make_mhdbouss_state(g)
+            p.mhdbouss_put_state(s.vx, s.vy, s.vz, s.pr, s.ax, s.ay, s.az, s.th, s.fx, s.fy, s.fz, s.mx, s.my, s.mz, s.fs)
+            p.mhdbouss_step(1e-3, 1e-3, 5e-3, 1e-3, b0=b0)
+            got = p.mhdbouss_get_state()
+            f = [p.mhdbouss_field(i) for i in (0, 1, 2, 10, 11, 12)]
+            bd = p.bdiagnostic(*f[3:])
+            d = {"mhdcheck": p.mhdcheck(*f), "bdiag": bd["conducting" if bc == (0, 0) else "vacuum"]}
+            p.close()
+            return dict(vx=got[0], vy=got[1], vz=got[2], ax=got[4], ay=got[5], az=got[6], th=got[8]), d
+        return run
+
+    def mhd():
+        g, p = make(lib, tables, *shape)
+        s = O.make_mhd_state(g)
+        p.mhd_put_state(s.vx, s.vy, s.vz, s.pr, s.ax, s.ay, s.az, s.fx, s.fy, s.fz, s.mx, s.my, s.mz)
+        p.mhd_step(1e-3, 1e-3, 5e-3)
+        got = p.mhd_get_state()
+        p.close()
+        return dict(vx=got[0], vy=got[1], vz=got[2], ax=got[4], ay=got[5], az=got[6]), None
+
+    golden_solver_runs({"bouss": bouss(False), "rotbouss": bouss(True), "mhd": mhd, "mhdbouss": mhdbouss((0, 0)),
+                        "mhdvacbouss": mhdbouss((1, 1))})
+
+
+def case_golden_hd_step1(lib, tables):
+    """Config 1 (HD 64^3 RK2): the spectral fields after the first step against hd64_step1.npz."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hd64_step1.npz"))
+    g, p = make(lib, tables, 64, 64, 64)
+    s = O.make_hd_state(g)
+    p.hd_put_state(s.vx, s.vy, s.vz, s.pr, s.fx, s.fy, s.fz)
+    p.hd_step(1e-3, 1e-3)
+    got = p.hd_get_state()
+    p.close()
+    scale = max(np.abs(gold[n]).max() for n in ("vx", "vy", "vz"))
+    for q, n in zip(got[:3], ("vx", "vy", "vz")):
+        assert np.abs(q[::4, ::4, ::2] - gold[n]).max() / scale < TOL_FIELD, n
+    nph = 64 - 25
+    a, b = got[3][::4, ::4, ::2], gold["pr"]
+    k = (nph + 1) // 2
+    assert rel(a[:, :, :k], b[:, :, :k]) < 100 * TOL_FIELD

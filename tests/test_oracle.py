@@ -288,3 +288,46 @@ def test_rotbouss_and_mhdbouss_substep_invariants(tables):
     out = O.mhdcheck(g, mb.vx, mb.vy, mb.vz, mb.ax, mb.ay, mb.az)
     assert np.isfinite(out).all() and out[0] > 0
     assert np.isfinite(O.pscheck(g, mb.th, mb.fs)).all()
+
+
+def test_oracle_reproduces_committed_goldens(tables):
+    # tests/golden/solvers32_step1.npz and hd64_step1.npz were written by the oracle (make_golden.py): any later
+    # change of the restatement that moves a field by more than rounding shows up here
+    import os
+    import parity_cases as P
+    gs = O.Grid(32, 32, 64, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, ord=2)
+    gs.load_neumann()
+
+    def bouss(rot):
+        def run():
+            s = O.make_bouss_state(gs)
+            if rot:
+                O.rotbouss_step(gs, s, 1e-3, 1e-3, 1e-3, omega=(0.3, -0.2, 1.5))
+                return dict(vx=s.vx, vy=s.vy, vz=s.vz, th=s.th), None
+            O.bouss_step(gs, s, 1e-3, 1e-3, 1e-3)
+            return dict(vx=s.vx, vy=s.vy, vz=s.vz, th=s.th), {"pscheck": O.pscheck(gs, s.th, s.vz)}
+        return run
+
+    def mhdbouss(bc):
+        def run():
+            m = O.make_mhdbouss_state(gs)
+            O.mhdbouss_step(gs, m, 1e-3, 1e-3, 5e-3, 1e-3, b0=(0.0, 0.0, 0.1), bczsta=bc[0], bczend=bc[1])
+            d = O.bdiagnostic(gs, m.ax, m.ay, m.az, *bc)
+            return (dict(vx=m.vx, vy=m.vy, vz=m.vz, ax=m.ax, ay=m.ay, az=m.az, th=m.th),
+                    {"mhdcheck": O.mhdcheck(gs, m.vx, m.vy, m.vz, m.ax, m.ay, m.az),
+                     "bdiag": d["conducting" if bc == (0, 0) else "vacuum"]})
+        return run
+
+    def mhd():
+        m = O.make_mhd_state(gs)
+        O.mhd_step(gs, m, 1e-3, 1e-3, 5e-3)
+        return dict(vx=m.vx, vy=m.vy, vz=m.vz, ax=m.ax, ay=m.ay, az=m.az), None
+
+    P.golden_solver_runs({"bouss": bouss(False), "rotbouss": bouss(True), "mhd": mhd, "mhdbouss": mhdbouss((0, 0)),
+                          "mhdvacbouss": mhdbouss((1, 1))})
+    g64 = O.Grid(64, 64, 64, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, ord=2)
+    s = O.make_hd_state(g64)
+    O.hd_step(g64, s, 1e-3, 1e-3)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hd64_step1.npz"))
+    for n in ("vx", "vy", "vz"):
+        assert np.abs(getattr(s, n)[::4, ::4, ::2] - gold[n]).max() < 1e-12 * np.abs(gold[n]).max()

@@ -122,3 +122,7 @@ def test_mhdbouss_substeps(emu_lib, tables):
 
 def test_solver_output_restart(emu_lib, tables, tmp_path):
     P.case_solver_output_restart(emu_lib, tables, (16, 16, 64), tmp_path)
+
+
+def test_golden_solvers(emu_lib, tables):
+    P.case_golden_solvers(emu_lib, tables)

@@ -149,3 +149,8 @@ def test_mhdbouss_substeps_cfg1(cuda_lib, tables):
 
 def test_solver_output_restart(cuda_lib, tables, tmp_path):
     P.case_solver_output_restart(cuda_lib, tables, (32, 32, 64), tmp_path)
+
+
+def test_golden_fixtures(cuda_lib, tables):
+    P.case_golden_solvers(cuda_lib, tables)
+    P.case_golden_hd_step1(cuda_lib, tables)
