@@ -194,6 +194,7 @@ static int plan_init(Plan& p, const sx_config& c) {
   if (const char* e = getenv("SX_ZCHUNKS")) p.knob_zchunks = atoi(e);
   if (const char* e = getenv("SX_TMA")) p.knob_tma = atoi(e);
   if (const char* e = getenv("SX_TMA_MIN")) p.knob_tma_min = atoi(e);
+  if (const char* e = getenv("SX_INV_STAGES")) p.knob_inv_stages = atoi(e);
   if (const char* e = getenv("SX_TILE_NP")) p.knob_np = atoi(e);
   if (const char* e = getenv("SX_TILE_MINB")) p.knob_minb = atoi(e);
   p.red_blocks = 148 * 4;

@@ -273,44 +273,55 @@ struct InvTmaMaps {
   int nblocks;
 };
 
-template <int N, int NP, int MINB>
+// S = input stages: the staging tile is a ring of S slots filled S tiles ahead (S = 1: one tile ahead, three CTAs
+// per SM; S = 2: two CTAs per SM, twice the bytes in flight per CTA and no gap between a slot's consumption and
+// the arrival of the next tile -- the load latency was the largest stall of the one-slot kernel, profiles/r1j)
+template <int N, int NP, int MINB, int S>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_inv_tma(InvTmaArgs a, const SX_GRID_CONSTANT InvTmaMaps m0,
                                                               const SX_GRID_CONSTANT InvTmaMaps m1, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem_raw);
   typedef TileGeo<N, NP> G;
   constexpr int T = G::T;
+  constexpr int STAGE = NP * G::PITCH;
   cplx* exch = smem_raw + smem_align128_offset(smem_raw);          // [row][NP]: exchange buffer and store tile
-  cplx* in = exch + (size_t)N * NP;              // [NP][PITCH]
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(in + (size_t)NP * G::PITCH);
+  cplx* in0 = exch + (size_t)N * NP;             // S x [NP][PITCH]
+  unsigned long long* bar0 = reinterpret_cast<unsigned long long*>(in0 + (size_t)S * STAGE);
   const int p = threadIdx.x % NP, j = threadIdx.x / NP;
   const bool lead = threadIdx.x == 0;
   TwRegs<N> twr;
   twr.load(tw, j);
   const SIdxPencil si{p, NP};
   const int tiles_l = cdiv(a.nlines, NP), ntiles = tiles_l * a.nplanes;
-  auto issue = [&](int t) {   // lead thread only
+  auto issue = [&](int t, int st) {   // lead thread only
     const int l0 = (t % tiles_l) * NP, pl = t / tiles_l;
     const int valid = a.nlines - l0 < NP ? a.nlines - l0 : NP;
+    cplx* in = in0 + (size_t)st * STAGE;
+    unsigned long long* bar = bar0 + st;
     mbar_expect(bar, (unsigned)(valid * N * sizeof(cplx)));
     for (int q = 0; q < valid; ++q)
       bulk_load_piece(in + (size_t)q * G::PITCH, a.in + ((size_t)(l0 + q) * a.line_stride + (size_t)pl * a.plane_stride) * N,
                       (unsigned)(N * sizeof(cplx)), bar);
   };
   if (lead) {
-    mbar_init(bar, 1);
+    for (int st = 0; st < S; ++st) mbar_init(bar0 + st, 1);
     mbar_init_fence();
   }
   __syncthreads();
   int t = blockIdx.x;
-  unsigned phase = 0;
-  if (lead && t < ntiles) issue(t);
+  unsigned phase = 0;   // bit st = parity of stage st
+  int cs = 0;           // stage of the current tile
+  if (lead)
+    for (int st = 0; st < S; ++st)
+      if (t + st * (int)gridDim.x < ntiles) issue(t + st * gridDim.x, st);
   for (; t < ntiles; t += gridDim.x) {
     const int l0 = (t % tiles_l) * NP, pl = t / tiles_l;
     const bool load = l0 + p < a.nlines;
-    const int tn = t + gridDim.x;
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    const cplx* mine = in + (size_t)p * G::PITCH + j;
+    const int tn = t + S * (int)gridDim.x;
+    const int st_now = cs;
+    mbar_wait(bar0 + cs, (phase >> cs) & 1u);
+    phase ^= 1u << cs;
+    const cplx* mine = in0 + (size_t)cs * STAGE + (size_t)p * G::PITCH + j;
+    if (++cs == S) cs = 0;
     auto store_tile = [&](const InvTmaMaps* m, cplx (&v)[8]) {
       __syncthreads();   // the last gather of the transform is done: the buffer becomes the store tile
 #pragma unroll
@@ -340,7 +351,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_inv_tma(InvTmaArgs a, cons
     for (int k = 0; k < 8; ++k) v[k] = load ? mine[k * T] : cmake(0.0, 0.0);
     // at the first barrier of this transform every thread has consumed the staging tile: refill it
     fft_regs<N, 1>(v, j, exch, si, twr,
-                   make_hook([&] { if (lead) tma_store_wait_read(); }, [&] { if (lead && tn < ntiles) issue(tn); }));
+                   make_hook([&] { if (lead) tma_store_wait_read(); }, [&] { if (lead && tn < ntiles) issue(tn, st_now); }));
     store_tile(&m0, v);
   }
   if (lead) tma_store_wait_all();
@@ -392,17 +403,28 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_yfwd_tma(YfwdArgs a, const
   }
 }
 
-template <int N, int NP> static size_t inv_tma_smem() {
-  return ((size_t)N * NP + (size_t)NP * TileGeo<N, NP>::PITCH) * sizeof(cplx) + 8 + TileGeo<N, NP>::ALIGN;
+template <int N, int NP> static size_t inv_tma_smem(int stages) {
+  return ((size_t)N * NP + (size_t)stages * NP * TileGeo<N, NP>::PITCH) * sizeof(cplx) + 8 * stages + TileGeo<N, NP>::ALIGN;
 }
 // returns -1 when the bulk-copy path does not apply (caller falls back to the register-path kernels)
 template <int N> static int run_inv_tma(Plan& p, Fused& f, int stage, const InvTmaArgs& a, const InvTmaMaps& m0, const InvTmaMaps& m1) {
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
-  auto kfn = k_inv_tma<N, NP, MINB>;
-  const size_t smem = inv_tma_smem<N, NP>();
-  int grid;
-  if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(a.nlines, NP) * a.nplanes, &grid)) return 1;
   const cplx* tw = stage == ST_ZINV ? p.tw_z : p.tw_y;
+  const int ntiles = cdiv(a.nlines, NP) * a.nplanes;
+  int grid;
+  // two input stages at two CTAs per SM (env SX_INV_STAGES: bit 0 zinv, bit 1 yinv), where two such CTAs fit an SM
+  if constexpr (N >= 256 && MINB >= 2) {
+    if (inv_tma_smem<N, NP>(2) * 2 <= 220 * 1024 && (p.knob_inv_stages & (stage == ST_ZINV ? 1 : 2))) {
+      auto kfn2 = k_inv_tma<N, NP, 2, 2>;
+      const size_t smem2 = inv_tma_smem<N, NP>(2);
+      if (persistent_grid(p, kfn2, NP * (N / 8), smem2, ntiles, &grid)) return 1;
+      SX_FUSED_LAUNCH(p, stage, kfn2, dim3(grid), NP * (N / 8), smem2, a, m0, m1, tw);
+      return 0;
+    }
+  }
+  auto kfn = k_inv_tma<N, NP, MINB, 1>;
+  const size_t smem = inv_tma_smem<N, NP>(1);
+  if (persistent_grid(p, kfn, NP * (N / 8), smem, ntiles, &grid)) return 1;
   SX_FUSED_LAUNCH(p, stage, kfn, dim3(grid), NP * (N / 8), smem, a, m0, m1, tw);
   return 0;
 }
