@@ -240,7 +240,7 @@ struct ProjBulkArgs {
   cplx phT[8];   // exp(+2 pi i k top / 8), k = 0..7: stride factors of the top-wall row of the backward transform
 };
 
-template <int N, int MINB>
+template <int N, int MINB, int L2PF = 0>
 __global__ void __launch_bounds__(N / 8, MINB) k_project_bulk(ProjBulkArgs pa, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   const ProjArgs& a = pa.a;
@@ -281,6 +281,14 @@ __global__ void __launch_bounds__(N / 8, MINB) k_project_bulk(ProjBulkArgs pa, c
   unsigned phase = 0;
   for (; g < npencils; g += gridDim.x) {
     const int gn = g + gridDim.x;
+    if (L2PF && lead && gn < npencils) {
+      // the next pencil's slots are refilled only under the last transforms of this one: pull its three lines (and
+      // the wall rows of p') into L2 now, so that those refills and loads are L2 hits
+      l2_prefetch(a.vx + (size_t)gn * N, PBYTES);
+      l2_prefetch(a.vy + (size_t)gn * N, PBYTES);
+      l2_prefetch(a.vz + (size_t)gn * N, PBYTES);
+      if (L2PF > 1) l2_prefetch(a.pr + (size_t)gn * N, PBYTES);
+    }
     const int kx_i = g / a.ny, ky_i = g - kx_i * a.ny;
     const size_t base = (size_t)g * N;
     const double x = __ldg(&a.kx[kx_i]), y = __ldg(&a.ky[ky_i]);
@@ -421,7 +429,7 @@ __global__ void __launch_bounds__(N / 8, MINB) k_project_bulk(ProjBulkArgs pa, c
   }
 }
 
-template <int N, int MINB> static int run_project_bulk(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
+template <int N, int MINB, int L2PF = 0> static int run_project_bulk(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
                                                        const double* zs, const double* ze) {
   constexpr int T = N / 8, NW = (T + 31) / 32;
   double tmp = 1.0 / (double)o;
@@ -438,7 +446,7 @@ template <int N, int MINB> static int run_project_bulk(Plan& p, Fused& f, cplx* 
     pa.phT[k] = cmake(r8[q][0], r8[q][1]);
   }
   const cplx* tw = p.tw_z;
-  auto kfn = k_project_bulk<N, MINB>;
+  auto kfn = k_project_bulk<N, MINB, L2PF>;
   const size_t smem = ((size_t)sidx_elem_stride<N>() + (size_t)3 * N + (size_t)2 * kMaxDF + (size_t)2 * NW) * sizeof(cplx) + 3 * 8;
   int grid;
   if (persistent_grid(p, kfn, T, smem, (int)pa.a.npencils, &grid)) return 1;
@@ -474,6 +482,8 @@ template <int N> static int run_project(Plan& p, Fused& f, cplx* vx, cplx* vy, c
       if constexpr (N == 512) {
         if (p.knob_pj == 11) return run_project_bulk<N, 4>(p, f, vx, vy, vz, pr, o, zs, ze);
         if (p.knob_pj == 12) return run_project_bulk<N, 6>(p, f, vx, vy, vz, pr, o, zs, ze);
+        if (p.knob_pj == 13) return run_project_bulk<N, 5, 1>(p, f, vx, vy, vz, pr, o, zs, ze);
+        if (p.knob_pj == 14) return run_project_bulk<N, 5, 2>(p, f, vx, vy, vz, pr, o, zs, ze);
       }
       return run_project_bulk<N, (N <= 512 ? 5 : (N == 1024 ? 2 : 1))>(p, f, vx, vy, vz, pr, o, zs, ze);
     }

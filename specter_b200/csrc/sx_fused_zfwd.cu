@@ -66,7 +66,7 @@ __device__ __forceinline__ void stash_boundary_tile(const cplx (&v)[8], int j, i
   }
 }
 
-template <int N, int NP, int MINB, bool HOIST, bool PF, bool L2PF = false, bool BATCH = false>
+template <int N, int NP, int MINB, bool HOIST, bool PF, bool L2PF = false, int BATCH = 0>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8, NT = NP * T;
@@ -129,6 +129,10 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
     // is covered by it (HOIST), or loaded at the point of use
     const size_t base = ((size_t)kxl * a.ny + (active ? ky : 0)) * N;
     cplx L[8], B[8], F[8];
+    if (BATCH == 2) {   // the linear-term pencil travels under the transform; f and v0 are loaded together after it
+#pragma unroll
+      for (int k = 0; k < 8; ++k) L[k] = a.v[base + j + k * T];
+    }
     if (HOIST) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -147,7 +151,33 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
       const double x = __ldg(&a.kx[kxl]), y = __ldg(&a.ky[ky]);
       const double f1 = __ldg(&a.fx[kxl]), f2 = __ldg(&a.fy[ky]);
       const double kh2 = x * x + y * y;
-      if (BATCH) {
+      if (BATCH == 2) {
+        // same arithmetic, association and order as the one-field-at-a-time form below; only the loads move
+        if (a.couple != nullptr) {
+          cplx Q[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) Q[k] = a.couple[base + j + k * T];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = caxpy(a.ccoef, Q[k], v[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          F[k] = a.f[base + j + k * T];
+          B[k] = a.v0[base + j + k * T];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          const double z = __ldg(&a.kz[e]), f3 = __ldg(&a.fz[e]);
+          const double lm = a.lap ? -(kh2 + z * z) : 1.0;
+          const cplx NL = cscale(cscale(cscale(v[k], f1), f2), f3);
+          v[k] = cmake(a.cL * (lm * L[k].x) + a.sNL * NL.x, a.cL * (lm * L[k].y) + a.sNL * NL.y);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = cmake((v[k].x + F[k].x) * a.dt * a.rmp, (v[k].y + F[k].y) * a.dt * a.rmp);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.vout[base + j + k * T] = cmake(B[k].x + v[k].x, B[k].y + v[k].y);
+      } else if (BATCH == 1) {
         // one field at a time, eight independent loads in flight per thread: at 80 registers the fused form
         // below only keeps three loads in flight and pays the memory latency once per element instead
         // of once per field (the arithmetic is associated exactly as below)
@@ -295,18 +325,22 @@ template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, const
     SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
     return 0;
   }
-  // default for length 512 (profiles/r1i_session4.md): the RK fields one at a time, 128 registers, two CTAs per SM
-  if ((p.knob_pf & 8) && N == 512 && (p.knob_zf == 0 || (p.knob_zf >= 4 && p.knob_zf <= 6))) {
-    if (p.knob_zf == 4) {
+  // length 512 (profiles/r1i_session4.md): 128 registers, two CTAs per SM; SX_ZF=6: the RK fields one at a time (previous default)
+  if ((p.knob_pf & 8) && N == 512 && (p.knob_zf == 0 || (p.knob_zf >= 4 && p.knob_zf <= 7))) {
+    if (p.knob_zf == 0 || p.knob_zf == 7) {   // default: linear-term pencil hoisted above the transform, f and v0 loaded together (1.074 -> 0.988 ms)
+      auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), false, true, false, 2>;
+      if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
+      SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
+    } else if (p.knob_zf == 4) {
       auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), false, true>;
       if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
       SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
     } else if (p.knob_zf == 5) {
-      auto kfn = k_zfwd_rk<N, NP, MINB, false, true, false, true>;
+      auto kfn = k_zfwd_rk<N, NP, MINB, false, true, false, 1>;
       if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
       SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
     } else {
-      auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), false, true, false, true>;
+      auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), false, true, false, 1>;
       if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
       SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
     }
