@@ -693,3 +693,55 @@ def case_golden_hd_step1(lib, tables):
     a, b = got[3][::4, ::4, ::2], gold["pr"]
     k = (nph + 1) // 2
     assert rel(a[:, :, :k], b[:, :, :k]) < 100 * TOL_FIELD
+
+
+# ---- BASELINE.json's full size: size-independent properties (no oracle at 512^3) -------------------------------------
+def case_full_size_properties(lib, tables, shape=(512, 512, 512), ord=4, dt=2e-4, nu=1e-3):
+    """HD 512^3 RK4 (BASELINE configs[1]) through properties that need no oracle:
+    (1) 3-D transform round trip = N x identity on the physical rows (tests/fft.f90:45-67);
+    (2) Parseval: energy(kin=1) of the transform equals the mean square of the real field (tests/energy.f90);
+    (3) the fused substep and the per-operator composition -- two independent implementations, each held to the
+        oracle at small sizes -- agree to the per-step field tolerance;
+    (4) after a substep the field is solenoidal and the wall-normal velocity vanishes (vdiagnostic)."""
+    import bench                                  # the synthetic initial condition of the bench (product API only)
+    nx, ny, nz = shape
+    p = api.Plan(nx, ny, nz, 25, 5, ord=ord, Lx=1.0, Ly=1.0, Lz=1.0, tdir=tables, lib=lib)
+    nph = nz - 25
+    N = float(nx) * ny * nz
+    rng = np.random.default_rng(11)
+    r = np.zeros(p.rshape)
+    r[:nph] = rng.standard_normal((nph, ny, nx))
+    # no x-Nyquist content: `energy' weights every kx > 0 plane by 2, the self-conjugate nx/2 plane included
+    # (pseudospec_hd.f90:602-628), which is only right for fields without it -- as in the reference's own test
+    r[:nph] = 0.5 * (r[:nph] + np.roll(r[:nph], 1, axis=2))
+    dr, dc, dr2 = p.real(r), p.spectral(), p.real()
+    p.fftp3d_real_to_complex(dr, dc)
+    p.fftp3d_complex_to_real(dc, dr2)
+    back = dr2.get()
+    assert np.abs(back[:nph] / N - r[:nph]).max() < 1e-12 * np.abs(back[:nph] / N).max()
+    zero = p.spectral(np.zeros(p.cshape, dtype=np.complex128))
+    eng = p.energy(dc, zero, zero, 1)
+    assert abs(eng / float(np.mean(r[:nph] ** 2)) - 1) < 1e-10, eng
+    del back
+    for d in (dr, dr2, dc, zero):
+        d.free()
+    st = bench.synthetic_state(p)
+    outs = []
+    for impl in (0, 1):
+        p.hd_put_state(*st)
+        p.hd_rkstep1()
+        p.hd_rkstep2(ord, dt, nu, impl=impl)
+        outs.append(p.hd_get_state())
+    scale = max(np.abs(q).max() for q in outs[1][:3])
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        assert np.isfinite(a).all()
+        assert np.abs(a - b).max() / scale < TOL_FIELD
+    assert rel(outs[0][3][:, :, :nph], outs[1][3][:, :, :nph]) < 100 * TOL_FIELD
+    v = [p.hd_field(i) for i in range(3)]
+    div, vt0, vtL, vn0, vnL = p.vdiagnostic(*v)
+    e1 = p.energy(*v, 1)
+    print("full-size properties:", shape, "div", div, "vt", vt0, vtL, "vn", vn0, vnL, "energy", e1)
+    assert e1 > 0 and div < 1e-5 * e1, (div, e1)      # limited by the FC(5) accuracy of the z derivative on coarse grids
+    assert vn0 < 1e-24 * e1 and vnL < 1e-24 * e1, (vn0, vnL, e1)
+    assert vt0 < 1e-3 * e1 and vtL < 1e-3 * e1, (vt0, vtL, e1)          # slip error of the p' prediction, O(dt^2)
+    p.close()

@@ -126,3 +126,8 @@ def test_solver_output_restart(emu_lib, tables, tmp_path):
 
 def test_golden_solvers(emu_lib, tables):
     P.case_golden_solvers(emu_lib, tables)
+
+
+def test_full_size_properties_small(emu_lib, tables):
+    # the property case of the GPU suite (512^3 there) on a grid the emulation finishes in seconds
+    P.case_full_size_properties(emu_lib, tables, shape=(32, 16, 64), ord=2, dt=1e-3)

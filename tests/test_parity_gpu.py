@@ -154,3 +154,8 @@ def test_solver_output_restart(cuda_lib, tables, tmp_path):
 def test_golden_fixtures(cuda_lib, tables):
     P.case_golden_solvers(cuda_lib, tables)
     P.case_golden_hd_step1(cuda_lib, tables)
+
+
+def test_full_size_properties_hd512(cuda_lib, tables):
+    """BASELINE.json configs[1] (HD 512^3 RK4) through size-independent properties."""
+    P.case_full_size_properties(cuda_lib, tables)
