@@ -262,7 +262,7 @@ int sx_mhd_rkstep2(sx_plan* plan, int o, double dt, double nu, double mu, const 
 
 /* ---- MHDBOUSS (include/mhdbouss/mhdbouss_rkstep{1,2}.f90) ------------------------------------------
  * state slots: the MHD ones (0..2 v, 3 pr, 4..6 f, 7..9 C1..C3, 10..12 a, 13 ph, 14..16 m, 17..19 C9..C11),
- * 20 th, 21 fs, 22 C7.  Only the per-operator composition (impl = 1) exists for this solver. */
+ * 20 th, 21 fs, 22 C7.  impl 0 = fused slab-parallel path (the MHD passes + a scalar-advection x pass), 1 = per-operator. */
 int sx_mhdbouss_put_state(sx_plan* plan, const double* vx_host, const double* vy_host, const double* vz_host,
                           const double* pr_host, const double* ax_host, const double* ay_host, const double* az_host,
                           const double* th_host, const double* fx_host, const double* fy_host, const double* fz_host,

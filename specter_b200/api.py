@@ -698,11 +698,11 @@ class Plan:
     def mhdbouss_rkstep1(self):
         self._call("sx_mhdbouss_rkstep1")
 
-    def mhdbouss_rkstep2(self, o, dt, nu, mu, kappa, xmom=1.0, xtemp=1.0, b0=(0.0, 0.0, 0.0), impl=1):
+    def mhdbouss_rkstep2(self, o, dt, nu, mu, kappa, xmom=1.0, xtemp=1.0, b0=(0.0, 0.0, 0.0), impl=0):
         b = (C.c_double * 3)(*[float(x) for x in b0])
         self._call("sx_mhdbouss_rkstep2", o, dt, nu, mu, kappa, xmom, xtemp, b, impl)
 
-    def mhdbouss_step(self, dt, nu, mu, kappa, xmom=1.0, xtemp=1.0, b0=(0.0, 0.0, 0.0), impl=1):
+    def mhdbouss_step(self, dt, nu, mu, kappa, xmom=1.0, xtemp=1.0, b0=(0.0, 0.0, 0.0), impl=0):
         self.mhdbouss_rkstep1()
         for o in range(self.ord, 0, -1):
             self.mhdbouss_rkstep2(o, dt, nu, mu, kappa, xmom, xtemp, b0, impl)

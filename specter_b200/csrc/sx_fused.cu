@@ -461,4 +461,74 @@ int mhd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, dou
   return a_imposebc_and_project(p, ax, ay, az, st[13]);
 }
 
+// mhdbouss_rkstep2.f90:3-106.  st: the MHD slots (0..19), 20 th, 21 fs, 22 C7.  The MHD passes plus theta: its
+// z-inverse (theta, dz theta), y-inverse (theta, dy theta; dz theta), a scalar-advection x pass fed by the velocity
+// lines the cross-product pass already reads, and a seventh nonlinear term on the way back.  theta is updated into
+// a scratch field first (the heat current reads the not yet updated v_z, the buoyancy the not yet updated theta) and
+// lands in st[20] through s_imposebc and the round trip of :102-105 (no filter here, unlike BOUSS).
+int mhdbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double mu, double kappa, double xmom,
+                           double xtemp, const double* b0) {
+  Fused* fp;
+  if (fused_begin(p, &fp, 14, 15, 7)) return 1;
+  Fused& f = *fp;
+  f.chunked_now = false;
+  const double rmp = 1.0 / (double)o;
+  const double N = (double)p.nx * (double)p.ny * (double)p.nz;
+  cplx *B[3], *Wv[3], *thn;
+  for (int c = 0; c < 3; ++c)
+    if (plan_cwork(p, 9 + c, &B[c]) || plan_cwork(p, 12 + c, &Wv[c])) return 1;
+  if (plan_cwork(p, 15, &thn)) return 1;
+  cplx *ax = st[10], *ay = st[11], *az = st[12], *th = st[20];
+  if (op_curlk(p, ay, az, B[0], 1) || op_curlk(p, ax, az, B[1], 2) || op_curlk(p, ax, ay, B[2], 3)) return 1;
+  if (p.ista == 1)
+    for (int c = 0; c < 3; ++c)
+      if (op_set_elem(p, B[c], 0, (b0 ? b0[c] : 0.0) * N, 0.0)) return 1;
+  if (op_curlk(p, B[1], B[2], ax, 1) || op_curlk(p, B[0], B[2], ay, 2) || op_curlk(p, B[0], B[1], az, 3)) return 1;
+  if (op_curlk(p, st[1], st[2], Wv[0], 1) || op_curlk(p, st[0], st[2], Wv[1], 2) || op_curlk(p, st[0], st[1], Wv[2], 3)) return 1;
+  const cplx* q[12] = {st[0], st[1], st[2], Wv[0], Wv[1], Wv[2], B[0], B[1], B[2], ax, ay, az};
+  for (int c = 0; c < 12; ++c) {
+    if (fused_zinv(p, f, q[c], f.W[c], nullptr)) return 1;
+    if (to_real_begin(p, f, c)) return 1;
+  }
+  if (fused_zinv(p, f, th, f.W[12], f.W[13])) return 1;
+  if (to_real_begin(p, f, 12) || to_real_begin(p, f, 13)) return 1;
+  for (int c = 0; c < 12; ++c) {
+    if (ex_wait(p, c)) return 1;
+    if (fused_yinv(p, f, f.R[c], f.V[c], nullptr)) return 1;
+  }
+  if (ex_wait(p, 12) || ex_wait(p, 13)) return 1;
+  if (fused_yinv(p, f, f.R[12], f.V[12], f.V[13])) return 1;     // theta, dy theta
+  if (fused_yinv(p, f, f.R[13], f.V[14], nullptr)) return 1;     // dz theta
+  {
+    const int Pi[2] = {0, 6}, Qi[2] = {3, 9};
+    const double sg[2] = {-1.0, 1.0};
+    if (fused_xcross(p, f, 2, Pi, Qi, sg, 0)) return 1;            // omega x v - J x B
+    const int Pe[1] = {0}, Qe[1] = {6};
+    const double se[1] = {1.0};
+    if (fused_xcross(p, f, 1, Pe, Qe, se, 3)) return 1;            // v x B
+  }
+  if (fused_xadvect(p, f, 0, 12, 6, p.d_kxg)) return 1;            // v . grad theta
+  if (nonlinear_to_spectral_begin(p, f, 7)) return 1;
+  RkTerm rt;
+  rt.cL = kappa; rt.couple = st[2]; rt.ccoef = -xtemp;
+  if (ex_wait(p, 16 + 6)) return 1;
+  if (fused_zfwd_rk(p, f, f.Uz[6], th, thn, st[22], st[21], rt, dt, rmp)) return 1;
+  for (int c = 0; c < 3; ++c) {
+    RkTerm rk;
+    rk.cL = nu;
+    if (c == 2) { rk.couple = th; rk.ccoef = -xmom; }
+    if (ex_wait(p, 16 + c)) return 1;
+    if (fused_zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk, dt, rmp)) return 1;
+  }
+  for (int c = 0; c < 3; ++c) {
+    RkTerm rk;
+    rk.cL = -mu; rk.lap = 0; rk.sNL = 1.0;
+    if (ex_wait(p, 16 + 3 + c)) return 1;
+    if (fused_zfwd_rk(p, f, f.Uz[3 + c], st[10 + c], st[10 + c], st[17 + c], st[14 + c], rk, dt, rmp)) return 1;
+  }
+  if (fused_project(p, f, st[0], st[1], st[2], st[3], o, nullptr, nullptr)) return 1;
+  if (a_imposebc_and_project(p, ax, ay, az, st[13])) return 1;
+  return s_imposebc(p, thn) || theta_roundtrip(p, thn, th);
+}
+
 }  // namespace sx

@@ -166,6 +166,7 @@ int fused_yinv(Plan& p, Fused& f, const cplx* in, cplx* o0, cplx* o1);
 int fused_yfwd(Plan& p, Fused& f, const cplx* in, cplx* out);
 int fused_xpass(Plan& p, Fused& f, int nc, const double* kxg);
 int fused_xcross(Plan& p, Fused& f, int npairs, const int* Pi, const int* Qi, const double* sgn, int xo);
+int fused_xadvect(Plan& p, Fused& f, int ui, int qi, int xo, const double* kxg);
 int fused_zfwd_rk(Plan& p, Fused& f, const cplx* nl, const cplx* v, cplx* vout, const cplx* v0, const cplx* frc,
                   const RkTerm& rk, double dt, double rmp);
 int fused_project(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o, const double* zs, const double* ze);

@@ -11,6 +11,7 @@ namespace sx {
 // ------------------------------------------------------------------------------------------
 struct XpassArgs {
   const cplx* V[12];  // q(NC), dy q(NC), dz q(NC) with q = (vx, vy, vz[, theta])   [zl][y][kx]
+  const cplx* U[3];   // advecting velocity when it is not q(0..2) (scalar advection, NC = 1); U[0] == nullptr: V[0..2]
   cplx* X[4];
   const double* kx;  // GLOBAL kx(1:nx/2+1)
   int ny, nxp, nzf;
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_gradre(XpassArgs a, 
   const int groups_y = cdiv(a.ny, 2 * LP), ngroups = groups_y * a.nzf;
   constexpr int NM = 3 + 3 * NC;  // inverse transforms per group: u(3), then d_x, d_y, d_z of each component
   auto field_of = [&](int m) -> const cplx* {
-    if (m < 3) return a.V[m];
+    if (m < 3) return a.U[0] != nullptr ? a.U[m] : a.V[m];
     const int c = (m - 3) / 3, d = (m - 3) % 3;
     return a.V[d * NC + c];
   };
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(N / 8, MINB) k_xpass_gradre_bulk(XpassArgs a, 
   size_t prow = mine > 0 ? row_of(0) : 0;
   auto issue_next = [&]() {
     if (pg >= mine) return;
-    const cplx* field = pi == 0 ? a.V[pd] : a.V[pd * NC + pi - 1];
+    const cplx* field = pi == 0 ? (a.U[0] != nullptr ? a.U[pd] : a.V[pd]) : a.V[pd * NC + pi - 1];
     bulk_load(stage + (size_t)ps * 2 * NXP, field + prow, BYTES, bar + ps);
     if (++ps == S) ps = 0;
     if (++pi == NC + 1) {
@@ -413,13 +414,21 @@ __global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_cross(XcrossArgs a, 
   }
 }
 
-template <int N, int LP, bool PF, int MINB, int NC> static int run_xpass_v(Plan& p, Fused& f, const double* d_kx_global) {
+// ui < 0: gradre / advect of q = V[0..NC) by its own first three components into X[0..NC);
+// ui >= 0 (NC = 1): the scalar q = V[qi], dy q = V[qi+1], dz q = V[qi+2] advected by V[ui..ui+2] into X[xo]
+static void xpass_fields(Plan& p, Fused& f, XpassArgs& a, int NC, int ui, int qi, int xo) {
+  const size_t zo = (size_t)f.z0() * p.ny * f.nxp;   // z window of the [zl][y][kx] arrays
+  for (int i = 0; i < 12; ++i) a.V[i] = nullptr;
+  for (int i = 0; i < 4; ++i) a.X[i] = nullptr;
+  for (int i = 0; i < 3; ++i) a.U[i] = ui >= 0 ? f.V[ui + i] + zo : nullptr;
+  for (int i = 0; i < 3 * NC; ++i) a.V[i] = f.V[(ui >= 0 ? qi : 0) + i] + zo;
+  for (int i = 0; i < NC; ++i) a.X[i] = f.X[(ui >= 0 ? xo : 0) + i] + zo;
+}
+template <int N, int LP, bool PF, int MINB, int NC> static int run_xpass_v(Plan& p, Fused& f, const double* d_kx_global, int ui, int qi, int xo) {
   constexpr int T = N / 8;
   if (f.zc() == 0) return 0;
   XpassArgs a;
-  const size_t zo = (size_t)f.z0() * p.ny * f.nxp;   // z window of the [zl][y][kx] arrays
-  for (int i = 0; i < 3 * NC; ++i) a.V[i] = f.V[i] + zo;
-  for (int i = 0; i < NC; ++i) a.X[i] = f.X[i] + zo;
+  xpass_fields(p, f, a, NC, ui, qi, xo);
   a.kx = d_kx_global;
   a.ny = p.ny;
   a.nxp = f.nxp;
@@ -435,14 +444,12 @@ template <int N, int LP, bool PF, int MINB, int NC> static int run_xpass_v(Plan&
   SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(grid), LP * T, smem, a, tw);
   return 0;
 }
-template <int N, int NC, int S, int MINB> static int run_xpass_bulk(Plan& p, Fused& f, const double* d_kx_global) {
+template <int N, int NC, int S, int MINB> static int run_xpass_bulk(Plan& p, Fused& f, const double* d_kx_global, int ui, int qi, int xo) {
   constexpr int T = N / 8;
   if (f.zc() == 0) return 0;
   SX_REQUIRE(f.nxp == XpassBulk<N>::NXP && p.ny % 2 == 0, "xpass (bulk): unexpected row padding");
   XpassArgs a;
-  const size_t zo = (size_t)f.z0() * p.ny * f.nxp;   // z window of the [zl][y][kx] arrays
-  for (int i = 0; i < 3 * NC; ++i) a.V[i] = f.V[i] + zo;
-  for (int i = 0; i < NC; ++i) a.X[i] = f.X[i] + zo;
+  xpass_fields(p, f, a, NC, ui, qi, xo);
   a.kx = d_kx_global;
   a.ny = p.ny;
   a.nxp = f.nxp;
@@ -458,7 +465,7 @@ template <int N, int NC, int S, int MINB> static int run_xpass_bulk(Plan& p, Fus
   SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(grid), T, smem, a, tw);
   return 0;
 }
-template <int N, int NC> static int run_xpass(Plan& p, Fused& f, const double* d_kx_global) {
+template <int N, int NC> static int run_xpass(Plan& p, Fused& f, const double* d_kx_global, int ui = -1, int qi = 0, int xo = 0) {
   constexpr int T = N / 8;
   constexpr int LP = T >= 128 ? 1 : 128 / T;
   // bulk-copy ring (TMA) + register accumulators: default from one warp per line pair upwards (SX_XP=9: previous kernels)
@@ -469,19 +476,19 @@ template <int N, int NC> static int run_xpass(Plan& p, Fused& f, const double* d
       // two-warp CTAs per SM (two warps per scheduler); the ring depth sets the bytes in flight
       if constexpr (N == 512) {
         switch (p.knob_xp) {
-          case 11: return run_xpass_bulk<N, NC, 2, 4>(p, f, d_kx_global);
-          case 12: return run_xpass_bulk<N, NC, 4, 4>(p, f, d_kx_global);
-          case 13: return run_xpass_bulk<N, NC, 3, 6>(p, f, d_kx_global);
+          case 11: return run_xpass_bulk<N, NC, 2, 4>(p, f, d_kx_global, ui, qi, xo);
+          case 12: return run_xpass_bulk<N, NC, 4, 4>(p, f, d_kx_global, ui, qi, xo);
+          case 13: return run_xpass_bulk<N, NC, 3, 6>(p, f, d_kx_global, ui, qi, xo);
           default: break;
         }
       }
-      return run_xpass_bulk<N, NC, 3, (N <= 512 ? 4 : (N == 1024 ? 2 : 1))>(p, f, d_kx_global);
+      return run_xpass_bulk<N, NC, 3, (N <= 512 ? 4 : (N == 1024 ? 2 : 1))>(p, f, d_kx_global, ui, qi, xo);
     }
   }
   if constexpr (N == 512) {   // measured best on B200 (profiles/r1h_knobs.md): one pair per CTA, direct loads
-    if (p.knob_xp == 0 || p.knob_xp == 9) return run_xpass_v<N, 1, false, 6, NC>(p, f, d_kx_global);
+    if (p.knob_xp == 0 || p.knob_xp == 9) return run_xpass_v<N, 1, false, 6, NC>(p, f, d_kx_global, ui, qi, xo);
   }
-  return run_xpass_v<N, LP, true, (N <= 1024 ? 2 : 1), NC>(p, f, d_kx_global);
+  return run_xpass_v<N, LP, true, (N <= 1024 ? 2 : 1), NC>(p, f, d_kx_global, ui, qi, xo);
 }
 // X[xo..xo+2] = sum_pairs sgn * (V[P] x V[Q]) / N^2; Pi/Qi index the first of three consecutive V fields
 template <int N> static int run_xcross(Plan& p, Fused& f, int npairs, const int* Pi, const int* Qi, const double* sgn, int xo) {
@@ -520,6 +527,13 @@ int fused_xpass(Plan& p, Fused& f, int nc, const double* kxg) {
   if (nc == 3) return xpass_nc<3>(p, f, kxg);
   if (nc == 4) return xpass_nc<4>(p, f, kxg);
   SX_REQUIRE(false, "xpass: 3 or 4 advected components");
+}
+// scalar advection: X[xo] = (V[ui..ui+2] . grad q) / N^2 with q = V[qi], dy q = V[qi+1], dz q = V[qi+2]
+// (advect, pseudospec_phd.f90:58-110, next to a cross-product x pass whose velocity is already in V)
+int fused_xadvect(Plan& p, Fused& f, int ui, int qi, int xo, const double* kxg) {
+#define C_(N) run_xpass<N, 1>(p, f, kxg, ui, qi, xo)
+  SX_SIZE_SWITCH(p.nx, C_);
+#undef C_
 }
 int fused_xcross(Plan& p, Fused& f, int npairs, const int* Pi, const int* Qi, const double* sgn, int xo) {
 #define C_(N) run_xcross<N>(p, f, npairs, Pi, Qi, sgn, xo)

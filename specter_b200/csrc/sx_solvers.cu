@@ -493,6 +493,8 @@ static int mhdbouss_rkstep2_modular(Plan& p, SolverState& s, int o, double dt, d
 
 int bouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double kappa, double xmom, double xtemp,
                         const double* zs, const double* ze);
+int mhdbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double mu, double kappa, double xmom,
+                           double xtemp, const double* b0);
 int rotbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double kappa, double xmom,
                            double xtemp, const double* om, const double* zs, const double* ze);
 int mhd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double mu, const double* b0);
@@ -670,16 +672,17 @@ int sx_mhdbouss_rkstep1(sx_plan* plan) {
     if (copy_field(p, s->f[7 + q], s->f[q]) || copy_field(p, s->f[17 + q], s->f[10 + q])) return 1;
   return copy_field(p, s->f[22], s->f[20]);
 }
-/* mhdbouss_rkstep2.f90:3-106; impl must be 1: this solver only has the per-operator composition so far */
+/* mhdbouss_rkstep2.f90:3-106 */
 int sx_mhdbouss_rkstep2(sx_plan* plan, int o, double dt, double nu, double mu, double kappa, double xmom,
                         double xtemp, const double b0[3], int impl) {
   SX_PLAN(plan);
   SX_REQUIRE(o >= 1 && o <= p.ord, "sx_mhdbouss_rkstep2: substep index o must be in 1..ord");
   SX_REQUIRE(p.Cz > 0, "wall BCs need a non-periodic z direction (Cz > 0)");
-  SX_REQUIRE(impl == 1, "sx_mhdbouss_rkstep2: only impl = 1 (per-operator composition) exists for MHDBOUSS");
   SolverState* s;
   if (state_get(p, &p.mhdbouss, kMhdBoussFields, &s)) return 1;
-  return mhdbouss_rkstep2_modular(p, *s, o, dt, nu, mu, kappa, xmom, xtemp, b0);
+  if (impl == 1) return mhdbouss_rkstep2_modular(p, *s, o, dt, nu, mu, kappa, xmom, xtemp, b0);
+  SX_REQUIRE(impl == 0, "sx_mhdbouss_rkstep2: impl must be 0 (fused) or 1 (per-operator)");
+  return mhdbouss_rkstep2_fused(p, s->f.data(), o, dt, nu, mu, kappa, xmom, xtemp, b0);
 }
 
 }  // extern "C"

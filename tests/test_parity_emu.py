@@ -115,9 +115,10 @@ def test_rotbouss_substeps(emu_lib, tables, impl):
     P.case_rotbouss_substeps(emu_lib, tables, SMALL, ord=2, nsteps=1, impl=impl)
 
 
-def test_mhdbouss_substeps(emu_lib, tables):
-    P.case_mhdbouss_substeps(emu_lib, tables, SMALL, ord=2, nsteps=1)
-    P.case_mhdbouss_substeps(emu_lib, tables, (16, 16, 64), ord=2, nsteps=1, bc=(0, 1))
+@pytest.mark.parametrize("impl", [1, 0])
+def test_mhdbouss_substeps(emu_lib, tables, impl):
+    P.case_mhdbouss_substeps(emu_lib, tables, SMALL, ord=2, nsteps=1, impl=impl)
+    P.case_mhdbouss_substeps(emu_lib, tables, (16, 16, 64), ord=2, nsteps=1, bc=(0, 1), impl=impl)
 
 
 def test_solver_output_restart(emu_lib, tables, tmp_path):

@@ -142,9 +142,15 @@ def test_rotbouss_substeps_rk4_moving_walls(cuda_lib, tables):
     P.case_rotbouss_substeps(cuda_lib, tables, (128, 64, 128), ord=4, nsteps=1, impl=0, walls=((0.2, -0.1), (-0.3, 0.1)))
 
 
-def test_mhdbouss_substeps_cfg1(cuda_lib, tables):
-    P.case_mhdbouss_substeps(cuda_lib, tables, CFG1, ord=2, nsteps=2)
-    P.case_mhdbouss_substeps(cuda_lib, tables, (32, 32, 64), ord=2, nsteps=1, bc=(1, 1))
+@pytest.mark.parametrize("impl", [1, 0])
+def test_mhdbouss_substeps_cfg1(cuda_lib, tables, impl):
+    P.case_mhdbouss_substeps(cuda_lib, tables, CFG1, ord=2, nsteps=2, impl=impl)
+    P.case_mhdbouss_substeps(cuda_lib, tables, (32, 32, 64), ord=2, nsteps=1, bc=(1, 1), impl=impl)
+
+
+def test_mhdbouss_substeps_long_x(cuda_lib, tables):
+    # the bulk-copy scalar-advection x pass (NC = 1, from nx = 256) next to the cross-product passes
+    P.case_mhdbouss_substeps(cuda_lib, tables, (256, 32, 64), ord=2, nsteps=1, impl=0)
 
 
 def test_solver_output_restart(cuda_lib, tables, tmp_path):
