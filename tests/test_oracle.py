@@ -331,3 +331,37 @@ def test_oracle_reproduces_committed_goldens(tables):
     gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hd64_step1.npz"))
     for n in ("vx", "vy", "vz"):
         assert np.abs(getattr(s, n)[::4, ::4, ::2] - gold[n]).max() < 1e-12 * np.abs(gold[n]).max()
+
+
+def test_laplace_z_branches_satisfy_their_wall_conditions(g):
+    # every branch of laplace_z (boundary_mod.fpp:499-624) is a closed form; its solution must meet the wall data:
+    # Dirichlet a = bc; Neumann da/dz = bc; Robin (da/dz - khom a)(0) = -bc1, (da/dz + khom a)(Lz) = bc2 -- the signs
+    # sol_project relies on when it feeds bc1 = C2 - khom C1, bc2 = -(C2 + khom C1) (:296-330)
+    rng = np.random.default_rng(3)
+    bc = rng.standard_normal((g.nxl, g.ny, 2)) + 1j * rng.standard_normal((g.nxl, g.ny, 2))
+    top = g.nz - g.Cz - 1
+    kh = g.khom
+    m = np.ones_like(kh, dtype=bool)
+    m[0, 0] = False                                  # the (0,0) mode is the linear profile, checked below
+    # modes with khom*Lz up to ~50: exp(-2 khom Lz) underflows harmlessly, the identities stay exact to rounding
+    tol = 1e-12
+    a, b = O.laplace_z(g, bc, 0, 0)
+    assert np.abs(a[:, :, 0] - bc[:, :, 0])[m].max() < tol and np.abs(a[:, :, top] - bc[:, :, 1])[m].max() < tol
+    a, b = O.laplace_z(g, bc, 1, 1)
+    assert np.abs(b[:, :, 0] - bc[:, :, 0])[m].max() < tol * kh.max() and np.abs(b[:, :, top] - bc[:, :, 1])[m].max() < tol * kh.max()
+    a, b = O.laplace_z(g, bc, 2, 2)
+    assert np.abs((b[:, :, 0] - kh * a[:, :, 0]) + bc[:, :, 0])[m].max() < tol * kh.max()
+    assert np.abs((b[:, :, top] + kh * a[:, :, top]) - bc[:, :, 1])[m].max() < tol * kh.max()
+    a, b = O.laplace_z(g, bc, 0, 2)
+    assert np.abs(a[:, :, 0] - bc[:, :, 0])[m].max() < tol
+    assert np.abs((b[:, :, top] + kh * a[:, :, top]) - bc[:, :, 1])[m].max() < tol * kh.max()
+    # harmonic: b is the z derivative of a and a'' = khom^2 a (centred differences on the uniform z grid)
+    dz = g.z[1] - g.z[0]
+    i, j = 2, 3
+    d1 = (a[i, j, 2:top + 1] - a[i, j, 0:top - 1]) / (2 * dz)
+    assert np.abs(d1 - b[i, j, 1:top]).max() < 1e-2 * np.abs(b[i, j]).max()
+    # (0,0) mode: real linear profile (:635-639)
+    a, b = O.laplace_z(g, bc, 0, 0)
+    assert np.allclose(a[0, 0].imag, 0) and abs(a[0, 0, top] - a[0, 0, 0] - (bc[0, 0, 1] - bc[0, 0, 0]).real) < 1e-12
+    with pytest.raises(ValueError, match="Unsupported BC combination"):
+        O.laplace_z(g, bc, 2, 0)
