@@ -55,6 +55,6 @@ def test_periodic_transforms_against_cufft(cuda_lib, shape):
     t_ours_b = _time_ours(p, lambda: p.fftp3d_complex_to_real(dc, dr2))
     t_cufft_b = _time_torch(torch, lambda: torch.fft.irfftn(F, s=(nz, ny, nx), dim=(0, 1, 2), norm="forward"))
     gb = 2 * 8.0 * nx * ny * nz / 1e9                            # one read + one write of the field per axis pass
-    print(f"\ncomparator {shape}: r2c ours {t_ours:.3f} ms (stand-alone operators, 3 passes = {3 * gb / t_ours:.0f} GB/s "
+    print(f"\ncomparator {shape}: r2c ours {t_ours:.3f} ms (stand-alone operators, 3 passes = {3e3 * gb / t_ours:.0f} GB/s "
           f"algorithmic) vs cuFFT {t_cufft:.3f} ms; c2r ours {t_ours_b:.3f} ms vs cuFFT {t_cufft_b:.3f} ms")
     p.close()
