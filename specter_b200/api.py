@@ -294,9 +294,10 @@ class Plan:
         return out
 
     # ---- multi-GPU ----
-    def init_comm_torch(self, dist, p2p=True, p2p_fields=(12, 6)):
+    def init_comm_torch(self, dist, p2p=True, p2p_fields=(14, 7)):
         """Create the plan's own NCCL communicator; the 128-byte unique id travels over the caller's
-        torch.distributed group (the Fortran driver would MPI_BCAST it)."""
+        torch.distributed group (the Fortran driver would MPI_BCAST it).  p2p_fields = (inverse, forward) transposed
+        fields the peer-to-peer arena is sized for: HD 6/3, BOUSS 8/4, MHD 12/6, MHDBOUSS 14/7 (the default)."""
         import torch
         buf = (C.c_char * 128)()
         if dist.get_rank() == 0:
