@@ -274,6 +274,23 @@ int sx_mhdbouss_rkstep1(sx_plan* plan);
 int sx_mhdbouss_rkstep2(sx_plan* plan, int o, double dt, double nu, double mu, double kappa, double xmom,
                         double xtemp, const double b0[3], int impl);
 
+/* ---- BOOTS regridder (tools/boots.fpp) ---------------------------------------------
+ * Prolongation of field files of an old grid (nxt, nyt, nzt physical rows, the `regrid' namelist) to the grid
+ * (nx, ny, nzp = nz-Cz physical rows) by zero padding in Fourier space; the non-periodic z direction is continued with
+ * the FC-Gram table A<Czt>-<ozt>.dat / Q<ozt>.dat of tdir on the old grid.  One GPU (`device', -1 = 0); x and y sizes
+ * are powers of two, the z sizes are free. */
+/* ref: boots.fpp:176-182: continuation points of the old grid (the table that is needed) and of the new grid */
+int sx_boots_points(int nzt, int nzp, int* Czt, int* Czn);
+/* ref: boots.fpp:249-303 for one field: in_host (nxt, nyt, nzt) -> out_host (nx, ny, nzp), Fortran order */
+int sx_boots_regrid(int device, int nxt, int nyt, int nzt, int ozt, const char* tdir, int nx, int ny, int nzp,
+                    const double* in_host, double* out_host);
+/* ref: the file loop of boots.fpp:228-312: fnlist = names separated by ';', read as `idir/name' (bmangle = 0),
+ * written as `odir/name_P<nx>-<ny>-<nzp>' (i5.5 each) */
+int sx_boots_files(int device, const char* idir, const char* odir, const char* tdir, const char* fnlist, int nxt, int nyt,
+                   int nzt, int ozt, int nx, int ny, int nzp);
+/* kernels launched by the regridder so far */
+unsigned long long sx_boots_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1341,3 +1341,73 @@ def solver_restart(g: Grid, idir, ext, dt, scalar=False, magnetic=False):
         ph[:, :, : g.nz - g.Cz] *= dt
         out["ph"] = ph
     return out
+
+
+# ----------------------------------------------------------------------------
+# BOOTS regridder                                          tools/boots.fpp
+# ----------------------------------------------------------------------------
+def boots_points(nzt: int, nzp: int):
+    """Continuation points of the old and the new grid (boots.fpp:181-182 with GCD :388-400): the two
+    z periods coincide, Lz (1 + 1/g) with g = gcd(nzt-1, nzp-1).  nzp = nz-Cz, the new physical rows."""
+    import math
+    g = math.gcd(nzt - 1, nzp - 1)
+    return (nzt - 1) // g - 1, (nzp - 1) // g - 1
+
+
+def boots_suffix(nx: int, ny: int, nzp: int) -> str:
+    """boots.fpp:174: '_P' i5.5 '-' i5.5 '-' i5.5 of nx, ny, nz-Cz."""
+    return "_P%05d-%05d-%05d" % (nx, ny, nzp)
+
+
+def boots_prolongate(C1t: np.ndarray, nx: int, ny: int, M: int) -> np.ndarray:
+    """The Fourier-space zero padding of boots.fpp:275-300, loop for loop (1-based indices as written there,
+    later assignments overwrite earlier ones).  C1t[i,j,k] (nxt/2+1, nyt, m) -> B1[i,j,k] (nx/2+1, ny, M).
+    As written the second loop of each direction starts one index early, so the old mode nyt/2-1 (and m/2-1)
+    is copied twice -- kept."""
+    nxth, nyt, m = C1t.shape
+    nxt = 2 * (nxth - 1)
+    fact = 1.0 / (float(nxt) * float(nyt) * float(m))
+    B1 = np.zeros((nx // 2 + 1, ny, M), dtype=np.complex128)
+    for j in range(1, nyt // 2 + 2):
+        B1[:nxth, j - 1, 0 : m // 2 + 1] = C1t[:, j - 1, 0 : m // 2 + 1] * fact
+        for k in range(M - m // 2, M + 1):
+            B1[:nxth, j - 1, k - 1] = C1t[:, j - 1, k - M + m - 1] * fact
+    for j in range(ny - nyt // 2, ny + 1):
+        B1[:nxth, j - 1, 0 : m // 2 + 1] = C1t[:, j - ny + nyt - 1, 0 : m // 2 + 1] * fact
+        for k in range(M - m // 2, M + 1):
+            B1[:nxth, j - 1, k - 1] = C1t[:, j - ny + nyt - 1, k - M + m - 1] * fact
+    return B1
+
+
+def boots_regrid(vt: np.ndarray, nx: int, ny: int, nzp: int, ozt: int, tdir: str) -> np.ndarray:
+    """One file of the BOOTS3D loop (boots.fpp:228-312) on one rank: vt[k,j,i] on the old physical grid
+    (nzt, nyt, nxt) -> FC continuation with Czt points + 3-D r2c on (nxt, nyt, nzt+Czt) -> zero padding ->
+    periodic 3-D c2r on (nx, ny, nzp+Czn) -> the first nzp planes (the io plan of :187 has nz-Cz planes)."""
+    nzt, nyt, nxt = vt.shape
+    if not (1 <= nxt <= nx and 1 <= nyt <= ny and 1 <= nzt <= nzp):
+        raise ValueError("MAIN: prolongation specification incorrect")      # boots.fpp:146-160
+    Czt, Czn = boots_points(nzt, nzp)
+    m, M = nzt + Czt, nzp + Czn
+    if not ((Czt == 0 and ozt == 0) or (Czt > 0 and ozt > 0)):                # fcgram_mod.f90:128-141
+        raise ValueError("Mismatch in continuation or matching points in z direction. Aborting...")
+    gt = Grid(nxt, nyt, m, Czt, ozt, tdir=tdir)
+    r = np.zeros((m, nyt, nxt))
+    r[:nzt] = vt
+    C1t = fftp3d_real_to_complex(gt, r)
+    B1 = boots_prolongate(C1t, nx, ny, M)
+    gn = Grid(nx, ny, M, 0, 0)
+    br = fftp3d_complex_to_real(gn, B1)
+    return np.ascontiguousarray(br[:nzp])
+
+
+def boots_files(idir, odir, tdir, fnlist: str, nxt: int, nyt: int, nzt: int, ozt: int, nx: int, ny: int, nzp: int):
+    """The file loop of boots.fpp:228-247, 305-312: names separated by ';', read as `idir/name` (bmangle = 0),
+    written as `odir/name` + suffix.  Returns the list of files written."""
+    out = []
+    for fname in [s.strip() for s in fnlist.split(";") if s.strip()]:
+        vt = np.fromfile(os.path.join(str(idir), fname), dtype=np.float64).reshape(nzt, nyt, nxt)
+        br = boots_regrid(vt, nx, ny, nzp, ozt, tdir)
+        fout = os.path.join(str(odir), fname + boots_suffix(nx, ny, nzp))
+        br.tofile(fout)
+        out.append(fout)
+    return out

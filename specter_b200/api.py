@@ -135,9 +135,13 @@ SIGNATURES = {
     "sx_mhdbouss_state_ptr": [_P, _I, C.POINTER(_D)],
     "sx_mhdbouss_rkstep1": [_P],
     "sx_mhdbouss_rkstep2": [_P, _I, _F, _F, _F, _F, _F, _F, _PD, _I],
+    "sx_boots_points": [_I, _I, _PI, _PI],
+    "sx_boots_regrid": [_I, _I, _I, _I, _I, C.c_char_p, _I, _I, _I, _D, _D],
+    "sx_boots_files": [_I, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _I, _I, _I, _I, _I, _I, _I],
+    "sx_boots_launch_count": [],
 }
 _RESTYPES = {"sx_stage_name": C.c_char_p, "sx_last_error": C.c_char_p, "sx_version": C.c_char_p,
-             "sx_plan_launch_count": C.c_ulonglong, "sx_spectral_bytes": C.c_size_t,
+             "sx_plan_launch_count": C.c_ulonglong, "sx_boots_launch_count": C.c_ulonglong, "sx_spectral_bytes": C.c_size_t,
              "sx_real_bytes": C.c_size_t}
 
 
@@ -201,6 +205,40 @@ def sx_range(n1, n2, nprocs, irank, lib: Optional[Library] = None):
     a, b = C.c_int(), C.c_int()
     lib.check(lib.dll.sx_range(n1, n2, nprocs, irank, C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+# ---- BOOTS regridder (tools/boots.fpp) ----
+def boots_points(nzt, nzp, lib: Optional[Library] = None):
+    """Continuation points (Czt, Czn) of the old / new grid (boots.fpp:176-182); nzp = nz-Cz of the new grid."""
+    lib = lib or load_library()
+    a, b = C.c_int(), C.c_int()
+    lib.check(lib.dll.sx_boots_points(int(nzt), int(nzp), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def boots_regrid(vt: np.ndarray, nx, ny, nzp, ozt, tdir, device=-1, lib: Optional[Library] = None) -> np.ndarray:
+    """One field of the BOOTS3D loop (boots.fpp:249-303): vt[k,j,i] on the old physical grid (nzt, nyt, nxt)
+    -> the field on (nzp, ny, nx)."""
+    lib = lib or load_library()
+    vt = np.ascontiguousarray(vt, dtype=np.float64)
+    nzt, nyt, nxt = vt.shape
+    out = np.empty((int(nzp), int(ny), int(nx)), dtype=np.float64)
+    lib.check(lib.dll.sx_boots_regrid(int(device), nxt, nyt, nzt, int(ozt), str(tdir).encode(), int(nx), int(ny), int(nzp),
+                                      vt.ctypes.data, out.ctypes.data))
+    return out
+
+
+def boots_files(idir, odir, tdir, fnlist, nxt, nyt, nzt, ozt, nx, ny, nzp, device=-1, lib: Optional[Library] = None):
+    """The `regrid' / `order' namelists of boots.inp as arguments: every file of fnlist (';' separated) in idir is
+    prolongated and written to odir with the suffix _P<nx>-<ny>-<nzp> (boots.fpp:174, 228-312)."""
+    lib = lib or load_library()
+    lib.check(lib.dll.sx_boots_files(int(device), str(idir).encode(), str(odir).encode(), str(tdir).encode(),
+                                     str(fnlist).encode(), int(nxt), int(nyt), int(nzt), int(ozt), int(nx), int(ny), int(nzp)))
+
+
+def boots_launch_count(lib: Optional[Library] = None) -> int:
+    lib = lib or load_library()
+    return int(lib.dll.sx_boots_launch_count())
 
 
 class DeviceArray:

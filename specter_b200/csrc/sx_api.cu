@@ -45,7 +45,7 @@ static int read_f64(const std::string& path, size_t count, std::vector<double>& 
 }
 
 // load_dirichlet_tables (fcgram_mod.f90:180-257): dir = A . Q^T, stored row-major [C][d]
-static int load_dirichlet(Plan& p, const std::string& tdir) {
+int load_dirichlet(Plan& p, const std::string& tdir) {
   const int C = p.Cz, d = p.oz;
   std::vector<double> A, Q;
   if (read_f64(tdir + "/A" + std::to_string(C) + "-" + std::to_string(d) + ".dat", (size_t)C * d, A)) return 1;

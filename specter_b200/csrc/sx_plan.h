@@ -150,6 +150,7 @@ int hd_state_free(Plan& p);
 int solver_states_free(Plan& p);
 int op_set_elem(Plan& p, cplx* a, size_t idx, double re, double im);
 int load_neumann(Plan& p);
+int load_dirichlet(Plan& p, const std::string& tdir);   // dir = A Q^T of (p.Cz, p.oz) into p.h_dir
 int fused_free(Plan& p);
 int comm_free(Plan& p);
 bool comm_ready(const Plan& p);

@@ -740,3 +740,59 @@ def case_full_size_properties(lib, tables, shape=(512, 512, 512), ord=4, dt=2e-4
     assert vn0 < 1e-24 * e1 and vnL < 1e-24 * e1, (vn0, vnL, e1)
     assert vt0 < 1e-3 * e1 and vtL < 1e-3 * e1, (vt0, vtL, e1)          # slip error of the p' prediction, O(dt^2)
     p.close()
+
+
+# ---- BOOTS regridder (tools/boots.fpp) ----------------------------------------------------------
+def boots_field(nz, ny, nx):
+    z = np.linspace(0.0, 1.0, nz)[:, None, None]
+    y = (2 * np.pi * np.arange(ny) / ny)[None, :, None]
+    x = (2 * np.pi * np.arange(nx) / nx)[None, None, :]
+    return np.exp(0.4 * z) * np.sin(2 * x) * np.cos(3 * y) + np.sin(3 * z) * np.cos(x)
+
+
+def case_boots(lib, tables, cases, tmpdir=None):
+    """cases: (nxt, nyt, nzt, ozt, nx, ny, nzp).  The regridded field against the oracle's restatement of the
+    BOOTS3D loop (FFT-based, as the reference does it) on a random and on a smooth wall-bounded field; the file
+    loop with the reference's names."""
+    rng = np.random.default_rng(11)
+    n0 = api.boots_launch_count(lib)
+    for nxt, nyt, nzt, ozt, nx, ny, nzp in cases:
+        assert api.boots_points(nzt, nzp, lib) == O.boots_points(nzt, nzp)
+        for vt in (rng.standard_normal((nzt, nyt, nxt)), boots_field(nzt, nyt, nxt)):
+            got = api.boots_regrid(vt, nx, ny, nzp, ozt, tables, lib=lib)
+            ref = O.boots_regrid(vt, nx, ny, nzp, ozt, tables)
+            assert got.shape == ref.shape
+            # the error is measured against the largest number the two computations add up: the continuation of
+            # white noise is up to |dir| ~ 1e4 (A25-5) .. 8e4 (A50-5) times the field, of a smooth field O(1)
+            scale = np.abs(ref).max()
+            Czt = O.boots_points(nzt, nzp)[0]
+            if Czt > 0:
+                a = np.zeros((nxt, nyt, nzt + Czt))
+                a[:, :, :nzt] = vt.transpose(2, 1, 0)
+                O.fc_continue_z(O.Grid(nxt, nyt, nzt + Czt, Czt, ozt, tdir=tables), a)
+                scale = max(scale, np.abs(a).max())
+            err = np.abs(got - ref).max() / scale
+            assert err < TOL_FIELD, (nxt, nyt, nzt, nx, ny, nzp, err)
+    assert api.boots_launch_count(lib) > n0
+    if tmpdir is not None:
+        nxt, nyt, nzt, ozt, nx, ny, nzp = cases[0]
+        idir, odir, rdir = tmpdir / "old", tmpdir / "new", tmpdir / "new_oracle"
+        for d in (idir, odir, rdir):
+            d.mkdir()
+        for name in ("vx.0001.out", "th.0001.out"):
+            rng.standard_normal((nzt, nyt, nxt)).tofile(str(idir / name))
+        fnlist = "vx.0001.out; th.0001.out"
+        api.boots_files(idir, odir, tables, fnlist, nxt, nyt, nzt, ozt, nx, ny, nzp, lib=lib)
+        for f in O.boots_files(idir, rdir, tables, fnlist, nxt, nyt, nzt, ozt, nx, ny, nzp):
+            import os
+            mine = np.fromfile(str(odir / os.path.basename(f)))
+            assert mine.size == nx * ny * nzp and rel(mine, np.fromfile(f)) < 10 * TOL_FIELD   # white noise, see above
+    # the reference's argument checks (boots.fpp:146-160; fcgram_mod.f90:128-141)
+    import pytest
+    small = np.zeros((20, 16, 16))
+    with pytest.raises(api.SpecterError, match="prolongation"):
+        api.boots_regrid(small, 16, 16, 19, 0, tables, lib=lib)
+    with pytest.raises(api.SpecterError, match="Mismatch"):
+        api.boots_regrid(small, 16, 16, 20, 5, tables, lib=lib)
+    with pytest.raises(api.SpecterError, match="table"):
+        api.boots_regrid(np.zeros((27, 16, 16)), 16, 16, 46, 4, tables, lib=lib)

@@ -365,3 +365,52 @@ def test_laplace_z_branches_satisfy_their_wall_conditions(g):
     assert np.allclose(a[0, 0].imag, 0) and abs(a[0, 0, top] - a[0, 0, 0] - (bc[0, 0, 1] - bc[0, 0, 0]).real) < 1e-12
     with pytest.raises(ValueError, match="Unsupported BC combination"):
         O.laplace_z(g, bc, 2, 0)
+
+
+# ---- BOOTS regridder (tools/boots.fpp) ---------------------------------------------------------------------
+def _boots_field(nz, ny, nx):
+    z = np.linspace(0.0, 1.0, nz)[:, None, None]
+    y = (2 * np.pi * np.arange(ny) / ny)[None, :, None]
+    x = (2 * np.pi * np.arange(nx) / nx)[None, None, :]
+    return np.exp(0.4 * z) * np.sin(2 * x) * np.cos(3 * y) + np.sin(3 * z) * np.cos(x)
+
+
+def test_boots_continuation_points_match_the_shipped_tables():
+    # boots.fpp:176-182: the two periods coincide; the shipped boots.inp (nzt = 487) with the shipped tables
+    # tables/boots/A{50,80,370,498,754}-5.dat covers e.g. 487 -> 979 rows (Czt = 80) and 103 -> 105 (A50-5)
+    assert O.boots_points(487, 979) == (80, 162)
+    assert O.boots_points(103, 105) == (50, 51)
+    assert O.boots_points(27, 46) == (25, 44)
+    for nzt, nzp in ((487, 979), (27, 46), (103, 105), (39, 39)):
+        czt, czn = O.boots_points(nzt, nzp)
+        assert (nzt + czt) * (nzp - 1) == (nzp + czn) * (nzt - 1)      # equal periods Lz (1 + 1/g)
+    assert O.boots_suffix(512, 256, 999) == "_P00512-00256-00999"
+
+
+def test_boots_regrid_interpolates_a_smooth_wall_bounded_field(tables):
+    # the known answer a regridder has: a smooth field that is NOT periodic in z, sampled on the old grid, comes
+    # out as its samples on the new grid to the accuracy of the d = 5 continuation (cf. tests/fc_dirichlet.f90)
+    out = O.boots_regrid(_boots_field(27, 16, 16), 32, 32, 46, 5, tables)
+    assert out.shape == (46, 32, 32)
+    assert np.abs(out - _boots_field(46, 32, 32)).max() < 2e-6
+    out = O.boots_regrid(_boots_field(103, 16, 16), 16, 32, 105, 5, tables)      # A50-5, odd period 153
+    assert np.abs(out - _boots_field(105, 32, 16)).max() < 1e-9
+    # same grid, periodic treatment (Czt = 0): the padding is the identity
+    vt = np.random.default_rng(0).standard_normal((20, 16, 16))
+    assert np.abs(O.boots_regrid(vt, 16, 16, 20, 0, tables) - vt).max() < 1e-14
+    with pytest.raises(ValueError, match="Mismatch"):
+        O.boots_regrid(vt, 16, 16, 20, 5, tables)          # Czt = 0 with matching points: fcgram_create_plan aborts
+    with pytest.raises(ValueError, match="prolongation"):
+        O.boots_regrid(vt, 8, 16, 20, 0, tables)
+
+
+def test_boots_padding_as_written():
+    # boots.fpp:275-300 copies the positive half 1..n/2+1 and the block n-n/2..n of each padded direction; as
+    # written the second block starts one index early, so old mode n/2-1 appears twice (kept by the restatement)
+    C = (np.arange(9 * 16 * 20).reshape(9, 16, 20) + 1).astype(np.complex128)
+    B = O.boots_prolongate(C, 32, 32, 41)
+    fact = 1.0 / (16 * 16 * 20)
+    assert B.shape == (17, 32, 41) and np.all(B[9:] == 0)
+    assert np.allclose(B[:9, :9, :11], C[:, :9, :11] * fact)
+    assert np.allclose(B[:9, 32 - 8 - 1:, 41 - 10 - 1:], C[:, 16 - 8 - 1:, 20 - 10 - 1:] * fact)
+    assert np.all(B[:9, 9:32 - 9, :] == 0) and np.all(B[:9, :, 11:41 - 11] == 0)

@@ -132,3 +132,10 @@ def test_golden_solvers(emu_lib, tables):
 def test_full_size_properties_small(emu_lib, tables):
     # the property case of the GPU suite (512^3 there) on a grid the emulation finishes in seconds
     P.case_full_size_properties(emu_lib, tables, shape=(32, 16, 64), ord=2, dt=1e-3)
+
+
+def test_boots_regridder(emu_lib, tables, tmp_path):
+    # (nxt, nyt, nzt, ozt, nx, ny, nzp): A25-5 (period 52 -> 90), A50-5 with an odd period (153 -> 156),
+    # periodic treatment with an odd old period (21 -> 42), identical grids
+    P.case_boots(emu_lib, tables, [(16, 16, 27, 5, 32, 32, 46), (16, 16, 103, 5, 16, 32, 105), (16, 32, 21, 0, 32, 32, 41),
+                                   (16, 16, 20, 0, 16, 16, 20)], tmp_path)

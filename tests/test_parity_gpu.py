@@ -165,3 +165,9 @@ def test_golden_fixtures(cuda_lib, tables):
 def test_full_size_properties_hd512(cuda_lib, tables):
     """BASELINE.json configs[1] (HD 512^3 RK4) through size-independent properties."""
     P.case_full_size_properties(cuda_lib, tables)
+
+
+def test_boots_regridder(cuda_lib, tables, tmp_path):
+    # (nxt, nyt, nzt, ozt, nx, ny, nzp); tile edges of the dense z operator in every direction
+    P.case_boots(cuda_lib, tables, [(16, 16, 27, 5, 32, 32, 46), (64, 32, 79, 5, 128, 64, 136), (32, 16, 103, 5, 32, 64, 105),
+                                    (16, 32, 21, 0, 32, 32, 41), (128, 128, 131, 5, 256, 128, 256)], tmp_path)
