@@ -26,6 +26,7 @@ def test_header_and_bindings_agree():
 
 def test_cuda_library_exports_every_symbol():
     lib = build.build_cuda()
+    api._preload_nccl()   # the same order api.Library uses: torch's NCCL first, so a later `import torch` still resolves
     dll = ctypes.CDLL(lib)
     for name in header_functions():
         assert hasattr(dll, name), name
