@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(256) k_zgemm(const cplx* __restrict__ A, int l
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          acc[r][c].x += a[r].x * b[c].x - a[r].y * b[c].y;
-          acc[r][c].y += a[r].x * b[c].y + a[r].y * b[c].x;
+          acc[r][c].x = fma(-a[r].y, b[c].y, fma(a[r].x, b[c].x, acc[r][c].x));   // 4 DFMA per complex product
+          acc[r][c].y = fma(a[r].y, b[c].x, fma(a[r].x, b[c].y, acc[r][c].y));
         }
     }
     __syncthreads();

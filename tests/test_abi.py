@@ -34,6 +34,18 @@ def test_cuda_library_exports_every_symbol():
     assert b"sm_100a" in dll.sx_version()
 
 
+def test_header_is_plain_c(tmp_path):
+    # the boundary is a C ABI: the header must compile as C99 on its own (no C++, no CUDA, no torch types), which is
+    # what a cgo / ISO_C_BINDING / ctypes user sees
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "specter_b200.h"\n'
+                   'int use(void) { sx_config c; sx_plan* p = 0; c.nx = 16; (void)p; return (int)sizeof c + c.nx; }\n')
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                        "-o", str(tmp_path / "use_header.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_no_cpu_fallback(tables):
     import torch
     if torch.cuda.is_available():
