@@ -6,6 +6,10 @@ this image -- no Fortran/MPI/FFTW -- and ships no golden vectors; see DESIGN.md 
 hd64_diag100.json   config 1 (HD 64^3, C=25 d=5, RK2, dt=1e-3, nu=1e-3, Lx=1 Ly=.5 Lz=1, seed=1000):
                     balance.txt columns (<v^2>, <w^2>-like, <v.f>) and <(div v)^2> every 10 steps.
 hd64_step1.npz      the same run, spectral fields after the first time step on a coarse sub-sample.
+solvers32_step1.npz one RK2 step of the other solvers on 32x32x64.
+boots_27_46.npz     the BOOTS regridder (tools/boots.fpp): a seeded field on 16x16x27 -> 32x32x46 (A25-5 continuation) and on
+                    16x32x21 -> 32x32x41 (periodic treatment, odd old period), outputs sub-sampled.
+                    `python tests/golden/make_golden.py boots` regenerates this file only.
 """
 import json
 import os
@@ -16,6 +20,25 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import specter_oracle as O  # noqa: E402
+
+
+
+sys.path.insert(0, os.path.dirname(HERE))
+from parity_cases import boots_golden_inputs as boots_inputs  # noqa: E402  (the seeded old-grid fields, shared with the tests)
+
+
+def boots_goldens():
+    a, b = boots_inputs()
+    tab = os.path.join(HERE, "tables")
+    ra = O.boots_regrid(a, 32, 32, 46, 5, tab)
+    rb = O.boots_regrid(b, 32, 32, 41, 0, tab)
+    np.savez_compressed(os.path.join(HERE, "boots_27_46.npz"), a=ra[::3, ::4, ::4], b=rb[::3, ::4, ::4])
+    print("boots_27_46.npz:", ra.shape, rb.shape)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "boots":
+    boots_goldens()
+    sys.exit(0)
 
 g = O.Grid(64, 64, 64, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=os.path.join(HERE, "tables"), ord=2)
 s = O.make_hd_state(g)
@@ -67,3 +90,4 @@ def solver_goldens():
 
 
 solver_goldens()
+boots_goldens()

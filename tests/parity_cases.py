@@ -750,6 +750,23 @@ def boots_field(nz, ny, nx):
     return np.exp(0.4 * z) * np.sin(2 * x) * np.cos(3 * y) + np.sin(3 * z) * np.cos(x)
 
 
+def boots_golden_inputs():
+    """The two seeded old-grid fields of tests/golden/boots_27_46.npz: a smooth wall-bounded part plus white noise."""
+    out = []
+    for seed, (nzt, nyt, nxt) in ((21, (27, 16, 16)), (22, (21, 32, 16))):
+        out.append(boots_field(nzt, nyt, nxt) + 1e-3 * np.random.default_rng(seed).standard_normal((nzt, nyt, nxt)))
+    return out
+
+
+def case_boots_golden(lib, tables, golden_path):
+    """The committed fixture (written by tests/golden/make_golden.py from the oracle): lib = None checks the oracle."""
+    gold = np.load(golden_path)
+    a, b = boots_golden_inputs()
+    for vt, key, (nx, ny, nzp, ozt) in ((a, "a", (32, 32, 46, 5)), (b, "b", (32, 32, 41, 0))):
+        got = O.boots_regrid(vt, nx, ny, nzp, ozt, tables) if lib is None else api.boots_regrid(vt, nx, ny, nzp, ozt, tables, lib=lib)
+        assert rel(got[::3, ::4, ::4], gold[key]) < TOL_FIELD
+
+
 def case_boots(lib, tables, cases, tmpdir=None):
     """cases: (nxt, nyt, nzt, ozt, nx, ny, nzp).  The regridded field against the oracle's restatement of the
     BOOTS3D loop (FFT-based, as the reference does it) on a random and on a smooth wall-bounded field; the file

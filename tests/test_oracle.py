@@ -414,3 +414,9 @@ def test_boots_padding_as_written():
     assert np.allclose(B[:9, :9, :11], C[:, :9, :11] * fact)
     assert np.allclose(B[:9, 32 - 8 - 1:, 41 - 10 - 1:], C[:, 16 - 8 - 1:, 20 - 10 - 1:] * fact)
     assert np.all(B[:9, 9:32 - 9, :] == 0) and np.all(B[:9, :, 11:41 - 11] == 0)
+
+
+def test_boots_oracle_reproduces_committed_golden(tables):
+    import os
+    import parity_cases as P
+    P.case_boots_golden(None, tables, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "boots_27_46.npz"))

@@ -139,3 +139,5 @@ def test_boots_regridder(emu_lib, tables, tmp_path):
     # periodic treatment with an odd old period (21 -> 42), identical grids
     P.case_boots(emu_lib, tables, [(16, 16, 27, 5, 32, 32, 46), (16, 16, 103, 5, 16, 32, 105), (16, 32, 21, 0, 32, 32, 41),
                                    (16, 16, 20, 0, 16, 16, 20)], tmp_path)
+    import os
+    P.case_boots_golden(emu_lib, tables, os.path.join(os.path.dirname(__file__), "golden", "boots_27_46.npz"))
