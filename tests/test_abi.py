@@ -46,6 +46,23 @@ def test_header_is_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
 
 
+def test_fortran_module_is_current_and_complete():
+    # include/specter_b200_mod.f90 is generated from the header (tools/gen_fortran_module.py): up to date, one
+    # BIND(C) interface per prototype, same number of dummies as the ctypes table has argument types
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_fortran_module.py"), "--check"])
+    assert r.returncode == 0, "run python tools/gen_fortran_module.py"
+    raw = open(os.path.join(ROOT, "include", "specter_b200_mod.f90")).read()
+    text = raw.replace("&\n", " ")
+    found = dict(re.findall(r"FUNCTION (sx_[a-z0-9_]+)\(([^)]*)\)\s+BIND\(C,\s+NAME='\1'\)", text))
+    assert sorted(found) == header_functions()
+    for name, dummies in found.items():
+        n = len([d for d in dummies.split(",") if d.strip()])
+        assert n == len(api.SIGNATURES[name]), name
+    assert max(len(ln) for ln in raw.splitlines()) <= 132      # free-form source line limit
+
+
 def test_no_cpu_fallback(tables):
     import torch
     if torch.cuda.is_available():
