@@ -222,3 +222,74 @@ def test_operators_multirank(world, shape, emu_lib, tables, tmp_path):
         for k in ("hd_modular", "output", "restart", "rotbouss"):
             assert errs[k] < 1e-11, (rank, k, errs[k])
         assert errs["maxabs"] < 1e-9 and errs["helicity"] < 1e-9, (rank, errs)
+
+
+def _worker_solvers(rank, world, port, solver, shape, emu_path, tables, q):
+    """The slab-parallel FUSED substeps of the other solvers (BOUSS, MHD, MHDBOUSS: 12 / 18 / 21 field transposes per
+    substep) against the single-rank oracle; theta is compared on the physical rows of the mixed domain
+    (parity_cases.phys_close)."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import specter_oracle as O
+    from specter_b200 import api
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        lib = api.Library(emu_path)
+        nx, ny, nz = shape
+        p = api.Plan(nx, ny, nz, 25, 5, ord=2, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, nprocs=world, myrank=rank, lib=lib)
+        _install_gloo_callbacks(p, dist, rank, world)
+        g = O.Grid(nx, ny, nz, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, ord=2)
+        g.load_neumann()
+        sl = slice(p.ista - 1, p.iend)
+        cut = lambda arrs: [np.ascontiguousarray(a[sl]) for a in arrs]
+        nph = nz - 25
+        phys = lambda a: np.fft.ifft(a, axis=2)[:, :, :nph]
+        if solver == "bouss":
+            s = O.make_bouss_state(g)
+            p.bouss_put_state(*cut((s.vx, s.vy, s.vz, s.pr, s.th, s.fx, s.fy, s.fz, s.fs)))
+            p.bouss_step(1e-3, 1e-3, 1e-3)
+            st = p.bouss_get_state()
+            O.bouss_step(g, s, 1e-3, 1e-3, 1e-3)
+            groups = [(st[:3], (s.vx, s.vy, s.vz)), ([phys(st[4])], (phys(s.th),))]
+        elif solver == "mhd":
+            s = O.make_mhd_state(g)
+            p.mhd_put_state(*cut((s.vx, s.vy, s.vz, s.pr, s.ax, s.ay, s.az, s.fx, s.fy, s.fz, s.mx, s.my, s.mz)))
+            p.mhd_step(1e-3, 1e-3, 5e-3, b0=(0.0, 0.0, 0.1))
+            st = p.mhd_get_state()
+            O.mhd_step(g, s, 1e-3, 1e-3, 5e-3, b0=(0.0, 0.0, 0.1))
+            groups = [(st[:3], (s.vx, s.vy, s.vz)), (st[4:7], (s.ax, s.ay, s.az))]
+        else:
+            s = O.make_mhdbouss_state(g)
+            p.mhdbouss_put_state(*cut((s.vx, s.vy, s.vz, s.pr, s.ax, s.ay, s.az, s.th, s.fx, s.fy, s.fz, s.mx, s.my, s.mz, s.fs)))
+            p.mhdbouss_step(1e-3, 1e-3, 5e-3, 1e-3, b0=(0.0, 0.0, 0.1))
+            st = p.mhdbouss_get_state()
+            O.mhdbouss_step(g, s, 1e-3, 1e-3, 5e-3, 1e-3, b0=(0.0, 0.0, 0.1))
+            groups = [(st[:3], (s.vx, s.vy, s.vz)), (st[4:7], (s.ax, s.ay, s.az)), ([phys(st[8])], (phys(s.th),))]
+        errs = []
+        for got, ref in groups:
+            scale = max(np.abs(r).max() for r in ref)
+            errs.append(float(max(np.abs(a - r[sl]).max() for a, r in zip(got, ref)) / scale))
+        q.put((rank, errs, p.comm_stats()["exchanges"], (p.ista, p.iend)))
+        p.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("solver,world,shape", [("bouss", 2, (32, 16, 64)), ("mhd", 2, (32, 16, 64)), ("mhdbouss", 2, (32, 16, 64)),
+                                                ("mhdbouss", 3, (16, 16, 64))])
+def test_fused_solvers_multirank(solver, world, shape, emu_lib, tables):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000) + world + {"bouss": 0, "mhd": 10, "mhdbouss": 20}[solver]
+    procs = [ctx.Process(target=_worker_solvers, args=(r, world, port, solver, shape, emu_lib.path, tables, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(timeout=900)
+    assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
+    covered = 0
+    for rank, errs, nex, (ista, iend) in sorted(q.get(timeout=10) for _ in range(world)):
+        assert all(e < 1e-11 for e in errs), (solver, rank, errs)
+        assert nex > 0
+        covered += iend - ista + 1
+    assert covered == shape[0] // 2 + 1
