@@ -136,6 +136,10 @@ int sx_vector(sx_plan* plan, const double* a, const double* b, const double* c, 
 int sx_variance(sx_plan* plan, const double* a, int kin, double* out);
 
 /* ---- boundary module -------------------------------------------------------- */
+/* ref: goto_domain_w_boundaries (boundary_mod.fpp:72-150): backward z transform, physical rows x 1/nz, of one to
+ * three fields in place (b, c may be NULL); goto_3d_fourier (:153-194): continuation + forward z transform */
+int sx_goto_domain_w_boundaries(sx_plan* plan, double* a, double* b, double* c);
+int sx_goto_3d_fourier(sx_plan* plan, double* a, double* b, double* c);
 /* ref: sol_project (boundary_mod.fpp:197-402); d returns the potential in the mixed domain */
 int sx_sol_project(sx_plan* plan, double* a, double* b, double* c, double* d, int bctarget, int bczsta, int bczend);
 /* ref: v_imposebc_and_project (vboundary.f90:67-151); no-slip walls, v_zsta/v_zend = wall (vx,vy) */

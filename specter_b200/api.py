@@ -93,6 +93,8 @@ SIGNATURES = {
     "sx_divergence": [_P, _D, _D, _D, _PD],
     "sx_cross": [_P, _D, _D, _D, _D, _D, _D, _I, _PD],
     "sx_hdcheck": [_P, _D, _D, _D, _D, _D, _D, _PD, _PD, _PD],
+    "sx_goto_domain_w_boundaries": [_P, _D, _D, _D],
+    "sx_goto_3d_fourier": [_P, _D, _D, _D],
     "sx_sol_project": [_P, _D, _D, _D, _D, _I, _I, _I],
     "sx_v_imposebc_and_project": [_P, _D, _D, _D, _D, _I, _PD, _PD],
     "sx_bouncheck_z": [_P, _PD, _PD, _D, _D],
@@ -500,6 +502,12 @@ class Plan:
         return tuple(x.value for x in o)
 
     # ---- boundary ----
+    def goto_domain_w_boundaries(self, a, b=None, c=None):
+        self._call("sx_goto_domain_w_boundaries", a.ptr, b.ptr if b is not None else None, c.ptr if c is not None else None)
+
+    def goto_3d_fourier(self, a, b=None, c=None):
+        self._call("sx_goto_3d_fourier", a.ptr, b.ptr if b is not None else None, c.ptr if c is not None else None)
+
     def sol_project(self, a, b, c, d, bctarget, bczsta, bczend):
         self._call("sx_sol_project", a.ptr, b.ptr, c.ptr, d.ptr, bctarget, bczsta, bczend)
 

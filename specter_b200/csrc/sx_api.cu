@@ -667,6 +667,24 @@ int sx_hdcheck(sx_plan* plan, const double* a, const double* b, const double* c,
   if (energy(p, C(a), C(b), C(c), 0, ens)) return 1;
   return cross(p, C(a), C(b), C(c), C(d), C(e), C(f), 1, pot);
 }
+// goto_domain_w_boundaries / goto_3d_fourier (boundary_mod.fpp:72-150, 153-194), 1-3 fields in place
+int sx_goto_domain_w_boundaries(sx_plan* plan, double* a, double* b, double* c) {
+  SX_PLAN(plan);
+  SX_REQUIRE(a != nullptr, "goto_domain_w_boundaries: the first field is required");
+  const double inv_nz = 1.0 / (double)p.nz;
+  double* f[3] = {a, b, c};
+  for (double* q : f)
+    if (q && fft1d_z_bwd(p, C(q), C(q), inv_nz)) return 1;   // physical rows x 1/nz, continuation rows as they come
+  return 0;
+}
+int sx_goto_3d_fourier(sx_plan* plan, double* a, double* b, double* c) {
+  SX_PLAN(plan);
+  SX_REQUIRE(a != nullptr, "goto_3d_fourier: the first field is required");
+  double* f[3] = {a, b, c};
+  for (double* q : f)
+    if (q && fft1d_z_fwd(p, C(q))) return 1;
+  return 0;
+}
 int sx_sol_project(sx_plan* plan, double* a, double* b, double* c, double* d, int bctarget, int bczsta, int bczend) {
   SX_PLAN(plan); return sol_project(p, C(a), C(b), C(c), C(d), bctarget, bczsta, bczend);
 }

@@ -57,6 +57,25 @@ def case_fft1d_z(lib, tables, shape, Cz=25):
     p.close()
 
 
+def case_goto_domain(lib, tables, shape):
+    """goto_domain_w_boundaries / goto_3d_fourier (boundary_mod.fpp:72-194) on one and on three fields."""
+    g, p = make(lib, tables, *shape)
+    nph = g.nz - g.Cz
+    f = [rand_spec(g, 20 + i) for i in range(3)]
+    d = [p.spectral(a) for a in f]
+    p.goto_domain_w_boundaries(d[0])
+    p.goto_domain_w_boundaries(d[1], d[2])
+    ref = [a.copy() for a in f]
+    O.goto_domain_w_boundaries(g, *ref)
+    for q, r in zip(d, ref):
+        assert rel(q.get()[:, :, :nph], r[:, :, :nph]) < TOL_OP      # rows above are overwritten by the continuation
+    p.goto_3d_fourier(d[0], d[1], d[2])
+    O.goto_3d_fourier(g, *ref)
+    for q, r in zip(d, ref):
+        assert rel(q.get(), r) < TOL_OP
+    p.close()
+
+
 def case_fft3d(lib, tables, shape, Cz=25):
     g, p = make(lib, tables, *shape, Cz=Cz, oz=5 if Cz else 0)
     rng = np.random.default_rng(2)

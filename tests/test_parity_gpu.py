@@ -171,3 +171,8 @@ def test_boots_regridder(cuda_lib, tables, tmp_path):
     # (nxt, nyt, nzt, ozt, nx, ny, nzp); tile edges of the dense z operator in every direction
     P.case_boots(cuda_lib, tables, [(16, 16, 27, 5, 32, 32, 46), (64, 32, 79, 5, 128, 64, 136), (32, 16, 103, 5, 32, 64, 105),
                                     (16, 32, 21, 0, 32, 32, 41), (128, 128, 131, 5, 256, 128, 256)], tmp_path)
+
+
+def test_goto_domain(cuda_lib, tables):
+    P.case_goto_domain(cuda_lib, tables, CFG1)
+    P.case_goto_domain(cuda_lib, tables, (32, 16, 512))
