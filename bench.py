@@ -319,6 +319,8 @@ def main():
     if world > 1:
         plan.init_comm_torch(dist, p2p_fields={"hd": (6, 3), "bouss": (8, 4), "mhd": (12, 6)}[solver])
     st = synthetic_state(plan)
+    if args.workload in ("hd1024", "hd2048", "bouss1024"):
+        plan.release_scratch()      # the set-up went through the per-operator entries: give their temporaries back (6 fields)
     zero = np.zeros_like(st[0])
     if solver == "hd":
         plan.hd_put_state(*st)

@@ -48,6 +48,10 @@ int sx_range(int n1, int n2, int nprocs, int irank, int* sta, int* end);
 /* kernels launched by this plan so far */
 unsigned long long sx_plan_launch_count(const sx_plan* plan);
 int sx_plan_synchronize(sx_plan* plan);
+/* The callee temporaries of the per-operator entries (the reference's automatic arrays C1.., R1.., pseudospec_hd.f90:233-240)
+ * are pooled per plan and kept between calls; this frees the pool (it is re-grown on demand), e.g. after a set-up phase
+ * and before the fused substep allocates its work fields. */
+int sx_plan_release_scratch(sx_plan* plan);
 /* CUDA-event timing on the plan's own stream (replaces the GTStart/GTStop wall timers around the
  * RK loop, specter.fpp:985-999): begin records an event, end records another, synchronises and
  * returns the elapsed device time in milliseconds. */

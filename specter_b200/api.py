@@ -50,6 +50,7 @@ SIGNATURES = {
     "sx_range": [_I, _I, _I, _I, _PI, _PI],
     "sx_plan_launch_count": [_P],
     "sx_plan_synchronize": [_P],
+    "sx_plan_release_scratch": [_P],
     "sx_plan_time_begin": [_P],
     "sx_plan_time_end": [_P, _PD],
     "sx_stage_count": [],
@@ -412,6 +413,10 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+    def release_scratch(self):
+        """Free the pooled temporaries of the per-operator entries (re-grown on demand)."""
+        self._call("sx_plan_release_scratch")
 
     def synchronize(self):
         self.lib.check(self.lib.dll.sx_plan_synchronize(self.handle))

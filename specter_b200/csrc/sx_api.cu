@@ -575,6 +575,18 @@ int sx_range(int n1, int n2, int nprocs, int irank, int* sta, int* end) {
 unsigned long long sx_plan_launch_count(const sx_plan* plan) { return plan ? plan->p.launches : 0ULL; }
 int sx_plan_synchronize(sx_plan* plan) { SX_PLAN(plan); SX_CUDA_CHECK(cudaStreamSynchronize(p.stream)); return 0; }
 
+// The callee temporaries of the per-operator entries (the reference's automatic arrays C1.., R1..) are pooled per plan
+// and kept between calls; a driver that only uses them for the set-up gives the memory back before the fused substep.
+int sx_plan_release_scratch(sx_plan* plan) {
+  SX_PLAN(plan);
+  SX_CUDA_CHECK(cudaStreamSynchronize(p.stream));
+  for (auto& q : p.cwork) if (q) { SX_CUDA_CHECK(cudaFree(q)); q = nullptr; }
+  for (auto& q : p.rwork) if (q) { SX_CUDA_CHECK(cudaFree(q)); q = nullptr; }
+  if (p.xy_T) { SX_CUDA_CHECK(cudaFree(p.xy_T)); p.xy_T = nullptr; }
+  if (p.xy_S) { SX_CUDA_CHECK(cudaFree(p.xy_S)); p.xy_S = nullptr; }
+  return 0;
+}
+
 int sx_plan_time_begin(sx_plan* plan) {
   SX_PLAN(plan);
   if (!p.ev_t0) { SX_CUDA_CHECK(cudaEventCreate(&p.ev_t0)); SX_CUDA_CHECK(cudaEventCreate(&p.ev_t1)); }

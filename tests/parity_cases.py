@@ -73,6 +73,15 @@ def case_goto_domain(lib, tables, shape):
     O.goto_3d_fourier(g, *ref)
     for q, r in zip(d, ref):
         assert rel(q.get(), r) < TOL_OP
+    # the scratch pool of the per-operator entries can be released and grows again on demand
+    rr, out = p.real(), p.spectral()
+    p.fftp3d_complex_to_real(d[0], rr)
+    first = rr.get()
+    p.release_scratch()
+    p.release_scratch()
+    p.fftp3d_complex_to_real(d[0], rr)
+    assert np.array_equal(first, rr.get())
+    p.fftp3d_real_to_complex(rr, out)
     p.close()
 
 
