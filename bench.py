@@ -256,7 +256,7 @@ def reference_arm(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "pts*substep/s", "cores": cores, "kind": "port", "sample": sample_s},
             "e2e": {"value": value, "unit": "pts*substep/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))   # the process's real stdout (fd 1 was pointed at stderr by quiet_stdout)
 
 
 _REAL_STDOUT = None
