@@ -406,7 +406,8 @@ def main():
                 "algorithmic_bytes_per_launch": dom.get("algorithmic_bytes_per_launch"),
                 "avg_launch_ms": dom.get("ms_per_launch"),
                 "whole_substep": {"algorithmic_bytes_per_point": b_alg,
-                                  "achieved": b_alg * value / world / 1e9, "frac": b_alg * value / world / 1e9 / peak}}
+                                  "achieved": b_alg * value / world / 1e9, "frac": b_alg * value / world / 1e9 / peak,
+                                  "frac_of_nominal_8000_gbs": b_alg * value / world / 1e9 / 8000.0}}   # both peaks
     if solver != "hd":   # per-kernel byte model exists for the HD kernels only: report the whole substep
         roofline.update(kernel="whole substep", achieved=roofline["whole_substep"]["achieved"],
                         frac=roofline["whole_substep"]["frac"], algorithmic_bytes_per_launch=b_alg * npts / world,
