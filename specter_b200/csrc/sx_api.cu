@@ -129,6 +129,8 @@ static int plan_init(Plan& p, const sx_config& c) {
   SX_REQUIRE(c.Cz == 0 || (c.oz <= 10 && c.Cz + 2 * c.oz < c.nz), "invalid Cz/oz for this nz");
   SX_REQUIRE(c.nprocs >= 1 && c.myrank >= 0 && c.myrank < c.nprocs, "invalid nprocs/myrank");
   SX_REQUIRE(c.ord >= 1, "ord must be >= 1");
+  // every rank owns at least one kx plane and one z plane (range, fftp.fpp:1154-1184: an empty slab has no block to exchange)
+  SX_REQUIRE(c.nprocs <= c.nx / 2 + 1 && c.nprocs <= c.nz, "too many ranks: nprocs must not exceed min(nx/2+1, nz)");
   p.nx = c.nx; p.ny = c.ny; p.nz = c.nz; p.Cz = c.Cz; p.oz = c.oz; p.ord = c.ord;
   p.Lx = c.Lx; p.Ly = c.Ly; p.Lz = c.Lz;
   p.nprocs = c.nprocs; p.myrank = c.myrank;

@@ -78,6 +78,8 @@ def test_argument_errors_on_emulated_build(emu_lib, tables):
         api.Plan(16, 16, 64, 25, 5, tdir="/nonexistent", lib=emu_lib)
     with pytest.raises(api.SpecterError, match="Mismatch"):
         api.Plan(16, 16, 64, 25, 0, tdir=tables, lib=emu_lib)
+    with pytest.raises(api.SpecterError, match="too many ranks"):
+        api.Plan(16, 16, 64, 25, 5, tdir=tables, nprocs=12, myrank=11, lib=emu_lib)
     p = api.Plan(16, 16, 64, 25, 5, tdir=tables, lib=emu_lib)
     a = p.spectral()
     with pytest.raises(api.SpecterError, match="dir"):
