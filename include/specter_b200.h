@@ -226,6 +226,12 @@ int sx_hd_restart(sx_plan* plan, const char* idir, const char* ext, double dt);
  * jx,jy,jz for outs == 2) and ph = ph'/dt */
 int sx_output(sx_plan* plan, const char* solver, const char* odir, const char* ext, double dt, int outs);
 int sx_restart(sx_plan* plan, const char* solver, const char* idir, const char* ext, double dt);
+/* ref: include/<solver>/<solver>_global.f90 on the plan-owned state: hdcheck (hel = 1) or mhdcheck (hel = crs = 1), pscheck,
+ * vdiagnostic, bdiagnostic, sdiagnostic, each appending its row to `<odir>/balance.txt', helicity.txt, energy.txt,
+ * cross.txt, scalar.txt, noslip_diagnostic.txt, conducting_ / vacuum_diagnostic.txt, scalar_constant_diagnostic.txt in the
+ * reference's FORMATs (pseudospec_hd.f90:991-1001, pseudospec_phd.f90:313-318, pseudospec_mhd.f90:189-209,
+ * vboundary.f90:260-264, bboundary.f90:400-425, sboundary.f90:201-205); time label (t-1) dt; rank 0 writes */
+int sx_global(sx_plan* plan, const char* solver, const char* odir, int t, double dt);
 /* ref: the benchmark.txt row of specter.fpp:1182-1228 (non-CUDA column set: nx ny nz nsteps nprocs nth TCPU TOMP
  * TWTIME TFFT TTRA TCOM TCONT TNEU TROB TTOT, seconds per step), appended by rank 0, header when the file is new.
  * TCPU/TOMP/TWTIME are the caller's totals; the T* columns come from the stage timers (sx_plan_stage_timing): the

@@ -1411,3 +1411,56 @@ def boots_files(idir, odir, tdir, fnlist: str, nxt: int, nyt: int, nzt: int, ozt
         br.tofile(fout)
         out.append(fout)
     return out
+
+
+# ----------------------------------------------------------------------------
+# global-quantity text files            include/*/*_global.f90 and the WRITE
+# statements of hdcheck / pscheck / mhdcheck / vdiagnostic / sdiagnostic / bdiagnostic
+# ----------------------------------------------------------------------------
+def fortran_e(x: float, w: int, d: int) -> str:
+    """One `1P Ew.d` field as gfortran / ifort print it: d.dddE+ee right-justified in w columns; three-digit
+    exponents drop the E (1.234560-100); NaN / Infinity by name; all stars when the field is too narrow."""
+    if x != x:
+        s = "NaN"
+    elif x in (float("inf"), float("-inf")):
+        s = "Infinity" if x > 0 else "-Infinity"
+    else:
+        m, e = ("%.*E" % (d, x)).split("E")
+        s = m + (("E%+03d" % int(e)) if abs(int(e)) < 100 else ("%+04d" % int(e)))
+    return "*" * w if len(s) > w else s.rjust(w)
+
+
+def _append_row(path, fields):
+    with open(path, "a") as f:
+        f.write("".join(fortran_e(x, w, d) for x, w, d in fields) + "\n")
+
+
+def solver_global(g: Grid, s, solver: str, odir, t: int, dt: float, bczsta: int = 0, bczend: int = 0):
+    """The `<solver>_global.f90` include (hdcheck / mhdcheck with hel = 1 (and crs = 1), pscheck, vdiagnostic,
+    sdiagnostic, bdiagnostic) with the reference's FORMATs: pseudospec_hd.f90:991-1001, pseudospec_phd.f90:313-318,
+    pseudospec_mhd.f90:189-209, vboundary.f90:260-264, sboundary.f90:201-205, bboundary.f90:400-425."""
+    tl = (t - 1) * dt
+    p = lambda name: os.path.join(str(odir), name)
+    mag = solver in ("MHD", "MHDBOUSS")
+    sca = solver in ("BOUSS", "ROTBOUSS", "MHDBOUSS")
+    if not mag:
+        eng, ens, pot = hdcheck(g, s.vx, s.vy, s.vz, s.fx, s.fy, s.fz)
+        _append_row(p("balance.txt"), [(tl, 13, 6), (eng, 23, 16), (ens, 23, 16), (pot, 24, 16)])
+        _append_row(p("helicity.txt"), [(tl, 13, 6), (helicity(g, s.vx, s.vy, s.vz), 24, 16)])
+    else:
+        eng, ens, cur, engk, engm, helk, helm, crh, asq = mhdcheck(g, s.vx, s.vy, s.vz, s.ax, s.ay, s.az)
+        _append_row(p("balance.txt"), [(tl, 13, 6), (eng, 23, 16), (ens, 23, 16), (cur, 23, 16)])
+        _append_row(p("energy.txt"), [(tl, 13, 6), (engk, 23, 16), (engm, 23, 16)])
+        _append_row(p("helicity.txt"), [(tl, 13, 6), (helk, 24, 16), (helm, 24, 16)])
+        _append_row(p("cross.txt"), [(tl, 13, 6), (crh, 23, 16), (asq, 24, 16)])
+    if sca:
+        e1, e2, e3 = pscheck(g, s.th, s.fs)
+        _append_row(p("scalar.txt"), [(tl, 13, 6), (e1, 22, 14), (e2, 22, 14), (e3, 23, 14)])
+    _append_row(p("noslip_diagnostic.txt"), [(tl, 13, 6)] + [(x, 13, 6) for x in vdiagnostic(g, s.vx, s.vy, s.vz)])
+    if mag:
+        d = bdiagnostic(g, s.ax, s.ay, s.az, bczsta, bczend)
+        for kind in ("conducting", "vacuum"):
+            if kind in d:
+                _append_row(p(kind + "_diagnostic.txt"), [(tl, 13, 6)] + [(x, 13, 6) for x in d[kind]])
+    if sca:
+        _append_row(p("scalar_constant_diagnostic.txt"), [(tl, 13, 6)] + [(x, 13, 6) for x in sdiagnostic(g, s.th)])

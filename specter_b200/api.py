@@ -66,6 +66,7 @@ SIGNATURES = {
     "sx_output": [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double, _I],
     "sx_restart": [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double],
     "sx_benchmark_write": [_P, C.c_char_p, _I, _I, _F, _F, _F],
+    "sx_global": [_P, C.c_char_p, C.c_char_p, _I, _F],
     "sx_plan_p2p_export": [_P, _I, _I, _D],
     "sx_plan_p2p_import": [_P, _D],
     "sx_plan_set_comm_callbacks": [_P, _D, _D, _D],
@@ -765,6 +766,10 @@ class Plan:
 
     def restart(self, solver, idir, ext, dt):
         self._call("sx_restart", solver.encode(), str(idir).encode(), ext.encode(), float(dt))
+
+    def global_quantities(self, solver, odir, t, dt):
+        """The `<solver>_global.f90` include: appends the rows of balance.txt & co. in the reference's formats."""
+        self._call("sx_global", solver.encode(), str(odir).encode(), int(t), float(dt))
 
     def benchmark_write(self, path, nsteps, nth=1, tcpu=0.0, tomp=0.0, twtime=0.0):
         self._call("sx_benchmark_write", str(path).encode(), int(nsteps), int(nth), float(tcpu), float(tomp), float(twtime))

@@ -289,6 +289,93 @@ int sx_restart(sx_plan* plan, const char* solver, const char* idir, const char* 
   return 0;
 }
 
+/* ---- the global-quantity text files (include/<solver>/<solver>_global.f90) ------------------------------------------
+ * One `1P Ew.d' field as the Fortran run-time prints it: d.dddE+ee right-justified; three-digit exponents drop the E. */
+static std::string fortran_e(double x, int w, int d) {
+  char buf[64];
+  std::string s;
+  if (x != x) s = "NaN";
+  else if (x > 1.7976931348623157e308) s = "Infinity";
+  else if (x < -1.7976931348623157e308) s = "-Infinity";
+  else {
+    snprintf(buf, sizeof buf, "%.*E", d, x);
+    s = buf;
+    const size_t e = s.find('E');
+    const int ex = atoi(s.c_str() + e + 1);
+    char eb[16];
+    if (ex > -100 && ex < 100) snprintf(eb, sizeof eb, "E%+03d", ex);
+    else snprintf(eb, sizeof eb, "%+04d", ex);
+    s = s.substr(0, e) + eb;
+  }
+  if ((int)s.size() > w) return std::string((size_t)w, '*');
+  return std::string((size_t)w - s.size(), ' ') + s;
+}
+struct Field { double x; int w, d; };
+static int append_row(const std::string& path, const std::vector<Field>& f) {
+  FILE* fp = fopen(path.c_str(), "a");
+  SX_REQUIRE(fp != nullptr, "cannot open " + path + " for appending");
+  std::string line;
+  for (const Field& q : f) line += fortran_e(q.x, q.w, q.d);
+  fprintf(fp, "%s\n", line.c_str());
+  fclose(fp);
+  return 0;
+}
+
+int sx_global(sx_plan* plan, const char* solver, const char* odir, int t, double dt) {
+  SX_PLAN(plan);
+  SX_REQUIRE(odir != nullptr, "sx_global: bad arguments");
+  cplx *v[4], *th, *a[3], *ph;
+  if (solver_fields(plan, solver, v, &th, a, &ph)) return 1;
+  const std::string s = solver, dir = std::string(odir) + "/";
+  const bool root = p.myrank == 0;   // the reductions are collective; rank 0 writes (IF (myrank.eq.0))
+  const double tl = (double)(t - 1) * dt;
+  int (*fn)(sx_plan*, int, double**) = s == "HD" ? sx_hd_state_ptr : (s == "MHD" ? sx_mhd_state_ptr
+                                       : (s == "MHDBOUSS" ? sx_mhdbouss_state_ptr : sx_bouss_state_ptr));
+  double *vx = (double*)v[0], *vy = (double*)v[1], *vz = (double*)v[2];
+  if (!ph) {   // hdcheck(vx,vy,vz,fx,fy,fz,t,dt,1,0): pseudospec_hd.f90:943-1005
+    double *f[3], eng, ens, pot, khe;
+    for (int q = 0; q < 3; ++q) if (fn(plan, 4 + q, &f[q])) return 1;
+    if (sx_hdcheck(plan, vx, vy, vz, f[0], f[1], f[2], &eng, &ens, &pot) || sx_helicity(plan, vx, vy, vz, &khe)) return 1;
+    if (root && (append_row(dir + "balance.txt", {{tl, 13, 6}, {eng, 23, 16}, {ens, 23, 16}, {pot, 24, 16}}) ||
+                 append_row(dir + "helicity.txt", {{tl, 13, 6}, {khe, 24, 16}}))) return 1;
+  } else {     // mhdcheck(vx,vy,vz,ax,ay,az,t,dt,1,1): pseudospec_mhd.f90:109-212
+    double o[9];
+    if (sx_mhdcheck(plan, vx, vy, vz, (double*)a[0], (double*)a[1], (double*)a[2], 1, 1, o)) return 1;
+    if (root && (append_row(dir + "balance.txt", {{tl, 13, 6}, {o[0], 23, 16}, {o[1], 23, 16}, {o[2], 23, 16}}) ||
+                 append_row(dir + "energy.txt", {{tl, 13, 6}, {o[3], 23, 16}, {o[4], 23, 16}}) ||
+                 append_row(dir + "helicity.txt", {{tl, 13, 6}, {o[5], 24, 16}, {o[6], 24, 16}}) ||
+                 append_row(dir + "cross.txt", {{tl, 13, 6}, {o[7], 23, 16}, {o[8], 24, 16}}))) return 1;
+  }
+  if (th) {    // pscheck(th,fs,t,dt): pseudospec_phd.f90:275-321
+    double *fs, o[3];
+    if (fn(plan, s == "MHDBOUSS" ? 21 : 11, &fs) || sx_pscheck(plan, (double*)th, fs, o)) return 1;
+    if (root && append_row(dir + "scalar.txt", {{tl, 13, 6}, {o[0], 22, 14}, {o[1], 22, 14}, {o[2], 23, 14}})) return 1;
+  }
+  {            // vdiagnostic: vboundary.f90:214-269
+    double o[5];
+    if (sx_vdiagnostic(plan, vx, vy, vz, o)) return 1;
+    if (root && append_row(dir + "noslip_diagnostic.txt",
+                           {{tl, 13, 6}, {o[0], 13, 6}, {o[1], 13, 6}, {o[2], 13, 6}, {o[3], 13, 6}, {o[4], 13, 6}})) return 1;
+  }
+  if (ph) {    // bdiagnostic: bboundary.f90:348-430
+    double c[6], vac[6];
+    int which = 0;
+    if (sx_bdiagnostic(plan, (double*)a[0], (double*)a[1], (double*)a[2], c, vac, &which)) return 1;
+    for (int k = 0; k < 2; ++k) {
+      if (!(which & (1 << k)) || !root) continue;
+      const double* o = k == 0 ? c : vac;
+      if (append_row(dir + (k == 0 ? "conducting_diagnostic.txt" : "vacuum_diagnostic.txt"),
+                     {{tl, 13, 6}, {o[0], 13, 6}, {o[1], 13, 6}, {o[2], 13, 6}, {o[3], 13, 6}, {o[4], 13, 6}, {o[5], 13, 6}})) return 1;
+    }
+  }
+  if (th) {    // sdiagnostic: sboundary.f90:168-210
+    double o[2];
+    if (sx_sdiagnostic(plan, (double*)th, o)) return 1;
+    if (root && append_row(dir + "scalar_constant_diagnostic.txt", {{tl, 13, 6}, {o[0], 13, 6}, {o[1], 13, 6}})) return 1;
+  }
+  return 0;
+}
+
 int sx_benchmark_write(sx_plan* plan, const char* path, int nsteps, int nth, double tcpu, double tomp, double twtime) {
   SX_PLAN(plan);
   return benchmark_write(p, path, nsteps, nth, tcpu, tomp, twtime);

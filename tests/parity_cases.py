@@ -841,3 +841,66 @@ def case_boots(lib, tables, cases, tmpdir=None):
         api.boots_regrid(small, 16, 16, 20, 5, tables, lib=lib)
     with pytest.raises(api.SpecterError, match="table"):
         api.boots_regrid(np.zeros((27, 16, 16)), 16, 16, 46, 4, tables, lib=lib)
+
+
+# ---- the global-quantity text files (include/<solver>/<solver>_global.f90) -------------------------------------------
+GLOBAL_WIDTHS = {"noslip_diagnostic.txt": [13] * 6, "conducting_diagnostic.txt": [13] * 7, "vacuum_diagnostic.txt": [13] * 7,
+                 "scalar_constant_diagnostic.txt": [13] * 3, "scalar.txt": [13, 22, 22, 23], "energy.txt": [13, 23, 23],
+                 "cross.txt": [13, 23, 24]}
+
+
+def _split_fixed(line, widths):
+    assert len(line) == sum(widths), (len(line), widths)
+    out, pos = [], 0
+    for w in widths:
+        out.append(line[pos:pos + w])
+        pos += w
+    return out
+
+
+def case_global_files(lib, tables, shape, tmpdir, dt=1e-3):
+    """sx_global for HD, BOUSS and MHDBOUSS (conducting bottom / vacuum top, so that both magnetic files appear): the
+    same files, the same fixed-width layout (the reference's FORMATs) and the same numbers as the oracle writes."""
+    import os
+    runs = []
+    for solver, bc in (("HD", None), ("BOUSS", None), ("MHDBOUSS", (0, 1))):
+        g, p = make(lib, tables, *shape)
+        g.load_neumann()
+        if solver == "HD":
+            s = O.make_hd_state(g)
+            p.hd_put_state(s.vx, s.vy, s.vz, s.pr, s.fx, s.fy, s.fz)
+        elif solver == "BOUSS":
+            s = O.make_bouss_state(g)
+            s.fs = rand_spec(g, 5) * 1e-3        # a scalar source so that the injection column is not identically zero
+            p.bouss_put_state(s.vx, s.vy, s.vz, s.pr, s.th, s.fx, s.fy, s.fz, s.fs)
+        else:
+            s = O.make_mhdbouss_state(g)
+            p.setup_bc("b", PERIODIC4 + [B_KIND[bc[0]], B_KIND[bc[1]]])
+            p.mhdbouss_put_state(s.vx, s.vy, s.vz, s.pr, s.ax, s.ay, s.az, s.th, s.fx, s.fy, s.fz, s.mx, s.my, s.mz, s.fs)
+        ours, ref = tmpdir / ("ours_" + solver), tmpdir / ("ref_" + solver)
+        ours.mkdir(), ref.mkdir()
+        for t in (1, 11):
+            p.global_quantities(solver, ours, t, dt)
+            O.solver_global(g, s, solver, ref, t, dt, *(bc or (0, 0)))
+        eng = O.energy(g, s.vx, s.vy, s.vz, 1)
+        assert sorted(os.listdir(ours)) == sorted(os.listdir(ref)), (solver, sorted(os.listdir(ours)))
+        for name in sorted(os.listdir(ref)):
+            widths = GLOBAL_WIDTHS.get(name)
+            la, lb = open(ours / name).read().split("\n"), open(ref / name).read().split("\n")
+            assert len(la) == len(lb) == 3 and la[2] == ""
+            for a, b in zip(la[:2], lb[:2]):
+                if widths is None:       # balance.txt / helicity.txt: the widths depend on the solver family
+                    widths_ = ({"balance.txt": [13, 23, 23, 24], "helicity.txt": [13, 24]} if solver != "MHDBOUSS" else
+                               {"balance.txt": [13, 23, 23, 23], "helicity.txt": [13, 24, 24]})[name]
+                else:
+                    widths_ = widths
+                fa, fb = _split_fixed(a, widths_), _split_fixed(b, widths_)
+                assert fa[0] == fb[0]                                   # the time label, character for character
+                for w, x, y in zip(widths_[1:], fa[1:], fb[1:]):
+                    assert x[-4] == y[-4] == "E" or x.strip() == y.strip(), (name, x, y)
+                    xv, yv = float(x), float(y)
+                    tol = TOL_DIAG if w > 13 else 2e-6                  # 16 / 14 digits printed, or 6
+                    assert abs(xv - yv) <= tol * abs(yv) + TOL_DIAG * eng, (solver, name, x, y)
+        runs.append(solver)
+        p.close()
+    return runs

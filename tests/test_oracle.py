@@ -420,3 +420,12 @@ def test_boots_oracle_reproduces_committed_golden(tables):
     import os
     import parity_cases as P
     P.case_boots_golden(None, tables, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "boots_27_46.npz"))
+
+
+def test_fortran_e_fields():
+    # the `1P Ew.d` fields of balance.txt & co. as the Fortran run-time prints them
+    f = O.fortran_e
+    assert f(1.23456e-3, 13, 6) == " 1.234560E-03" and f(-1.5, 13, 6) == "-1.500000E+00" and f(0.0, 13, 6) == " 0.000000E+00"
+    assert f(2.0, 23, 16) == " 2.0000000000000000E+00" and f(0.5, 22, 14) == "  5.00000000000000E-01"
+    assert f(1e-120, 13, 6) == " 1.000000-120" and f(-3e200, 13, 6) == "-3.000000+200"      # three-digit exponents drop the E
+    assert f(float("nan"), 13, 6) == "          NaN" and f(-1e-120, 12, 6) == "*" * 12

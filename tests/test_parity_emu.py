@@ -145,3 +145,7 @@ def test_boots_regridder(emu_lib, tables, tmp_path):
                                    (16, 16, 20, 0, 16, 16, 20)], tmp_path)
     import os
     P.case_boots_golden(emu_lib, tables, os.path.join(os.path.dirname(__file__), "golden", "boots_27_46.npz"))
+
+
+def test_global_quantity_files(emu_lib, tables, tmp_path):
+    assert P.case_global_files(emu_lib, tables, (16, 16, 64), tmp_path) == ["HD", "BOUSS", "MHDBOUSS"]

@@ -176,3 +176,7 @@ def test_boots_regridder(cuda_lib, tables, tmp_path):
 def test_goto_domain(cuda_lib, tables):
     P.case_goto_domain(cuda_lib, tables, CFG1)
     P.case_goto_domain(cuda_lib, tables, (32, 16, 512))
+
+
+def test_global_quantity_files(cuda_lib, tables, tmp_path):
+    assert P.case_global_files(cuda_lib, tables, (32, 32, 64), tmp_path) == ["HD", "BOUSS", "MHDBOUSS"]
