@@ -123,6 +123,12 @@ int sx_fc_filter(sx_plan* plan, double* a);                                     
 int sx_gradre(sx_plan* plan, const double* a, const double* b, const double* c, double* d, double* e, double* f);
 /* ref: prodre (pseudospec_hd.f90:322-402): curl(A) x A */
 int sx_prodre(sx_plan* plan, const double* a, const double* b, const double* c, double* d, double* e, double* f);
+/* ref: normvec (pseudospec_hd.f90:1238-1286): (a,b,c) *= sqrt(d / energy(a,b,c,kin)); normsca (pseudospec_phd.f90:324-368):
+ * a *= sqrt(b / variance(a,kin)); normalize (module_dns.f90:13-42): (fx,fy,fz) *= f0 / sqrt(energy(fx,fy,fz,kin)).
+ * What the initial-condition and forcing hooks call after filling a field. */
+int sx_normvec(sx_plan* plan, double* a, double* b, double* c, double d, int kin);
+int sx_normsca(sx_plan* plan, double* a, double b, int kin);
+int sx_normalize(sx_plan* plan, double* fx, double* fy, double* fz, double f0, int kin);
 /* diagnostics; results valid on rank 0 after the caller's reduction (single rank: final) */
 int sx_energy(sx_plan* plan, const double* a, const double* b, const double* c, int kin, double* out);   /* ref: :405-635 */
 int sx_divergence(sx_plan* plan, const double* a, const double* b, const double* c, double* out);        /* ref: :1118-1235 */

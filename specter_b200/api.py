@@ -91,6 +91,9 @@ SIGNATURES = {
     "sx_fc_filter": [_P, _D],
     "sx_gradre": [_P, _D, _D, _D, _D, _D, _D],
     "sx_prodre": [_P, _D, _D, _D, _D, _D, _D],
+    "sx_normvec": [_P, _D, _D, _D, _F, _I],
+    "sx_normsca": [_P, _D, _F, _I],
+    "sx_normalize": [_P, _D, _D, _D, _F, _I],
     "sx_energy": [_P, _D, _D, _D, _I, _PD],
     "sx_divergence": [_P, _D, _D, _D, _PD],
     "sx_cross": [_P, _D, _D, _D, _D, _D, _D, _I, _PD],
@@ -486,6 +489,15 @@ class Plan:
 
     def prodre(self, a, b, c, d, e, f):
         self._call("sx_prodre", a.ptr, b.ptr, c.ptr, d.ptr, e.ptr, f.ptr)
+
+    def normvec(self, a, b, c, d, kin):
+        self._call("sx_normvec", a.ptr, b.ptr, c.ptr, float(d), int(kin))
+
+    def normsca(self, a, b, kin):
+        self._call("sx_normsca", a.ptr, float(b), int(kin))
+
+    def normalize(self, fx, fy, fz, f0, kin):
+        self._call("sx_normalize", fx.ptr, fy.ptr, fz.ptr, float(f0), int(kin))
 
     def energy(self, a, b, c, kin) -> float:
         out = C.c_double()

@@ -681,6 +681,28 @@ int sx_hdcheck(sx_plan* plan, const double* a, const double* b, const double* c,
   if (energy(p, C(a), C(b), C(c), 0, ens)) return 1;
   return cross(p, C(a), C(b), C(c), C(d), C(e), C(f), 1, pot);
 }
+// normvec (pseudospec_hd.f90:1238-1286), normsca (pseudospec_phd.f90:324-368), normalize (module_dns.f90:13-42): the
+// initial-condition / forcing hooks scale a field to a prescribed energy, variance or amplitude
+int sx_normvec(sx_plan* plan, double* a, double* b, double* c, double d, int kin) {
+  SX_PLAN(plan);
+  double tmp = 0.0;
+  if (energy(p, C(a), C(b), C(c), kin, &tmp)) return 1;   // all-reduced: every rank holds it (the reference broadcasts)
+  const double rmp = std::sqrt(d / tmp);
+  return op_scale_copy(p, C(a), C(a), rmp) || op_scale_copy(p, C(b), C(b), rmp) || op_scale_copy(p, C(c), C(c), rmp);
+}
+int sx_normsca(sx_plan* plan, double* a, double b, int kin) {
+  SX_PLAN(plan);
+  double tmp = 0.0;
+  if (variance(p, C(a), kin, &tmp)) return 1;
+  return op_scale_copy(p, C(a), C(a), std::sqrt(b / tmp));
+}
+int sx_normalize(sx_plan* plan, double* fx, double* fy, double* fz, double f0, int kin) {
+  SX_PLAN(plan);
+  double tmp = 0.0;
+  if (energy(p, C(fx), C(fy), C(fz), kin, &tmp)) return 1;
+  const double rmp = f0 / std::sqrt(tmp);
+  return op_scale_copy(p, C(fx), C(fx), rmp) || op_scale_copy(p, C(fy), C(fy), rmp) || op_scale_copy(p, C(fz), C(fz), rmp);
+}
 // goto_domain_w_boundaries / goto_3d_fourier (boundary_mod.fpp:72-150, 153-194), 1-3 fields in place
 int sx_goto_domain_w_boundaries(sx_plan* plan, double* a, double* b, double* c) {
   SX_PLAN(plan);

@@ -57,6 +57,30 @@ def case_fft1d_z(lib, tables, shape, Cz=25):
     p.close()
 
 
+def case_normalisations(lib, tables, shape):
+    """normvec / normsca / normalize (pseudospec_hd.f90:1238-1286, pseudospec_phd.f90:324-368, module_dns.f90:13-42)."""
+    g, p = make(lib, tables, *shape)
+    v = smooth_velocity(g, 4)
+    for kin, d in ((1, 2.5), (0, 0.7), (2, 1.3)):
+        dev = [p.spectral(a) for a in v]
+        p.normvec(*dev, d, kin)
+        ref = [a.copy() for a in v]
+        O.normvec(g, *ref, d, kin)
+        fields_close([q.get() for q in dev], ref, tol=TOL_OP * 10)
+        assert abs(p.energy(*dev, kin) / d - 1) < TOL_DIAG
+    for kin, b in ((1, 0.5), (0, 3.0)):
+        dev = p.spectral(v[0])
+        p.normsca(dev, b, kin)
+        ref = v[0].copy()
+        O.normsca(g, ref, b, kin)
+        fields_close([dev.get()], [ref], tol=TOL_OP * 10)
+    dev = [p.spectral(a) for a in v]
+    p.normalize(*dev, 0.3, 1)
+    rmp = 0.3 / np.sqrt(O.energy(g, *v, 1))
+    fields_close([q.get() for q in dev], [a * rmp for a in v], tol=TOL_OP * 10)
+    p.close()
+
+
 def case_goto_domain(lib, tables, shape):
     """goto_domain_w_boundaries / goto_3d_fourier (boundary_mod.fpp:72-194) on one and on three fields."""
     g, p = make(lib, tables, *shape)

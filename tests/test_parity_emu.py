@@ -14,6 +14,10 @@ def test_fft1d_z(emu_lib, tables):
     P.case_fft1d_z(emu_lib, tables, (16, 16, 32), Cz=0)
 
 
+def test_normalisations(emu_lib, tables):
+    P.case_normalisations(emu_lib, tables, SMALL)
+
+
 def test_goto_domain(emu_lib, tables):
     P.case_goto_domain(emu_lib, tables, SMALL)
 

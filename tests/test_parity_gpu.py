@@ -180,3 +180,7 @@ def test_goto_domain(cuda_lib, tables):
 
 def test_global_quantity_files(cuda_lib, tables, tmp_path):
     assert P.case_global_files(cuda_lib, tables, (32, 32, 64), tmp_path) == ["HD", "BOUSS", "MHDBOUSS"]
+
+
+def test_normalisations(cuda_lib, tables):
+    P.case_normalisations(cuda_lib, tables, CFG1)
