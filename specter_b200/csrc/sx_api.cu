@@ -235,6 +235,16 @@ static void plan_release(Plan& p) {
     SX_KERNEL_CHECK();                                                                          \
   } while (0)
 
+__global__ void k_scale_all(cplx* a, size_t n, double s) {   // a *= s on all nz rows, in place
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
+    a[t] = cmake(a[t].x * s, a[t].y * s);
+}
+static int scale_all(Plan& p, cplx* a, double s) {
+  const size_t n = p.csize();
+  SX_EW_LAUNCH_API(p, k_scale_all, n, a, n, s);
+  return 0;
+}
+
 // ---- composite transforms -------------------------------------------------------------
 static inline cplx* C(double* a) { return reinterpret_cast<cplx*>(a); }
 static inline const cplx* C(const double* a) { return reinterpret_cast<const cplx*>(a); }
@@ -688,20 +698,20 @@ int sx_normvec(sx_plan* plan, double* a, double* b, double* c, double d, int kin
   double tmp = 0.0;
   if (energy(p, C(a), C(b), C(c), kin, &tmp)) return 1;   // all-reduced: every rank holds it (the reference broadcasts)
   const double rmp = std::sqrt(d / tmp);
-  return op_scale_copy(p, C(a), C(a), rmp) || op_scale_copy(p, C(b), C(b), rmp) || op_scale_copy(p, C(c), C(c), rmp);
+  return scale_all(p, C(a), rmp) || scale_all(p, C(b), rmp) || scale_all(p, C(c), rmp);
 }
 int sx_normsca(sx_plan* plan, double* a, double b, int kin) {
   SX_PLAN(plan);
   double tmp = 0.0;
   if (variance(p, C(a), kin, &tmp)) return 1;
-  return op_scale_copy(p, C(a), C(a), std::sqrt(b / tmp));
+  return scale_all(p, C(a), std::sqrt(b / tmp));
 }
 int sx_normalize(sx_plan* plan, double* fx, double* fy, double* fz, double f0, int kin) {
   SX_PLAN(plan);
   double tmp = 0.0;
   if (energy(p, C(fx), C(fy), C(fz), kin, &tmp)) return 1;
   const double rmp = f0 / std::sqrt(tmp);
-  return op_scale_copy(p, C(fx), C(fx), rmp) || op_scale_copy(p, C(fy), C(fy), rmp) || op_scale_copy(p, C(fz), C(fz), rmp);
+  return scale_all(p, C(fx), rmp) || scale_all(p, C(fy), rmp) || scale_all(p, C(fz), rmp);
 }
 // goto_domain_w_boundaries / goto_3d_fourier (boundary_mod.fpp:72-150, 153-194), 1-3 fields in place
 int sx_goto_domain_w_boundaries(sx_plan* plan, double* a, double* b, double* c) {
