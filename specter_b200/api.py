@@ -202,7 +202,11 @@ def load_library() -> Library:
     """The product library (CUDA, sm_100a).  Never falls back to anything else."""
     global _LIB
     if _LIB is None:
-        _LIB = Library(LIB_PATH)
+        lib = Library(LIB_PATH)
+        if "sm_100a" not in lib.version():   # e.g. SPECTER_B200_LIB pointing at the tests' kernel-emulation build
+            raise SpecterError(f"{LIB_PATH} is not the nvcc-built sm_100a library ({lib.version()}); "
+                               "specter_b200 has no CPU fallback")
+        _LIB = lib
     return _LIB
 
 

@@ -71,6 +71,18 @@ def test_no_cpu_fallback(tables):
         api.Plan(16, 16, 64, 25, 5, tdir=tables)
 
 
+def test_product_loader_refuses_the_emulation_build(emu_lib):
+    # the tests hand the emulation build to api.Library explicitly; the product entry point (load_library) must not
+    # accept it, whatever SPECTER_B200_LIB says
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\nfrom specter_b200 import api\n"
+            "try:\n    api.load_library()\nexcept api.SpecterError as e:\n    print('refused:', e)\n" % ROOT)
+    env = dict(os.environ, SPECTER_B200_LIB=emu_lib.path)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "refused:" in r.stdout and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
 def test_argument_errors_on_emulated_build(emu_lib, tables):
     with pytest.raises(api.SpecterError, match="power"):
         api.Plan(24, 16, 64, 25, 5, tdir=tables, lib=emu_lib)
