@@ -265,6 +265,29 @@ def _worker_solvers(rank, world, port, solver, shape, emu_path, tables, q):
             st = p.mhdbouss_get_state()
             O.mhdbouss_step(g, s, 1e-3, 1e-3, 5e-3, 1e-3, b0=(0.0, 0.0, 0.1))
             groups = [(st[:3], (s.vx, s.vy, s.vz)), (st[4:7], (s.ax, s.ay, s.az)), ([phys(st[8])], (phys(s.th),))]
+            # the <solver>_global.f90 include on several ranks: every reduction is collective, rank 0 writes the rows
+            import tempfile
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import parity_cases as P
+            odir = tempfile.mkdtemp()
+            p.global_quantities("MHDBOUSS", odir, 2, 1e-3)
+            if rank == 0:
+                rdir = tempfile.mkdtemp()
+                O.solver_global(g, s, "MHDBOUSS", rdir, 2, 1e-3)
+                assert sorted(os.listdir(odir)) == sorted(os.listdir(rdir))
+                eng = O.energy(g, s.vx, s.vy, s.vz, 1)
+                for name in os.listdir(rdir):
+                    a = open(os.path.join(odir, name)).read().split("\n")[0]
+                    b = open(os.path.join(rdir, name)).read().split("\n")[0]
+                    assert len(a) == len(b) and a[:13] == b[:13], name
+                    widths = dict(P.GLOBAL_WIDTHS, **{"balance.txt": [13, 23, 23, 23], "helicity.txt": [13, 24, 24]})[name]
+                    w = 13 if "diagnostic" in name else None
+                    xs = [P._fortran_float(t) for t in P._split_fixed(a, widths)[1:]]
+                    ys = [P._fortran_float(t) for t in P._split_fixed(b, widths)[1:]]
+                    for x, y in zip(xs, ys):
+                        assert abs(x - y) <= (2e-6 if w else 1e-9) * abs(y) + 1e-9 * eng, (name, x, y)
+            else:
+                assert os.listdir(odir) == []
         errs = []
         for got, ref in groups:
             scale = max(np.abs(r).max() for r in ref)
