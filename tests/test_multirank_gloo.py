@@ -301,8 +301,7 @@ def _worker_solvers(rank, world, port, solver, shape, emu_path, tables, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("solver,world,shape", [("bouss", 2, (32, 16, 64)), ("mhd", 2, (32, 16, 64)), ("mhdbouss", 2, (32, 16, 64)),
-                                                ("mhdbouss", 3, (16, 16, 64))])
+@pytest.mark.parametrize("solver,world,shape", [("bouss", 2, (32, 16, 64)), ("mhd", 3, (16, 16, 64)), ("mhdbouss", 2, (32, 16, 64))])
 def test_fused_solvers_multirank(solver, world, shape, emu_lib, tables):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
