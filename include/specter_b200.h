@@ -70,8 +70,8 @@ int sx_plan_stage_times(sx_plan* plan, double* ms, long long* counts, int n);
 int sx_nccl_unique_id(void* id128);
 int sx_plan_set_comm(sx_plan* plan, const void* id128);
 /* Peer-to-peer slab exchange for one process per GPU on an NVLink / NVSwitch node.  The receive buffers of the
- * fused substep (n_inverse fields on the way to real space, n_forward on the way back; HD 6/3, BOUSS 8/4,
- * MHD 12/6) live in one device allocation per rank.  sx_plan_p2p_export creates it and writes its 64-byte CUDA
+ * fused substep (n_inverse fields on the way to real space, n_forward on the way back; HD 6/3, BOUSS / ROTBOUSS 8/4,
+ * MHD 12/6, MHDBOUSS 14/7) live in one device allocation per rank.  sx_plan_p2p_export creates it and writes its 64-byte CUDA
  * IPC handle; the caller gathers the handles of all ranks (MPI_ALLGATHER in the Fortran driver,
  * torch.distributed in the Python harness) and passes the nprocs x 64 bytes to sx_plan_p2p_import.  From then on
  * every block of the all-to-all-v is written straight into the destination GPU's buffer by the copy engines and
