@@ -129,7 +129,8 @@ int sx_prodre(sx_plan* plan, const double* a, const double* b, const double* c, 
 int sx_normvec(sx_plan* plan, double* a, double* b, double* c, double d, int kin);
 int sx_normsca(sx_plan* plan, double* a, double b, int kin);
 int sx_normalize(sx_plan* plan, double* fx, double* fy, double* fz, double f0, int kin);
-/* diagnostics; results valid on rank 0 after the caller's reduction (single rank: final) */
+/* diagnostics; the sums and maxima are all-reduced over the plan's communicator INSIDE the library: the result is final
+   on every rank (do not add an MPI_REDUCE in the caller; the reference's MPI_REDUCE to rank 0 is subsumed) */
 int sx_energy(sx_plan* plan, const double* a, const double* b, const double* c, int kin, double* out);   /* ref: :405-635 */
 int sx_divergence(sx_plan* plan, const double* a, const double* b, const double* c, double* out);        /* ref: :1118-1235 */
 int sx_cross(sx_plan* plan, const double* a, const double* b, const double* c, const double* d,
@@ -211,7 +212,9 @@ int sx_hd_rkstep1(sx_plan* plan);
 /* ref: hd_rkstep2.f90:3-36, one substep `o` of `ord`.  impl = 0: fused B200 path (default);
  * impl = 1: the same substep composed from the per-operator entry points above. */
 int sx_hd_rkstep2(sx_plan* plan, int o, double dt, double nu, const double v_zsta[2], const double v_zend[2], int impl);
-/* one full time step (rkstep1 + ord substeps) on host arrays: H2D of v,pr,f, compute, D2H of v,pr */
+/* one full time step (rkstep1 + ord substeps) on host arrays: H2D of v,pr,f, compute, D2H of v,pr.  fx/fy/fz_host may
+ * be NULL: the forcing uploaded by an earlier call (or by sx_hd_put_state) stays on the device.  The uploads run on a
+ * copy stream and the first substep starts on vx while vy, vz, pr still travel. */
 int sx_hd_step_host(sx_plan* plan, double* vx_host, double* vy_host, double* vz_host, double* pr_host,
                     const double* fx_host, const double* fy_host, const double* fz_host, double dt, double nu,
                     const double v_zsta[2], const double v_zend[2]);

@@ -591,14 +591,16 @@ class Plan:
         self._call("sx_hd_restart", str(idir).encode(), ext.encode(), float(dt))
 
     def hd_step_host(self, vx, vy, vz, pr, fx, fy, fz, dt, nu, v_zsta=(0.0, 0.0), v_zend=(0.0, 0.0)):
-        """One full step on HOST arrays (in place): H2D, rkstep1 + ord substeps, D2H."""
+        """One full step on HOST arrays (in place): H2D, rkstep1 + ord substeps, D2H.  fx / fy / fz may be None:
+        the forcing of an earlier call (or of hd_put_state) is kept on the device."""
         for a in (vx, vy, vz, pr, fx, fy, fz):
-            if not (a.flags["C_CONTIGUOUS"] and a.dtype == np.complex128 and a.shape == tuple(self.cshape)):
+            if a is not None and not (a.flags["C_CONTIGUOUS"] and a.dtype == np.complex128 and a.shape == tuple(self.cshape)):
                 raise SpecterError("hd_step_host needs C-contiguous complex128 arrays of the plan's spectral shape")
+        if any(a is None for a in (vx, vy, vz, pr)):
+            raise SpecterError("hd_step_host: vx, vy, vz, pr are required")
         self._call("sx_hd_step_host", vx.ctypes.data, vy.ctypes.data, vz.ctypes.data, pr.ctypes.data,
-                   fx.ctypes.data, fy.ctypes.data, fz.ctypes.data, dt, nu, _vec2(v_zsta), _vec2(v_zend))
+                   *[None if a is None else a.ctypes.data for a in (fx, fy, fz)], dt, nu, _vec2(v_zsta), _vec2(v_zend))
 
-    # ---- Boussinesq / MHD operators (pseudospec_phd.f90, pseudospec_mhd.f90, sboundary.f90, bboundary.f90) ----
     def advect(self, a, b, c, d, e):
         self._call("sx_advect", a.ptr, b.ptr, c.ptr, d.ptr, e.ptr)
 

@@ -89,7 +89,8 @@ int stage_mark_slow(Plan& p, int id) {
   SX_CUDA_CHECK(cudaEventRecord(t.ev[t.n], p.stream));
   t.ids[t.n] = id;
   t.n++;
-  if (t.n >= 8192) return stage_flush(p);
+  // the closing mark of stage_flush (id < 0) must not flush again: that recursion never ended once 8192 marks were pending
+  if (id >= 0 && t.n >= 8192) return stage_flush(p);
   return 0;
 }
 int stage_flush(Plan& p) {
@@ -189,16 +190,22 @@ static int plan_init(Plan& p, const sx_config& c) {
   if (upload_twiddles(p.nx, &p.tw_x)) return 1;
   if (upload_twiddles(p.ny, &p.tw_y)) return 1;
   if (upload_twiddles(p.nz, &p.tw_z)) return 1;
-  if (const char* e = getenv("SX_ZF")) p.knob_zf = atoi(e);
-  if (const char* e = getenv("SX_XP")) p.knob_xp = atoi(e);
-  if (const char* e = getenv("SX_PJ")) p.knob_pj = atoi(e);
-  if (const char* e = getenv("SX_TILE_PF")) p.knob_pf = atoi(e);
-  if (const char* e = getenv("SX_ZCHUNKS")) p.knob_zchunks = atoi(e);
-  if (const char* e = getenv("SX_TMA")) p.knob_tma = atoi(e);
-  if (const char* e = getenv("SX_TMA_MIN")) p.knob_tma_min = atoi(e);
-  if (const char* e = getenv("SX_INV_STAGES")) p.knob_inv_stages = atoi(e);
-  if (const char* e = getenv("SX_TILE_NP")) p.knob_np = atoi(e);
-  if (const char* e = getenv("SX_TILE_MINB")) p.knob_minb = atoi(e);
+  // tuning knobs (debugging / A-B timing): every value is range-checked against the variants that exist, so a stray
+  // environment variable cannot silently select an untested configuration
+  struct Knob { const char* name; int* v; int lo, hi; };
+  const Knob knobs[] = {{"SX_ZF", &p.knob_zf, 0, 7},          {"SX_XP", &p.knob_xp, 0, 19},      {"SX_PJ", &p.knob_pj, 0, 19},
+                        {"SX_TILE_PF", &p.knob_pf, 0, 15},    {"SX_ZCHUNKS", &p.knob_zchunks, 1, 8}, {"SX_TMA", &p.knob_tma, 0, 15},
+                        {"SX_TMA_MIN", &p.knob_tma_min, 16, 4096}, {"SX_INV_STAGES", &p.knob_inv_stages, 0, 3},
+                        {"SX_TILE_NP", &p.knob_np, 0, 32},    {"SX_TILE_MINB", &p.knob_minb, 1, 8}, {"SX_ZS", &p.knob_zs, 0, 9}};
+  for (const Knob& k : knobs) {
+    const char* e = getenv(k.name);
+    if (!e || !*e) continue;
+    char* end = nullptr;
+    const long val = strtol(e, &end, 10);
+    SX_REQUIRE(end != e && *end == 0 && val >= k.lo && val <= k.hi,
+               std::string("invalid value of the tuning variable ") + k.name + "=" + e + " (integer in [" + std::to_string(k.lo) + "," + std::to_string(k.hi) + "])");
+    *k.v = (int)val;
+  }
   p.red_blocks = 148 * 4;
   SX_CUDA_CHECK(cudaMalloc((void**)&p.d_red, p.red_blocks * sizeof(double)));
   SX_CUDA_CHECK(cudaMallocHost((void**)&p.h_red, p.red_blocks * sizeof(double)));
@@ -220,6 +227,8 @@ static void plan_release(Plan& p) {
   if (p.h_red) cudaFreeHost(p.h_red);
   if (p.ev_t0) cudaEventDestroy(p.ev_t0);
   if (p.ev_t1) cudaEventDestroy(p.ev_t1);
+  for (int i = 0; i < 4; ++i) if (p.h2d_ev[i]) cudaEventDestroy(p.h2d_ev[i]);
+  if (p.copy_stream) cudaStreamDestroy(p.copy_stream);
   if (p.stream) cudaStreamDestroy(p.stream);
 }
 

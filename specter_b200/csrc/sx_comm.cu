@@ -33,12 +33,16 @@ struct Comm {
   sx_allreduce_fn allred = nullptr;
   void* user = nullptr;
   cudaEvent_t ready[32] = {nullptr}, done[32] = {nullptr};
-  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  // timing mode: one event pair per exchange, resolved lazily (comm_resolve) so that the exchange is never
+  // synchronised with the host and keeps overlapping the compute stream while it is being measured
+  std::vector<cudaEvent_t> tev;
+  size_t ntev = 0;
   double* d_scal = nullptr;
   double* h_scal = nullptr;
   float* d_bar = nullptr;   // payload of the completion barrier of the peer-to-peer exchange
-  cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // extra copy streams: one copy engine does not fill NVLink
-  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+  static constexpr int kSide = 7;
+  cudaStream_t side[kSide] = {nullptr};   // extra copy streams: one copy engine does not fill NVLink
+  cudaEvent_t fork = nullptr, join[kSide] = {nullptr};
   int nsplit = 2;
   // accounting for the NVLink roofline
   double bytes_sent = 0.0, ms = 0.0;
@@ -55,12 +59,11 @@ int comm_free(Plan& p) {
     if (c->ready[i]) cudaEventDestroy(c->ready[i]);
     if (c->done[i]) cudaEventDestroy(c->done[i]);
   }
-  if (c->t0) cudaEventDestroy(c->t0);
-  if (c->t1) cudaEventDestroy(c->t1);
+  for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->d_scal) cudaFree(c->d_scal);
   if (c->d_bar) cudaFree(c->d_bar);
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < Comm::kSide; ++i) {
     if (c->side[i]) cudaStreamDestroy(c->side[i]);
     if (c->join[i]) cudaEventDestroy(c->join[i]);
   }
@@ -80,20 +83,44 @@ static int comm_get(Plan& p, Comm** out) {
       SX_CUDA_CHECK(cudaEventCreate(&c->ready[i]));
       SX_CUDA_CHECK(cudaEventCreate(&c->done[i]));
     }
-    SX_CUDA_CHECK(cudaEventCreate(&c->t0));
-    SX_CUDA_CHECK(cudaEventCreate(&c->t1));
     SX_CUDA_CHECK(cudaMalloc((void**)&c->d_scal, 64 * sizeof(double)));
     SX_CUDA_CHECK(cudaMalloc((void**)&c->d_bar, 64));
     SX_CUDA_CHECK(cudaMemset(c->d_bar, 0, 64));
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < Comm::kSide; ++i) {
       SX_CUDA_CHECK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
       SX_CUDA_CHECK(cudaEventCreate(&c->join[i]));
     }
     SX_CUDA_CHECK(cudaEventCreate(&c->fork));
-    if (const char* e = getenv("SX_P2P_SPLIT")) c->nsplit = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
+    // copy streams (= copy engines) per exchange: one per peer up to 4 by default (env SX_P2P_SPLIT: 1..8)
+    c->nsplit = p.nprocs <= 2 ? 2 : (p.nprocs - 1 < 4 ? p.nprocs - 1 : 4);
+    if (const char* e = getenv("SX_P2P_SPLIT")) {
+      const int v = atoi(e);
+      SX_REQUIRE(v >= 1 && v <= Comm::kSide + 1, "invalid value of the tuning variable SX_P2P_SPLIT (1..8)");
+      c->nsplit = v;
+    }
     SX_CUDA_CHECK(cudaMallocHost((void**)&c->h_scal, 64 * sizeof(double)));
   }
   *out = p.comm;
+  return 0;
+}
+
+static int comm_tmark(Comm& c) {   // next timing event on the communication stream
+  if (c.ntev == c.tev.size()) {
+    cudaEvent_t e;
+    SX_CUDA_CHECK(cudaEventCreate(&e));
+    c.tev.push_back(e);
+  }
+  SX_CUDA_CHECK(cudaEventRecord(c.tev[c.ntev++], c.stream));
+  return 0;
+}
+static int comm_resolve(Comm& c) {   // add the elapsed time of every recorded (begin, end) pair
+  for (size_t i = 0; i + 1 < c.ntev; i += 2) {
+    SX_CUDA_CHECK(cudaEventSynchronize(c.tev[i + 1]));
+    float f = 0.f;
+    SX_CUDA_CHECK(cudaEventElapsedTime(&f, c.tev[i], c.tev[i + 1]));
+    c.ms += f;
+  }
+  c.ntev = 0;
   return 0;
 }
 
@@ -137,7 +164,7 @@ int exchange_begin(Plan& p, int ev, const cplx* send, cplx* recv, const size_t* 
   SX_CUDA_CHECK(cudaEventRecord(c.ready[ev], p.stream));
   SX_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ready[ev], 0));
   const bool timing = p.timer.on;
-  if (timing) SX_CUDA_CHECK(cudaEventRecord(c.t0, c.stream));
+  if (timing && comm_tmark(c)) return 1;
   ncclResult_t st = ncclGroupStart();
   for (int q = 0; q < p.nprocs && st == ncclSuccess; ++q) {
     // start with the neighbour so that all pairs are busy (any order is correct inside a group)
@@ -149,11 +176,8 @@ int exchange_begin(Plan& p, int ev, const cplx* send, cplx* recv, const size_t* 
   SX_REQUIRE(st == ncclSuccess && st2 == ncclSuccess,
              std::string("NCCL all-to-all failed: ") + ncclGetErrorString(st != ncclSuccess ? st : st2));
   if (timing) {
-    SX_CUDA_CHECK(cudaEventRecord(c.t1, c.stream));
-    SX_CUDA_CHECK(cudaEventSynchronize(c.t1));
-    float f = 0.f;
-    SX_CUDA_CHECK(cudaEventElapsedTime(&f, c.t0, c.t1));
-    c.ms += f;
+    if (comm_tmark(c)) return 1;
+    if (c.ntev >= 4096 && comm_resolve(c)) return 1;
   }
   SX_CUDA_CHECK(cudaEventRecord(c.done[ev], c.stream));
   p.launches++;
@@ -183,7 +207,7 @@ int exchange_begin_p2p(Plan& p, int ev, const cplx* send, const size_t* sdispl, 
   SX_CUDA_CHECK(cudaEventRecord(c.ready[ev], p.stream));
   SX_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ready[ev], 0));
   const bool timing = p.timer.on;
-  if (timing) SX_CUDA_CHECK(cudaEventRecord(c.t0, c.stream));
+  if (timing && comm_tmark(c)) return 1;
   // every block is cut into nsplit pieces that travel on different streams (= different copy engines)
   const int ns = c.nsplit;
   if (ns > 1) {
@@ -209,11 +233,8 @@ int exchange_begin_p2p(Plan& p, int ev, const cplx* send, const size_t* sdispl, 
   ncclResult_t st = ncclAllReduce(c.d_bar, c.d_bar, 1, ncclFloat, ncclSum, c.nccl, c.stream);
   SX_REQUIRE(st == ncclSuccess, std::string("NCCL barrier failed: ") + ncclGetErrorString(st));
   if (timing) {
-    SX_CUDA_CHECK(cudaEventRecord(c.t1, c.stream));
-    SX_CUDA_CHECK(cudaEventSynchronize(c.t1));
-    float f = 0.f;
-    SX_CUDA_CHECK(cudaEventElapsedTime(&f, c.t0, c.t1));
-    c.ms += f;
+    if (comm_tmark(c)) return 1;
+    if (c.ntev >= 4096 && comm_resolve(c)) return 1;
   }
   SX_CUDA_CHECK(cudaEventRecord(c.done[ev], c.stream));
   p.launches++;
@@ -239,7 +260,7 @@ int p2p_round(Plan& p, const int* wait_slots, int nwait, const P2PCopy* cp, int 
   if (stage_mark(p, ST_EXCHANGE)) return 1;
   for (int i = 0; i < nwait; ++i) SX_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ready[wait_slots[i]], 0));
   const bool timing = p.timer.on;
-  if (timing) SX_CUDA_CHECK(cudaEventRecord(c.t0, c.stream));
+  if (timing && comm_tmark(c)) return 1;
   const int ns = c.nsplit;
   if (ns > 1 && n > 0) {
     SX_CUDA_CHECK(cudaEventRecord(c.fork, c.stream));
@@ -264,11 +285,8 @@ int p2p_round(Plan& p, const int* wait_slots, int nwait, const P2PCopy* cp, int 
     c.exchanges++;
   }
   if (timing) {
-    SX_CUDA_CHECK(cudaEventRecord(c.t1, c.stream));
-    SX_CUDA_CHECK(cudaEventSynchronize(c.t1));
-    float f = 0.f;
-    SX_CUDA_CHECK(cudaEventElapsedTime(&f, c.t0, c.t1));
-    c.ms += f;
+    if (comm_tmark(c)) return 1;
+    if (c.ntev >= 4096 && comm_resolve(c)) return 1;
   }
   if (done_slot >= 0) SX_CUDA_CHECK(cudaEventRecord(c.done[done_slot], c.stream));
   p.launches++;
@@ -379,6 +397,7 @@ int sx_plan_p2p_import(sx_plan* plan, const void* handles) {
 int sx_plan_comm_stats(sx_plan* plan, double* bytes_sent, double* ms, long long* exchanges, int reset) {
   SX_PLAN(plan);
   Comm* c = p.comm;
+  if (c && comm_resolve(*c)) return 1;
   if (bytes_sent) *bytes_sent = c ? c->bytes_sent : 0.0;
   if (ms) *ms = c ? c->ms : 0.0;
   if (exchanges) *exchanges = c ? c->exchanges : 0;

@@ -69,7 +69,7 @@ static int fused_init(Plan& p, Fused** out) {
   zrange(f->nph, p.nprocs, p.myrank, &f->zf0, &f->nzf);
   f->nxp = (p.nxh + 7) / 8 * 8;
   f->wsize = (size_t)p.nxl * f->nph * p.ny;
-  f->vsize = (size_t)f->nzf * p.ny * f->nxp;
+  f->vsize = 0;   // set by fused_reserve (whole slab, or one z chunk)
   std::vector<ZMap> zm(f->nph);
   long long base = 0;
   for (int r = 0; r < p.nprocs; ++r) {
@@ -94,8 +94,11 @@ static int fused_init(Plan& p, Fused** out) {
   return 0;
 }
 
-// grow the work-field pools: nw transposed inverse fields, nv real-side inputs of the x pass, nx nonlinear terms
-static int fused_reserve(Plan& p, Fused& f, int nw, int nv, int nx) {
+static bool chunked(const Plan& p, const Fused& f);
+
+// grow the work-field pools: nw transposed inverse fields, nv real-side inputs of the x pass, nx nonlinear terms.
+// window: the caller runs the z-chunked xy pipeline, so V / X only need the rows of one chunk (Fused::vwin).
+static int fused_reserve(Plan& p, Fused& f, int nw, int nv, int nx, bool window) {
   const size_t rsize = (size_t)p.nxh * f.nzf * p.ny;  // y-stage side [kx][zl][ky]
   const size_t both = f.wsize > rsize ? f.wsize : rsize;
   if (f.arena) SX_REQUIRE(nw <= f.arena_nw && nx <= f.arena_nx, "the peer-to-peer arena was exported for fewer fields than this solver transposes");
@@ -108,19 +111,31 @@ static int fused_reserve(Plan& p, Fused& f, int nw, int nv, int nx) {
     f.W.push_back(w);
     f.R.push_back(r);
   }
+  const int rows = window ? cdiv(f.nzf, p.knob_zchunks) : f.nzf;
+  f.vwin = window && rows < f.nzf;
+  if (rows > f.vrows) {   // a solver that needs whole-slab V / X after a windowed one: start the pools again
+    SX_CUDA_CHECK(cudaStreamSynchronize(p.stream));
+    release_fields(f.V);
+    release_fields(f.X);
+    f.vrows = rows;
+    f.vsize = (size_t)rows * p.ny * f.nxp;
+  }
   while ((int)f.V.size() < nv) {
     cplx* v = nullptr;
-    SX_CUDA_CHECK(cudaMalloc((void**)&v, f.vsize * sizeof(cplx)));
+    SX_CUDA_CHECK(cudaMalloc((void**)&v, (f.vsize ? f.vsize : 1) * sizeof(cplx)));
     f.V.push_back(v);
   }
   while ((int)f.X.size() < nx) {
-    cplx *x = nullptr, *u = nullptr, *uz = nullptr;
-    SX_CUDA_CHECK(cudaMalloc((void**)&x, f.vsize * sizeof(cplx)));
+    cplx* x = nullptr;
+    SX_CUDA_CHECK(cudaMalloc((void**)&x, (f.vsize ? f.vsize : 1) * sizeof(cplx)));
+    f.X.push_back(x);
+  }
+  while ((int)f.U.size() < nx) {
+    cplx *u = nullptr, *uz = nullptr;
     SX_CUDA_CHECK(cudaMalloc((void**)&u, both * sizeof(cplx)));
     if (p.nprocs == 1) uz = u;
-    else if (f.arena) uz = f.arena + f.arena_nw * arena_rs(p, p.myrank) + f.X.size() * arena_ws(p, p.myrank);
+    else if (f.arena) uz = f.arena + f.arena_nw * arena_rs(p, p.myrank) + f.U.size() * arena_ws(p, p.myrank);
     else SX_CUDA_CHECK(cudaMalloc((void**)&uz, f.wsize * sizeof(cplx)));
-    f.X.push_back(x);
     f.U.push_back(u);
     f.Uz.push_back(uz);
   }
@@ -158,15 +173,26 @@ static int to_spec_begin(Plan& p, Fused& f, int slot) {
 }
 static int ex_wait(Plan& p, int ev) { return (p.nprocs == 1 || (p.fused && p.fused->chunked_now)) ? 0 : exchange_wait(p, ev); }
 
-static int fused_begin(Plan& p, Fused** fp, int nw, int nv, int nx) {
+static int fused_begin(Plan& p, Fused** fp, int nw, int nv, int nx, bool may_chunk = false) {
   if (fused_init(p, fp)) return 1;
   SX_REQUIRE(comm_ready(p), "multi-rank plan without a communicator: call sx_plan_set_comm or sx_plan_set_comm_callbacks");
-  return fused_reserve(p, **fp, nw, nv, nx);
+  return fused_reserve(p, **fp, nw, nv, nx, may_chunk && chunked(p, **fp));
+}
+
+// host-buffer entries (sx_hd_step_host): the upload of state field i is still in flight on the copy stream; the first
+// kernel that reads it waits for its event (once)
+static int consume_wait(Plan& p, int i) {
+  if (p.pre_wait[i]) {
+    SX_CUDA_CHECK(cudaStreamWaitEvent(p.stream, p.pre_wait[i], 0));
+    p.pre_wait[i] = nullptr;
+  }
+  return 0;
 }
 
 // inverse half shared by HD and BOUSS: q_c -> V[c], V[NC+c] (dy), V[2NC+c] (dz)
 template <int NC> static int gradient_fields_to_real(Plan& p, Fused& f, const cplx* const* q) {
   for (int c = 0; c < NC; ++c) {
+    if (c < 3 && consume_wait(p, c)) return 1;
     if (fused_zinv(p, f, q[c], f.W[2 * c], f.W[2 * c + 1])) return 1;
     if (to_real_begin(p, f, 2 * c) || to_real_begin(p, f, 2 * c + 1)) return 1;
   }
@@ -190,6 +216,7 @@ static bool chunked(const Plan& p, const Fused& f) {
   return p.nprocs > 1 && f.p2p && p.knob_zchunks > 1 && p.knob_zchunks <= 8;
 }
 
+
 template <int NC> static int xy_stage_chunked(Plan& p, Fused& f, const cplx* const* q) {
   const int nch = p.knob_zchunks;
   int xs_me, xc_me;
@@ -201,6 +228,7 @@ template <int NC> static int xy_stage_chunked(Plan& p, Fused& f, const cplx* con
   }
   // z stage: all inverse fields (the local block goes straight into R when the tensor-map kernel runs)
   for (int c = 0; c < NC; ++c) {
+    if (c < 3 && consume_wait(p, c)) return 1;
     if (fused_zinv(p, f, q[c], f.W[2 * c], f.W[2 * c + 1])) return 1;
     if (p2p_mark(p, c)) return 1;
   }
@@ -311,7 +339,7 @@ int fused_p2p_import(Plan& p, const void* handles) {
 // hd_rkstep2.f90:3-36.  st[0..2] v, st[3] pr, st[4..6] f, st[7..9] RK base.
 int hd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, const double* zs, const double* ze) {
   Fused* fp;
-  if (fused_begin(p, &fp, 6, 9, 3)) return 1;
+  if (fused_begin(p, &fp, 6, 9, 3, true)) return 1;
   Fused& f = *fp;
   const double rmp = 1.0 / (double)o;
   f.chunked_now = false;
@@ -328,6 +356,7 @@ int hd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, cons
     if (ex_wait(p, 16 + c)) return 1;
     if (fused_zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk, dt, rmp)) return 1;
   }
+  if (consume_wait(p, 3)) return 1;
   return fused_project(p, f, st[0], st[1], st[2], st[3], o, zs, ze);
 }
 
@@ -339,7 +368,7 @@ int a_imposebc_and_project(Plan& p, cplx* ax, cplx* ay, cplx* az, cplx* ph);
 int bouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double kappa, double xmom, double xtemp,
                         const double* zs, const double* ze) {
   Fused* fp;
-  if (fused_begin(p, &fp, 8, 12, 4)) return 1;
+  if (fused_begin(p, &fp, 8, 12, 4, true)) return 1;
   Fused& f = *fp;
   const double rmp = 1.0 / (double)o;
   const cplx* q[4] = {st[0], st[1], st[2], st[10]};
@@ -377,7 +406,7 @@ int rot_couple(Plan& p, cplx* const* f, const double* om, double xmom, cplx* cx,
 int rotbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double kappa, double xmom,
                            double xtemp, const double* om, const double* zs, const double* ze) {
   Fused* fp;
-  if (fused_begin(p, &fp, 8, 12, 4)) return 1;
+  if (fused_begin(p, &fp, 8, 12, 4, true)) return 1;
   Fused& f = *fp;
   const double rmp = 1.0 / (double)o;
   cplx* cpl[3];

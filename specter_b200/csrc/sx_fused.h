@@ -45,6 +45,12 @@ struct Fused {
   bool chunked_now = false;   // the current substep ran the chunked pipeline (its exchanges are already waited for)
   int z0() const { return zwc < 0 ? 0 : zw0; }
   int zc() const { return zwc < 0 ? nzf : zwc; }
+  // The [zl][y][kx] arrays V / X only live between the y-inverse and the y-forward kernels of one z window: the
+  // chunked pipeline allocates them for the rows of ONE chunk (vwin) and every chunk reuses them from row 0, which is
+  // what lets 2048 x 2048 x 1024 on 8 GPUs fit 180 GB (V[9] + X[3] are 12 of the 40 work fields otherwise).
+  int vrows = 0;        // rows the V / X pools are allocated for
+  bool vwin = false;    // this substep addresses V / X relative to the current z window
+  size_t vz0() const { return vwin ? 0 : (size_t)z0(); }
 };
 
 inline void range0(int n, int nprocs, int r, int* sta, int* cnt) {  // `range` on [0,n)

@@ -468,7 +468,7 @@ template <int N> static int run_yinv_tma(Plan& p, Fused& f, const cplx* in, cplx
   if (f.nzf == 0) return 0;
   InvTmaMaps m0, m1;
   m0.nblocks = m1.nblocks = 0;
-  const size_t zo = (size_t)f.z0() * p.ny * f.nxp;   // z window of the [zl][y][kx] outputs
+  const size_t zo = f.vz0() * p.ny * f.nxp;   // z window of the [zl][y][kx] outputs
   if (f.zc() == 0) return 0;
   if (add_block(m0, out0 + zo, f.nxp, 0, N, f.zc(), f.nxp, (size_t)p.ny * f.nxp, NP)) return 1;
   if (add_block(m1, (out1 ? out1 : out0) + zo, f.nxp, 0, N, f.zc(), f.nxp, (size_t)p.ny * f.nxp, NP)) return 1;
@@ -496,8 +496,8 @@ template <int N> static int run_yfwd_tma(Plan& p, Fused& f, const cplx* in, cplx
   if (f.nzf == 0) return 0;
   TmaMap min;
   if (f.zc() == 0) return 0;
-  if (tma_encode(&min, in + (size_t)f.z0() * p.ny * f.nxp, f.nxp, p.ny, f.zc(), f.nxp, (size_t)p.ny * f.nxp, NP, G::ROWS)) return 1;
-  YfwdArgs a{in + (size_t)f.z0() * p.ny * f.nxp, out + (size_t)f.z0() * N, p.nxh, f.nxp, f.nzf, f.zc(),
+  if (tma_encode(&min, in + f.vz0() * p.ny * f.nxp, f.nxp, p.ny, f.zc(), f.nxp, (size_t)p.ny * f.nxp, NP, G::ROWS)) return 1;
+  YfwdArgs a{in + f.vz0() * p.ny * f.nxp, out + (size_t)f.z0() * N, p.nxh, f.nxp, f.nzf, f.zc(),
              {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, {0}, 0};
   if (yfwd_peers(p, f, out, a)) return 1;
   auto kfn = k_yfwd_tma<N, NP, MINB>;
@@ -532,7 +532,7 @@ template <int N> static int run_yinv(Plan& p, Fused& f, const cplx* in, cplx* ou
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
   if (const int rc = run_yinv_tma<N>(p, f, in, out0, out1); rc >= 0) return rc;
   if (f.zc() == 0) return 0;
-  const size_t zo = (size_t)f.z0() * N * f.nxp;
+  const size_t zo = f.vz0() * N * f.nxp;
   YinvArgs a{in + (size_t)f.z0() * N, out0 + zo, out1 ? out1 + zo : nullptr, p.d_ky, p.nxh, f.nxp, f.nzf, f.zc()};
   const cplx* tw = p.tw_y;
   int grid;
@@ -553,7 +553,7 @@ template <int N> static int run_yfwd(Plan& p, Fused& f, const cplx* in, cplx* ou
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
   if (const int rc = run_yfwd_tma<N>(p, f, in, out); rc >= 0) return rc;
   if (f.zc() == 0) return 0;
-  YfwdArgs a{in + (size_t)f.z0() * p.ny * f.nxp, out + (size_t)f.z0() * N, p.nxh, f.nxp, f.nzf, f.zc(),
+  YfwdArgs a{in + f.vz0() * p.ny * f.nxp, out + (size_t)f.z0() * N, p.nxh, f.nxp, f.nzf, f.zc(),
              {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, {0}, 0};
   if (yfwd_peers(p, f, out, a)) return 1;
   const cplx* tw = p.tw_y;

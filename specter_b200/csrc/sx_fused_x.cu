@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_cross(XcrossArgs a, 
 // ui < 0: gradre / advect of q = V[0..NC) by its own first three components into X[0..NC);
 // ui >= 0 (NC = 1): the scalar q = V[qi], dy q = V[qi+1], dz q = V[qi+2] advected by V[ui..ui+2] into X[xo]
 static void xpass_fields(Plan& p, Fused& f, XpassArgs& a, int NC, int ui, int qi, int xo) {
-  const size_t zo = (size_t)f.z0() * p.ny * f.nxp;   // z window of the [zl][y][kx] arrays
+  const size_t zo = f.vz0() * p.ny * f.nxp;   // z window of the [zl][y][kx] arrays
   for (int i = 0; i < 12; ++i) a.V[i] = nullptr;
   for (int i = 0; i < 4; ++i) a.X[i] = nullptr;
   for (int i = 0; i < 3; ++i) a.U[i] = ui >= 0 ? f.V[ui + i] + zo : nullptr;
@@ -498,13 +498,13 @@ template <int N> static int run_xcross(Plan& p, Fused& f, int npairs, const int*
   XcrossArgs a;
   for (int q = 0; q < 2; ++q)
     for (int c = 0; c < 3; ++c) {
-      a.P[q][c] = f.V[Pi[q < npairs ? q : 0] + c] + (size_t)f.z0() * p.ny * f.nxp;
-      a.Q[q][c] = f.V[Qi[q < npairs ? q : 0] + c] + (size_t)f.z0() * p.ny * f.nxp;
+      a.P[q][c] = f.V[Pi[q < npairs ? q : 0] + c] + f.vz0() * p.ny * f.nxp;
+      a.Q[q][c] = f.V[Qi[q < npairs ? q : 0] + c] + f.vz0() * p.ny * f.nxp;
     }
   a.sgn[0] = sgn[0];
   a.sgn[1] = npairs > 1 ? sgn[1] : 0.0;
   a.npairs = npairs;
-  for (int c = 0; c < 3; ++c) a.X[c] = f.X[xo + c] + (size_t)f.z0() * p.ny * f.nxp;
+  for (int c = 0; c < 3; ++c) a.X[c] = f.X[xo + c] + f.vz0() * p.ny * f.nxp;
   a.ny = p.ny;
   a.nxp = f.nxp;
   a.nzf = f.zc();

@@ -46,6 +46,11 @@ struct Plan {
   cplx *tw_x = nullptr, *tw_y = nullptr, *tw_z = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // sx_plan_time_begin/end
+  // host-buffer step (sx_hd_step_host): copy stream, one event per uploaded state field, and the events the fused
+  // substep still has to wait for before it first reads vx, vy, vz, pr (consumed by sx_fused.cu)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t h2d_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pre_wait[4] = {nullptr, nullptr, nullptr, nullptr};
   // scratch pool (lazily grown): complex spectral-sized and real-sized work arrays
   std::vector<cplx*> cwork;
   std::vector<double*> rwork;
@@ -66,6 +71,7 @@ struct Plan {
   StageTimer timer;
   int num_sms = 148;                // multiProcessorCount of the device
   int knob_zf = 0;
+  int knob_zs = 0;                  // z-stage variant (env SX_ZS): 0 = merged z-forward / RK / projection kernel where it applies, 1 = separate kernels
   int knob_xp = 0, knob_pj = 0;     // kernel-variant experiments (env SX_XP, SX_PJ)
   int knob_pf = 13;                 // cp.async prefetch per tile kernel: bit 0 zinv, 1 yinv, 2 yfwd, 3 zfwd (env SX_TILE_PF)
   int knob_tma = 3;                 // bulk-copy (TMA) tile kernels: bit 0 zinv, 1 yinv, 2 yfwd, 3 zfwd (env SX_TMA)

@@ -111,14 +111,41 @@ int sx_hd_rkstep2(sx_plan* plan, int o, double dt, double nu, const double v_zst
   return hd_rkstep2_fused(p, s->f, o, dt, nu, v_zsta, v_zend);
 }
 
+// One whole time step on HOST arrays (in place).  fx / fy / fz may be NULL: the forcing uploaded by an earlier call
+// (or by sx_hd_put_state) is kept -- a constant body force is 3 of the 7 input fields.  The uploads run on a copy
+// stream, each followed by the rkstep1 copy of that component; the first kernel of the first substep that reads a
+// field waits for that field only (Plan::pre_wait), so the z-inverse of vx runs while vy, vz and pr still travel.
 int sx_hd_step_host(sx_plan* plan, double* vx, double* vy, double* vz, double* pr, const double* fx,
                     const double* fy, const double* fz, double dt, double nu, const double v_zsta[2],
                     const double v_zend[2]) {
   SX_PLAN(plan);
-  if (sx_hd_put_state(plan, vx, vy, vz, pr, fx, fy, fz)) return 1;
-  if (sx_hd_rkstep1(plan)) return 1;
-  for (int o = p.ord; o >= 1; --o)
-    if (sx_hd_rkstep2(plan, o, dt, nu, v_zsta, v_zend, 0)) return 1;
+  SX_REQUIRE(vx && vy && vz && pr, "sx_hd_step_host: vx, vy, vz, pr must not be NULL");
+  HdState* s;
+  if (hd_state(p, &s)) return 1;
+  if (!p.copy_stream) {
+    SX_CUDA_CHECK(cudaStreamCreateWithFlags(&p.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) SX_CUDA_CHECK(cudaEventCreateWithFlags(&p.h2d_ev[i], cudaEventDisableTiming));
+  }
+  const size_t bytes = p.csize() * sizeof(cplx);
+  SX_CUDA_CHECK(cudaStreamSynchronize(p.stream));   // nothing in flight still reads the state that is overwritten
+  const double* fh[3] = {fx, fy, fz};
+  for (int i = 0; i < 3; ++i)
+    if (fh[i]) SX_CUDA_CHECK(cudaMemcpyAsync(s->f[4 + i], fh[i], bytes, cudaMemcpyHostToDevice, p.copy_stream));
+  double* h[4] = {vx, vy, vz, pr};
+  for (int i = 0; i < 4; ++i) {
+    SX_CUDA_CHECK(cudaMemcpyAsync(s->f[i], h[i], bytes, cudaMemcpyHostToDevice, p.copy_stream));
+    if (i < 3)   // rkstep1 (hd_rkstep1.f90:4-6)
+      SX_CUDA_CHECK(cudaMemcpyAsync(s->f[7 + i], s->f[i], bytes, cudaMemcpyDeviceToDevice, p.copy_stream));
+    SX_CUDA_CHECK(cudaEventRecord(p.h2d_ev[i], p.copy_stream));
+    p.pre_wait[i] = p.h2d_ev[i];
+  }
+  int rc = 0;
+  for (int o = p.ord; o >= 1 && !rc; --o) rc = sx_hd_rkstep2(plan, o, dt, nu, v_zsta, v_zend, 0);
+  for (int i = 0; i < 4; ++i) p.pre_wait[i] = nullptr;
+  if (rc) {
+    cudaStreamSynchronize(p.copy_stream);
+    return 1;
+  }
   return sx_hd_get_state(plan, vx, vy, vz, pr);
 }
 

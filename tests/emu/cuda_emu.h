@@ -208,6 +208,8 @@ static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event(); return 0; }
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new emu_event(); return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0) { e->t = std::chrono::steady_clock::now(); return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }

@@ -102,3 +102,33 @@ def test_argument_errors_on_emulated_build(emu_lib, tables):
         p.hd_rkstep2(3, 1e-3, 1e-3)
     assert api.sx_range(1, 33, 8, 0, lib=emu_lib) == (1, 5)
     p.close()
+
+
+def test_stage_timing_survives_more_marks_than_one_flush(emu_lib, tables):
+    # with stage timing on, the 8192nd mark flushed, and the closing mark of that flush flushed again
+    # (unbounded recursion -> segfault after ~150 HD steps of examples/hd_driver.c).  More than 8192 marks must work,
+    # and all of them must be counted.
+    p = api.Plan(16, 16, 16, 0, 0, tdir=tables, lib=emu_lib)
+    a = p.spectral()
+    p.stage_timing(True)
+    n = 8192 + 300
+    for _ in range(n):
+        p.fc_filter(a)
+    st = p.stage_times()
+    assert sum(c for _, c in st.values()) == n
+    p.stage_timing(False)
+    p.close()
+
+
+def test_tuning_knobs_are_validated(emu_lib, tables):
+    # a stray value of a tuning variable must fail plan creation instead of selecting an untested variant
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\nfrom specter_b200 import api\n"
+            "lib = api.Library(%r)\n"
+            "try:\n    api.Plan(16, 16, 64, 25, 5, tdir=%r, lib=lib)\n    print('created')\n"
+            "except api.SpecterError as e:\n    print('refused:', e)\n" % (ROOT, emu_lib.path, tables))
+    for var, val, ok in (("SX_ZCHUNKS", "0", False), ("SX_XP", "abc", False), ("SX_TILE_NP", "64", False), ("SX_ZCHUNKS", "2", True)):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **{var: val}))
+        assert r.returncode == 0, r.stderr
+        assert ("created" in r.stdout) == ok and (ok or var in r.stdout), (var, val, r.stdout)

@@ -117,6 +117,18 @@ def test_hd_substeps_length_1024_2048_kernels(cuda_lib, tables):
     P.case_hd_substeps(cuda_lib, tables, (16, 16, 1024), ord=2, nsteps=1, impl=0)
 
 
+def test_mhd_bouss_baseline_lengths(cuda_lib, tables):
+    """The kernel instantiations of BASELINE configs[3] (MHD 512^3: cross-product x pass, conducting-wall kernels at
+    nz = 512) and configs[2] (BOUSS 1024x1024x512: four-component x pass at nx = 1024), one axis at a time on grids the
+    oracle finishes in seconds."""
+    P.case_mhd_substeps(cuda_lib, tables, (512, 16, 64), ord=2, nsteps=1, impl=0)
+    P.case_mhd_substeps(cuda_lib, tables, (16, 512, 64), ord=2, nsteps=1, impl=0)
+    P.case_mhd_substeps(cuda_lib, tables, (16, 16, 512), ord=2, nsteps=1, impl=0)
+    P.case_bouss_substeps(cuda_lib, tables, (1024, 16, 64), ord=2, nsteps=1, impl=0)
+    P.case_bouss_substeps(cuda_lib, tables, (16, 1024, 64), ord=2, nsteps=1, impl=0)
+    P.case_bouss_substeps(cuda_lib, tables, (16, 16, 512), ord=2, nsteps=1, impl=0)
+
+
 def test_io_output_restart(cuda_lib, tables, tmp_path):
     P.case_io_output_restart(cuda_lib, tables, CFG1, tmp_path)
 
