@@ -19,6 +19,18 @@ def rel(x, y):
     return float(np.abs(x - y).max()) / (d if d > 0 else 1.0)
 
 
+def pr_close(got_pr, want_pr, nph, vfields):
+    """p' = dt_sub * p (mixed domain, physical rows).  It is a dt-sized difference of O(|v|) quantities (the wall
+    values of v_z and the particular solution -i k.v/k^2), and it only re-enters the path as i k p'_wall added to the
+    wall rows of v (vboundary.f90:195-196): its error is held to 1e-9 of its own maximum, or -- on thin grids where
+    |p'| / |v| ~ 1e-5 -- to 1e-11 of the velocity maximum, the scale it is formed from and acts on."""
+    a, b = got_pr[:, :, :nph], want_pr[:, :, :nph]
+    err = float(np.abs(a - b).max())
+    vscale = max(float(np.abs(q).max()) for q in vfields)
+    pscale = float(np.abs(b).max())
+    assert err <= 100 * TOL_FIELD * pscale or err <= TOL_FIELD * vscale, (err, pscale, vscale)
+
+
 def make(lib, tables, nx, ny, nz, Cz=25, oz=5, ord=2, Lx=1.0, Ly=0.5, Lz=1.0):
     g = O.Grid(nx, ny, nz, Cz, oz, Lx=Lx, Ly=Ly, Lz=Lz, tdir=tables if Cz else "", ord=ord)
     p = api.Plan(nx, ny, nz, Cz, oz, ord=ord, Lx=Lx, Ly=Ly, Lz=Lz, tdir=tables if Cz else "", lib=lib)
@@ -391,7 +403,7 @@ def case_bouss_substeps(lib, tables, shape, ord=2, nsteps=1, impl=0, dt=1e-3, nu
             fields_close(got[:3], (s.vx, s.vy, s.vz))
             phys_close(g, [got[4]], [s.th])
             fields_close([got[4]], [s.th], tol=TOL_RECONTINUED)
-            assert rel(got[3][:, :, :nph], s.pr[:, :, :nph]) < 100 * TOL_FIELD
+            pr_close(got[3], s.pr, nph, (s.vx, s.vy, s.vz))
     p.close()
 
 
@@ -410,7 +422,7 @@ def case_mhd_substeps(lib, tables, shape, ord=2, nsteps=1, impl=0, dt=1e-3, nu=1
             got = p.mhd_get_state()
             fields_close(got[:3], (s.vx, s.vy, s.vz))
             fields_close(got[4:7], (s.ax, s.ay, s.az))
-            assert rel(got[3][:, :, :nph], s.pr[:, :, :nph]) < 100 * TOL_FIELD
+            pr_close(got[3], s.pr, nph, (s.vx, s.vy, s.vz))
             fields_close([got[7]], [s.ph], rows=nph, tol=100 * TOL_FIELD)
     p.close()
 
@@ -569,7 +581,7 @@ def case_rotbouss_substeps(lib, tables, shape, ord=2, nsteps=1, impl=0, dt=1e-3,
             got = p.bouss_get_state()
             fields_close(got[:3], (s.vx, s.vy, s.vz))
             fields_close([got[4]], [s.th])
-            assert rel(got[3][:, :, :nph], s.pr[:, :, :nph]) < 100 * TOL_FIELD
+            pr_close(got[3], s.pr, nph, (s.vx, s.vy, s.vz))
     p.close()
 
 
@@ -593,7 +605,7 @@ def case_mhdbouss_substeps(lib, tables, shape, ord=2, nsteps=1, dt=1e-3, nu=1e-3
             fields_close(got[4:7], (s.ax, s.ay, s.az))
             phys_close(g, [got[8]], [s.th])
             fields_close([got[8]], [s.th], tol=TOL_RECONTINUED)
-            assert rel(got[3][:, :, :nph], s.pr[:, :, :nph]) < 100 * TOL_FIELD
+            pr_close(got[3], s.pr, nph, (s.vx, s.vy, s.vz))
             fields_close([got[7]], [s.ph], rows=nph, tol=100 * TOL_FIELD)
     p.close()
 
