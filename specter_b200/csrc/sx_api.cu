@@ -75,7 +75,7 @@ static int upload_twiddles(int n, cplx** d) {
 
 const char* stage_name(int id) {
   static const char* names[ST_COUNT] = {"other", "zfft", "yfft", "xfft", "elementwise", "reduce", "zinv_tile",
-                                        "yinv_tile", "xpass", "yfwd_tile", "zfwd_rk", "project", "exchange"};
+                                        "yinv_tile", "xpass", "yfwd_tile", "zfwd_rk", "project", "zstage", "exchange"};
   return (id >= 0 && id < ST_COUNT) ? names[id] : "?";
 }
 int stage_mark_slow(Plan& p, int id) {

@@ -260,6 +260,113 @@ __device__ __forceinline__ void fft_regs(cplx (&v)[8], int j, cplx* s, const SI&
 #endif
 }
 
+// ---- two transforms at once ------------------------------------------------------------------------------------
+// Two independent pencils per thread (v, w: same length, possibly different directions) share every barrier and the
+// twiddle powers of each pass: twice the independent work between two barriers and half the barriers per transform,
+// which is what the transform-bound z-stage kernel needs at 8 warps per SM.  s0 / s1 are two exchange buffers.
+template <int D, bool CONJ> __device__ __forceinline__ cplx tw_dir(cplx w) {   // table twiddles are the forward (-1) ones
+  (void)D;
+  return CONJ ? cmake(w.x, -w.y) : w;
+}
+template <int N, int D0, int D1, int P, class SI>
+__device__ __forceinline__ void fft_pass2(cplx (&v)[8], cplx (&w)[8], const int j, cplx* s0, cplx* s1, const SI& si,
+                                          const TwRegs<N>& twr) {
+  typedef Fft1D<N> F;
+  constexpr int r = F::radix(P), nb = 8 / r, Ns = F::ns(P), T = F::T;
+  constexpr bool first = (P == 0), last = (P == F::npass - 1);
+#ifdef SX_SWIZZLE
+  constexpr bool linear = false;
+#else
+  constexpr bool linear = (T % 8 == 0);
+#endif
+  if (!first) {
+    if constexpr (linear) {
+      const int g0 = si(j);
+#pragma unroll
+      for (int b = 0; b < nb; ++b) {
+#pragma unroll
+        for (int m = 0; m < r; ++m) {
+          v[b + m * nb] = s0[g0 + si.stride(b * T + m * (N / r))];
+          w[b + m * nb] = s1[g0 + si.stride(b * T + m * (N / r))];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < nb; ++b) {
+#pragma unroll
+        for (int m = 0; m < r; ++m) {
+          v[b + m * nb] = s0[si(j + b * T + m * (N / r))];
+          w[b + m * nb] = s1[si(j + b * T + m * (N / r))];
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < nb; ++b) {
+      // powers of the forward root; a backward transform multiplies by their conjugates
+      const cplx w1 = twr.w[TwSlots<N>::off(P) + b];
+      cplx pw[8];
+      pw[1] = w1;
+      if constexpr (r >= 4) {
+        pw[2] = csqr(w1);
+        pw[3] = cmul(pw[2], w1);
+        if constexpr (r == 8) {
+          pw[4] = csqr(pw[2]);
+          pw[5] = cmul(pw[4], w1);
+          pw[6] = csqr(pw[3]);
+          pw[7] = cmul(pw[4], pw[3]);
+        }
+      }
+#pragma unroll
+      for (int m = 1; m < r; ++m) {
+        v[b + m * nb] = cmul(v[b + m * nb], tw_dir<D0, (D0 > 0)>(pw[m]));
+        w[b + m * nb] = cmul(w[b + m * nb], tw_dir<D1, (D1 > 0)>(pw[m]));
+      }
+    }
+  }
+  butterflies<r, D0>(v);
+  butterflies<r, D1>(w);
+  if (!last) {
+    __syncthreads();  // WAR: everybody has finished reading both buffers
+#pragma unroll
+    for (int b = 0; b < nb; ++b) {
+      const int jb = j + b * T;
+      const int j0 = (jb / Ns) * (Ns * r) + (jb & (Ns - 1));
+      if constexpr (linear) {
+        const int q0 = si(j0);
+#pragma unroll
+        for (int m = 0; m < r; ++m) {
+          s0[q0 + si.stride(m * Ns)] = v[b + m * nb];
+          s1[q0 + si.stride(m * Ns)] = w[b + m * nb];
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < r; ++m) {
+          s0[si(j0 + m * Ns)] = v[b + m * nb];
+          s1[si(j0 + m * Ns)] = w[b + m * nb];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+template <int N, int D0, int D1, int P, class SI>
+__device__ __forceinline__ void fft_run2(cplx (&v)[8], cplx (&w)[8], int j, cplx* s0, cplx* s1, const SI& si,
+                                         const TwRegs<N>& twr) {
+  fft_pass2<N, D0, D1, P, SI>(v, w, j, s0, s1, si, twr);
+  if constexpr (P + 1 < Fft1D<N>::npass) fft_run2<N, D0, D1, P + 1, SI>(v, w, j, s0, s1, si, twr);
+}
+// v, w <-> elements j + k*T on entry and exit; every thread of the CTA calls this together
+template <int N, int D0, int D1, class SI>
+__device__ __forceinline__ void fft_regs2(cplx (&v)[8], cplx (&w)[8], int j, cplx* s0, cplx* s1, const SI& si,
+                                          const TwRegs<N>& twr) {
+#ifdef SX_NOFFT
+  (void)v; (void)w; (void)j; (void)s0; (void)s1; (void)si; (void)twr;
+  __syncthreads();
+#else
+  fft_run2<N, D0, D1, 0, SI>(v, w, j, s0, s1, si, twr);
+#endif
+}
+
 // host: twiddle table for Fft1D<N> (forward sign), long-double accurate
 void build_twiddles(int N, cplx* out, int* count);
 int twiddle_count(int N);

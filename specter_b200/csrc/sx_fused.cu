@@ -336,6 +336,29 @@ int fused_p2p_import(Plan& p, const void* handles) {
 #endif
 }
 
+// velocity part of every solver's substep: nonlinear terms Uz[0..2] -> RK update of st[0..2] (base st[7..9], forcing
+// st[4..6]) -> v_imposebc_and_project.  One kernel (sx_fused_zstage.cu), or the three z-forward / RK launches and the
+// projection kernel (SX_ZS=1).
+static int velocity_zstage(Plan& p, Fused& f, cplx* const* st, const RkTerm* rk, int o, double dt, double rmp,
+                           const double* zs, const double* ze) {
+  if (zstage_enabled(p)) {
+    for (int c = 0; c < 3; ++c)
+      if (ex_wait(p, 16 + c)) return 1;
+    if (consume_wait(p, 3)) return 1;
+    const cplx* nl[3] = {f.Uz[0], f.Uz[1], f.Uz[2]};
+    cplx* v[3] = {st[0], st[1], st[2]};
+    const cplx* v0[3] = {st[7], st[8], st[9]};
+    const cplx* frc[3] = {st[4], st[5], st[6]};
+    return fused_zstage(p, f, nl, v, v0, frc, rk, st[3], o, dt, rmp, zs, ze);
+  }
+  for (int c = 0; c < 3; ++c) {
+    if (ex_wait(p, 16 + c)) return 1;
+    if (fused_zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk[c], dt, rmp)) return 1;
+  }
+  if (consume_wait(p, 3)) return 1;
+  return fused_project(p, f, st[0], st[1], st[2], st[3], o, zs, ze);
+}
+
 // hd_rkstep2.f90:3-36.  st[0..2] v, st[3] pr, st[4..6] f, st[7..9] RK base.
 int hd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, const double* zs, const double* ze) {
   Fused* fp;
@@ -350,14 +373,9 @@ int hd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, cons
     if (fused_xpass(p, f, 3, p.d_kxg)) return 1;
     if (nonlinear_to_spectral_begin(p, f, 3)) return 1;
   }
-  RkTerm rk;
-  rk.cL = nu;
-  for (int c = 0; c < 3; ++c) {
-    if (ex_wait(p, 16 + c)) return 1;
-    if (fused_zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk, dt, rmp)) return 1;
-  }
-  if (consume_wait(p, 3)) return 1;
-  return fused_project(p, f, st[0], st[1], st[2], st[3], o, zs, ze);
+  RkTerm rk[3];
+  for (int c = 0; c < 3; ++c) rk[c].cL = nu;
+  return velocity_zstage(p, f, st, rk, o, dt, rmp, zs, ze);
 }
 
 int s_imposebc(Plan& p, cplx* th);
@@ -386,14 +404,13 @@ int bouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, d
   rt.cL = kappa; rt.couple = st[2]; rt.ccoef = -xtemp;
   if (ex_wait(p, 16 + 3)) return 1;
   if (fused_zfwd_rk(p, f, f.Uz[3], st[10], st[13], st[12], st[11], rt, dt, rmp)) return 1;
-  for (int c = 0; c < 3; ++c) {
-    RkTerm rk;
-    rk.cL = nu;
-    if (c == 2) { rk.couple = st[10]; rk.ccoef = -xmom; }
-    if (ex_wait(p, 16 + c)) return 1;
-    if (fused_zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk, dt, rmp)) return 1;
+  {
+    RkTerm rk[3];
+    for (int c = 0; c < 3; ++c) rk[c].cL = nu;
+    rk[2].couple = st[10];
+    rk[2].ccoef = -xmom;
+    if (velocity_zstage(p, f, st, rk, o, dt, rmp, zs, ze)) return 1;
   }
-  if (fused_project(p, f, st[0], st[1], st[2], st[3], o, zs, ze)) return 1;
   // s_imposebc, fc_filter and the theta round trip (bouss_rkstep2.f90:53-59); all pencil-local
   return s_imposebc(p, st[13]) || op_fc_filter(p, st[13]) || theta_roundtrip(p, st[13], st[10]);
 }
@@ -425,13 +442,11 @@ int rotbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu
   rt.cL = kappa; rt.couple = st[2]; rt.ccoef = -xtemp;
   if (ex_wait(p, 16 + 3)) return 1;
   if (fused_zfwd_rk(p, f, f.Uz[3], st[10], st[10], st[12], st[11], rt, dt, rmp)) return 1;
-  for (int c = 0; c < 3; ++c) {
-    RkTerm rk;
-    rk.cL = nu; rk.couple = cpl[c]; rk.ccoef = 1.0;
-    if (ex_wait(p, 16 + c)) return 1;
-    if (fused_zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk, dt, rmp)) return 1;
+  {
+    RkTerm rk[3];
+    for (int c = 0; c < 3; ++c) { rk[c].cL = nu; rk[c].couple = cpl[c]; rk[c].ccoef = 1.0; }
+    if (velocity_zstage(p, f, st, rk, o, dt, rmp, zs, ze)) return 1;
   }
-  if (fused_project(p, f, st[0], st[1], st[2], st[3], o, zs, ze)) return 1;
   return s_imposebc(p, st[10]);
 }
 
@@ -474,11 +489,10 @@ int mhd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, dou
     if (fused_xcross(p, f, 1, Pe, Qe, se, 3)) return 1;
   }
   if (nonlinear_to_spectral_begin(p, f, 6)) return 1;
-  for (int c = 0; c < 3; ++c) {
-    RkTerm rk;
-    rk.cL = nu;
-    if (ex_wait(p, 16 + c)) return 1;
-    if (fused_zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk, dt, rmp)) return 1;
+  {
+    RkTerm rk[3];
+    for (int c = 0; c < 3; ++c) rk[c].cL = nu;
+    if (velocity_zstage(p, f, st, rk, o, dt, rmp, nullptr, nullptr)) return 1;
   }
   for (int c = 0; c < 3; ++c) {
     RkTerm rk;
@@ -486,7 +500,6 @@ int mhd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, dou
     if (ex_wait(p, 16 + 3 + c)) return 1;
     if (fused_zfwd_rk(p, f, f.Uz[3 + c], st[10 + c], st[10 + c], st[17 + c], st[14 + c], rk, dt, rmp)) return 1;
   }
-  if (fused_project(p, f, st[0], st[1], st[2], st[3], o, nullptr, nullptr)) return 1;
   return a_imposebc_and_project(p, ax, ay, az, st[13]);
 }
 
@@ -542,12 +555,12 @@ int mhdbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu
   rt.cL = kappa; rt.couple = st[2]; rt.ccoef = -xtemp;
   if (ex_wait(p, 16 + 6)) return 1;
   if (fused_zfwd_rk(p, f, f.Uz[6], th, thn, st[22], st[21], rt, dt, rmp)) return 1;
-  for (int c = 0; c < 3; ++c) {
-    RkTerm rk;
-    rk.cL = nu;
-    if (c == 2) { rk.couple = th; rk.ccoef = -xmom; }
-    if (ex_wait(p, 16 + c)) return 1;
-    if (fused_zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk, dt, rmp)) return 1;
+  {
+    RkTerm rk[3];
+    for (int c = 0; c < 3; ++c) rk[c].cL = nu;
+    rk[2].couple = th;
+    rk[2].ccoef = -xmom;
+    if (velocity_zstage(p, f, st, rk, o, dt, rmp, nullptr, nullptr)) return 1;
   }
   for (int c = 0; c < 3; ++c) {
     RkTerm rk;
@@ -555,7 +568,6 @@ int mhdbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu
     if (ex_wait(p, 16 + 3 + c)) return 1;
     if (fused_zfwd_rk(p, f, f.Uz[3 + c], st[10 + c], st[10 + c], st[17 + c], st[14 + c], rk, dt, rmp)) return 1;
   }
-  if (fused_project(p, f, st[0], st[1], st[2], st[3], o, nullptr, nullptr)) return 1;
   if (a_imposebc_and_project(p, ax, ay, az, st[13])) return 1;
   return s_imposebc(p, thn) || theta_roundtrip(p, thn, th);
 }

@@ -15,7 +15,7 @@ struct SolverState;  // BOUSS / MHD device state (sx_solvers.cu)
 // fftp_mod.fpp:32-37, re-cast per kernel family).
 enum Stage {
   ST_OTHER = 0, ST_ZFFT, ST_YFFT, ST_XFFT, ST_EW, ST_REDUCE,          // per-operator path
-  ST_ZINV, ST_YINV, ST_XPASS, ST_YFWD, ST_ZFWD_RK, ST_PROJECT, ST_EXCHANGE,  // fused substep
+  ST_ZINV, ST_YINV, ST_XPASS, ST_YFWD, ST_ZFWD_RK, ST_PROJECT, ST_ZSTAGE, ST_EXCHANGE,  // fused substep
   ST_COUNT
 };
 const char* stage_name(int id);

@@ -784,7 +784,8 @@ def case_full_size_properties(lib, tables, shape=(512, 512, 512), ord=4, dt=2e-4
     del back
     for d in (dr, dr2, dc, zero):
         d.free()
-    st = bench.synthetic_state(p)
+    bench.device_state(p, "hd")       # the bench's synthetic state, built in place on the device
+    st = p.hd_get_state() + [p.hd_field(4 + i).get() for i in range(3)]
     outs = []
     for impl in (0, 1):
         p.hd_put_state(*st)
