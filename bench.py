@@ -50,18 +50,17 @@ B_ALG = 440.0
 def stage_bytes_per_pt(r, solver="hd"):
     """Algorithmic bytes per grid point and SUBSTEP of each kernel family as built (DESIGN.md "Kernels"): F = 8 B per
     point per full-field read or write; r = physical rows / nz (only physical rows cross the transposition).
-    `zstage` is the merged z-forward / RK / projection kernel (HD, BOUSS velocity part); when it runs, `zfwd_rk`
-    only holds the launches that stay separate (theta in BOUSS, the potential in MHD)."""
+"""
     F = 8.0
     if solver == "hd":
         return {"zinv_tile": (3 + 6 * r) * F, "yinv_tile": 15 * r * F, "xpass": 12 * r * F, "yfwd_tile": 6 * r * F,
-                "zfwd_rk": (12 + 3 * r) * F, "project": 7 * F, "zstage": (13 + 3 * r) * F}
+                "zfwd_rk": (12 + 3 * r) * F, "project": 7 * F}
     if solver == "bouss":   # theta rides with v: 4 components, its z-forward reads v_z and v_z's reads theta
         return {"zinv_tile": (4 + 8 * r) * F, "yinv_tile": 20 * r * F, "xpass": 16 * r * F, "yfwd_tile": 8 * r * F,
-                "zfwd_rk": (18 + 4 * r) * F, "project": 7 * F, "zstage": (14 + 3 * r) * F, "zfwd_rk@zstage": (5 + r) * F}
+                "zfwd_rk": (18 + 4 * r) * F, "project": 7 * F}
     # MHD: 12 plain inverse fields (v, omega, B, J), two cross-product x passes (12 + 6 lines in, 3 + 3 out)
     return {"zinv_tile": 12 * (1 + r) * F, "yinv_tile": 24 * r * F, "xpass": 24 * r * F, "yfwd_tile": 12 * r * F,
-            "zfwd_rk": (24 + 6 * r) * F, "project": 7 * F, "zstage": (13 + 3 * r) * F, "zfwd_rk@zstage": (12 + 3 * r) * F}
+            "zfwd_rk": (24 + 6 * r) * F, "project": 7 * F}
 
 
 def sources_hash():
@@ -509,11 +508,10 @@ def main():
     stage_report, dominant = {}, None
     tot_ms = sum(v[0] for v in stages.values()) or 1.0
     model = stage_bytes_per_pt((nz - CZ) / nz, solver)
-    merged = "zstage" in stages
     for name, (sms, cnt) in stages.items():
         per_launch = sms / cnt
         launches_per_substep = cnt / (2.0 * ord_)
-        bpp = model.get(name + "@zstage") if (merged and name + "@zstage" in model) else model.get(name)
+        bpp = model.get(name)
         entry = {"ms_per_launch": per_launch, "launches_per_substep": launches_per_substep, "share": sms / tot_ms}
         if bpp:
             alg_bytes = bpp * npts / world / launches_per_substep

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["sx_api.cu", "sx_kernels_fft.cu", "sx_kernels_ops.cu", "sx_rkstep.cu", "sx_solvers.cu", "sx_fused.cu", "sx_fused_tiles.cu",
-           "sx_fused_zfwd.cu", "sx_fused_zstage.cu", "sx_fused_x.cu", "sx_fused_project.cu", "sx_tma.cu", "sx_io.cu", "sx_comm.cu", "sx_walls_diag.cu", "sx_boots.cu"]
+           "sx_fused_zfwd.cu", "sx_fused_x.cu", "sx_fused_project.cu", "sx_tma.cu", "sx_io.cu", "sx_comm.cu", "sx_walls_diag.cu", "sx_boots.cu"]
 LIB = os.path.join(CSRC, "libspecter_b200.so")
 EMU_DIR = os.path.join(ROOT, "tests", "emu", "_build")
 EMU_LIB = os.path.join(EMU_DIR, "libspecter_emu.so")

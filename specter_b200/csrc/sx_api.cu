@@ -75,7 +75,7 @@ static int upload_twiddles(int n, cplx** d) {
 
 const char* stage_name(int id) {
   static const char* names[ST_COUNT] = {"other", "zfft", "yfft", "xfft", "elementwise", "reduce", "zinv_tile",
-                                        "yinv_tile", "xpass", "yfwd_tile", "zfwd_rk", "project", "zstage", "exchange"};
+                                        "yinv_tile", "xpass", "yfwd_tile", "zfwd_rk", "project", "exchange"};
   return (id >= 0 && id < ST_COUNT) ? names[id] : "?";
 }
 int stage_mark_slow(Plan& p, int id) {
@@ -196,7 +196,7 @@ static int plan_init(Plan& p, const sx_config& c) {
   const Knob knobs[] = {{"SX_ZF", &p.knob_zf, 0, 7},          {"SX_XP", &p.knob_xp, 0, 19},      {"SX_PJ", &p.knob_pj, 0, 19},
                         {"SX_TILE_PF", &p.knob_pf, 0, 15},    {"SX_ZCHUNKS", &p.knob_zchunks, 1, 8}, {"SX_TMA", &p.knob_tma, 0, 15},
                         {"SX_TMA_MIN", &p.knob_tma_min, 16, 4096}, {"SX_INV_STAGES", &p.knob_inv_stages, 0, 3},
-                        {"SX_TILE_NP", &p.knob_np, 0, 32},    {"SX_TILE_MINB", &p.knob_minb, 1, 8}, {"SX_ZS", &p.knob_zs, 0, 9}};
+                        {"SX_TILE_NP", &p.knob_np, 0, 32},    {"SX_TILE_MINB", &p.knob_minb, 1, 8}};
   for (const Knob& k : knobs) {
     const char* e = getenv(k.name);
     if (!e || !*e) continue;

@@ -337,20 +337,12 @@ int fused_p2p_import(Plan& p, const void* handles) {
 }
 
 // velocity part of every solver's substep: nonlinear terms Uz[0..2] -> RK update of st[0..2] (base st[7..9], forcing
-// st[4..6]) -> v_imposebc_and_project.  One kernel (sx_fused_zstage.cu), or the three z-forward / RK launches and the
-// projection kernel (SX_ZS=1).
+// st[4..6]) -> v_imposebc_and_project.  Three z-forward / RK launches (memory-bound, 0.82 of the HBM peak) and the
+// projection kernel: a single merged kernel was built and measured in round 2 and LOST (7.4 ms against 5.8 ms: the
+// per-pencil state of the projection forces 8 warps per SM onto the streaming RK part as well;
+// profiles/r2_zstage_experiment.md), so the two stay separate.
 static int velocity_zstage(Plan& p, Fused& f, cplx* const* st, const RkTerm* rk, int o, double dt, double rmp,
                            const double* zs, const double* ze) {
-  if (zstage_enabled(p)) {
-    for (int c = 0; c < 3; ++c)
-      if (ex_wait(p, 16 + c)) return 1;
-    if (consume_wait(p, 3)) return 1;
-    const cplx* nl[3] = {f.Uz[0], f.Uz[1], f.Uz[2]};
-    cplx* v[3] = {st[0], st[1], st[2]};
-    const cplx* v0[3] = {st[7], st[8], st[9]};
-    const cplx* frc[3] = {st[4], st[5], st[6]};
-    return fused_zstage(p, f, nl, v, v0, frc, rk, st[3], o, dt, rmp, zs, ze);
-  }
   for (int c = 0; c < 3; ++c) {
     if (ex_wait(p, 16 + c)) return 1;
     if (fused_zfwd_rk(p, f, f.Uz[c], st[c], st[c], st[7 + c], st[4 + c], rk[c], dt, rmp)) return 1;

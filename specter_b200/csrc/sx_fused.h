@@ -176,9 +176,5 @@ int fused_xadvect(Plan& p, Fused& f, int ui, int qi, int xo, const double* kxg);
 int fused_zfwd_rk(Plan& p, Fused& f, const cplx* nl, const cplx* v, cplx* vout, const cplx* v0, const cplx* frc,
                   const RkTerm& rk, double dt, double rmp);
 int fused_project(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o, const double* zs, const double* ze);
-// merged z stage (sx_fused_zstage.cu): RK update of the three velocity components + v_imposebc_and_project in one kernel
-bool zstage_enabled(const Plan& p);
-int fused_zstage(Plan& p, Fused& f, const cplx* const* nl, cplx* const* v, const cplx* const* v0, const cplx* const* frc,
-                 const RkTerm* rk, cplx* pr, int o, double dt, double rmp, const double* zs, const double* ze);
 
 }  // namespace sx

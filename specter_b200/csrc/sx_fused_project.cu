@@ -429,6 +429,311 @@ __global__ void __launch_bounds__(N / 8, MINB) k_project_bulk(ProjBulkArgs pa, c
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// project, paired version: the same pencil-per-CTA organisation as k_project_bulk with three changes measured or
+// derived in round 2 (profiles/r2_zstage_experiment.md):
+//   * SIX transforms instead of seven, in THREE rounds of two (fft_regs2: both pencils of a round share every barrier
+//     and the twiddle powers): (IFFT v_x, IFFT v_y), (FFT v_x, FFT v_y), (IFFT d, FFT e).  The harmonic correction
+//     phi = c1 e^{kh (z - Lz)} + c2 e^{-kh z} and its derivative are linear in the two exponentials, and so are the
+//     continuation and the transform: phi^ = c1 E+^ + c2 E-^, phi'^ = kh (c1 E+^ - c2 E-^) with E-^ = FFT(cont(e^{-kh z})),
+//     ONE real-input transform instead of the two complex ones of boundary_mod.fpp:385-399.  E+ is the mirror image of
+//     E- on the grid (z_k = k dz, Lz = z_top) and the FC-Gram continuation commutes with that reflection (fftp.fpp:760-770
+//     is symmetric under ii -> C-ii+1 with the two boundary stencils swapped), so E+^(k) = conj(e^{2 pi i k top / N} E-^(k)).
+//     The mean pencil (kx = ky = 0) has phi = Re(c1) z + Re(c2): its phi^ multiplies kx = ky = 0 and drops out, and
+//     phi'^ = Re(c1) FFT(cont(1)) takes the place of E-^;
+//   * ONE copy of the forward transform in a rolled loop over the rounds (a backward transform is the forward one
+//     between two conjugations): the unrolled kernel is 152 KB of instructions, 9 % of its stall samples are
+//     instruction fetches, and the merged z-stage experiment lost a factor of three to them;
+//   * one reciprocal instead of two divisions per element in the Poisson step.
+// ------------------------------------------------------------------------------------------
+template <int N> struct ProjPairGeo {
+  static constexpr int T = N / 8, XS = sidx_elem_stride<N>(), NW = (T + 31) / 32;
+  static size_t smem_bytes(int C) {
+    return ((size_t)2 * XS + (size_t)3 * N + (size_t)4 * kMaxDF + (size_t)2 * C + (size_t)2 * NW) * sizeof(cplx) + 3 * 8;
+  }
+};
+
+template <int N, int MINB>
+__global__ void __launch_bounds__(N / 8, MINB) k_project_pair(ProjBulkArgs pa, double dkz, const cplx* __restrict__ tw) {
+  SX_DYN_SMEM(cplx, smem);
+  const ProjArgs& a = pa.a;
+  typedef ProjPairGeo<N> G;
+  constexpr int T = G::T, XS = G::XS, NW = G::NW;
+  constexpr unsigned PBYTES = N * sizeof(cplx);
+  const int j = threadIdx.x;
+  const bool lead = j == 0;
+  TwRegs<N> twr;
+  twr.load(tw, j);
+  const SIdxElem si{0};
+  cplx* ex0 = smem;
+  cplx* ex1 = ex0 + XS;
+  cplx* sx = ex1 + XS;
+  cplx* sy = sx + N;
+  cplx* sz = sy + N;
+  cplx* bnd = sz + N;                 // [a * 2d + q]: boundary rows of the two arrays of a round
+  cplx* cv = bnd + 4 * kMaxDF;        // [a * C + ii]: their continuation rows
+  cplx* red = cv + 2 * a.C;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 2 * NW);
+  const int top = a.nph - 1;
+  // phase of the top-wall row at this thread's first element
+  cplx phj;
+  {
+    double sn, cs;
+    sincospi(2.0 * (double)(((long)j * top) % N) / (double)N, &sn, &cs);
+    phj = cmake(cs, sn);
+  }
+  const double zj = __ldg(&a.zc[j]), z7 = __ldg(&a.zc[j + 7 * T]), dzT = __ldg(&a.zc[T]) - __ldg(&a.zc[0]);
+  if (lead) {
+    for (int b = 0; b < 3; ++b) mbar_init(bar + b, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  int g = blockIdx.x;   // pencil index: ny * nxl < 2^31
+  const int npencils = (int)a.npencils;
+  if (lead && g < npencils) {
+    bulk_load(sx, a.vx + (size_t)g * N, PBYTES, bar);
+    bulk_load(sy, a.vy + (size_t)g * N, PBYTES, bar + 1);
+    bulk_load(sz, a.vz + (size_t)g * N, PBYTES, bar + 2);
+  }
+  unsigned phase = 0;
+  for (; g < npencils; g += gridDim.x) {
+    const int gn = g + gridDim.x;
+    const int kx_i = g / a.ny, ky_i = g - kx_i * a.ny;
+    const size_t base = (size_t)g * N;
+    const double x = __ldg(&a.kx[kx_i]), y = __ldg(&a.ky[ky_i]);
+    const double kh = sqrt(x * x + y * y);
+    const bool mean = a.has_mean && g == 0;
+    const cplx pr0 = a.pr[base], prT = a.pr[base + top];
+    cplx c1 = cmake(0.0, 0.0), c2 = cmake(0.0, 0.0);
+    double st = 0.0, em = 0.0;
+    cplx v[8], w[8];
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+      // ---- inputs of the round ----
+      if (r == 0) {
+        mbar_wait(bar, phase);
+        mbar_wait(bar + 1, phase);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[k] = cconj(sx[j + k * T]);
+          w[k] = cconj(sy[j + k * T]);
+        }
+      } else if (r == 2) {
+        // d for its backward transform, and the real sequence whose continued transform carries the harmonic correction:
+        // e^{-kh z} (mean pencil: the constant Re(c1) = phi') on the physical rows, geometric in the thread's stride
+        double q = em;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[k].y = -v[k].y;
+          w[k] = cmake(mean ? c1.x : q, 0.0);
+          q *= st;
+        }
+      }
+      if (r > 0) {
+        // FC-Gram continuation (fftp.fpp:757-772) of w, and of v in round 1: boundary rows to shared memory, the first
+        // C threads form one row each for both arrays, every thread picks up the rows it owns
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          int q = -1;
+          if (e < a.d) q = e;
+          if (e >= a.nph - a.d && e < a.nph) q = a.d + e - (a.nph - a.d);
+          if (q >= 0) {
+            bnd[q] = v[k];
+            bnd[2 * a.d + q] = w[k];
+          }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int ii = j; ii < a.C; ii += T) {
+          double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+          for (int jj = 0; jj < a.d; ++jj) {
+            const double w1 = __ldg(&a.dir[ii * a.d + jj]);
+            const double w2 = __ldg(&a.dir[(a.C - 1 - ii) * a.d + jj]);
+            const cplx f1 = bnd[a.d + jj], f2 = bnd[a.d - 1 - jj];
+            const cplx g1 = bnd[3 * a.d + jj], g2 = bnd[3 * a.d - 1 - jj];
+            ax = fma(w2, f2.x, fma(w1, f1.x, ax));
+            ay = fma(w2, f2.y, fma(w1, f1.y, ay));
+            bx = fma(w2, g2.x, fma(w1, g1.x, bx));
+            by = fma(w2, g2.y, fma(w1, g1.y, by));
+          }
+          cv[ii] = cmake(ax, ay);
+          cv[a.C + ii] = cmake(bx, by);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          if (e >= a.nph) {
+            if (r == 1) v[k] = cv[e - a.nph];
+            w[k] = cv[a.C + e - a.nph];
+          }
+        }
+      }
+      fft_regs2<N, -1, -1>(v, w, j, ex0, ex1, si, twr);
+      // ---- results of the round ----
+      if (r == 0) {
+        // no-slip rows of vx, vy in the mixed domain (vboundary.f90:116-145); v, w hold the conjugates
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          v[k] = cmake(v[k].x * a.inv_nz, -v[k].y * a.inv_nz);
+          w[k] = cmake(w[k].x * a.inv_nz, -w[k].y * a.inv_nz);
+          if (e == 0 || e == top) {
+            const cplx P = e == 0 ? pr0 : prT;
+            v[k] = cmake(-x * P.y * a.tmp_noslip, x * P.x * a.tmp_noslip);
+            w[k] = cmake(-y * P.y * a.tmp_noslip, y * P.x * a.tmp_noslip);
+            if (mean) {
+              v[k] = cmake(e == 0 ? a.mx0 : a.mx1, 0.0);
+              w[k] = cmake(e == 0 ? a.my0 : a.my1, 0.0);
+            }
+          }
+        }
+      } else if (r == 1) {
+        // particular solution and its gradient (boundary_mod.fpp:405-448, 249-259)
+        mbar_wait(bar + 2, phase);
+        phase ^= 1;
+        cplx s0 = cmake(0.0, 0.0), s1 = cmake(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          const double z = (double)(e < N / 2 ? e : e - N) * dkz;   // the product the host table holds
+          const double kk2 = x * x + y * y + z * z;
+          cplx Cc = sz[e];
+          const cplx s = cmake(x * v[k].x + y * w[k].x + z * Cc.x, x * v[k].y + y * w[k].y + z * Cc.y);
+          const double ik2 = 1.0 / kk2;
+          cplx D = cmake(s.y * ik2, -s.x * ik2);
+          if (mean && e == 0) D = cmake(0.0, 0.0);
+          sx[e] = cmake(v[k].x + x * D.y, v[k].y - x * D.x);
+          sy[e] = cmake(w[k].x + y * D.y, w[k].y - y * D.x);
+          Cc = cmake(Cc.x + z * D.y, Cc.y - z * D.x);
+          sz[e] = Cc;   // parked in the slots (own elements only)
+          v[k] = D;
+          // wall values of v_z (boundary_mod.fpp:275-338): rows 0 and top of IFFT_z(v_z)/nz
+          s0 = cadd(s0, Cc);
+          s1 = cadd(s1, cmul(Cc, pa.phT[k]));
+        }
+        s1 = cmul(s1, phj);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s0.x += __shfl_xor_sync(0xffffffffu, s0.x, o);
+          s0.y += __shfl_xor_sync(0xffffffffu, s0.y, o);
+          s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o);
+          s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+        }
+        if ((j & 31) == 0) {
+          red[2 * (j >> 5)] = s0;
+          red[2 * (j >> 5) + 1] = s1;
+        }
+        __syncthreads();   // partial sums visible
+        cplx bc1 = red[0], bc2 = red[1];
+#pragma unroll
+        for (int q = 1; q < NW; ++q) {
+          bc1 = cadd(bc1, red[2 * q]);
+          bc2 = cadd(bc2, red[2 * q + 1]);
+        }
+        bc1 = cscale(bc1, a.inv_nz);
+        bc2 = cscale(bc2, a.inv_nz);
+        // laplace_z, Neumann-Neumann (boundary_mod.fpp:531-560, 635-675)
+        if (mean) {
+          c1 = bc1;
+          c2 = cmake(0.0, 0.0);
+        } else {
+          const double e1 = exp(-kh * a.Lz), tt = 1.0 / (kh * (1.0 - e1 * e1));
+          c1 = cmake((bc2.x - bc1.x * e1) * tt, (bc2.y - bc1.y * e1) * tt);
+          c2 = cmake((-bc1.x + bc2.x * e1) * tt, (-bc1.y + bc2.y * e1) * tt);
+          st = exp(-kh * dzT);
+          em = exp(-kh * zj);
+        }
+      } else {
+        // p' = IFFT_z(d)/nz + phi (boundary_mod.fpp:371-380); v holds the conjugate of the backward transform
+        {
+          double ep[8];
+          if (!mean) {
+            ep[7] = exp(kh * (z7 - a.Lz));
+#pragma unroll
+            for (int k = 6; k >= 0; --k) ep[k] = ep[k + 1] * st;
+          }
+          double q = em;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int e = j + k * T;
+            cplx ph;
+            if (mean) {
+              const double z = __ldg(&a.zc[e]);
+              ph = cmake(c1.x * z + c2.x, 0.0);
+            } else {
+              ph = cmake(c1.x * ep[k] + c2.x * q, c1.y * ep[k] + c2.y * q);
+              q *= st;
+            }
+            a.pr[base + e] = cmake(v[k].x * a.inv_nz + ph.x, -v[k].y * a.inv_nz + ph.y);
+          }
+        }
+        // the harmonic correction subtracted (boundary_mod.fpp:385-399).  The parked fields come back to registers
+        // first, so that the slots can be refilled for the next pencil while the results are formed and stored.
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = sz[j + k * T];
+        cplx A[8], B[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          A[k] = sx[j + k * T];
+          B[k] = sy[j + k * T];
+        }
+        __syncthreads();   // every thread is done with the three slots
+        if (lead && gn < npencils) {
+          bulk_load(sx, a.vx + (size_t)gn * N, PBYTES, bar);
+          bulk_load(sy, a.vy + (size_t)gn * N, PBYTES, bar + 1);
+          bulk_load(sz, a.vz + (size_t)gn * N, PBYTES, bar + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          cplx h, hz;   // phi^, phi'^
+          if (mean) {
+            h = cmake(0.0, 0.0);
+            hz = w[k];
+          } else {
+            const cplx Em = w[k];
+            const cplx Ep = cconj(cmul(cmul(pa.phT[k], phj), Em));
+            const cplx t1 = cmul(c1, Ep), t2 = cmul(c2, Em);
+            h = cadd(t1, t2);
+            hz = cscale(csub(t1, t2), kh);
+          }
+          a.vx[base + e] = cmake(A[k].x + x * h.y, A[k].y - x * h.x);
+          a.vy[base + e] = cmake(B[k].x + y * h.y, B[k].y - y * h.x);
+          a.vz[base + e] = cmake(v[k].x - hz.x, v[k].y - hz.y);
+        }
+      }
+    }
+  }
+}
+
+template <int N, int MINB> static int run_project_pair(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
+                                                       const double* zs, const double* ze) {
+  constexpr int T = N / 8;
+  double tmp = 1.0 / (double)o;
+  if (o != p.ord) tmp = (double)(o + 1) * tmp;   // vboundary.f90:195-196
+  const double sc = (double)p.nx * (double)p.ny;
+  ProjBulkArgs pa;
+  pa.a = ProjArgs{vx, vy, vz, pr, p.d_kx, p.d_ky, p.d_kz, p.d_z, p.d_dir, (long)p.ny * p.nxl,
+                  p.ny, f.nph, p.Cz, p.oz, p.ista == 1 ? 1 : 0, p.Lz, tmp, 1.0 / (double)p.nz,
+                  sc * (zs ? zs[0] : 0.0), sc * (zs ? zs[1] : 0.0), sc * (ze ? ze[0] : 0.0), sc * (ze ? ze[1] : 0.0)};
+  static const double r8[8][2] = {{1, 0}, {0.70710678118654752440, 0.70710678118654752440}, {0, 1}, {-0.70710678118654752440, 0.70710678118654752440},
+                                  {-1, 0}, {-0.70710678118654752440, -0.70710678118654752440}, {0, -1}, {0.70710678118654752440, -0.70710678118654752440}};
+  for (int k = 0; k < 8; ++k) {
+    const int q = (int)(((long)k * (f.nph - 1)) % 8);
+    pa.phT[k] = cmake(r8[q][0], r8[q][1]);
+  }
+  const cplx* tw = p.tw_z;
+  const double dkz = p.Dkz;
+  auto kfn = k_project_pair<N, MINB>;
+  const size_t smem = ProjPairGeo<N>::smem_bytes(p.Cz);
+  int grid;
+  if (persistent_grid(p, kfn, T, smem, (int)pa.a.npencils, &grid)) return 1;
+  SX_FUSED_LAUNCH(p, ST_PROJECT, kfn, dim3(grid), T, smem, pa, dkz, tw);
+  return 0;
+}
+
 template <int N, int MINB, int L2PF = 0> static int run_project_bulk(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
                                                        const double* zs, const double* ze) {
   constexpr int T = N / 8, NW = (T + 31) / 32;
@@ -478,7 +783,10 @@ template <int N> static int run_project(Plan& p, Fused& f, cplx* vx, cplx* vy, c
   constexpr int NPB = T >= 128 ? 1 : 128 / T;
   // bulk-copy version: default from one warp per pencil upwards (SX_PJ=9: previous kernel; SX_PJ=10: force)
   if constexpr (N >= 256 && N <= 2048) {
-    if ((p.knob_pj == 0 && N >= p.knob_tma_min) || (p.knob_pj >= 10 && p.knob_pj < 20)) {
+    // paired six-transform kernel, four CTAs per SM (five spill at 204 registers: 2.93 ms against 2.49 ms, profiles/r2g)
+    if ((p.knob_pj == 0 && N >= p.knob_tma_min) || p.knob_pj == 15)
+      return run_project_pair<N, (N <= 512 ? 4 : (N == 1024 ? 2 : 1))>(p, f, vx, vy, vz, pr, o, zs, ze);
+    if (p.knob_pj >= 10 && p.knob_pj < 20) {
       if constexpr (N == 512) {
         if (p.knob_pj == 11) return run_project_bulk<N, 4>(p, f, vx, vy, vz, pr, o, zs, ze);
         if (p.knob_pj == 12) return run_project_bulk<N, 6>(p, f, vx, vy, vz, pr, o, zs, ze);

@@ -15,7 +15,7 @@ struct SolverState;  // BOUSS / MHD device state (sx_solvers.cu)
 // fftp_mod.fpp:32-37, re-cast per kernel family).
 enum Stage {
   ST_OTHER = 0, ST_ZFFT, ST_YFFT, ST_XFFT, ST_EW, ST_REDUCE,          // per-operator path
-  ST_ZINV, ST_YINV, ST_XPASS, ST_YFWD, ST_ZFWD_RK, ST_PROJECT, ST_ZSTAGE, ST_EXCHANGE,  // fused substep
+  ST_ZINV, ST_YINV, ST_XPASS, ST_YFWD, ST_ZFWD_RK, ST_PROJECT, ST_EXCHANGE,  // fused substep
   ST_COUNT
 };
 const char* stage_name(int id);
@@ -71,7 +71,6 @@ struct Plan {
   StageTimer timer;
   int num_sms = 148;                // multiProcessorCount of the device
   int knob_zf = 0;
-  int knob_zs = 0;                  // z-stage variant (env SX_ZS): 0 = merged z-forward / RK / projection kernel where it applies, 1 = separate kernels
   int knob_xp = 0, knob_pj = 0;     // kernel-variant experiments (env SX_XP, SX_PJ)
   int knob_pf = 13;                 // cp.async prefetch per tile kernel: bit 0 zinv, 1 yinv, 2 yfwd, 3 zfwd (env SX_TILE_PF)
   int knob_tma = 3;                 // bulk-copy (TMA) tile kernels: bit 0 zinv, 1 yinv, 2 yfwd, 3 zfwd (env SX_TMA)
