@@ -342,6 +342,15 @@ class Plan:
         out[...] = a
         return out
 
+    def pinned_empty(self) -> np.ndarray:
+        """An uninitialised page-locked host array of the plan's spectral shape (freed by close())."""
+        n = int(np.prod(self.cshape)) * 16
+        ptr = C.c_void_p()
+        self.lib.check(self.lib.dll.sx_malloc_host(max(n, 16), C.byref(ptr)))
+        self._pinned.append(ptr)
+        buf = (C.c_char * n).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.complex128).reshape(self.cshape)
+
     # ---- multi-GPU ----
     def init_comm_torch(self, dist, p2p=True, p2p_fields=(14, 7)):
         """Create the plan's own NCCL communicator; the 128-byte unique id travels over the caller's
