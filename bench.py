@@ -33,6 +33,8 @@ WORKLOADS = {
     "hd1024c": (1024, 1024, 1024, 4, 1e-4, "HD 1024x1024x1024 FP64 RK4 (the per-GPU problem of BASELINE configs[4] on 2 GPUs)"),
     "hd2048h": (2048, 1024, 1024, 4, 5e-5, "HD 2048x1024x1024 FP64 RK4 (the per-GPU problem of BASELINE configs[4] on 4 GPUs)"),
     "hd2048": (2048, 2048, 1024, 4, 5e-5, "HD 2048x2048x1024 FP64 RK4 (BASELINE configs[4]; 8 GPUs)"),
+    "hdxy2048": (2048, 2048, 64, 4, 5e-5, "HD 2048x2048x64 (single-GPU tuning grid for the length-2048 x / y kernels of configs[4]; not a BASELINE config)"),
+    "hdz1024": (256, 256, 1024, 4, 5e-5, "HD 256x256x1024 (single-GPU tuning grid for the length-1024 z kernels of configs[4]; not a BASELINE config)"),
     "bouss512": (512, 512, 512, 4, 2e-4, "BOUSS Rayleigh-Benard 512x512x512 FP64 RK4, no-slip + constant-temperature walls"),
     "bouss1024": (1024, 1024, 512, 4, 1e-4, "BOUSS Rayleigh-Benard 1024x1024x512 FP64 RK4 (BASELINE configs[2]; 8 GPUs)"),
     "mhd512": (512, 512, 512, 4, 2e-4, "MHD vector potential 512x512x512 FP64 RK4, no-slip + conducting walls (BASELINE configs[3])"),

@@ -370,6 +370,8 @@ int hd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, cons
   return velocity_zstage(p, f, st, rk, o, dt, rmp, zs, ze);
 }
 
+int mhd_curls(Plan& p, const cplx* vx, const cplx* vy, const cplx* vz, cplx* ax, cplx* ay, cplx* az, cplx* const* W,
+              cplx* const* B, const double* b0);
 int s_imposebc(Plan& p, cplx* th);
 int theta_roundtrip(Plan& p, cplx* th, cplx* out);
 int a_imposebc_and_project(Plan& p, cplx* ax, cplx* ay, cplx* az, cplx* ph);
@@ -454,13 +456,8 @@ int mhd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, dou
   for (int c = 0; c < 3; ++c)
     if (plan_cwork(p, 9 + c, &B[c]) || plan_cwork(p, 12 + c, &Wv[c])) return 1;
   cplx *ax = st[10], *ay = st[11], *az = st[12];
-  // B = curl A (+ uniform field at the mean mode), J = curl B written over A, omega = curl v   (:6-20, prodre)
-  if (op_curlk(p, ay, az, B[0], 1) || op_curlk(p, ax, az, B[1], 2) || op_curlk(p, ax, ay, B[2], 3)) return 1;
-  if (p.ista == 1)
-    for (int c = 0; c < 3; ++c)
-      if (op_set_elem(p, B[c], 0, (b0 ? b0[c] : 0.0) * N, 0.0)) return 1;
-  if (op_curlk(p, B[1], B[2], ax, 1) || op_curlk(p, B[0], B[2], ay, 2) || op_curlk(p, B[0], B[1], az, 3)) return 1;
-  if (op_curlk(p, st[1], st[2], Wv[0], 1) || op_curlk(p, st[0], st[2], Wv[1], 2) || op_curlk(p, st[0], st[1], Wv[2], 3)) return 1;
+  // B = curl A (+ uniform field at the mean mode), J = curl B written over A, omega = curl v   (:6-20, prodre): one pass
+  if (mhd_curls(p, st[0], st[1], st[2], ax, ay, az, Wv, B, b0)) return 1;
   // twelve plain fields to real space: v -> V[0..2], omega -> V[3..5], B -> V[6..8], J -> V[9..11]
   const cplx* q[12] = {st[0], st[1], st[2], Wv[0], Wv[1], Wv[2], B[0], B[1], B[2], ax, ay, az};
   for (int c = 0; c < 12; ++c) {
@@ -513,12 +510,7 @@ int mhdbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu
     if (plan_cwork(p, 9 + c, &B[c]) || plan_cwork(p, 12 + c, &Wv[c])) return 1;
   if (plan_cwork(p, 15, &thn)) return 1;
   cplx *ax = st[10], *ay = st[11], *az = st[12], *th = st[20];
-  if (op_curlk(p, ay, az, B[0], 1) || op_curlk(p, ax, az, B[1], 2) || op_curlk(p, ax, ay, B[2], 3)) return 1;
-  if (p.ista == 1)
-    for (int c = 0; c < 3; ++c)
-      if (op_set_elem(p, B[c], 0, (b0 ? b0[c] : 0.0) * N, 0.0)) return 1;
-  if (op_curlk(p, B[1], B[2], ax, 1) || op_curlk(p, B[0], B[2], ay, 2) || op_curlk(p, B[0], B[1], az, 3)) return 1;
-  if (op_curlk(p, st[1], st[2], Wv[0], 1) || op_curlk(p, st[0], st[2], Wv[1], 2) || op_curlk(p, st[0], st[1], Wv[2], 3)) return 1;
+  if (mhd_curls(p, st[0], st[1], st[2], ax, ay, az, Wv, B, b0)) return 1;
   const cplx* q[12] = {st[0], st[1], st[2], Wv[0], Wv[1], Wv[2], B[0], B[1], B[2], ax, ay, az};
   for (int c = 0; c < 12; ++c) {
     if (fused_zinv(p, f, q[c], f.W[c], nullptr)) return 1;

@@ -492,7 +492,9 @@ static int yfwd_peers(Plan& p, Fused& f, const cplx* out, YfwdArgs& a) {
 template <int N> static int run_yfwd_tma(Plan& p, Fused& f, const cplx* in, cplx* out) {
   constexpr int NP = TileNP<N>::value, MINB = TileMinB<N>::value;
   typedef TileGeo<N, NP> G;
-  if (N < p.knob_tma_min || f.nxp % NP != 0 || !(p.knob_tma & 4)) return -1;
+  // tensor-map box loads of the strided side: slower than the cp.async slots at N = 512 (r1h), faster from N = 1024
+  // (0.773 -> 0.613 ms per launch at ny = 2048, profiles/r2j)
+  if (N < p.knob_tma_min || f.nxp % NP != 0 || !((p.knob_tma & 4) || N >= 1024)) return -1;
   if (f.nzf == 0) return 0;
   TmaMap min;
   if (f.zc() == 0) return 0;

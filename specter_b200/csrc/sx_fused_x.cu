@@ -414,6 +414,146 @@ __global__ void __launch_bounds__(LP*(N / 8), MINB) k_xpass_cross(XcrossArgs a, 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// xpass (cross products), bulk-copy version: the ring of k_xpass_gradre_bulk (one elected thread streams the two
+// half-spectrum rows of every inverse transform into S shared-memory stages with cp.async.bulk, S-1 transforms ahead)
+// for X = sum over pairs s (P x Q) / N^2.  The six lines of a pair are transformed in the order of the cycle
+// Px - Qy - Pz - Qx - Py - Qz (- Px) of the products a cross product needs, so that only the previous line and Px
+// have to be kept: Px waits in a thread-private shared-memory park (written once, read twice), the previous line and
+// the three accumulators live in registers.
+//   z += Px Qy;  x -= Pz Qy;  y += Pz Qx;  z -= Py Qx;  x += Py Qz;  y -= Px Qz
+// ------------------------------------------------------------------------------------------
+template <int N, int S, int MINB>
+__global__ void __launch_bounds__(N / 8, MINB) k_xpass_cross_bulk(XcrossArgs a, const cplx* __restrict__ tw) {
+  SX_DYN_SMEM(cplx, smem);
+  constexpr int T = N / 8, XS = XpassBulk<N>::XS, NXP = XpassBulk<N>::NXP;
+  constexpr unsigned BYTES = 2 * NXP * sizeof(cplx);
+  const int t = threadIdx.x;
+  TwRegs<N> twr;
+  twr.load(tw, t);
+  const SIdxElem si{0};
+  cplx* stage = smem + XS;
+  cplx* park = stage + (size_t)S * 2 * NXP + t;    // park[k * T]: Px of the current pair
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(stage + (size_t)S * 2 * NXP + N);
+  const int groups_y = a.ny / 2, ngroups = groups_y * a.nzf;
+  const int mine = ((int)blockIdx.x < ngroups) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto row_of = [&](int gi) -> size_t {
+    const int g = blockIdx.x + gi * gridDim.x;
+    return ((size_t)(g / groups_y) * a.ny + (size_t)(g % groups_y) * 2) * NXP;
+  };
+  // producer state (lead thread): next load = line pm of pair pp of group pg into stage ps
+  int pg = 0, pp = 0, pm = 0, ps = 0;
+  size_t prow = mine > 0 ? row_of(0) : 0;
+  auto issue_next = [&]() {
+    if (pg >= mine) return;
+    // cycle order Px Qy Pz Qx Py Qz
+    const cplx* field = pm == 0 ? a.P[pp][0] : pm == 1 ? a.Q[pp][1] : pm == 2 ? a.P[pp][2] : pm == 3 ? a.Q[pp][0]
+                      : pm == 4 ? a.P[pp][1] : a.Q[pp][2];
+    bulk_load(stage + (size_t)ps * 2 * NXP, field + prow, BYTES, bar + ps);
+    if (++ps == S) ps = 0;
+    if (++pm == 6) {
+      pm = 0;
+      if (++pp == a.npairs) {
+        pp = 0;
+        if (++pg < mine) prow = row_of(pg);
+      }
+    }
+  };
+  if (t == 0) {
+    for (int q = 0; q < S; ++q) mbar_init(bar + q, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (t == 0)
+    for (int q = 0; q < S - 1; ++q) issue_next();
+  int cs = 0;
+  unsigned cph = 0;
+  for (int gi = 0; gi < mine; ++gi) {
+    const size_t rowA = row_of(gi), rowB = rowA + NXP;
+    cplx ax[8], ay[8], az[8], prev[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ax[k] = ay[k] = az[k] = prev[k] = cmake(0.0, 0.0);
+#pragma unroll 1
+    for (int pr = 0; pr < a.npairs; ++pr) {
+      const double sg = a.sgn[pr];
+#pragma unroll 1
+      for (int m = 0; m < 6; ++m) {
+        if (t == 0) issue_next();   // the stage consumed by the previous transform was read before its barriers
+        mbar_wait(bar + cs, cph);
+        const cplx* sA = stage + (size_t)cs * 2 * NXP;
+        const cplx* sB = sA + NXP;
+        if (++cs == S) {
+          cs = 0;
+          cph ^= 1;
+        }
+        cplx v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = t + k * T;
+          const int kx = e <= N / 2 ? e : N - e;
+          cplx A = sA[kx], B = sB[kx];
+          if (kx == 0 || kx == N / 2) { A.y = 0.0; B.y = 0.0; }
+          if (e > N / 2) { A.y = -A.y; B.y = -B.y; }
+          v[k] = cmake(A.x - B.y, A.y + B.x);
+        }
+        fft_regs<N, 1>(v, t, smem, si, twr);
+        // products with the previous line of the cycle (and with Px at its end)
+        if (m == 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) park[k * T] = v[k];
+        } else if (m == 1) {      // Qy: z += Px Qy
+#pragma unroll
+          for (int k = 0; k < 8; ++k) az[k] = cmake(fma(sg * prev[k].x, v[k].x, az[k].x), fma(sg * prev[k].y, v[k].y, az[k].y));
+        } else if (m == 2) {      // Pz: x -= Pz Qy
+#pragma unroll
+          for (int k = 0; k < 8; ++k) ax[k] = cmake(fma(-sg * v[k].x, prev[k].x, ax[k].x), fma(-sg * v[k].y, prev[k].y, ax[k].y));
+        } else if (m == 3) {      // Qx: y += Pz Qx
+#pragma unroll
+          for (int k = 0; k < 8; ++k) ay[k] = cmake(fma(sg * prev[k].x, v[k].x, ay[k].x), fma(sg * prev[k].y, v[k].y, ay[k].y));
+        } else if (m == 4) {      // Py: z -= Py Qx
+#pragma unroll
+          for (int k = 0; k < 8; ++k) az[k] = cmake(fma(-sg * v[k].x, prev[k].x, az[k].x), fma(-sg * v[k].y, prev[k].y, az[k].y));
+        } else {                  // Qz: x += Py Qz, y -= Px Qz
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const cplx px = park[k * T];
+            ax[k] = cmake(fma(sg * prev[k].x, v[k].x, ax[k].x), fma(sg * prev[k].y, v[k].y, ax[k].y));
+            ay[k] = cmake(fma(-sg * px.x, v[k].x, ay[k].x), fma(-sg * px.y, v[k].y, ay[k].y));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) prev[k] = v[k];
+      }
+    }
+    // forward transforms of the three packed pairs and split into the half spectra
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      cplx w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const cplx s3 = c == 0 ? ax[k] : (c == 1 ? ay[k] : az[k]);
+        w[k] = cmake(s3.x * a.tmp, s3.y * a.tmp);
+      }
+      fft_regs<N, -1>(w, t, smem, si, twr);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) smem[si(t + k * T)] = w[k];
+      __syncthreads();
+      cplx* out = a.X[c];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int kk = t + k * T;
+        if (kk <= N / 2) {
+          const cplx Zk = w[k];
+          const cplx Zn = smem[si((N - kk) & (N - 1))];
+          out[rowA + kk] = cmake(0.5 * (Zk.x + Zn.x), 0.5 * (Zk.y - Zn.y));
+          out[rowB + kk] = cmake(0.5 * (Zk.y + Zn.y), -0.5 * (Zk.x - Zn.x));
+        }
+      }
+    }
+  }
+}
+
 // ui < 0: gradre / advect of q = V[0..NC) by its own first three components into X[0..NC);
 // ui >= 0 (NC = 1): the scalar q = V[qi], dy q = V[qi+1], dz q = V[qi+2] advected by V[ui..ui+2] into X[xo]
 static void xpass_fields(Plan& p, Fused& f, XpassArgs& a, int NC, int ui, int qi, int xo) {
@@ -511,6 +651,18 @@ template <int N> static int run_xcross(Plan& p, Fused& f, int npairs, const int*
   const double Ntot = (double)p.nx * (double)p.ny * (double)p.nz;
   a.tmp = 1.0 / (Ntot * Ntot);
   const cplx* tw = p.tw_x;
+  // bulk-copy ring from one warp per line pair upwards (SX_XP=9: the previous kernel with cp.async slots and parked P lines)
+  if constexpr (N >= 256 && N <= 2048) {
+    if (p.knob_xp != 9 && f.nxp == XpassBulk<N>::NXP && p.ny % 2 == 0) {
+      constexpr int S = 3, MINB = N <= 512 ? 4 : (N == 1024 ? 2 : 1);
+      auto kfn = k_xpass_cross_bulk<N, S, MINB>;
+      const size_t smem = ((size_t)XpassBulk<N>::XS + (size_t)S * 2 * XpassBulk<N>::NXP + (size_t)N) * sizeof(cplx) + (size_t)S * 8;
+      int grid;
+      if (persistent_grid(p, kfn, T, smem, (p.ny / 2) * f.zc(), &grid)) return 1;
+      SX_FUSED_LAUNCH(p, ST_XPASS, kfn, dim3(grid), T, smem, a, tw);
+      return 0;
+    }
+  }
   auto kfn = k_xpass_cross<N, LP, (N <= 1024 ? 2 : 1)>;
   const size_t smem = ((size_t)LP * sidx_elem_stride<N>() + (size_t)40 * LP * T) * sizeof(cplx);
   int grid;

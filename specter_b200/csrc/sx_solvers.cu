@@ -144,6 +144,37 @@ __global__ void k_rk_axpy_a(size_t n, cplx* __restrict__ a, const cplx* __restri
   }
 }
 
+// MHD substep, all three curls in one pass (mhd_rkstep2.f90:6-20 and the prodre call at :29): omega = curl v,
+// B = curl A with the uniform field injected at the mean mode (B(1,1,1) = b0 N), J = curl B written over A.  The nine
+// curlk calls it replaces move 27 full-field reads / writes; this pass reads 6 and writes 9.  Same expressions as
+// k_curlk (sx_kernels_ops.cu): curl_1 = i ky c - i kz b, curl_2 = i kz a - i kx c, curl_3 = i kx b - i ky a.
+__device__ __forceinline__ void curl3(double x, double y, double z, cplx a, cplx b, cplx c, cplx& o1, cplx& o2, cplx& o3) {
+  o1 = csub(cmake(-y * c.y, y * c.x), cmake(-z * b.y, z * b.x));
+  o2 = csub(cmake(-z * a.y, z * a.x), cmake(-x * c.y, x * c.x));
+  o3 = csub(cmake(-x * b.y, x * b.x), cmake(-y * a.y, y * a.x));
+}
+__global__ void k_mhd_curls(Dims d, const cplx* __restrict__ vx, const cplx* __restrict__ vy, const cplx* __restrict__ vz,
+                            cplx* __restrict__ ax, cplx* __restrict__ ay, cplx* __restrict__ az, cplx* __restrict__ wx,
+                            cplx* __restrict__ wy, cplx* __restrict__ wz, cplx* __restrict__ bx, cplx* __restrict__ by,
+                            cplx* __restrict__ bz, const double* __restrict__ kx, const double* __restrict__ ky,
+                            const double* __restrict__ kz, int mean, double m0, double m1, double m2) {
+  SX_GRID_STRIDE(idx, d.n) {
+    const int k = (int)(idx % d.nz);
+    const size_t ji = idx / d.nz;
+    const int j = (int)(ji % d.ny), i = (int)(ji / d.ny);
+    const double x = __ldg(&kx[i]), y = __ldg(&ky[j]), z = __ldg(&kz[k]);
+    cplx o1, o2, o3;
+    curl3(x, y, z, vx[idx], vy[idx], vz[idx], o1, o2, o3);
+    wx[idx] = o1; wy[idx] = o2; wz[idx] = o3;
+    curl3(x, y, z, ax[idx], ay[idx], az[idx], o1, o2, o3);
+    if (mean && idx == 0) { o1 = cmake(m0, 0.0); o2 = cmake(m1, 0.0); o3 = cmake(m2, 0.0); }
+    bx[idx] = o1; by[idx] = o2; bz[idx] = o3;
+    cplx j1, j2, j3;
+    curl3(x, y, z, o1, o2, o3, j1, j2, j3);
+    ax[idx] = j1; ay[idx] = j2; az[idx] = j3;
+  }
+}
+
 __global__ void k_set_elem(cplx* __restrict__ a, size_t idx, double re, double im) {
   if (blockIdx.x == 0 && threadIdx.x == 0) a[idx] = cmake(re, im);
 }
@@ -166,6 +197,17 @@ __global__ void k_hermitian_plane(cplx* __restrict__ plane, int nz, int ny, int 
 static int op_sub(Plan& p, cplx* a, const cplx* b) {
   const size_t n = p.csize();
   SX_EW_LAUNCH(p, k_sub, n, n, a, b);
+  return 0;
+}
+int mhd_curls(Plan& p, const cplx* vx, const cplx* vy, const cplx* vz, cplx* ax, cplx* ay, cplx* az, cplx* const* W,
+              cplx* const* B, const double* b0) {
+  const Dims d = dims_of(p);
+  const double N = (double)p.nx * (double)p.ny * (double)p.nz;
+  const double *kx = p.d_kx, *ky = p.d_ky, *kz = p.d_kz;
+  const int mean = p.ista == 1 ? 1 : 0;
+  const double m0 = (b0 ? b0[0] : 0.0) * N, m1 = (b0 ? b0[1] : 0.0) * N, m2 = (b0 ? b0[2] : 0.0) * N;
+  cplx *w0 = W[0], *w1 = W[1], *w2 = W[2], *c0 = B[0], *c1 = B[1], *c2 = B[2];
+  SX_EW_LAUNCH(p, k_mhd_curls, d.n, d, vx, vy, vz, ax, ay, az, w0, w1, w2, c0, c1, c2, kx, ky, kz, mean, m0, m1, m2);
   return 0;
 }
 int op_set_elem(Plan& p, cplx* a, size_t idx, double re, double im) {
