@@ -429,3 +429,33 @@ def test_fortran_e_fields():
     assert f(2.0, 23, 16) == " 2.0000000000000000E+00" and f(0.5, 22, 14) == "  5.00000000000000E-01"
     assert f(1e-120, 13, 6) == " 1.000000-120" and f(-3e200, 13, 6) == "-3.000000+200"      # three-digit exponents drop the E
     assert f(float("nan"), 13, 6) == "          NaN" and f(-1e-120, 12, 6) == "*" * 12
+
+
+def test_oracle_matches_independent_statement(tables):
+    """the oracle against a second, code-independent statement of the HD substep (dense DFT
+    matrices, full Hermitian x spectrum, longdouble arithmetic; tests/independent_hd.py) on 8 x 8 x 48, both RK2
+    substeps (the second one exercises the (o+1)/o slip factor).  A restatement error that is self-consistent inside
+    the oracle cannot hide here; what remains unpinned is only what BOTH statements take from SURVEY Appendix A."""
+    from independent_hd import Independent
+    n = (8, 8, 48)
+    L = (1.0, 0.5, 1.0)
+    g = O.Grid(*n, 25, 5, Lx=L[0], Ly=L[1], Lz=L[2], tdir=tables, ord=2)
+    s = O.make_hd_state(g)
+    rng = np.random.default_rng(5)
+    s.pr = (rng.standard_normal(s.pr.shape) + 1j * rng.standard_normal(s.pr.shape)) * 1e-3 * np.abs(s.vx).max()
+    ind = Independent(*n, 25, 5, *L, tables, 2)
+    v = [s.vx.copy(), s.vy.copy(), s.vz.copy()]
+    v0 = [q.copy() for q in v]
+    f = [s.fx.copy(), s.fy.copy(), s.fz.copy()]
+    pr = s.pr.copy()
+    C = [q.copy() for q in v]
+    dt, nu = 1e-3, 1e-3
+    for o in (2, 1):
+        O.hd_rkstep2(g, s, *C, o, dt, nu)
+        v, pr = ind.rkstep2(v, v0, f, pr, o, dt, nu)
+        scale = max(float(np.abs(q).max()) for q in (s.vx, s.vy, s.vz))
+        for a, b in zip(v, (s.vx, s.vy, s.vz)):
+            assert float(np.abs(a.astype(np.complex128) - b).max()) / scale < 1e-12
+        nph = g.nz - g.Cz
+        perr = float(np.abs(pr.astype(np.complex128) - s.pr)[:, :, :nph].max())
+        assert perr < 1e-9 * float(np.abs(s.pr[:, :, :nph]).max()) or perr < 1e-12 * scale
