@@ -372,6 +372,7 @@ int hd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, cons
 
 int mhd_curls(Plan& p, const cplx* vx, const cplx* vy, const cplx* vz, cplx* ax, cplx* ay, cplx* az, cplx* const* W,
               cplx* const* B, const double* b0);
+static int a_project(Plan& p, cplx* ax, cplx* ay, cplx* az, cplx* ph);
 int s_imposebc(Plan& p, cplx* th);
 int theta_roundtrip(Plan& p, cplx* th, cplx* out);
 int a_imposebc_and_project(Plan& p, cplx* ax, cplx* ay, cplx* az, cplx* ph);
@@ -444,6 +445,12 @@ int rotbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu
   return s_imposebc(p, st[10]);
 }
 
+// vector-potential boundary step of the fused MHD substeps: one pencil kernel where it applies
+static int a_project(Plan& p, cplx* ax, cplx* ay, cplx* az, cplx* ph) {
+  const int rc = fused_aproject(p, ax, ay, az, ph);
+  return rc >= 0 ? rc : a_imposebc_and_project(p, ax, ay, az, ph);
+}
+
 // mhd_rkstep2.f90:3-84.  st[0..2] v, 3 pr, 4..6 f, 7..9 C1..C3, 10..12 a, 13 ph, 14..16 m, 17..19 C9..C11.
 int mhd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, double mu, const double* b0) {
   Fused* fp;
@@ -489,7 +496,7 @@ int mhd_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu, dou
     if (ex_wait(p, 16 + 3 + c)) return 1;
     if (fused_zfwd_rk(p, f, f.Uz[3 + c], st[10 + c], st[10 + c], st[17 + c], st[14 + c], rk, dt, rmp)) return 1;
   }
-  return a_imposebc_and_project(p, ax, ay, az, st[13]);
+  return a_project(p, ax, ay, az, st[13]);
 }
 
 // mhdbouss_rkstep2.f90:3-106.  st: the MHD slots (0..19), 20 th, 21 fs, 22 C7.  The MHD passes plus theta: its
@@ -552,7 +559,7 @@ int mhdbouss_rkstep2_fused(Plan& p, cplx* const* st, int o, double dt, double nu
     if (ex_wait(p, 16 + 3 + c)) return 1;
     if (fused_zfwd_rk(p, f, f.Uz[3 + c], st[10 + c], st[10 + c], st[17 + c], st[14 + c], rk, dt, rmp)) return 1;
   }
-  if (a_imposebc_and_project(p, ax, ay, az, st[13])) return 1;
+  if (a_project(p, ax, ay, az, st[13])) return 1;
   return s_imposebc(p, thn) || theta_roundtrip(p, thn, th);
 }
 

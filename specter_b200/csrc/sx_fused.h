@@ -176,5 +176,7 @@ int fused_xadvect(Plan& p, Fused& f, int ui, int qi, int xo, const double* kxg);
 int fused_zfwd_rk(Plan& p, Fused& f, const cplx* nl, const cplx* v, cplx* vout, const cplx* v0, const cplx* frc,
                   const RkTerm& rk, double dt, double rmp);
 int fused_project(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o, const double* zs, const double* ze);
+// a_imposebc_and_project as one pencil kernel (conducting walls); -1: not applicable, compose the operators
+int fused_aproject(Plan& p, cplx* ax, cplx* ay, cplx* az, cplx* ph);
 
 }  // namespace sx

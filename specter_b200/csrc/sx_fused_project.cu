@@ -734,6 +734,374 @@ template <int N, int MINB> static int run_project_pair(Plan& p, Fused& f, cplx* 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// a_imposebc_and_project for conducting walls at both ends (bboundary.f90:100-189 with int_conducting_z :192-236,
+// sol_project(...,0,0,0) boundary_mod.fpp:197-402 and conducting_z :239-290 -> neumann_reconstruct
+// fcgram_mod.f90:456-499), one (ky,kx) pencil per CTA like k_project_pair: TWELVE transforms in six paired rounds
+// instead of the thirteen stand-alone z transforms and eight elementwise passes of the per-operator composition
+// (10.8 of the 40.6 ms of an MHD 512^3 substep, profiles/r2l_mhd512_launches.md).
+//   round 0: IFFT (a_x, a_y)                     -> wall rows <- 0
+//   round 1: FFT  (a_x, a_y), continued          -> d = -i k.a / k^2, a -= i k d (parked)
+//   round 2: IFFT d, FFT cont(e^{-kh z})         -> wall values of d, Dirichlet laplace_z, ph = d + phi, a -= grad(phi)
+//   round 3: IFFT (a_x, a_y)                     -> wall rows <- second-order Neumann reconstruction
+//   round 4: FFT a_x (continued), IFFT a_z       -> a_x final; wall rows of a_z <- first-order reconstruction
+//   round 5: FFT (a_y, a_z), continued           -> final
+// The harmonic correction uses the same single real-input transform as k_project_pair.
+// ------------------------------------------------------------------------------------------
+struct AprojArgs {
+  cplx *ax, *ay, *az, *ph;
+  const double *kx, *ky, *zc, *dir;
+  long npencils;
+  int ny, nph, C, d, has_mean;
+  double Lz, inv_nz, dkz;
+  double neu1[kMaxDF], neu2[kMaxDF];   // neumann_reconstruct weights of order 1 and 2 (fcgram_mod.f90:355-361)
+  cplx phT[8];
+};
+
+template <int N, int MINB>
+__global__ void __launch_bounds__(N / 8, MINB) k_aproject_pair(AprojArgs a, const cplx* __restrict__ tw) {
+  SX_DYN_SMEM(cplx, smem);
+  typedef ProjPairGeo<N> G;
+  constexpr int T = G::T, XS = G::XS, NW = G::NW;
+  constexpr unsigned PBYTES = N * sizeof(cplx);
+  const int j = threadIdx.x;
+  const bool lead = j == 0;
+  TwRegs<N> twr;
+  twr.load(tw, j);
+  const SIdxElem si{0};
+  cplx* ex0 = smem;
+  cplx* ex1 = ex0 + XS;
+  cplx* sx = ex1 + XS;
+  cplx* sy = sx + N;
+  cplx* sz = sy + N;
+  cplx* bnd = sz + N;                 // [arr * 2d + q]
+  cplx* cv = bnd + 4 * kMaxDF;        // [arr * C + ii]
+  cplx* red = cv + 2 * a.C;           // wall values of d
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 2 * NW);
+  const int top = a.nph - 1;
+  cplx phj;
+  {
+    double sn, cs;
+    sincospi(2.0 * (double)(((long)j * top) % N) / (double)N, &sn, &cs);
+    phj = cmake(cs, sn);
+  }
+  const double zj = __ldg(&a.zc[j]), z7 = __ldg(&a.zc[j + 7 * T]), dzT = __ldg(&a.zc[T]) - __ldg(&a.zc[0]);
+  if (lead) {
+    for (int b = 0; b < 3; ++b) mbar_init(bar + b, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  int g = blockIdx.x;
+  const int npencils = (int)a.npencils;
+  if (lead && g < npencils) {
+    bulk_load(sx, a.ax + (size_t)g * N, PBYTES, bar);
+    bulk_load(sy, a.ay + (size_t)g * N, PBYTES, bar + 1);
+    bulk_load(sz, a.az + (size_t)g * N, PBYTES, bar + 2);
+  }
+  unsigned phase = 0;
+  for (; g < npencils; g += gridDim.x) {
+    const int gn = g + gridDim.x;
+    const int kx_i = g / a.ny, ky_i = g - kx_i * a.ny;
+    const size_t base = (size_t)g * N;
+    const double x = __ldg(&a.kx[kx_i]), y = __ldg(&a.ky[ky_i]);
+    const double kh = sqrt(x * x + y * y);
+    const bool mean = a.has_mean && g == 0;
+    cplx v[8], w[8];
+#pragma unroll 1
+    for (int r = 0; r < 6; ++r) {
+      // which arrays are continued (c) / reconstructed at the walls with weights of order (o) before this round's transform
+      const bool cvv = r == 1 || r == 4 || r == 5, cvw = r == 1 || r == 2 || r == 5;
+      const int ov = 0, ow = r == 5 ? 1 : 0;
+      // ---- inputs of the round ----
+      if (r == 0) {
+        mbar_wait(bar, phase);
+        mbar_wait(bar + 1, phase);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[k] = cconj(sx[j + k * T]);
+          w[k] = cconj(sy[j + k * T]);
+        }
+      } else if (r == 4) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          sy[j + k * T] = w[k];               // a_y (mixed domain, walls reconstructed) waits for round 5
+          w[k] = cconj(sz[j + k * T]);        // a_z for its backward transform
+        }
+      } else if (r == 5) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = sy[j + k * T];
+      }
+      if (cvv || cvw) {
+        // boundary rows to shared memory; optional Neumann reconstruction of the wall rows (their prescribed datum is
+        // zero: neu(d) * 0 + sum_k neu(k) f(.)); then the continuation rows, one per thread for both arrays
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          int q = -1;
+          if (e < a.d) q = e;
+          if (e >= a.nph - a.d && e < a.nph) q = a.d + e - (a.nph - a.d);
+          if (q >= 0) {
+            bnd[q] = v[k];
+            bnd[2 * a.d + q] = w[k];
+          }
+        }
+        __syncthreads();
+        if (ov || ow) {
+          if (j < 4) {   // thread 2 * arr + wall
+            const int arr = j >> 1, upper = j & 1, o = arr == 0 ? ov : ow;
+            if (o) {
+              const double* wt = o == 1 ? a.neu1 : a.neu2;
+              cplx* b = bnd + arr * 2 * a.d;
+              double sx_ = 0.0, sy_ = 0.0;
+              for (int k = 1; k < a.d; ++k) {
+                const cplx f = upper ? b[a.d + k - 1] : b[a.d - k];
+                sx_ += wt[k - 1] * f.x;
+                sy_ += wt[k - 1] * f.y;
+              }
+              b[upper ? 2 * a.d - 1 : 0] = cmake(sx_, sy_);
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int e = j + k * T;
+            if (e == 0 || e == top) {
+              if (ov) v[k] = bnd[e == 0 ? 0 : 2 * a.d - 1];
+              if (ow) w[k] = bnd[2 * a.d + (e == 0 ? 0 : 2 * a.d - 1)];
+            }
+          }
+        }
+#pragma unroll 1
+        for (int ii = j; ii < a.C; ii += T) {
+          double ax_ = 0.0, ay_ = 0.0, bx_ = 0.0, by_ = 0.0;
+          for (int jj = 0; jj < a.d; ++jj) {
+            const double w1 = __ldg(&a.dir[ii * a.d + jj]);
+            const double w2 = __ldg(&a.dir[(a.C - 1 - ii) * a.d + jj]);
+            const cplx f1 = bnd[a.d + jj], f2 = bnd[a.d - 1 - jj];
+            const cplx g1 = bnd[3 * a.d + jj], g2 = bnd[3 * a.d - 1 - jj];
+            ax_ = fma(w2, f2.x, fma(w1, f1.x, ax_));
+            ay_ = fma(w2, f2.y, fma(w1, f1.y, ay_));
+            bx_ = fma(w2, g2.x, fma(w1, g1.x, bx_));
+            by_ = fma(w2, g2.y, fma(w1, g1.y, by_));
+          }
+          cv[ii] = cmake(ax_, ay_);
+          cv[a.C + ii] = cmake(bx_, by_);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          if (e >= a.nph) {
+            if (cvv) v[k] = cv[e - a.nph];
+            if (cvw) w[k] = cv[a.C + e - a.nph];
+          }
+        }
+      }
+      fft_regs2<N, -1, -1>(v, w, j, ex0, ex1, si, twr);
+      // ---- results of the round ----
+      if (r == 0 || r == 3) {
+        // mixed domain (goto_domain_w_boundaries): scale, wall rows <- 0 (int_conducting_z / conducting_z); in round 3
+        // the second-order reconstruction of both wall rows follows from the neighbouring rows
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          v[k] = cmake(v[k].x * a.inv_nz, -v[k].y * a.inv_nz);
+          w[k] = cmake(w[k].x * a.inv_nz, -w[k].y * a.inv_nz);
+          if (e == 0 || e == top) v[k] = w[k] = cmake(0.0, 0.0);
+        }
+        if (r == 3) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int e = j + k * T;
+            int q = -1;
+            if (e < a.d) q = e;
+            if (e >= a.nph - a.d && e < a.nph) q = a.d + e - (a.nph - a.d);
+            if (q >= 0) {
+              bnd[q] = v[k];
+              bnd[2 * a.d + q] = w[k];
+            }
+          }
+          __syncthreads();
+          if (j < 4) {
+            const int arr = j >> 1, upper = j & 1;
+            cplx* b = bnd + arr * 2 * a.d;
+            double sx_ = 0.0, sy_ = 0.0;
+            for (int k = 1; k < a.d; ++k) {
+              const cplx f = upper ? b[a.d + k - 1] : b[a.d - k];
+              sx_ += a.neu2[k - 1] * f.x;
+              sy_ += a.neu2[k - 1] * f.y;
+            }
+            cv[j] = cmake(sx_, sy_);
+          }
+          __syncthreads();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int e = j + k * T;
+            if (e == 0 || e == top) {
+              v[k] = cv[e == 0 ? 0 : 1];
+              w[k] = cv[e == 0 ? 2 : 3];
+            }
+          }
+        }
+      } else if (r == 1) {
+        // particular solution and its gradient (boundary_mod.fpp:405-448, 249-259); a_z(1,1,1) = 0 first (bboundary.f90:147-149)
+        mbar_wait(bar + 2, phase);
+        phase ^= 1;
+        double q = 0.0, st = 0.0;
+        if (!mean) {
+          st = exp(-kh * dzT);
+          q = exp(-kh * zj);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          const double z = (double)(e < N / 2 ? e : e - N) * a.dkz;
+          const double kk2 = x * x + y * y + z * z;
+          cplx Cc = sz[e];
+          if (mean && e == 0) Cc = cmake(0.0, 0.0);
+          const cplx s = cmake(x * v[k].x + y * w[k].x + z * Cc.x, x * v[k].y + y * w[k].y + z * Cc.y);
+          const double ik2 = 1.0 / kk2;
+          cplx D = cmake(s.y * ik2, -s.x * ik2);
+          if (mean && e == 0) D = cmake(0.0, 0.0);
+          sx[e] = cmake(v[k].x + x * D.y, v[k].y - x * D.x);
+          sy[e] = cmake(w[k].x + y * D.y, w[k].y - y * D.x);
+          sz[e] = cmake(Cc.x + z * D.y, Cc.y - z * D.x);
+          v[k] = cmake(D.x, -D.y);              // conjugate: backward transform in round 2
+          w[k] = cmake(mean ? 1.0 : q, 0.0);    // e^{-kh z} (mean pencil: the constant 1), physical rows
+          q *= st;
+        }
+      } else if (r == 2) {
+        // C1 = IFFT_z(d)/nz (v holds its conjugate); wall values, Dirichlet laplace_z (boundary_mod.fpp:499-528, 635-675)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          v[k] = cmake(v[k].x * a.inv_nz, -v[k].y * a.inv_nz);
+          if (e == 0) red[0] = v[k];
+          if (e == top) red[1] = v[k];
+        }
+        __syncthreads();
+        const cplx bc1 = cmake(-red[0].x, -red[0].y), bc2 = cmake(-red[1].x, -red[1].y);
+        cplx c1, c2;
+        double st = 0.0, em = 0.0;
+        if (mean) {
+          c1 = cmake((bc2.x - bc1.x) / a.Lz, (bc2.y - bc1.y) / a.Lz);
+          c2 = bc1;
+        } else {
+          const double e1 = exp(-kh * a.Lz), tt = 1.0 / (1.0 - e1 * e1);
+          c1 = cmake((bc2.x - bc1.x * e1) * tt, (bc2.y - bc1.y * e1) * tt);
+          c2 = cmake((bc1.x - bc2.x * e1) * tt, (bc1.y - bc2.y * e1) * tt);
+          st = exp(-kh * dzT);
+          em = exp(-kh * zj);
+        }
+        {
+          double ep[8];
+          if (!mean) {
+            ep[7] = exp(kh * (z7 - a.Lz));
+#pragma unroll
+            for (int k = 6; k >= 0; --k) ep[k] = ep[k + 1] * st;
+          }
+          double q = em;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int e = j + k * T;
+            cplx phi;
+            if (mean) {
+              const double z = __ldg(&a.zc[e]);
+              phi = cmake(c1.x * z + c2.x, 0.0);
+            } else {
+              phi = cmake(c1.x * ep[k] + c2.x * q, c1.y * ep[k] + c2.y * q);
+              q *= st;
+            }
+            a.ph[base + e] = cadd(v[k], phi);   // d = C1 + C2 (boundary_mod.fpp:371-380)
+          }
+        }
+        // a -= grad(phi) in Fourier space, then straight on to the backward transforms of round 3
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          cplx h, hz;
+          if (mean) {
+            h = cmake(0.0, 0.0);
+            hz = cscale(w[k], c1.x);
+          } else {
+            const cplx Em = w[k];
+            const cplx Ep = cconj(cmul(cmul(a.phT[k], phj), Em));
+            const cplx t1 = cmul(c1, Ep), t2 = cmul(c2, Em);
+            h = cadd(t1, t2);
+            hz = cscale(csub(t1, t2), kh);
+          }
+          const cplx A = sx[e], B = sy[e], Cc = sz[e];
+          v[k] = cmake(A.x + x * h.y, -(A.y - x * h.x));     // conjugates: backward transforms next
+          w[k] = cmake(B.x + y * h.y, -(B.y - y * h.x));
+          sz[e] = cmake(Cc.x - hz.x, Cc.y - hz.y);
+        }
+      } else if (r == 4) {
+        // a_x is final; a_z reaches the mixed domain: scale, wall rows <- 0 (reconstructed with the first-order weights
+        // at the start of round 5)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = j + k * T;
+          a.ax[base + e] = v[k];
+          w[k] = cmake(w[k].x * a.inv_nz, -w[k].y * a.inv_nz);
+          if (e == 0 || e == top) w[k] = cmake(0.0, 0.0);
+        }
+      } else {
+        __syncthreads();   // every thread is done with the three slots: refill them for the next pencil
+        if (lead && gn < npencils) {
+          bulk_load(sx, a.ax + (size_t)gn * N, PBYTES, bar);
+          bulk_load(sy, a.ay + (size_t)gn * N, PBYTES, bar + 1);
+          bulk_load(sz, a.az + (size_t)gn * N, PBYTES, bar + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a.ay[base + j + k * T] = v[k];
+          a.az[base + j + k * T] = w[k];
+        }
+      }
+    }
+  }
+}
+
+// returns -1 when the fused kernel does not apply (other wall kinds, short pencils): the caller composes the operators
+int fused_aproject(Plan& p, cplx* ax, cplx* ay, cplx* az, cplx* ph) {
+  if (p.b_bczsta != 0 || p.b_bczend != 0 || p.Cz <= 0 || p.nz < 256 || p.nz > 2048 || p.knob_pj == 9) return -1;
+  if (load_neumann(p)) return 1;
+  AprojArgs a;
+  a.ax = ax; a.ay = ay; a.az = az; a.ph = ph;
+  a.kx = p.d_kx; a.ky = p.d_ky; a.zc = p.d_z; a.dir = p.d_dir;
+  a.npencils = (long)p.ny * p.nxl;
+  a.ny = p.ny; a.nph = p.nphys(); a.C = p.Cz; a.d = p.oz; a.has_mean = p.ista == 1 ? 1 : 0;
+  a.Lz = p.Lz; a.inv_nz = 1.0 / (double)p.nz; a.dkz = p.Dkz;
+  for (int k = 0; k < kMaxDF; ++k) {
+    a.neu1[k] = k < p.oz ? p.h_neu[k] : 0.0;
+    a.neu2[k] = k < p.oz ? p.h_neu2[k] : 0.0;
+  }
+  static const double r8[8][2] = {{1, 0}, {0.70710678118654752440, 0.70710678118654752440}, {0, 1}, {-0.70710678118654752440, 0.70710678118654752440},
+                                  {-1, 0}, {-0.70710678118654752440, -0.70710678118654752440}, {0, -1}, {0.70710678118654752440, -0.70710678118654752440}};
+  for (int k = 0; k < 8; ++k) {
+    const int q = (int)(((long)k * (p.nphys() - 1)) % 8);
+    a.phT[k] = cmake(r8[q][0], r8[q][1]);
+  }
+  const cplx* tw = p.tw_z;
+#define SX_APROJ_(N, MINB)                                                                          \
+  case N: {                                                                                         \
+    auto kfn = k_aproject_pair<N, MINB>;                                                            \
+    const size_t smem = ProjPairGeo<N>::smem_bytes(p.Cz);                                           \
+    int grid;                                                                                       \
+    if (persistent_grid(p, kfn, N / 8, smem, (int)a.npencils, &grid)) return 1;                     \
+    SX_FUSED_LAUNCH(p, ST_PROJECT, kfn, dim3(grid), N / 8, smem, a, tw);                            \
+    return 0;                                                                                       \
+  }
+  switch (p.nz) {
+    SX_APROJ_(256, 4)
+    SX_APROJ_(512, 4)
+    SX_APROJ_(1024, 2)
+    SX_APROJ_(2048, 1)
+  }
+#undef SX_APROJ_
+  return -1;
+}
+
 template <int N, int MINB, int L2PF = 0> static int run_project_bulk(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
                                                        const double* zs, const double* ze) {
   constexpr int T = N / 8, NW = (T + 31) / 32;
