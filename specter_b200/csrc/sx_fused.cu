@@ -151,7 +151,7 @@ static int to_real_begin(Plan& p, Fused& f, int slot) {
     for (int r = 0; r < p.nprocs; ++r) {
       dst[r] = peer_r_dst(p, f, slot, r);
       // blocks the z-inverse kernel already stored into their destination (sx_fused_tiles.cu) are not copied
-      if (f.zinv_direct && (f.direct >= 2 || (f.direct == 1 && r == p.myrank))) cnt[r] = 0;
+      if (f.zinv_direct && direct_to(p, f, r)) cnt[r] = 0;
     }
     return exchange_begin_p2p(p, slot, f.W[slot], f.z_displ.data(), cnt.data(), dst.data());
   }
@@ -165,7 +165,7 @@ static int to_spec_begin(Plan& p, Fused& f, int slot) {
     std::vector<size_t> cnt(f.x_count);
     for (int r = 0; r < p.nprocs; ++r) {
       dst[r] = peer_uz_dst(p, f, slot, r);
-      if (f.yfwd_direct && (f.direct >= 2 || (f.direct == 1 && r == p.myrank))) cnt[r] = 0;
+      if (f.yfwd_direct && direct_to(p, f, r)) cnt[r] = 0;
     }
     return exchange_begin_p2p(p, 16 + slot, f.U[slot], f.x_displ.data(), cnt.data(), dst.data());
   }
@@ -240,7 +240,7 @@ template <int NC> static int xy_stage_chunked(Plan& p, Fused& f, const cplx* con
       for (int h = 0; h < 2; ++h)
         for (int qd = 1; qd <= p.nprocs; ++qd) {
           const int r = (p.myrank + qd) % p.nprocs;
-          if (r == p.myrank && zdirect) continue;
+          if (zdirect && direct_to(p, f, r)) continue;
           int c0, cc;
           range0(zc[r], nch, k, &c0, &cc);
           cp.push_back(P2PCopy{peer_r_dst(p, f, 2 * c + h, r) + (size_t)c0 * p.ny, f.W[2 * c + h] + f.z_displ[r] + (size_t)c0 * p.ny,
@@ -270,7 +270,7 @@ template <int NC> static int xy_stage_chunked(Plan& p, Fused& f, const cplx* con
     for (int c = 0; c < NC; ++c)
       for (int qd = 1; qd <= p.nprocs; ++qd) {
         const int r = (p.myrank + qd) % p.nprocs;
-        if (r == p.myrank && ydirect) continue;
+        if (ydirect && direct_to(p, f, r)) continue;
         int xs, xc;
         range0(p.nxh, p.nprocs, r, &xs, &xc);
         cp.push_back(P2PCopy{peer_uz_dst(p, f, c, r) + (size_t)c0 * p.ny, f.U[c] + f.x_displ[r] + (size_t)c0 * p.ny,
@@ -328,7 +328,14 @@ int fused_p2p_import(Plan& p, const void* handles) {
     f->peer_arena[r] = (cplx*)ptr;
   }
   f->p2p = true;
-  if (const char* e = getenv("SX_P2P_DIRECT")) f->direct = atoi(e);
+  if (const char* e = getenv("SX_P2P_DIRECT")) {
+    SX_REQUIRE(e[0] >= '0' && e[0] <= '2' && e[1] == 0, "invalid value of the tuning variable SX_P2P_DIRECT (0, 1 or 2)");
+    f->direct = e[0] - '0';
+  }
+  if (const char* e = getenv("SX_P2P_DIRECT_PEERS")) {
+    SX_REQUIRE(e[0] >= '0' && e[0] <= '7' && e[1] == 0, "invalid value of the tuning variable SX_P2P_DIRECT_PEERS (0..7)");
+    f->direct_peers = e[0] - '0';
+  }
   return 0;
 #else
   (void)p; (void)handles;

@@ -38,6 +38,9 @@ struct Fused {
   // which blocks the producing kernels store straight into the destination rank's buffer instead of the send
   // buffer: 0 none (all blocks travel by copy engine), 1 the local block, 2 every block (stores over NVLink)
   int direct = 1;
+  // with direct == 1: the blocks of the next `direct_peers` ranks (ring order) are ALSO stored straight over NVLink by the
+  // producing kernels while the copy engines carry the rest -- the two paths add up on the links (env SX_P2P_DIRECT_PEERS)
+  int direct_peers = 0;
   bool zinv_direct = false, yfwd_direct = false;   // set by the launchers when the kernel variant in use does so
   // z window of the xy stage (y-inverse, x pass, y-forward launchers): rows [zw0, zw0 + zwc) of the local slab;
   // zwc < 0 = the whole slab.  The chunked multi-rank pipeline (sx_fused.cu) moves it from chunk to chunk.
@@ -52,6 +55,13 @@ struct Fused {
   bool vwin = false;    // this substep addresses V / X relative to the current z window
   size_t vz0() const { return vwin ? 0 : (size_t)z0(); }
 };
+
+// does the producing kernel store the block of rank r itself (instead of leaving it to the copy engines)?
+inline bool direct_to(const Plan& p, const Fused& f, int r) {
+  if (f.direct >= 2) return true;
+  if (f.direct < 1) return false;
+  return (r - p.myrank + p.nprocs) % p.nprocs <= f.direct_peers;
+}
 
 inline void range0(int n, int nprocs, int r, int* sta, int* cnt) {  // `range` on [0,n)
   const int w = n / nprocs, m = n % nprocs;

@@ -453,7 +453,7 @@ template <int N> static int run_zinv_tma(Plan& p, Fused& f, const cplx* in, cplx
   f.zinv_direct = f.p2p && s0 >= 0 && s1 >= 0;
   for (int r = 0; r < p.nprocs; ++r) {
     if (zc[r] == 0) continue;
-    const bool direct = f.zinv_direct && (f.direct >= 2 || (f.direct == 1 && r == p.myrank));
+    const bool direct = f.zinv_direct && direct_to(p, f, r);
     cplx* b0 = direct ? peer_r_dst(p, f, s0, r) : out0 + f.z_displ[r];
     cplx* b1 = direct ? peer_r_dst(p, f, s1, r) : (out1 ? out1 : out0) + f.z_displ[r];
     if (add_block(m0, b0, p.ny, z0[r], zc[r], p.nxl, p.ny, (size_t)zc[r] * p.ny, NP)) return 1;
@@ -485,7 +485,7 @@ static int yfwd_peers(Plan& p, Fused& f, const cplx* out, YfwdArgs& a) {
     range0(p.nxh, p.nprocs, d, &xs, &xc);
     a.xs[d] = xs;
     a.xs[d + 1] = xs + xc;
-    a.peer[d] = (f.direct >= 2 || d == p.myrank) ? peer_uz_dst(p, f, slot, d) + (size_t)f.z0() * p.ny : nullptr;
+    a.peer[d] = direct_to(p, f, d) ? peer_uz_dst(p, f, slot, d) + (size_t)f.z0() * p.ny : nullptr;
   }
   return 0;
 }
