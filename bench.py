@@ -6,8 +6,8 @@
 A "step" is one full Runge-Kutta time step (rkstep1 + `ord` substeps, specter.fpp:1142-1161) of the solver on
 synthetic initial conditions; value = nx*ny*nz*ord*K / device seconds (continuation planes included, as the
 reference's benchmark.txt counts them).  Default workload: BASELINE.json configs[1] (HD channel flow 512^3, FP64,
-RK4) on one B200; configs[4] (HD 2048x2048x1024) on 8 GPUs, and the same 4 x 512^3 points per GPU on 2 and 4
-GPUs (1024^3, 2048x1024x1024).  Prints ONE JSON line on rank 0.
+RK4) on one B200 and 512^3 points per GPU on 2 and 4 (weak scaling of that configuration); configs[4] (HD 2048x2048x1024) on 8
+GPUs.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -39,9 +39,11 @@ WORKLOADS = {
     "bouss1024": (1024, 1024, 512, 4, 1e-4, "BOUSS Rayleigh-Benard 1024x1024x512 FP64 RK4 (BASELINE configs[2]; 8 GPUs)"),
     "mhd512": (512, 512, 512, 4, 2e-4, "MHD vector potential 512x512x512 FP64 RK4, no-slip + conducting walls (BASELINE configs[3])"),
 }
-# --gpus N without --workload: the headline configuration on one GPU, the north star's scaling configuration
-# (BASELINE configs[4]) on 8, and that configuration's per-GPU problem (4 x 512^3 points) on 2 and 4
-DEFAULT_WORKLOAD = {1: "hd512", 2: "hd1024c", 4: "hd2048h", 8: "hd2048"}
+# --gpus N without --workload: the headline configuration (BASELINE configs[1]) on one GPU, its weak-scaling series of
+# 512^3 points per GPU on 2 and 4 (1024x512x512, 1024x1024x512), and the north star's scaling configuration
+# (BASELINE configs[4], 2048x2048x1024 = 4 x 512^3 points per GPU) on 8.  The per-GPU problem of configs[4] on fewer
+# GPUs is --workload hd1024c (2) / hd2048h (4); profiles/r2h, r2i4.
+DEFAULT_WORKLOAD = {1: "hd512", 2: "hd512", 4: "hd512", 8: "hd2048"}
 CZ, OZ, NU = 25, 5, 1e-3
 KAPPA, MU = 1e-3, 5e-3
 # algorithmic HBM bytes per grid-point-substep (55 F / 73 F / 98 F, F = 8 B/pt)
@@ -285,10 +287,21 @@ def parity_check(world, rank, local, dist):
     return out
 
 
-def reference_workload(args):
-    if args.workload:
-        return args.workload
-    return DEFAULT_WORKLOAD.get(args.gpus, "hd512")
+def resolve_workload(args, world):
+    """(name, nx, ny, nz, ord, dt, description, scaling) of this run: both arms use the same rule."""
+    named = args.workload is not None
+    wl = args.workload or ("hd512" if (args.strong or args.weak512) else DEFAULT_WORKLOAD.get(world, "hd512"))
+    nx, ny, nz, ord_, dt, desc = WORKLOADS[wl]
+    scaling = "weak"
+    if world > 1 and not named:
+        if args.weak512 or (wl == "hd512" and not args.strong):
+            nx, ny = {2: (1024, 512), 4: (1024, 1024), 8: (2048, 1024)}.get(world, (512 * world, 512))
+            desc = f"HD channel flow {nx}x{ny}x{nz} FP64 RK4 (512^3 points per GPU on {world} GPUs), no-slip walls, FC-Gram C=25 d=5"
+        elif args.strong:
+            scaling = "strong"
+    elif world > 1:
+        scaling = "strong"      # a named grid on N GPUs: total work fixed
+    return wl, nx, ny, nz, ord_, dt, desc, scaling
 
 
 def reference_arm(args, rank, world):
@@ -298,8 +311,7 @@ def reference_arm(args, rank, world):
     substep of a bounded sample grid of the configured solver; the sample actually run is named in config.workload."""
     if rank != 0:
         return
-    wl = reference_workload(args)
-    nx, ny, nz, ord_, dt, desc = WORKLOADS[wl]
+    wl, nx, ny, nz, ord_, dt, desc, _ = resolve_workload(args, max(world, args.gpus))
     solver = "bouss" if wl.startswith("bouss") else ("mhd" if wl.startswith("mhd") else "hd")
     try:
         cores = len(os.sched_getaffinity(0))
@@ -424,18 +436,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    explicit = args.workload is not None
-    wl = args.workload or ("hd512" if (args.strong or args.weak512) else DEFAULT_WORKLOAD.get(world, "hd512"))
-    nx, ny, nz, ord_, dt, desc = WORKLOADS[wl]
-    scaling = "weak"
-    if world > 1 and not explicit:
-        if args.weak512:
-            nx, ny = {2: (1024, 512), 4: (1024, 1024), 8: (2048, 1024)}.get(world, (512 * world, 512))
-            desc = f"HD channel flow {nx}x{ny}x{nz} FP64 RK4 (512^3 points per GPU on {world} GPUs), no-slip walls, FC-Gram C=25 d=5"
-        elif args.strong:
-            scaling = "strong"
-    elif world > 1:
-        scaling = "strong"      # a named grid on N GPUs: total work fixed
+    wl, nx, ny, nz, ord_, dt, desc, scaling = resolve_workload(args, world)
     solver = "bouss" if wl.startswith("bouss") else ("mhd" if wl.startswith("mhd") else "hd")
     b_alg = B_ALG_BY_SOLVER[solver]
 
