@@ -40,7 +40,8 @@ def to_ms(v, unit):
 
 STAGE_OF = {"k_zinv_tile": "zinv_tile", "k_yinv_tile": "yinv_tile", "k_yfwd_tile": "yfwd_tile", "k_yfwd_tma": "yfwd_tile",
             "k_zfwd_rk": "zfwd_rk", "k_zfwd_rk_tma": "zfwd_rk", "k_project": "project", "k_project_bulk": "project",
-            "k_xpass_gradre": "xpass", "k_xpass_gradre_bulk": "xpass", "k_xpass_cross": "xpass"}
+            "k_xpass_gradre": "xpass", "k_xpass_gradre_bulk": "xpass", "k_xpass_cross": "xpass", "k_xpass_cross_bulk": "xpass",
+            "k_project_pair": "project", "k_aproject_pair": "project"}
 
 
 def summarise_rep(tag, reps, workload="hd512"):
@@ -117,15 +118,28 @@ def summarise_rep(tag, reps, workload="hd512"):
         e["dram_bytes_per_launch"] /= e["launches"]
     path = os.path.join(ROOT, "profiles", f"{tag}_ncu_full.md")
     with open(path, "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on, one RK substep of HD 512^3 ({tag})\n\n"
+        f.write(f"# ncu --set full --clock-control none --import-source on, kernels of one RK substep of {workload} ({tag})\n\n"
                 "Per-launch averages over the captured launches (cold caches, serialised replays: compare shares and\n"
                 "traffic, not absolute times).  `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per launch.\n"
                 "Captured with tools/gpu_ncu3.sh (three reports covering zinv/yinv, xpass/yfwd, zfwd_rk/project).\n\n")
         f.write("\n".join(out) + "\n")
     print("wrote", path)
-    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as f:
-        json.dump({"workload": workload, "capture": tag, "metric": "dram__bytes_read.sum + dram__bytes_write.sum per launch",
-                   "stages": traffic}, f, indent=1)
+    # one entry per workload, tied to the kernel sources it was captured from (bench.py drops it when they differ)
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(tpath) as f:
+            doc = json.load(f)
+        if "workloads" not in doc:
+            doc = {"workloads": {}}
+    except (OSError, ValueError):
+        doc = {"workloads": {}}
+    doc["metric"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch"
+    doc["workloads"][workload] = {"capture": tag, "sources_hash": bench.sources_hash(), "stages": traffic}
+    with open(tpath, "w") as f:
+        json.dump(doc, f, indent=1)
     print("wrote profiles/ncu_traffic.json")
 
 
@@ -160,9 +174,10 @@ if __name__ == "__main__":
     ap.add_argument("tag")
     ap.add_argument("--rep", nargs="+")
     ap.add_argument("--launches")
+    ap.add_argument("--workload", default="hd512")
     a = ap.parse_args()
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     if a.rep:
-        summarise_rep(a.tag, a.rep)
+        summarise_rep(a.tag, a.rep, a.workload)
     if a.launches:
         summarise_launches(a.tag, a.launches)
