@@ -193,10 +193,9 @@ static int plan_init(Plan& p, const sx_config& c) {
   // tuning knobs (debugging / A-B timing): every value is range-checked against the variants that exist, so a stray
   // environment variable cannot silently select an untested configuration
   struct Knob { const char* name; int* v; int lo, hi; };
-  const Knob knobs[] = {{"SX_ZF", &p.knob_zf, 0, 7},          {"SX_XP", &p.knob_xp, 0, 19},      {"SX_PJ", &p.knob_pj, 0, 19},
-                        {"SX_TILE_PF", &p.knob_pf, 0, 15},    {"SX_ZCHUNKS", &p.knob_zchunks, 1, 8}, {"SX_TMA", &p.knob_tma, 0, 15},
-                        {"SX_TMA_MIN", &p.knob_tma_min, 16, 4096}, {"SX_INV_STAGES", &p.knob_inv_stages, 0, 3},
-                        {"SX_TILE_NP", &p.knob_np, 0, 32},    {"SX_TILE_MINB", &p.knob_minb, 1, 8}};
+  const Knob knobs[] = {{"SX_XP", &p.knob_xp, 0, 10},         {"SX_PJ", &p.knob_pj, 0, 10},       {"SX_TILE_PF", &p.knob_pf, 0, 15},
+                        {"SX_ZCHUNKS", &p.knob_zchunks, 1, 8}, {"SX_TMA", &p.knob_tma, 0, 7},     {"SX_TMA_MIN", &p.knob_tma_min, 16, 4096},
+                        {"SX_INV_STAGES", &p.knob_inv_stages, 0, 3}};
   for (const Knob& k : knobs) {
     const char* e = getenv(k.name);
     if (!e || !*e) continue;

@@ -224,214 +224,19 @@ __global__ void __launch_bounds__(NPB*(N / 8), MINB) k_project(ProjArgs a, const
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// project, bulk-copy version: one pencil per CTA (N/8 threads), persistent.  Differences from k_project:
-//   * the three spectral pencils arrive as 8 KB cp.async.bulk copies (TMA) into three shared-memory slots; the
-//     slots then park the intermediate fields (every thread only touches its own elements); the vx / vy slots
-//     are refilled for the next pencil while the last transform of this one runs, the vz slot right after it;
-//   * the wall values of v_z are the two rows k = 1 and k = nz-Cz of the backward transform: two dot products
-//     with a block reduction instead of a whole transform (boundary_mod.fpp:275-338 only uses those rows);
-//   * e^{-kh z} and e^{kh (z - Lz)} on the uniform grid are geometric sequences in the thread's stride: three
-//     exponentials per thread and pencil instead of sixteen, each sequence started at its large end so that
-//     underflow follows the true values.
-// ------------------------------------------------------------------------------------------
+// pencil arguments plus the stride factors of the top-wall row of the backward transform
 struct ProjBulkArgs {
   ProjArgs a;
   cplx phT[8];   // exp(+2 pi i k top / 8), k = 0..7: stride factors of the top-wall row of the backward transform
 };
 
-template <int N, int MINB, int L2PF = 0>
-__global__ void __launch_bounds__(N / 8, MINB) k_project_bulk(ProjBulkArgs pa, const cplx* __restrict__ tw) {
-  SX_DYN_SMEM(cplx, smem);
-  const ProjArgs& a = pa.a;
-  constexpr int T = N / 8, XS = sidx_elem_stride<N>(), NW = (T + 31) / 32;
-  constexpr unsigned PBYTES = N * sizeof(cplx);
-  const int j = threadIdx.x;
-  const bool lead = j == 0;
-  TwRegs<N> twr;
-  twr.load(tw, j);
-  const SIdxElem si{0};
-  cplx* sx = smem + XS;
-  cplx* sy = sx + N;
-  cplx* sz = sy + N;
-  cplx* bnd = sz + N;
-  cplx* red = bnd + 2 * kMaxDF;
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 2 * NW);
-  const int top = a.nph - 1;
-  // phase of the top-wall row at this thread's first element
-  cplx phj;
-  {
-    double sn, cs;
-    sincospi(2.0 * (double)(((long)j * top) % N) / (double)N, &sn, &cs);
-    phj = cmake(cs, sn);
-  }
-  const double zj = __ldg(&a.zc[j]), z7 = __ldg(&a.zc[j + 7 * T]), dzT = __ldg(&a.zc[T]) - __ldg(&a.zc[0]);
-  if (lead) {
-    for (int b = 0; b < 3; ++b) mbar_init(bar + b, 1);
-    mbar_init_fence();
-  }
-  __syncthreads();
-  int g = blockIdx.x;   // pencil index: ny * nxl < 2^31
-  const int npencils = (int)a.npencils;
-  if (lead && g < npencils) {
-    bulk_load(sx, a.vx + (size_t)g * N, PBYTES, bar);
-    bulk_load(sy, a.vy + (size_t)g * N, PBYTES, bar + 1);
-    bulk_load(sz, a.vz + (size_t)g * N, PBYTES, bar + 2);
-  }
-  unsigned phase = 0;
-  for (; g < npencils; g += gridDim.x) {
-    const int gn = g + gridDim.x;
-    if (L2PF && lead && gn < npencils) {
-      // the next pencil's slots are refilled only under the last transforms of this one: pull its three lines (and
-      // the wall rows of p') into L2 now, so that those refills and loads are L2 hits
-      l2_prefetch(a.vx + (size_t)gn * N, PBYTES);
-      l2_prefetch(a.vy + (size_t)gn * N, PBYTES);
-      l2_prefetch(a.vz + (size_t)gn * N, PBYTES);
-      if (L2PF > 1) l2_prefetch(a.pr + (size_t)gn * N, PBYTES);
-    }
-    const int kx_i = g / a.ny, ky_i = g - kx_i * a.ny;
-    const size_t base = (size_t)g * N;
-    const double x = __ldg(&a.kx[kx_i]), y = __ldg(&a.ky[ky_i]);
-    const bool mean = a.has_mean && g == 0;
-    const cplx pr0 = a.pr[base], prT = a.pr[base + top];
-
-    // ---- no-slip rows of vx, vy in the mixed domain, back to Fourier (vboundary.f90:116-145) ----
-    cplx v[8];
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      const double kc = c == 0 ? x : y;
-      cplx* sc = c == 0 ? sx : sy;
-      mbar_wait(bar + c, phase);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = sc[j + k * T];
-      fft_regs<N, 1>(v, j, smem, si, twr);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int e = j + k * T;
-        v[k] = cscale(v[k], a.inv_nz);
-        if (e == 0 || e == top) {
-          const cplx P = e == 0 ? pr0 : prT;
-          v[k] = cmake(-kc * P.y * a.tmp_noslip, kc * P.x * a.tmp_noslip);
-          if (mean) v[k] = cmake(e == 0 ? (c == 0 ? a.mx0 : a.my0) : (c == 0 ? a.mx1 : a.my1), 0.0);
-        }
-      }
-      fc_fft_fwd<N>(v, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, twr);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) sc[j + k * T] = v[k];   // parked in its own slot
-    }
-    // ---- particular solution and its gradient (boundary_mod.fpp:405-448, 249-259) ----
-    cplx dd[8];
-    mbar_wait(bar + 2, phase);
-    phase ^= 1;
-    cplx s0 = cmake(0.0, 0.0), s1 = cmake(0.0, 0.0);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int e = j + k * T;
-      const double z = __ldg(&a.kz[e]);
-      const double kk2 = x * x + y * y + z * z;
-      cplx A = sx[e], B = sy[e];
-      cplx Cc = sz[e];
-      const cplx s = cmake(x * A.x + y * B.x + z * Cc.x, x * A.y + y * B.y + z * Cc.y);
-      cplx D = cmake(s.y / kk2, -s.x / kk2);
-      if (mean && e == 0) D = cmake(0.0, 0.0);
-      A = cmake(A.x + x * D.y, A.y - x * D.x);
-      B = cmake(B.x + y * D.y, B.y - y * D.x);
-      Cc = cmake(Cc.x + z * D.y, Cc.y - z * D.x);
-      sx[e] = A;
-      sy[e] = B;
-      sz[e] = Cc;   // parked like vx, vy (own elements only)
-      dd[k] = D;
-      // ---- wall values of v_z (boundary_mod.fpp:275-338): rows 0 and top of IFFT_z(v_z)/nz ----
-      s0 = cadd(s0, Cc);
-      s1 = cadd(s1, cmul(Cc, pa.phT[k]));
-    }
-    s1 = cmul(s1, phj);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s0.x += __shfl_xor_sync(0xffffffffu, s0.x, o);
-      s0.y += __shfl_xor_sync(0xffffffffu, s0.y, o);
-      s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o);
-      s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
-    }
-    if ((j & 31) == 0) {
-      red[2 * (j >> 5)] = s0;
-      red[2 * (j >> 5) + 1] = s1;
-    }
-    __syncthreads();   // partial sums visible
-    cplx bc1 = red[0], bc2 = red[1];
-#pragma unroll
-    for (int w = 1; w < NW; ++w) {
-      bc1 = cadd(bc1, red[2 * w]);
-      bc2 = cadd(bc2, red[2 * w + 1]);
-    }
-    bc1 = cscale(bc1, a.inv_nz);
-    bc2 = cscale(bc2, a.inv_nz);
-    // ---- laplace_z, Neumann-Neumann (boundary_mod.fpp:531-560, 635-675) ----
-    const double kh = sqrt(x * x + y * y);
-    cplx c1, c2;
-    if (mean) {
-      c1 = bc1;
-      c2 = cmake(0.0, 0.0);
-    } else {
-      const double e1 = exp(-kh * a.Lz), tt = 1.0 / (kh * (1.0 - e1 * e1));
-      c1 = cmake((bc2.x - bc1.x * e1) * tt, (bc2.y - bc1.y * e1) * tt);
-      c2 = cmake((-bc1.x + bc2.x * e1) * tt, (-bc1.y + bc2.y * e1) * tt);
-    }
-    // p' = IFFT_z(d)/nz + phi  (boundary_mod.fpp:371-380); all nz rows like the reference
-    fft_regs<N, 1>(dd, j, smem, si, twr);
-    double ep[8], em = 0.0, st = 0.0;
-    if (!mean) {
-      st = exp(-kh * dzT);
-      em = exp(-kh * zj);
-      ep[7] = exp(kh * (z7 - a.Lz));
-#pragma unroll
-      for (int k = 6; k >= 0; --k) ep[k] = ep[k + 1] * st;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int e = j + k * T;
-      cplx A, B;
-      if (mean) {
-        const double z = __ldg(&a.zc[e]);
-        A = cmake(c1.x * z + c2.x, 0.0);
-        B = cmake(c1.x, 0.0);
-      } else {
-        A = cmake(c1.x * ep[k] + c2.x * em, c1.y * ep[k] + c2.y * em);
-        B = cmake(kh * (c1.x * ep[k] - c2.x * em), kh * (c1.y * ep[k] - c2.y * em));
-        em *= st;
-      }
-      a.pr[base + e] = cmake(dd[k].x * a.inv_nz + A.x, dd[k].y * a.inv_nz + A.y);
-      dd[k] = A;   // phi
-      v[k] = B;    // d(phi)/dz
-    }
-    // ---- subtract the harmonic correction (boundary_mod.fpp:385-399); vx, vy first: their slots are then free ----
-    fc_fft_fwd<N>(dd, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, twr);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int e = j + k * T;
-      const cplx A = sx[e], B = sy[e], h = dd[k];
-      a.vx[base + e] = cmake(A.x + x * h.y, A.y - x * h.x);
-      a.vy[base + e] = cmake(B.x + y * h.y, B.y - y * h.x);
-    }
-    __syncthreads();   // every thread is done with the vx / vy slots: refill them under the last transform
-    if (lead && gn < npencils) {
-      bulk_load(sx, a.vx + (size_t)gn * N, PBYTES, bar);
-      bulk_load(sy, a.vy + (size_t)gn * N, PBYTES, bar + 1);
-    }
-    fc_fft_fwd<N>(v, j, smem, si, bnd, a.nph, a.C, a.d, a.dir, twr);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const cplx Cc = sz[j + k * T];
-      a.vz[base + j + k * T] = cmake(Cc.x - v[k].x, Cc.y - v[k].y);
-    }
-    __syncthreads();   // the v_z slot is free; its refill lands during the four transforms that precede its use
-    if (lead && gn < npencils) bulk_load(sz, a.vz + (size_t)gn * N, PBYTES, bar + 2);
-  }
-}
-
 // ------------------------------------------------------------------------------------------
-// project, paired version: the same pencil-per-CTA organisation as k_project_bulk with three changes measured or
-// derived in round 2 (profiles/r2_zstage_experiment.md):
+// project, paired version: one pencil per CTA (N/8 threads), persistent.  The three spectral pencils arrive as 8 KB
+// cp.async.bulk copies (TMA) into three shared-memory slots, which then park the intermediate fields (every thread only
+// touches its own elements) and are refilled for the next pencil while the results are formed; the wall values of v_z
+// are two dot products with a block reduction (boundary_mod.fpp:275-338 only uses rows 1 and nz-Cz); e^{-kh z} and
+// e^{kh (z - Lz)} on the uniform grid are geometric sequences in the thread's stride.  Against the round-1 kernel
+// (profiles/r2_zstage_experiment.md):
 //   * SIX transforms instead of seven, in THREE rounds of two (fft_regs2: both pencils of a round share every barrier
 //     and the twiddle powers): (IFFT v_x, IFFT v_y), (FFT v_x, FFT v_y), (IFFT d, FFT e).  The harmonic correction
 //     phi = c1 e^{kh (z - Lz)} + c2 e^{-kh z} and its derivative are linear in the two exponentials, and so are the
@@ -442,8 +247,9 @@ __global__ void __launch_bounds__(N / 8, MINB) k_project_bulk(ProjBulkArgs pa, c
 //     The mean pencil (kx = ky = 0) has phi = Re(c1) z + Re(c2): its phi^ multiplies kx = ky = 0 and drops out, and
 //     phi'^ = Re(c1) FFT(cont(1)) takes the place of E-^;
 //   * ONE copy of the forward transform in a rolled loop over the rounds (a backward transform is the forward one
-//     between two conjugations): the unrolled kernel is 152 KB of instructions, 9 % of its stall samples are
-//     instruction fetches, and the merged z-stage experiment lost a factor of three to them;
+//     between two conjugations): the unrolled round-1 kernel (k_project_bulk, seven transform instances) was 152 KB of
+//     instructions with 9 % of its stall samples on instruction fetches, and the merged z-stage experiment lost a
+//     factor of three to them;
 //   * one reciprocal instead of two divisions per element in the Poisson step.
 // ------------------------------------------------------------------------------------------
 template <int N> struct ProjPairGeo {
@@ -1102,31 +908,6 @@ int fused_aproject(Plan& p, cplx* ax, cplx* ay, cplx* az, cplx* ph) {
   return -1;
 }
 
-template <int N, int MINB, int L2PF = 0> static int run_project_bulk(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
-                                                       const double* zs, const double* ze) {
-  constexpr int T = N / 8, NW = (T + 31) / 32;
-  double tmp = 1.0 / (double)o;
-  if (o != p.ord) tmp = (double)(o + 1) * tmp;   // vboundary.f90:195-196
-  const double sc = (double)p.nx * (double)p.ny;
-  ProjBulkArgs pa;
-  pa.a = ProjArgs{vx, vy, vz, pr, p.d_kx, p.d_ky, p.d_kz, p.d_z, p.d_dir, (long)p.ny * p.nxl,
-                  p.ny, f.nph, p.Cz, p.oz, p.ista == 1 ? 1 : 0, p.Lz, tmp, 1.0 / (double)p.nz,
-                  sc * (zs ? zs[0] : 0.0), sc * (zs ? zs[1] : 0.0), sc * (ze ? ze[0] : 0.0), sc * (ze ? ze[1] : 0.0)};
-  static const double r8[8][2] = {{1, 0}, {0.70710678118654752440, 0.70710678118654752440}, {0, 1}, {-0.70710678118654752440, 0.70710678118654752440},
-                                  {-1, 0}, {-0.70710678118654752440, -0.70710678118654752440}, {0, -1}, {0.70710678118654752440, -0.70710678118654752440}};
-  for (int k = 0; k < 8; ++k) {
-    const int q = (int)(((long)k * (f.nph - 1)) % 8);
-    pa.phT[k] = cmake(r8[q][0], r8[q][1]);
-  }
-  const cplx* tw = p.tw_z;
-  auto kfn = k_project_bulk<N, MINB, L2PF>;
-  const size_t smem = ((size_t)sidx_elem_stride<N>() + (size_t)3 * N + (size_t)2 * kMaxDF + (size_t)2 * NW) * sizeof(cplx) + 3 * 8;
-  int grid;
-  if (persistent_grid(p, kfn, T, smem, (int)pa.a.npencils, &grid)) return 1;
-  SX_FUSED_LAUNCH(p, ST_PROJECT, kfn, dim3(grid), T, smem, pa, tw);
-  return 0;
-}
-
 template <int N, int NPB, bool PF, int MINB> static int run_project_v(Plan& p, Fused& f, cplx* vx, cplx* vy, cplx* vz, cplx* pr, int o,
                                         const double* zs, const double* ze) {
   constexpr int T = N / 8;
@@ -1149,23 +930,11 @@ template <int N> static int run_project(Plan& p, Fused& f, cplx* vx, cplx* vy, c
                                         const double* zs, const double* ze) {
   constexpr int T = N / 8;
   constexpr int NPB = T >= 128 ? 1 : 128 / T;
-  // bulk-copy version: default from one warp per pencil upwards (SX_PJ=9: previous kernel; SX_PJ=10: force)
+  // paired six-transform kernel from one warp per pencil upwards, four CTAs per SM (five spill at 204 registers: 2.93 ms
+  // against 2.49 ms, profiles/r2g); SX_PJ=9: the slot kernel the short pencils use
   if constexpr (N >= 256 && N <= 2048) {
-    // paired six-transform kernel, four CTAs per SM (five spill at 204 registers: 2.93 ms against 2.49 ms, profiles/r2g)
-    if ((p.knob_pj == 0 && N >= p.knob_tma_min) || p.knob_pj == 15)
+    if ((p.knob_pj == 0 && N >= p.knob_tma_min) || p.knob_pj == 10)
       return run_project_pair<N, (N <= 512 ? 4 : (N == 1024 ? 2 : 1))>(p, f, vx, vy, vz, pr, o, zs, ze);
-    if (p.knob_pj >= 10 && p.knob_pj < 20) {
-      if constexpr (N == 512) {
-        if (p.knob_pj == 11) return run_project_bulk<N, 4>(p, f, vx, vy, vz, pr, o, zs, ze);
-        if (p.knob_pj == 12) return run_project_bulk<N, 6>(p, f, vx, vy, vz, pr, o, zs, ze);
-        if (p.knob_pj == 13) return run_project_bulk<N, 5, 1>(p, f, vx, vy, vz, pr, o, zs, ze);
-        if (p.knob_pj == 14) return run_project_bulk<N, 5, 2>(p, f, vx, vy, vz, pr, o, zs, ze);
-      }
-      return run_project_bulk<N, (N <= 512 ? 5 : (N == 1024 ? 2 : 1))>(p, f, vx, vy, vz, pr, o, zs, ze);
-    }
-  }
-  if constexpr (N == 512) {   // previous best (profiles/r1h_knobs.md): one pencil per CTA, cp.async slots
-    if (p.knob_pj == 0 || p.knob_pj == 9) return run_project_v<N, 1, true, 6>(p, f, vx, vy, vz, pr, o, zs, ze);
   }
   return run_project_v<N, NPB, true, (N <= 512 ? 3 : 1)>(p, f, vx, vy, vz, pr, o, zs, ze);
 }

@@ -608,25 +608,13 @@ template <int N, int NC, int S, int MINB> static int run_xpass_bulk(Plan& p, Fus
 template <int N, int NC> static int run_xpass(Plan& p, Fused& f, const double* d_kx_global, int ui = -1, int qi = 0, int xo = 0) {
   constexpr int T = N / 8;
   constexpr int LP = T >= 128 ? 1 : 128 / T;
-  // bulk-copy ring (TMA) + register accumulators: default from one warp per line pair upwards (SX_XP=9: previous kernels)
+  // bulk-copy ring (TMA) + register accumulators from one warp per line pair upwards: 255 registers (accumulators, velocity
+  // line and one transform live in the register file), four two-warp CTAs per SM at N = 512, ring of three stages.
+  // SX_XP=9: the cp.async slot kernel the short lines use.
+  // SX_XP=10 forces it from N = 64 (the emulation tests run it on small grids).
   if constexpr (N >= 64 && N <= 2048) {
-    const bool want = p.knob_xp == 0 ? N >= 256 : (p.knob_xp >= 10 && p.knob_xp < 20);
-    if (want) {
-      // 255 registers: accumulators, velocity line and one transform live in the register file, so four
-      // two-warp CTAs per SM (two warps per scheduler); the ring depth sets the bytes in flight
-      if constexpr (N == 512) {
-        switch (p.knob_xp) {
-          case 11: return run_xpass_bulk<N, NC, 2, 4>(p, f, d_kx_global, ui, qi, xo);
-          case 12: return run_xpass_bulk<N, NC, 4, 4>(p, f, d_kx_global, ui, qi, xo);
-          case 13: return run_xpass_bulk<N, NC, 3, 6>(p, f, d_kx_global, ui, qi, xo);
-          default: break;
-        }
-      }
+    if (p.knob_xp == 0 ? N >= 256 : p.knob_xp == 10)
       return run_xpass_bulk<N, NC, 3, (N <= 512 ? 4 : (N == 1024 ? 2 : 1))>(p, f, d_kx_global, ui, qi, xo);
-    }
-  }
-  if constexpr (N == 512) {   // measured best on B200 (profiles/r1h_knobs.md): one pair per CTA, direct loads
-    if (p.knob_xp == 0 || p.knob_xp == 9) return run_xpass_v<N, 1, false, 6, NC>(p, f, d_kx_global, ui, qi, xo);
   }
   return run_xpass_v<N, LP, true, (N <= 1024 ? 2 : 1), NC>(p, f, d_kx_global, ui, qi, xo);
 }
@@ -652,8 +640,8 @@ template <int N> static int run_xcross(Plan& p, Fused& f, int npairs, const int*
   a.tmp = 1.0 / (Ntot * Ntot);
   const cplx* tw = p.tw_x;
   // bulk-copy ring from one warp per line pair upwards (SX_XP=9: the previous kernel with cp.async slots and parked P lines)
-  if constexpr (N >= 256 && N <= 2048) {
-    if (p.knob_xp != 9 && f.nxp == XpassBulk<N>::NXP && p.ny % 2 == 0) {
+  if constexpr (N >= 64 && N <= 2048) {
+    if ((p.knob_xp == 0 ? N >= 256 : p.knob_xp == 10) && f.nxp == XpassBulk<N>::NXP && p.ny % 2 == 0) {
       constexpr int S = 3, MINB = N <= 512 ? 4 : (N == 1024 ? 2 : 1);
       auto kfn = k_xpass_cross_bulk<N, S, MINB>;
       const size_t smem = ((size_t)XpassBulk<N>::XS + (size_t)S * 2 * XpassBulk<N>::NXP + (size_t)N) * sizeof(cplx) + (size_t)S * 8;

@@ -1,6 +1,5 @@
 // Fused substep: FC-Gram continuation + z-FFT + fc_filter + RK update (see sx_fused.cu for the pass structure).
 #include "sx_fused.h"
-#include "sx_tma.cuh"
 
 namespace sx {
 
@@ -66,7 +65,12 @@ __device__ __forceinline__ void stash_boundary_tile(const cplx (&v)[8], int j, i
   }
 }
 
-template <int N, int NP, int MINB, bool HOIST, bool PF, bool L2PF = false, int BATCH = 0>
+// BATCH: how the three (four) spectral pencils of the RK update are loaded.  true (N = 512, 128 registers, two CTAs per
+// SM): the linear-term pencil travels under the transform, the forcing and the RK base are loaded together after it
+// (16 loads in flight per thread; 1.074 -> 0.988 ms per launch, profiles/r1k_session5.md).  false: at the point of use.
+// Variants that lost in round 1 (all three pencils hoisted, L2 prefetch of the next tile's pencils, tensor-map box loads
+// of the nonlinear term) are in the history and in profiles/r1i_session4.md.
+template <int N, int NP, int MINB, bool PF, bool BATCH>
 __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const cplx* __restrict__ tw) {
   SX_DYN_SMEM(cplx, smem);
   constexpr int T = N / 8, NT = NP * T;
@@ -82,15 +86,6 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
   auto issue = [&](int t) {
     if (!PF) return;
     const int ky = (t % tiles_y) * NP + p, kxl = t / tiles_y;
-    // the three (four) spectral pencils of the RK update of that tile are loaded at the point of use, a whole
-    // tile later: pull them into L2 now (NP adjacent ky pencils are one contiguous range)
-    if (L2PF && threadIdx.x < 4) {
-      const int ky0 = (t % tiles_y) * NP;
-      const int np = a.ny - ky0 < NP ? a.ny - ky0 : NP;
-      const size_t tb = ((size_t)kxl * a.ny + ky0) * N;
-      const cplx* fld = threadIdx.x == 0 ? a.v : (threadIdx.x == 1 ? a.v0 : (threadIdx.x == 2 ? a.f : a.couple));
-      if (fld != nullptr) l2_prefetch(fld + tb, (unsigned)((size_t)np * N * sizeof(cplx)));
-    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int z = j + k * T;
@@ -125,22 +120,11 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
       }
     }
     if (t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
-    // the three spectral pencils of the RK update: issued before the transform so that their latency
-    // is covered by it (HOIST), or loaded at the point of use
     const size_t base = ((size_t)kxl * a.ny + (active ? ky : 0)) * N;
-    cplx L[8], B[8], F[8];
-    if (BATCH == 2) {   // the linear-term pencil travels under the transform; f and v0 are loaded together after it
+    cplx L[8];
+    if (BATCH) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) L[k] = a.v[base + j + k * T];
-    }
-    if (HOIST) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int e = j + k * T;
-        L[k] = a.v[base + e];
-        B[k] = a.v0[base + e];
-        F[k] = a.f[base + e];
-      }
     }
     __syncthreads();  // bnd and the exchange buffer of the previous tile are free
     stash_boundary_tile<N, NP>(v, j, p, bnd, a.nph, a.d);
@@ -151,7 +135,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
       const double x = __ldg(&a.kx[kxl]), y = __ldg(&a.ky[ky]);
       const double f1 = __ldg(&a.fx[kxl]), f2 = __ldg(&a.fy[ky]);
       const double kh2 = x * x + y * y;
-      if (BATCH == 2) {
+      if (BATCH) {
         // same arithmetic, association and order as the one-field-at-a-time form below; only the loads move
         if (a.couple != nullptr) {
           cplx Q[8];
@@ -160,6 +144,7 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = caxpy(a.ccoef, Q[k], v[k]);
         }
+        cplx B[8], F[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           F[k] = a.f[base + j + k * T];
@@ -177,125 +162,20 @@ __global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk(ZfwdArgs a, const 
         for (int k = 0; k < 8; ++k) v[k] = cmake((v[k].x + F[k].x) * a.dt * a.rmp, (v[k].y + F[k].y) * a.dt * a.rmp);
 #pragma unroll
         for (int k = 0; k < 8; ++k) a.vout[base + j + k * T] = cmake(B[k].x + v[k].x, B[k].y + v[k].y);
-      } else if (BATCH == 1) {
-        // one field at a time, eight independent loads in flight per thread: at 80 registers the fused form
-        // below only keeps three loads in flight and pays the memory latency once per element instead
-        // of once per field (the arithmetic is associated exactly as below)
-        if (a.couple != nullptr) {
-          cplx Q[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) Q[k] = a.couple[base + j + k * T];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = caxpy(a.ccoef, Q[k], v[k]);
-        }
-        cplx Q[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) Q[k] = a.v[base + j + k * T];
+      } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int e = j + k * T;
           const double z = __ldg(&a.kz[e]), f3 = __ldg(&a.fz[e]);
           const double lm = a.lap ? -(kh2 + z * z) : 1.0;
-          const cplx NL = cscale(cscale(cscale(v[k], f1), f2), f3);
-          v[k] = cmake(a.cL * (lm * Q[k].x) + a.sNL * NL.x, a.cL * (lm * Q[k].y) + a.sNL * NL.y);
+          cplx NL = v[k];
+          if (a.couple != nullptr) NL = caxpy(a.ccoef, a.couple[base + e], NL);
+          NL = cscale(cscale(cscale(NL, f1), f2), f3);
+          const cplx Lk = a.v[base + e], Bk = a.v0[base + e], Fk = a.f[base + e];
+          a.vout[base + e] = cmake(Bk.x + a.dt * (a.cL * (lm * Lk.x) + a.sNL * NL.x + Fk.x) * a.rmp,
+                                   Bk.y + a.dt * (a.cL * (lm * Lk.y) + a.sNL * NL.y + Fk.y) * a.rmp);
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) Q[k] = a.f[base + j + k * T];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = cmake((v[k].x + Q[k].x) * a.dt * a.rmp, (v[k].y + Q[k].y) * a.dt * a.rmp);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) Q[k] = a.v0[base + j + k * T];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a.vout[base + j + k * T] = cmake(Q[k].x + v[k].x, Q[k].y + v[k].y);
-      } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int e = j + k * T;
-        const double z = __ldg(&a.kz[e]), f3 = __ldg(&a.fz[e]);
-        const double lm = a.lap ? -(kh2 + z * z) : 1.0;
-        cplx NL = v[k];
-        if (a.couple != nullptr) NL = caxpy(a.ccoef, a.couple[base + e], NL);
-        NL = cscale(cscale(cscale(NL, f1), f2), f3);
-        const cplx Lk = HOIST ? L[k] : a.v[base + e], Bk = HOIST ? B[k] : a.v0[base + e], Fk = HOIST ? F[k] : a.f[base + e];
-        a.vout[base + e] = cmake(Bk.x + a.dt * (a.cL * (lm * Lk.x) + a.sNL * NL.x + Fk.x) * a.rmp,
-                                 Bk.y + a.dt * (a.cL * (lm * Lk.y) + a.sNL * NL.y + Fk.y) * a.rmp);
       }
-      }
-    }
-  }
-}
-
-// Bulk-copy (TMA) version for one rank: the nonlinear-term tile (64-byte pieces of NP adjacent ky pencils,
-// physical rows only) arrives as tensor-map boxes clipped at nph, one tile ahead; everything after the load is
-// the same arithmetic as k_zfwd_rk.
-template <int N, int NP, int MINB>
-__global__ void __launch_bounds__(NP*(N / 8), MINB) k_zfwd_rk_tma(ZfwdArgs a, const SX_GRID_CONSTANT TmaMap min,
-                                                                  const cplx* __restrict__ tw) {
-  SX_DYN_SMEM(cplx, smem_raw);
-  constexpr int T = N / 8, ROWS = N < 256 ? N : 256, NBOX = N / ROWS;
-#ifndef SX_EMU
-  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
-#else
-  const uintptr_t sbase = reinterpret_cast<uintptr_t>(smem_raw);
-#endif
-  cplx* exch = smem_raw + ((128u - (unsigned)(sbase & 127u)) & 127u) / sizeof(cplx);   // offset form keeps the shared address space
-  cplx* in = exch + (size_t)N * NP;              // [row][NP]
-  cplx* bnd = in + (size_t)N * NP;
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(bnd + (size_t)2 * kMaxDF * NP);
-  const int p = threadIdx.x % NP, j = threadIdx.x / NP;
-  const bool lead = threadIdx.x == 0;
-  TwRegs<N> twr;
-  twr.load(tw, j);
-  const int tiles_y = a.ny / NP, ntiles = tiles_y * a.nxl;
-  auto issue = [&](int t) {
-    const int ky0 = (t % tiles_y) * NP, kxl = t / tiles_y;
-    mbar_expect(bar, (unsigned)((size_t)N * NP * sizeof(cplx)));
-#pragma unroll
-    for (int b = 0; b < NBOX; ++b) tma_load_3d(in + (size_t)b * ROWS * NP, &min, 2 * ky0, b * ROWS, kxl, bar);
-    const size_t tb = ((size_t)kxl * a.ny + ky0) * N;
-    const unsigned bytes = (unsigned)((size_t)NP * N * sizeof(cplx));
-    l2_prefetch(a.v + tb, bytes);
-    l2_prefetch(a.v0 + tb, bytes);
-    l2_prefetch(a.f + tb, bytes);
-    if (a.couple != nullptr) l2_prefetch(a.couple + tb, bytes);
-  };
-  if (lead) {
-    mbar_init(bar, 1);
-    mbar_init_fence();
-  }
-  __syncthreads();
-  int t = blockIdx.x;
-  unsigned phase = 0;
-  if (lead && t < ntiles) issue(t);
-  for (; t < ntiles; t += gridDim.x) {
-    const int ky = (t % tiles_y) * NP + p, kxl = t / tiles_y;
-    const int tn = t + gridDim.x;
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    cplx v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = in[(size_t)(j + k * T) * NP + p];   // rows >= nph are zero-filled, and continued below
-    const size_t base = ((size_t)kxl * a.ny + ky) * N;
-    __syncthreads();  // bnd and the exchange buffer of the previous tile are free; the staging tile is consumed
-    if (lead && tn < ntiles) issue(tn);
-    stash_boundary_tile<N, NP>(v, j, p, bnd, a.nph, a.d);
-    __syncthreads();
-    fc_continue_tile<N, NP>(v, j, p, bnd, a.nph, a.C, a.d, a.dir);
-    fft_regs<N, -1>(v, j, exch, SIdxPencil{p, NP}, twr);
-    const double x = __ldg(&a.kx[kxl]), y = __ldg(&a.ky[ky]);
-    const double f1 = __ldg(&a.fx[kxl]), f2 = __ldg(&a.fy[ky]);
-    const double kh2 = x * x + y * y;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int e = j + k * T;
-      const double z = __ldg(&a.kz[e]), f3 = __ldg(&a.fz[e]);
-      const double lm = a.lap ? -(kh2 + z * z) : 1.0;
-      cplx NL = v[k];
-      if (a.couple != nullptr) NL = caxpy(a.ccoef, a.couple[base + e], NL);
-      NL = cscale(cscale(cscale(NL, f1), f2), f3);
-      const cplx Lk = a.v[base + e], Bk = a.v0[base + e], Fk = a.f[base + e];
-      a.vout[base + e] = cmake(Bk.x + a.dt * (a.cL * (lm * Lk.x) + a.sNL * NL.x + Fk.x) * a.rmp,
-                               Bk.y + a.dt * (a.cL * (lm * Lk.y) + a.sNL * NL.y + Fk.y) * a.rmp);
     }
   }
 }
@@ -306,54 +186,18 @@ template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, const
   ZfwdArgs a{nl, v, vout, v0, frc, rk.couple, rk.ccoef, rk.cL, rk.sNL, rk.lap, f.d_zmap, p.d_kx, p.d_ky, p.d_kz,
              p.d_fx, p.d_fy, p.d_fz, p.d_dir, p.ny, p.nxl, f.nph, p.Cz, p.oz, dt, rmp};
   const cplx* tw = p.tw_z;
-  if (N >= p.knob_tma_min && p.nprocs == 1 && p.ny % NP == 0 && (p.knob_tma & 8)) {
-    constexpr int ROWS = N < 256 ? N : 256;
-    TmaMap min;
-    if (tma_encode(&min, nl, p.ny, f.nph, p.nxl, p.ny, (size_t)f.nph * p.ny, NP, ROWS)) return 1;
-    auto kfn = k_zfwd_rk_tma<N, NP, MINB>;
-    const size_t smem_t = ((size_t)2 * NP * N + (size_t)2 * kMaxDF * NP) * sizeof(cplx) + 8 + 128;
-    int grid_t;
-    if (persistent_grid(p, kfn, NP * (N / 8), smem_t, (p.ny / NP) * p.nxl, &grid_t)) return 1;
-    SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid_t), NP * (N / 8), smem_t, a, min, tw);
-    return 0;
-  }
   const size_t smem = ((size_t)2 * NP * N + (size_t)2 * kMaxDF * NP) * sizeof(cplx) + (size_t)N * sizeof(ZMap);
   int grid;
-  if (N == 512 && p.knob_zf == 1) {
-    auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), true, true>;
+  if (!(p.knob_pf & 8)) {   // SX_TILE_PF bit 3 off: no cp.async prefetch of the nonlinear-term tile
+    auto kfn = k_zfwd_rk<N, NP, MINB, false, false>;
     if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
     SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
-    return 0;
-  }
-  // length 512 (profiles/r1i_session4.md): 128 registers, two CTAs per SM; SX_ZF=6: the RK fields one at a time (previous default)
-  if ((p.knob_pf & 8) && N == 512 && (p.knob_zf == 0 || (p.knob_zf >= 4 && p.knob_zf <= 7))) {
-    if (p.knob_zf == 0 || p.knob_zf == 7) {   // default: linear-term pencil hoisted above the transform, f and v0 loaded together (1.074 -> 0.988 ms)
-      auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), false, true, false, 2>;
-      if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
-      SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
-    } else if (p.knob_zf == 4) {
-      auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), false, true>;
-      if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
-      SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
-    } else if (p.knob_zf == 5) {
-      auto kfn = k_zfwd_rk<N, NP, MINB, false, true, false, 1>;
-      if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
-      SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
-    } else {
-      auto kfn = k_zfwd_rk<N, NP, (N == 512 ? 2 : MINB), false, true, false, 1>;
-      if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
-      SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
-    }
-  } else if ((p.knob_pf & 8) && p.knob_zf == 3) {   // L2 prefetch of the RK pencils: measured slower (1.20 -> 1.38 ms), kept as an experiment
-    auto kfn = k_zfwd_rk<N, NP, MINB, false, true, true>;
-    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
-    SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
-  } else if (p.knob_pf & 8) {
-    auto kfn = k_zfwd_rk<N, NP, MINB, false, true>;
+  } else if (N == 512) {    // 128 registers, two CTAs per SM (profiles/r1i_session4.md)
+    auto kfn = k_zfwd_rk<N, NP, 2, true, true>;
     if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
     SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   } else {
-    auto kfn = k_zfwd_rk<N, NP, MINB, false, false>;
+    auto kfn = k_zfwd_rk<N, NP, MINB, true, false>;
     if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
     SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   }

@@ -70,14 +70,12 @@ struct Plan {
   Comm* comm = nullptr;
   StageTimer timer;
   int num_sms = 148;                // multiProcessorCount of the device
-  int knob_zf = 0;
-  int knob_xp = 0, knob_pj = 0;     // kernel-variant experiments (env SX_XP, SX_PJ)
+  int knob_xp = 0, knob_pj = 0;     // 0: bulk-copy x pass / paired projection where they apply; 9: the slot kernels; 10: forced (tests) (env SX_XP, SX_PJ)
   int knob_pf = 13;                 // cp.async prefetch per tile kernel: bit 0 zinv, 1 yinv, 2 yfwd, 3 zfwd (env SX_TILE_PF)
   int knob_tma = 3;                 // bulk-copy (TMA) tile kernels: bit 0 zinv, 1 yinv, 2 yfwd, 3 zfwd (env SX_TMA)
   int knob_tma_min = 256;           // smallest transform length the bulk-copy tile kernels are used for (env SX_TMA_MIN)
   int knob_inv_stages = 2;          // two-stage input ring of the bulk-copy inverse tile kernels: bit 0 zinv, bit 1 yinv (env SX_INV_STAGES)
   int knob_zchunks = 4;             // z chunks of the multi-rank xy stage pipeline (env SX_ZCHUNKS; 1 = unchunked)
-  int knob_np = 0, knob_minb = 1;   // tuning experiments (env SX_TILE_NP, SX_TILE_MINB)
   unsigned long long launches = 0;  // kernels launched by this plan (bench "gpu_launches")
 
   size_t csize() const { return (size_t)nz * ny * nxl; }   // complex elements per spectral field

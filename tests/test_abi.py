@@ -128,7 +128,7 @@ def test_tuning_knobs_are_validated(emu_lib, tables):
             "lib = api.Library(%r)\n"
             "try:\n    api.Plan(16, 16, 64, 25, 5, tdir=%r, lib=lib)\n    print('created')\n"
             "except api.SpecterError as e:\n    print('refused:', e)\n" % (ROOT, emu_lib.path, tables))
-    for var, val, ok in (("SX_ZCHUNKS", "0", False), ("SX_XP", "abc", False), ("SX_TILE_NP", "64", False), ("SX_ZCHUNKS", "2", True)):
+    for var, val, ok in (("SX_ZCHUNKS", "0", False), ("SX_XP", "abc", False), ("SX_TMA", "64", False), ("SX_ZCHUNKS", "2", True)):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **{var: val}))
         assert r.returncode == 0, r.stderr
         assert ("created" in r.stdout) == ok and (ok or var in r.stdout), (var, val, r.stdout)

@@ -102,6 +102,13 @@ def test_hd_substeps_bulk_project(emu_lib, tables, monkeypatch):
     P.case_hd_substeps(emu_lib, tables, (16, 16, 256), ord=2, nsteps=2, impl=0, walls=((0.2, -0.1), (-0.3, 0.1)))
 
 
+def test_mhd_substeps_bulk_kernels(emu_lib, tables, monkeypatch):
+    # the cross-product x pass on the bulk-copy ring (forced on a short line) and, from nz = 256, the fused
+    # vector-potential boundary kernel (conducting walls) with a uniform field
+    monkeypatch.setenv("SX_XP", "10")
+    P.case_mhd_substeps(emu_lib, tables, (64, 16, 256), ord=2, nsteps=1, impl=0, b0=(0.1, 0.0, 0.2))
+
+
 def test_io_output_restart(emu_lib, tables, tmp_path):
     P.case_io_output_restart(emu_lib, tables, SMALL, tmp_path)
 
