@@ -9,15 +9,20 @@ It is a literal restatement -- same pass structure, same (non)normalisation,
 same quirks -- of the reference's Fortran for this path.  Every function cites
 the reference ``file:line`` (relative to /root/reference/src) it follows.
 
-PARITY PINNING.  The reference (Fortran + MPI + FFTW) cannot be compiled in
-this image (no gfortran / MPI / FFTW) and ships no golden
-vectors: its own tests (src/tests/*.f90) only *print* error norms of analytic
-identities.  The oracle is therefore pinned against (i) those analytic
-known-answer identities re-stated as assertions (tests/test_oracle_*.py),
-(ii) the reference's FC-Gram table fixtures, (iii) mpmath spot checks.  Bitwise
-parity with an FFTW build is "unpinned" beyond FFT rounding (FFTW is a
-third-party dependency absent from /root/reference; the DFT is mathematically
-fixed: forward sign -1, backward +1, both unnormalised).
+PARITY PINNING: "parity unpinned" against the reference binary.  The reference
+(Fortran + MPI + FFTW) cannot be compiled in this image nor on the GPU box (no
+gfortran / MPI / FFTW on either: DESIGN.md 9, profiles/r2a_gpu_box_probe.txt)
+and ships no golden vectors: its own tests (src/tests/*.f90) only *print*
+error norms of analytic identities.  The oracle is therefore pinned against
+(i) those analytic known-answer identities re-stated as assertions
+(tests/test_oracle.py), (ii) the reference's FC-Gram table fixtures, and
+(iii) an INDEPENDENT second statement of the HD substep (tests/independent_hd.py:
+dense DFT matrices, full Hermitian x spectrum, longdouble; no shared code),
+which it matches to 3e-14 / 6e-13 over two substeps.  FFTW is a third-party
+dependency absent from /root/reference (only hint of a version: 3.3.8,
+src/Makefile.in:59); the DFT is mathematically fixed (forward sign -1, backward
++1, both unnormalised), so bitwise parity with an FFTW build is unpinned only
+beyond FFT rounding.
 
 Array conventions (memory-identical to the Fortran arrays):
   spectral / mixed  Fortran ``a(nz,ny,ista:iend)``  <->  numpy ``a[i,j,k]`` shape (nxl,ny,nz), C order

@@ -192,12 +192,10 @@ template <int N> static int run_zfwd_rk(Plan& p, Fused& f, const cplx* nl, const
     auto kfn = k_zfwd_rk<N, NP, MINB, false, false>;
     if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
     SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
-  } else if (N == 512) {    // 128 registers, two CTAs per SM (profiles/r1i_session4.md)
-    auto kfn = k_zfwd_rk<N, NP, 2, true, true>;
-    if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
-    SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   } else {
-    auto kfn = k_zfwd_rk<N, NP, MINB, true, false>;
+    // N = 512: 128 registers, two CTAs per SM, batched loads of the RK pencils (profiles/r1i_session4.md)
+    constexpr bool B512 = N == 512;
+    auto kfn = k_zfwd_rk<N, NP, (B512 ? 2 : MINB), true, B512>;
     if (persistent_grid(p, kfn, NP * (N / 8), smem, cdiv(p.ny, NP) * p.nxl, &grid)) return 1;
     SX_FUSED_LAUNCH(p, ST_ZFWD_RK, kfn, dim3(grid), NP * (N / 8), smem, a, tw);
   }
