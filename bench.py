@@ -575,10 +575,11 @@ def main():
             t = torch.tensor([te], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             te = float(t.item())
-        e2e = {"value": npts * ord_ * ksteps / te, "unit": "pts*substep/s", "h2d_bytes_per_step": 4 * fb * world,
+        wall_rows = 2 * 16 * ny * (nx // 2 + 1)   # the two wall rows of p' (all the step reads of it), summed over the ranks
+        e2e = {"value": npts * ord_ * ksteps / te, "unit": "pts*substep/s", "h2d_bytes_per_step": 3 * fb * world + wall_rows,
                "d2h_bytes_per_step": 4 * fb * world, "steps": ksteps, "ms_per_step": 1e3 * te / ksteps,
-               "api": "sx_hd_step_host (pinned host arrays in the reference layout; v, p' up and down every step, the constant "
-                      "body force uploaded once and kept resident)"}
+               "api": "sx_hd_step_host (pinned host arrays in the reference layout; v up, the wall rows of p' up -- the step reads "
+                      "nothing else of it --, v and p' down every step; the constant body force uploaded once and kept resident)"}
         e2e["finite"] = all(bool(np.isfinite(a).all()) for a in pinned[:4])
 
     cpu = None

@@ -214,7 +214,8 @@ int sx_hd_rkstep1(sx_plan* plan);
 int sx_hd_rkstep2(sx_plan* plan, int o, double dt, double nu, const double v_zsta[2], const double v_zend[2], int impl);
 /* one full time step (rkstep1 + ord substeps) on host arrays: H2D of v,pr,f, compute, D2H of v,pr.  fx/fy/fz_host may
  * be NULL: the forcing uploaded by an earlier call (or by sx_hd_put_state) stays on the device.  The uploads run on a
- * copy stream and the first substep starts on vx while vy, vz, pr still travel. */
+ * copy stream and the first substep starts on vx while vy, vz, pr still travel.  Of pr_host only the two wall rows are
+ * uploaded: they are all the step reads of it (noslip_z, vboundary.f90:154-211) before every row is overwritten. */
 int sx_hd_step_host(sx_plan* plan, double* vx_host, double* vy_host, double* vz_host, double* pr_host,
                     const double* fx_host, const double* fy_host, const double* fz_host, double dt, double nu,
                     const double v_zsta[2], const double v_zend[2]);

@@ -133,9 +133,20 @@ int sx_hd_step_host(sx_plan* plan, double* vx, double* vy, double* vz, double* p
     if (fh[i]) SX_CUDA_CHECK(cudaMemcpyAsync(s->f[4 + i], fh[i], bytes, cudaMemcpyHostToDevice, p.copy_stream));
   double* h[4] = {vx, vy, vz, pr};
   for (int i = 0; i < 4; ++i) {
-    SX_CUDA_CHECK(cudaMemcpyAsync(s->f[i], h[i], bytes, cudaMemcpyHostToDevice, p.copy_stream));
-    if (i < 3)   // rkstep1 (hd_rkstep1.f90:4-6)
+    if (i < 3) {
+      SX_CUDA_CHECK(cudaMemcpyAsync(s->f[i], h[i], bytes, cudaMemcpyHostToDevice, p.copy_stream));
+      // rkstep1 (hd_rkstep1.f90:4-6)
       SX_CUDA_CHECK(cudaMemcpyAsync(s->f[7 + i], s->f[i], bytes, cudaMemcpyDeviceToDevice, p.copy_stream));
+    } else {
+      // of p' the step only READS the two wall rows (noslip_z, vboundary.f90:154-211: pr(1,j,i) and pr(nz-Cz,j,i)) before the
+      // projection of the first substep overwrites every row (boundary_mod.fpp:371-380): two strided copies of one complex
+      // number per pencil instead of the whole field
+      const size_t pitch = (size_t)p.nz * sizeof(cplx), npen = (size_t)p.ny * p.nxl;
+      const int rows[2] = {0, p.nphys() - 1};
+      for (int q = 0; q < 2; ++q)
+        SX_CUDA_CHECK(cudaMemcpy2DAsync(s->f[3] + rows[q], pitch, reinterpret_cast<const cplx*>(pr) + rows[q], pitch, sizeof(cplx), npen,
+                                        cudaMemcpyHostToDevice, p.copy_stream));
+    }
     SX_CUDA_CHECK(cudaEventRecord(p.h2d_ev[i], p.copy_stream));
     p.pre_wait[i] = p.h2d_ev[i];
   }
