@@ -89,50 +89,70 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler is started before the warm-up
+    (nvidia-smi needs a few hundred ms to deliver its first line, longer than a short timed region) and its lines carry
+    timestamps; the report uses the lines that fall inside the timed region, or, when the region was too short to catch
+    one, the lines since the start of the warm-up -- the same kernels under the same load -- and says which."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.proc, self.path = index, None, f"/tmp/sx_clocks_{os.getpid()}.csv"
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)    # let the line that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         for line in open(self.path):
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 7:
+            if len(c) < 8:
                 continue
             try:
-                sm.append(float(c[0])); mx.append(float(c[1]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), c[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
         try:
             os.remove(self.path)
         except OSError:
             pass
-        if not sm:
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= (self.t1 or r[0]) + 0.05]
+        window = "timed region"
+        if not inside:
+            inside, window = rows, "warm-up + timed region (the timed region was shorter than the sampling latency)"
+        if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside),
+                "reasons": sorted(reasons), "samples": len(inside), "window": window}
 
 
 def _fill_low_modes(plan, buf, seed, c, kmax=4):
@@ -483,18 +503,20 @@ def main():
             except Exception as e:      # e.g. not enough page-locked host memory for the largest grids
                 pinned, e2e_skip = None, f"{type(e).__name__}: {e}"
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     n0 = plan.launch_count
     barrier()
+    sampler.mark_begin()
     plan.time_begin()
     for _ in range(args.steps):
         step()
     ms = plan.time_end()
+    sampler.mark_end()
     barrier()
     launches = plan.launch_count - n0
     clocks = sampler.stop() if rank == 0 else None
