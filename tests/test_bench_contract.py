@@ -43,3 +43,27 @@ def test_our_arm_needs_a_gpu():
         pytest.skip("a GPU is present")
     r = run(["--steps", "1", "--warmup", "3", "--workload", "hd64", "--no-e2e", "--no-cpu-baseline"])
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_workload_rule_and_byte_models():
+    """The workload both arms run for a rank count (BASELINE configs[1] on 1 GPU, 512^3 per GPU on 2 / 4, configs[4] on 8)
+    and the per-kernel byte models: their HD sum is what the kernels move as built, never less than the
+    440 B per point of SURVEY 8(d) that the whole-substep fraction is quoted on."""
+    import argparse
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    ns = lambda **kw: argparse.Namespace(**{"workload": None, "strong": False, "weak512": False, **kw})
+    assert bench.resolve_workload(ns(), 1)[:4] == ("hd512", 512, 512, 512)
+    assert bench.resolve_workload(ns(), 2)[1:4] == (1024, 512, 512) and bench.resolve_workload(ns(), 2)[7] == "weak"
+    assert bench.resolve_workload(ns(), 4)[1:4] == (1024, 1024, 512)
+    assert bench.resolve_workload(ns(), 8)[:4] == ("hd2048", 2048, 2048, 1024)
+    assert bench.resolve_workload(ns(strong=True), 4)[1:4] == (512, 512, 512) and bench.resolve_workload(ns(strong=True), 4)[7] == "strong"
+    assert bench.resolve_workload(ns(workload="mhd512"), 8)[7] == "strong"
+    r = (512 - 25) / 512
+    hd = bench.stage_bytes_per_pt(r, "hd")
+    assert abs(sum(hd.values()) / 8 - (22 + 42 * r)) < 1e-9          # 62 F as built
+    assert sum(hd.values()) >= bench.B_ALG_BY_SOLVER["hd"]
+    for solver in ("bouss", "mhd"):
+        assert sum(bench.stage_bytes_per_pt(r, solver).values()) >= bench.B_ALG_BY_SOLVER[solver] * 0.95
+    assert len(bench.sources_hash()) == 12

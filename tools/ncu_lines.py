@@ -1,15 +1,18 @@
 """Aggregate the pc samples of an `ncu --page source --csv` dump by CUDA source line (line table from `nvdisasm -g -c`
-of the same cubin).  usage: python tools/ncu_lines.py dump.csv nvdisasm.txt <mangled-kernel-name> [top]"""
+of the same cubin).  usage: python tools/ncu_lines.py dump.csv nvdisasm.txt <mangled-kernel-name> [top [section]]"""
 import collections
 import csv
 import re
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
-start = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'][0]
+secs = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+which = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+start = secs[which]
+end = secs[which + 1] if which + 1 < len(secs) else len(rows)
 hdr = rows[start + 1]
 idx = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[start + 2:] if len(r) == len(hdr)]
+data = [r for r in rows[start + 2:end] if len(r) == len(hdr)]
 lines, cur, infn = [], None, False
 for line in open(sys.argv[2]):
     if '.section' in line and '.text.' in line:
