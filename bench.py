@@ -62,9 +62,10 @@ def stage_bytes_per_pt(r, solver="hd"):
     if solver == "bouss":   # theta rides with v: 4 components, its z-forward reads v_z and v_z's reads theta
         return {"zinv_tile": (4 + 8 * r) * F, "yinv_tile": 20 * r * F, "xpass": 16 * r * F, "yfwd_tile": 8 * r * F,
                 "zfwd_rk": (18 + 4 * r) * F, "project": 7 * F}
-    # MHD: 12 plain inverse fields (v, omega, B, J), two cross-product x passes (12 + 6 lines in, 3 + 3 out)
-    return {"zinv_tile": 12 * (1 + r) * F, "yinv_tile": 24 * r * F, "xpass": 24 * r * F, "yfwd_tile": 12 * r * F,
-            "zfwd_rk": (24 + 6 * r) * F, "project": 7 * F}
+    # MHD: one pass for the nine curls (6 F in, 9 F out), 12 plain inverse fields (v, omega, B, J), two cross-product x
+    # passes (12 + 6 lines in, 3 + 3 out), two pencil kernels at the end (velocity: 3 in, 3 + p' out; potential: 3 in, 3 + ph out)
+    return {"elementwise": 15 * F, "zinv_tile": 12 * (1 + r) * F, "yinv_tile": 24 * r * F, "xpass": 24 * r * F, "yfwd_tile": 12 * r * F,
+            "zfwd_rk": (24 + 6 * r) * F, "project": 14 * F}
 
 
 def sources_hash():
