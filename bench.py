@@ -68,16 +68,21 @@ def stage_bytes_per_pt(r, solver="hd"):
             "zfwd_rk": (24 + 6 * r) * F, "project": 14 * F}
 
 
+# the files that define the fused-substep kernels (and the headers they include): what a kernel's DRAM traffic depends on
+KERNEL_SOURCES = ("sx_common.cuh", "sx_fft.cuh", "sx_tma.cuh", "sx_plan.h", "sx_fused.h", "sx_fused_tiles.cu", "sx_fused_x.cu",
+                  "sx_fused_zfwd.cu", "sx_fused_project.cu", "sx_solvers.cu")
+
+
 def sources_hash():
     """Content hash of the kernel sources: ties a committed ncu capture (profiles/ncu_traffic.json) to the code it
-    was taken from (the GPU box has no .git)."""
+    was taken from (the GPU box has no .git).  Host-side orchestration (sx_fused.cu, sx_comm.cu, sx_api.cu ...) is not
+    part of it: it does not change what a launch of a kernel reads and writes."""
     h = hashlib.sha1()
     d = os.path.join(ROOT, "specter_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h")):
-            h.update(f.encode())
-            with open(os.path.join(d, f), "rb") as fh:
-                h.update(fh.read())
+    for f in KERNEL_SOURCES:
+        h.update(f.encode())
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(fh.read())
     return h.hexdigest()[:12]
 
 

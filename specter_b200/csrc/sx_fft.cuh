@@ -238,7 +238,7 @@ __device__ __forceinline__ void fft_run(cplx (&v)[8], int j, cplx* s, const SI& 
 template <int N, int DIR, class SI>
 __device__ __forceinline__ void fft_regs(cplx (&v)[8], int j, cplx* s, const SI& si,
                                          const cplx* __restrict__ tw) {
-#ifdef SX_NOFFT  // timing experiment only (tools/build_variant.sh -DSX_NOFFT; profiles/r1k_session5.md): data movement without the transforms
+#ifdef SX_NOFFT  // timing experiment only (tools/gpu_nofft.sh): data movement without the transforms
   (void)v; (void)j; (void)s; (void)si; (void)tw;
 #else
   fft_run<N, DIR, 0, SI, NoHook>(v, j, s, si, tw, nullptr, NoHook());

@@ -171,7 +171,13 @@ static int to_spec_begin(Plan& p, Fused& f, int slot) {
   }
   return exchange_begin(p, 16 + slot, f.U[slot], f.Uz[slot], f.x_displ.data(), f.x_count.data(), f.z_displ.data(), f.z_count.data());
 }
-static int ex_wait(Plan& p, int ev) { return (p.nprocs == 1 || (p.fused && p.fused->chunked_now)) ? 0 : exchange_wait(p, ev); }
+static int ex_wait(Plan& p, int ev) {
+  if (p.nprocs == 1) return 0;
+  // chunked pipeline: the inverse side was waited for chunk by chunk; the way back of component c is complete when the
+  // per-component round of the last chunk (event slot 24 + c) is -- the rounds complete in issue order
+  if (p.fused && p.fused->chunked_now) return ev >= 16 ? exchange_wait(p, 24 + (ev - 16)) : 0;
+  return exchange_wait(p, ev);
+}
 
 static int fused_begin(Plan& p, Fused** fp, int nw, int nv, int nx, bool may_chunk = false) {
   if (fused_init(p, fp)) return 1;
@@ -262,12 +268,8 @@ template <int NC> static int xy_stage_chunked(Plan& p, Fused& f, const cplx* con
       if (fused_yinv(p, f, f.R[2 * c + 1], f.V[2 * NC + c], nullptr)) return 1;
     }
     if (fused_xpass(p, f, NC, p.d_kxg)) return 1;
-    for (int c = 0; c < NC; ++c)
-      if (fused_yfwd(p, f, f.X[c], f.U[c])) return 1;
-    if (p2p_mark(p, 16 + k)) return 1;
-    const bool ydirect = f.yfwd_direct && f.direct >= 1;
-    cp.clear();
-    for (int c = 0; c < NC; ++c)
+    auto out_copies = [&](int c) {   // after the y-forward launch of component c (its launcher sets yfwd_direct)
+      const bool ydirect = f.yfwd_direct && f.direct >= 1;
       for (int qd = 1; qd <= p.nprocs; ++qd) {
         const int r = (p.myrank + qd) % p.nprocs;
         if (ydirect && direct_to(p, f, r)) continue;
@@ -276,12 +278,32 @@ template <int NC> static int xy_stage_chunked(Plan& p, Fused& f, const cplx* con
         cp.push_back(P2PCopy{peer_uz_dst(p, f, c, r) + (size_t)c0 * p.ny, f.U[c] + f.x_displ[r] + (size_t)c0 * p.ny,
                              (size_t)cc * p.ny, (size_t)xc, (size_t)f.nzf * p.ny, (size_t)f.nzf * p.ny, r != p.myrank});
       }
-    const int w = 16 + k;
-    if (p2p_round(p, &w, 1, cp.data(), (int)cp.size(), true, 16 + k)) return 1;
+    };
+    if (k < nch - 1) {
+      for (int c = 0; c < NC; ++c)
+        if (fused_yfwd(p, f, f.X[c], f.U[c])) return 1;
+      if (p2p_mark(p, 16 + k)) return 1;
+      cp.clear();
+      for (int c = 0; c < NC; ++c) out_copies(c);
+      const int w = 16 + k;
+      if (p2p_round(p, &w, 1, cp.data(), (int)cp.size(), true, 16 + k)) return 1;
+    } else {
+      // last chunk: one round per component, in the order the z stage consumes them (theta first in BOUSS), so that
+      // the z-forward kernel of a component starts when ITS last rows have landed while the others still travel
+      for (int i = 0; i < NC; ++i) {
+        const int c = NC == 4 ? (i + 3) % 4 : i;
+        if (fused_yfwd(p, f, f.X[c], f.U[c])) return 1;
+        if (p2p_mark(p, 24 + c)) return 1;
+        cp.clear();
+        out_copies(c);
+        const int w = 24 + c;
+        if (p2p_round(p, &w, 1, cp.data(), (int)cp.size(), true, 24 + c)) return 1;
+      }
+    }
   }
   f.zwc = -1;
   f.zw0 = 0;
-  return exchange_wait(p, 16 + nch - 1);   // the rounds complete in order: the last one covers them all
+  return 0;   // the z stage waits per component (ex_wait: event slots 24 + c)
 }
 
 static int nonlinear_to_spectral_begin(Plan& p, Fused& f, int nx) {
