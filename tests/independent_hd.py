@@ -180,3 +180,153 @@ class Independent:
         for c in range(3):
             new.append(v0[c].astype(CLD) + LD(dt) * (LD(nu) * (-kk2 * v[c]) - nl[c] + f[c]) / LD(o))
         return self.impose_and_project(new, pr.astype(CLD), o)
+
+
+# =====================================================================================================================
+# BOUSS and MHD: the same independent machinery (dense DFT matrices, longdouble) for the other two solvers of
+# BASELINE.json.  Written from the Fortran includes and boundary modules cited at each step, not from the oracle.
+# =====================================================================================================================
+class IndependentSolvers(Independent):
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        tdir = a[8] if len(a) > 8 else kw["tdir"]
+        d = self.d
+        # load_neumann_tables (fcgram_mod.f90:300-365): Q(d,d); Q<ord>n<d>.dat = dxp, Qn(d,d); neu = Q(d,:) Qn^T, last entry
+        # scaled by (dz/dxp)^ord
+        Q = np.fromfile(f"{tdir}/Q{d}.dat", dtype="<f8").reshape((d, d)).T.astype(LD)
+        self.neu = {}
+        for order in (1, 2):
+            raw = np.fromfile(f"{tdir}/Q{order}n{d}.dat", dtype="<f8")
+            dxp, Qn = LD(raw[0]), raw[1:1 + d * d].reshape((d, d)).T.astype(LD)
+            w = np.array([sum(Q[d - 1, m] * Qn[k, m] for m in range(d)) for k in range(d)], dtype=LD)
+            w[d - 1] = w[d - 1] * (self.dz / dxp) ** order
+            self.neu[order] = w
+
+    # ---- spectral operators (pseudospec_hd.f90:161-202) ----
+    def curl(self, a, b, c):
+        kx, ky, kz = self.kx[:, None, None], self.ky[None, :, None], self.kz[None, None, :]
+        return [1j * ky * c - 1j * kz * b, 1j * kz * a - 1j * kx * c, 1j * kx * b - 1j * ky * a]
+
+    def _products_to_spectral(self, r):
+        N = LD(self.nx) * self.ny * self.nz
+        r = r / (N * N)
+        r[self.nph:] = 0
+        return self.to_spectral(r)
+
+    def cross(self, P, Q):
+        """FFT3[P x Q]/N^2 with the products on the physical planes (prodre pseudospec_hd.f90:357-399, vector pseudospec_mhd.f90:87-102)."""
+        p = [self.to_real(c) for c in P]
+        q = [self.to_real(c) for c in Q]
+        return [self._products_to_spectral(p[1] * q[2] - p[2] * q[1]),
+                self._products_to_spectral(p[2] * q[0] - p[0] * q[2]),
+                self._products_to_spectral(p[0] * q[1] - p[1] * q[0])]
+
+    def advect(self, v, th):
+        """FFT3[v . grad th]/N^2 (pseudospec_phd.f90:58-110)."""
+        acc = 0
+        for dd in range(3):
+            acc = acc + self.to_real(v[dd]) * self.to_real(self.deriv(th, dd + 1))
+        return self._products_to_spectral(acc)
+
+    def mixed(self, a):
+        """goto_domain_w_boundaries (boundary_mod.fpp:72-135): z backward, 1/nz."""
+        return self.z_backward(a) / LD(self.nz)
+
+    # ---- BOUSS (include/bouss/bouss_rkstep2.f90:3-59) ----
+    def bouss_rkstep2(self, v, th, v0, th0, f, fs, pr, o, dt, nu, kappa, xmom=1.0, xtemp=1.0):
+        nl = self.gradre(v)
+        adv = self.advect(v, th)
+        nl[2] = nl[2] - LD(xmom) * th          # buoyancy
+        adv = adv - LD(xtemp) * v[2]           # heat current
+        nl = [self.fc_filter(c) for c in nl]
+        adv = self.fc_filter(adv)
+        kk2 = self.kx[:, None, None] ** 2 + self.ky[None, :, None] ** 2 + self.kz[None, None, :] ** 2
+        new = [v0[c].astype(CLD) + LD(dt) * (LD(nu) * (-kk2 * v[c]) - nl[c] + f[c]) / LD(o) for c in range(3)]
+        thn = th0.astype(CLD) + LD(dt) * (LD(kappa) * (-kk2 * th) - adv + fs) / LD(o)
+        new, pnew = self.impose_and_project(new, pr.astype(CLD), o)
+        # s_imposebc (sboundary.f90:67-119): constant (zero) temperature at both walls
+        m = self.mixed(thn)
+        m[:, :, 0] = 0
+        m[:, :, self.nph - 1] = 0
+        thn = self.fc_filter(self.z_forward_continued(m))
+        # the theta "hack" (:57-59): to real space and back, which re-continues theta from its physical values
+        N = LD(self.nx) * self.ny * self.nz
+        thn = self.to_spectral(self.to_real(thn) / N)
+        return new, thn, pnew
+
+    # ---- MHD with conducting walls (include/mhd/mhd_rkstep2.f90:3-84, bboundary.f90:100-189) ----
+    def _neumann(self, m, order):
+        d, top, w = self.d, self.nph - 1, self.neu[order]
+        lo = w[d - 1] * m[:, :, 0]
+        hi = w[d - 1] * m[:, :, top]
+        for k in range(1, d):
+            lo = lo + w[k - 1] * m[:, :, d - k]            # f(dz+1-k)        fcgram_mod.f90:461-465
+            hi = hi + w[k - 1] * m[:, :, top - d + k]      # f(nz-Cz-dz+k)    :483-487
+        m[:, :, 0], m[:, :, top] = lo, hi
+
+    def a_imposebc_and_project(self, a):
+        nz, top = self.nz, self.nph - 1
+        kx, ky, kz = self.kx[:, None, None], self.ky[None, :, None], self.kz[None, None, :]
+        ax, ay, az = [c.astype(CLD).copy() for c in a]
+        az[0, 0, 0] = 0                                                    # bboundary.f90:147-149
+        w = []
+        for c in (ax, ay):                                                 # int_conducting_z :192-236
+            m = self.mixed(c)
+            m[:, :, 0] = 0
+            m[:, :, top] = 0
+            w.append(self.z_forward_continued(m))
+        ax, ay = w
+        # sol_project(ax, ay, az, ph, 0, 0, 0) (boundary_mod.fpp:197-402)
+        kk2 = kx ** 2 + ky ** 2 + kz ** 2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dd = -1j * (kx * ax + ky * ay + kz * az) / kk2
+        dd[0, 0, 0] = 0
+        ax, ay, az = ax - 1j * kx * dd, ay - 1j * ky * dd, az - 1j * kz * dd
+        C1 = self.z_backward(dd / LD(nz))
+        bc1, bc2 = -C1[:, :, 0], -C1[:, :, top]
+        kh = np.sqrt(self.kx[:, None] ** 2 + self.ky[None, :] ** 2)
+        phi = np.zeros((self.nxh, self.ny, nz), dtype=CLD)
+        dphi = np.zeros_like(phi)
+        Lz = self.Lz
+        for i in range(self.nxh):                                          # laplace_z, pure Dirichlet :499-528, 635-675
+            for j in range(self.ny):
+                k_h = kh[i, j]
+                if i == 0 and j == 0:
+                    c1, c2 = (bc2[0, 0] - bc1[0, 0]) / Lz, bc1[0, 0]
+                    phi[0, 0] = c1.real * self.z + c2.real
+                    dphi[0, 0] = c1.real
+                else:
+                    t = 1 / (1 - np.exp(-2 * k_h * Lz))
+                    c1 = (bc2[i, j] - bc1[i, j] * np.exp(-k_h * Lz)) * t
+                    c2 = (bc1[i, j] - bc2[i, j] * np.exp(-k_h * Lz)) * t
+                    ep, em = np.exp(k_h * (self.z - Lz)), np.exp(-k_h * self.z)
+                    phi[i, j] = c1 * ep + c2 * em
+                    dphi[i, j] = k_h * (c1 * ep - c2 * em)
+        ph = C1 + phi
+        ph_hat, dph_hat = self.z_forward_continued(phi), self.z_forward_continued(dphi)
+        ax, ay, az = ax - 1j * kx * ph_hat, ay - 1j * ky * ph_hat, az - dph_hat
+        out = []
+        for c, order in ((ax, 2), (ay, 2), (az, 1)):                       # conducting_z :239-290
+            m = self.mixed(c)
+            m[:, :, 0] = 0
+            m[:, :, top] = 0
+            self._neumann(m, order)
+            out.append(self.z_forward_continued(m))
+        return out, ph
+
+    def mhd_rkstep2(self, v, a, v0, a0, f, mf, pr, o, dt, nu, mu, b0=(0.0, 0.0, 0.0)):
+        N = LD(self.nx) * self.ny * self.nz
+        B = self.curl(*a)
+        for c in range(3):
+            B[c][0, 0, 0] = LD(b0[c]) * N                                  # mhd_rkstep2.f90:11-15
+        J = self.curl(*B)                                                  # written over a (:18-20)
+        nl = self.cross(self.curl(*v), v)                                  # prodre: omega x v
+        lor = self.cross(J, B)
+        nl = [self.fc_filter(nl[c] - lor[c]) for c in range(3)]
+        emf = [self.fc_filter(c) for c in self.cross(v, B)]
+        kk2 = self.kx[:, None, None] ** 2 + self.ky[None, :, None] ** 2 + self.kz[None, None, :] ** 2
+        vn = [v0[c].astype(CLD) + LD(dt) * (LD(nu) * (-kk2 * v[c]) - nl[c] + f[c]) / LD(o) for c in range(3)]
+        an = [a0[c].astype(CLD) + LD(dt) * (-LD(mu) * J[c] + emf[c] + mf[c]) / LD(o) for c in range(3)]
+        vn, pnew = self.impose_and_project(vn, pr.astype(CLD), o)
+        an, ph = self.a_imposebc_and_project(an)
+        return vn, an, pnew, ph

@@ -459,3 +459,52 @@ def test_oracle_matches_independent_statement(tables):
         nph = g.nz - g.Cz
         perr = float(np.abs(pr.astype(np.complex128) - s.pr)[:, :, :nph].max())
         assert perr < 1e-9 * float(np.abs(s.pr[:, :, :nph]).max()) or perr < 1e-12 * scale
+
+
+def test_oracle_bouss_mhd_match_independent_statement(tables):
+    """The BOUSS and MHD substeps of the oracle against the independent longdouble dense-DFT statement
+    (tests/independent_hd.py:IndependentSolvers) on 8 x 8 x 48, both RK2 substeps: buoyancy / heat-current coupling, the
+    scalar wall step and the theta round trip; curls, Lorentz force and EMF, the conducting-wall step of the vector
+    potential with its Dirichlet laplace_z and the Neumann reconstructions of orders 2, 2, 1."""
+    from independent_hd import IndependentSolvers
+    n, L = (8, 8, 48), (1.0, 0.5, 1.0)
+    dt, nu, kappa, mu = 1e-3, 1e-3, 1e-3, 5e-3
+    g = O.Grid(*n, 25, 5, Lx=L[0], Ly=L[1], Lz=L[2], tdir=tables, ord=2)
+    ind = IndependentSolvers(*n, 25, 5, *L, tables, 2)
+    nph = g.nz - g.Cz
+    c128 = lambda q: q.astype(np.complex128)
+
+    def close(a, b, scale, tol):
+        return float(np.abs(c128(a) - b).max()) / scale < tol
+
+    # ---- BOUSS ----
+    s = O.make_bouss_state(g)
+    v, th = [s.vx.copy(), s.vy.copy(), s.vz.copy()], s.th.copy()
+    v0, th0 = [q.copy() for q in v], th.copy()
+    f, fs, pr = [s.fx.copy(), s.fy.copy(), s.fz.copy()], s.fs.copy(), s.pr.copy()
+    C = [q.copy() for q in v] + [th.copy()]
+    for o in (2, 1):
+        O.bouss_rkstep2(g, s, *C, o, dt, nu, kappa)
+        v, th, pr = ind.bouss_rkstep2(v, th, v0, th0, f, fs, pr, o, dt, nu, kappa)
+        scale = max(float(np.abs(q).max()) for q in (s.vx, s.vy, s.vz))
+        assert all(close(a, b, scale, 1e-12) for a, b in zip(v, (s.vx, s.vy, s.vz)))
+        # theta on the physical rows of the mixed domain (its continuation rows' coefficients amplify rounding: parity_cases.phys_close)
+        a = np.fft.ifft(c128(th), axis=2)[:, :, :nph]
+        b = np.fft.ifft(s.th, axis=2)[:, :, :nph]
+        assert float(np.abs(a - b).max()) / float(np.abs(b).max()) < 1e-11
+    # ---- MHD, conducting walls, with a uniform field ----
+    s = O.make_mhd_state(g)
+    b0 = (0.1, 0.0, 0.2)
+    v, a = [s.vx.copy(), s.vy.copy(), s.vz.copy()], [s.ax.copy(), s.ay.copy(), s.az.copy()]
+    v0, a0 = [q.copy() for q in v], [q.copy() for q in a]
+    f, mf, pr = [s.fx.copy(), s.fy.copy(), s.fz.copy()], [s.mx.copy(), s.my.copy(), s.mz.copy()], s.pr.copy()
+    C = [q.copy() for q in v] + [q.copy() for q in a]
+    for o in (2, 1):
+        O.mhd_rkstep2(g, s, *C, o, dt, nu, mu, b0)
+        v, a, pr, ph = ind.mhd_rkstep2(v, a, v0, a0, f, mf, pr, o, dt, nu, mu, b0)
+        vs = max(float(np.abs(q).max()) for q in (s.vx, s.vy, s.vz))
+        as_ = max(float(np.abs(q).max()) for q in (s.ax, s.ay, s.az))
+        assert all(close(x, y, vs, 1e-12) for x, y in zip(v, (s.vx, s.vy, s.vz)))
+        assert all(close(x, y, as_, 1e-11) for x, y in zip(a, (s.ax, s.ay, s.az)))
+        assert float(np.abs(c128(ph) - s.ph)[:, :, :nph].max()) < 1e-9 * max(float(np.abs(s.ph[:, :, :nph]).max()), 1e-30) or \
+            float(np.abs(c128(ph) - s.ph)[:, :, :nph].max()) < 1e-11 * as_
