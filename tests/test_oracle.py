@@ -508,3 +508,20 @@ def test_oracle_bouss_mhd_match_independent_statement(tables):
         assert all(close(x, y, as_, 1e-11) for x, y in zip(a, (s.ax, s.ay, s.az)))
         assert float(np.abs(c128(ph) - s.ph)[:, :, :nph].max()) < 1e-9 * max(float(np.abs(s.ph[:, :, :nph]).max()), 1e-30) or \
             float(np.abs(c128(ph) - s.ph)[:, :, :nph].max()) < 1e-11 * as_
+
+
+def test_energy_diagnostic_is_the_physical_space_mean(tables):
+    """energy(kin=1) (pseudospec_hd.f90:441-631: a Parseval sum over (kx,ky) of |IFFT_z|^2 on the physical rows) against
+    the quantity it stands for, evaluated without Parseval: the mean of |u|^2 over the physical grid points, from the
+    independent dense-DFT transform to real space.  Valid for fields without x-Nyquist content (the reference weights
+    every kx > 0 plane by 2, :602-628), which the initial condition satisfies."""
+    from independent_hd import Independent, LD
+    n, L = (16, 8, 48), (1.0, 0.5, 1.0)       # kup = 4 < nx/2: the band of the initial condition stays below the x Nyquist
+    g = O.Grid(*n, 25, 5, Lx=L[0], Ly=L[1], Lz=L[2], tdir=tables, ord=2)
+    s = O.make_hd_state(g)
+    ind = Independent(*n, 25, 5, *L, tables, 2)
+    N = LD(n[0]) * n[1] * n[2]
+    nph = g.nz - g.Cz
+    assert float(np.abs(s.vx[n[0] // 2]).max()) == 0.0      # no x-Nyquist content
+    mean = sum(float(np.mean((ind.to_real(q)[:nph] / N) ** 2)) for q in (s.vx, s.vy, s.vz))
+    assert abs(O.energy(g, s.vx, s.vy, s.vz, 1) / mean - 1) < 1e-12
