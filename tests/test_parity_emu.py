@@ -160,3 +160,27 @@ def test_boots_regridder(emu_lib, tables, tmp_path):
 
 def test_global_quantity_files(emu_lib, tables, tmp_path):
     assert P.case_global_files(emu_lib, tables, (16, 16, 64), tmp_path) == ["HD", "BOUSS", "MHDBOUSS"]
+
+
+# The reference ships continuation tables for O = 3..9 matching points and C = 15..34 continuation points
+# (tables/README.info); BASELINE.json uses A25-5 throughout.  Smallest, largest-C and largest-O members:
+OTHER_TABLES = [(15, 3), (34, 8), (33, 9)]
+
+
+@pytest.mark.parametrize("fc", OTHER_TABLES)
+def test_other_fc_tables_operators(emu_lib, tables, fc):
+    P.case_operators_other_table(emu_lib, tables, (16, 16, 64), *fc)
+
+
+@pytest.mark.parametrize("fc", OTHER_TABLES)
+@pytest.mark.parametrize("solver", ["hd", "bouss", "mhd"])
+def test_other_fc_tables_substeps(emu_lib, tables, fc, solver):
+    for impl in (0, 1):
+        P.case_substeps_other_table(emu_lib, tables, (16, 16, 64), *fc, solver, impl=impl)
+
+
+def test_other_fc_tables_long_pencils(emu_lib, tables):
+    # the paired projection kernels (velocity: from nz = 256; vector potential, conducting walls) with d = 9 and d = 3
+    for fc in ((33, 9), (15, 3)):
+        for solver in ("hd", "mhd"):
+            P.case_substeps_other_table(emu_lib, tables, (16, 16, 256), *fc, solver)

@@ -196,3 +196,17 @@ def test_global_quantity_files(cuda_lib, tables, tmp_path):
 
 def test_normalisations(cuda_lib, tables):
     P.case_normalisations(cuda_lib, tables, CFG1)
+
+
+# ---- the reference's other continuation tables (O = 3..9, C = 15..34; tables/README.info) -------------------------
+@pytest.mark.parametrize("fc", [(15, 3), (34, 8), (33, 9)])
+def test_other_fc_tables(cuda_lib, tables, fc):
+    P.case_operators_other_table(cuda_lib, tables, CFG1, *fc)
+    for solver, impl in (("hd", 0), ("hd", 1), ("bouss", 0), ("mhd", 0)):
+        P.case_substeps_other_table(cuda_lib, tables, CFG1, *fc, solver, impl=impl)
+    if fc == (34, 8):
+        return
+    # the long-line kernel families (bulk-copy tiles, x-pass ring, paired projections), one axis at a time
+    for shape in ((16, 16, 512), (512, 16, 64), (16, 512, 64)):
+        for solver in ("hd", "mhd"):
+            P.case_substeps_other_table(cuda_lib, tables, shape, *fc, solver)
