@@ -10,6 +10,8 @@ solvers32_step1.npz one RK2 step of the other solvers on 32x32x64.
 boots_27_46.npz     the BOOTS regridder (tools/boots.fpp): a seeded field on 16x16x27 -> 32x32x46 (A25-5 continuation) and on
                     16x32x21 -> 32x32x41 (periodic treatment, odd old period), outputs sub-sampled.
                     `python tests/golden/make_golden.py boots` regenerates this file only.
+solvers64_diag100.json  BOUSS and MHD (conducting walls) on 64^3, 100 RK2 steps, the columns of bouss_global.f90 /
+                    mhd_global.f90 every 10 steps (`python tests/golden/make_golden.py diag` regenerates this file only).
 """
 import json
 import os
@@ -36,8 +38,23 @@ def boots_goldens():
     print("boots_27_46.npz:", ra.shape, rb.shape)
 
 
+def solver_diag_goldens():
+    import parity_cases as P
+    out = {"config": "64^3 Cz=25 oz=5 RK2 dt=1e-3 nu=1e-3 kappa=1e-3 mu=5e-3 Lx=1 Ly=0.5 Lz=1 seed=1000, sampled every 10 steps"}
+    for solver in ("bouss", "mhd"):
+        gd = O.Grid(64, 64, 64, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=os.path.join(HERE, "tables"), ord=2)
+        rows = P.oracle_solver_diagnostics(gd, solver, nsteps=100, every=10)
+        out[solver] = {"columns": ["step"] + list(P._DIAG_COLS[solver]), "rows": [[float(x) for x in r] for r in rows]}
+        print(solver, rows[-1])
+    with open(os.path.join(HERE, "solvers64_diag100.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if len(sys.argv) > 1 and sys.argv[1] == "boots":
     boots_goldens()
+    sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "diag":
+    solver_diag_goldens()
     sys.exit(0)
 
 g = O.Grid(64, 64, 64, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=os.path.join(HERE, "tables"), ord=2)
@@ -91,3 +108,4 @@ def solver_goldens():
 
 solver_goldens()
 boots_goldens()
+solver_diag_goldens()

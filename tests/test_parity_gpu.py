@@ -198,6 +198,16 @@ def test_normalisations(cuda_lib, tables):
     P.case_normalisations(cuda_lib, tables, CFG1)
 
 
+@pytest.mark.parametrize("solver", ["bouss", "mhd"])
+def test_solver_diagnostics_100_steps_cfg1(cuda_lib, tables, solver):
+    """BOUSS and MHD (conducting walls) on 64^3, 100 RK2 steps: the columns of bouss_global.f90 / mhd_global.f90 every
+    10 steps against the committed oracle goldens (tests/golden/solvers64_diag100.json), 1e-9."""
+    with open(os.path.join(GOLD, "solvers64_diag100.json")) as f:
+        gold = json.load(f)
+    rows, _, _ = P.case_solver_diagnostics(cuda_lib, tables, CFG1, solver, nsteps=100, every=10, golden=gold[solver]["rows"])
+    assert rows.shape[0] == 10
+
+
 # ---- the reference's other continuation tables (O = 3..9, C = 15..34; tables/README.info) -------------------------
 @pytest.mark.parametrize("fc", [(15, 3), (34, 8), (33, 9)])
 def test_other_fc_tables(cuda_lib, tables, fc):
