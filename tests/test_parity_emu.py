@@ -189,4 +189,4 @@ def test_other_fc_tables_long_pencils(emu_lib, tables):
 @pytest.mark.parametrize("solver", ["bouss", "mhd"])
 def test_solver_diagnostics_several_steps(emu_lib, tables, solver):
     # bouss_global.f90 / mhd_global.f90 columns over a few steps (the GPU suite runs 100 steps at 64^3 against goldens)
-    P.case_solver_diagnostics(emu_lib, tables, (16, 16, 64), solver, nsteps=3, every=1)
+    P.case_solver_diagnostics(emu_lib, tables, (16, 16, 64), solver, nsteps=2, every=1)
