@@ -247,6 +247,28 @@ def device_state(plan, solver):
     del hs
 
 
+def final_state_check(plan, solver, after_steps):
+    """Size-independent properties of the device state at the full size of the workload: finite positive energy,
+    solenoidal field, vanishing wall-normal velocity, small slip at the walls.  Never raises."""
+    import math
+    try:
+        fld = {"hd": plan.hd_field, "bouss": plan.bouss_field, "mhd": plan.mhd_field}[solver]
+        v = [fld(i) for i in range(3)]
+        div, vt0, vtL, vn0, vnL = plan.vdiagnostic(*v)
+        eng = plan.energy(*v, 1)
+        plan.synchronize()
+        plan.release_scratch()
+        out = {"after_steps": after_steps, "energy": eng, "divergence_over_energy": div / eng,
+               "wall_normal_over_energy": max(vn0, vnL) / eng, "wall_tangential_over_energy": max(vt0, vtL) / eng,
+               "thresholds": {"divergence": 1e-4, "wall_normal": 1e-20, "wall_tangential": 1e-2},
+               "what": "vdiagnostic / energy(kin=1) on the device state (vboundary.f90:214-264, pseudospec_hd.f90:405-635)"}
+        out["ok"] = bool(math.isfinite(eng) and eng > 0 and div < 1e-4 * eng and max(vn0, vnL) < 1e-20 * eng
+                         and max(vt0, vtL) < 1e-2 * eng)
+        return out
+    except Exception as e:
+        return {"ok": None, "error": f"{type(e).__name__}: {e}"}
+
+
 def _oracle_case(solver, g):
     from oracle import specter_oracle as O
     if solver == "hd":
@@ -442,6 +464,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the 64^3 HD / BOUSS / MHD parity check before the timing")
+    ap.add_argument("--no-state-check", action="store_true", help="skip the full-size property check of the final state (1 GPU)")
     ap.add_argument("--strong", action="store_true", help="N > 1 without --workload: keep the 512^3 grid (strong scaling)")
     ap.add_argument("--weak512", action="store_true", help="N > 1 without --workload: 512^3 points per GPU (round-1 weak-scaling line)")
     args = ap.parse_args()
@@ -584,6 +607,13 @@ def main():
                                   "achieved": b_alg * value / world / 1e9, "frac": b_alg * value / world / 1e9 / peak,
                                   "frac_of_nominal_8000_gbs": b_alg * value / world / 1e9 / 8000.0}}   # both peaks
 
+    # ---- size-independent properties of the state the timed steps produced, at the FULL size of the workload (the oracle
+    # never runs there): finite energy, solenoidal field, vanishing wall-normal velocity, small slip at the walls.  One
+    # GPU only (the 8-GPU workload leaves no room for the diagnostics' temporaries); never fatal for the bench line.
+    state_check = None
+    if world == 1 and not args.no_state_check:
+        state_check = final_state_check(plan, solver, args.warmup + args.steps + 2)
+
     # ---- end to end through the host-buffer C-ABI entry (H2D + ord substeps + D2H per step) ----
     e2e = None
     if not args.no_e2e and pinned is None:
@@ -633,7 +663,7 @@ def main():
                            "l2": "inputs larger than L2 (each pass streams >= 3 GB; L2 = 126 MB)",
                            "parallelism": f"slab x{world}", "exchange": ("peer-to-peer copies + NCCL barrier" if getattr(plan, "p2p", False) else "NCCL send/recv") if world > 1 else "none"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "parity_check": parity, "stages": stage_report}
+                "parity_check": parity, "state_check": state_check, "stages": stage_report}
         if comm and comm["exchanges"] and comm["ms"] > 0:
             # NVLink roofline: bytes this rank sent / device time of the exchange rounds on the communication stream in the
             # stage-timing pass (event pairs resolved after the pass: the exchange overlaps the compute stream as in the

@@ -29,7 +29,8 @@ def tables():
 def emu_lib():
     """The kernel sources compiled for CPU threads (tests only; never loaded by the product)."""
     from specter_b200 import api, build
-    return api.Library(build.build_emu())
+    # SPECTER_EMU_LIB: another build of the same sources, e.g. the AddressSanitizer one of tools/emu_asan.sh
+    return api.Library(os.environ.get("SPECTER_EMU_LIB") or build.build_emu())
 
 
 @pytest.fixture(scope="session")

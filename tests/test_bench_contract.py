@@ -67,3 +67,22 @@ def test_workload_rule_and_byte_models():
     for solver in ("bouss", "mhd"):
         assert sum(bench.stage_bytes_per_pt(r, solver).values()) >= bench.B_ALG_BY_SOLVER[solver] * 0.95
     assert len(bench.sources_hash()) == 12
+
+
+def test_final_state_check_on_the_emulation(emu_lib, tables):
+    """bench.py's full-size property check of the final state (state_check in the JSON line), here on a small grid through
+    the emulation build: the synthetic state after a step is solenoidal, has no wall-normal velocity and finite energy;
+    a failing call is reported, never raised."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    from specter_b200 import api
+    for solver in ("hd", "bouss", "mhd"):
+        p = api.Plan(32, 16, 64, 25, 5, ord=2, tdir=tables, lib=emu_lib)
+        bench.device_state(p, solver)
+        {"hd": lambda: p.hd_step(1e-3, 1e-3), "bouss": lambda: p.bouss_step(1e-3, 1e-3, 1e-3),
+         "mhd": lambda: p.mhd_step(1e-3, 1e-3, 5e-3)}[solver]()
+        sc = bench.final_state_check(p, solver, 1)
+        assert sc["ok"] is True, sc
+        p.close()
+    assert bench.final_state_check(None, "hd", 0)["ok"] is None
