@@ -330,3 +330,160 @@ class IndependentSolvers(Independent):
         vn, pnew = self.impose_and_project(vn, pr.astype(CLD), o)
         an, ph = self.a_imposebc_and_project(an)
         return vn, an, pnew, ph
+
+
+# =====================================================================================================================
+# The remaining wall kinds and solvers of SURVEY 8(f) row 2: vacuum (Robin) walls of the vector potential, ROTBOUSS and
+# MHDBOUSS.  Same machinery, written from bboundary.f90:100-344, boundary_mod.fpp:264-369 / 563-678,
+# fcgram_mod.f90:612-635 and the rotbouss / mhdbouss includes.
+# =====================================================================================================================
+class IndependentWalls(IndependentSolvers):
+    def _robin(self, m, wall):
+        """robin_reconstruct (fcgram_mod.f90:612-635) with a = khom: f' + khom f = g, g stored in the wall row."""
+        d, top, w = self.d, self.nph - 1, self.neu[1]
+        kh = np.sqrt(self.kx[:, None] ** 2 + self.ky[None, :] ** 2)
+        if wall == 0:
+            acc = w[d - 1] * m[:, :, 0]
+            for k in range(1, d):
+                acc = acc + w[k - 1] * m[:, :, d - k]
+            m[:, :, 0] = acc / (kh * w[d - 1] + 1)
+        else:
+            acc = w[d - 1] * m[:, :, top]
+            for k in range(1, d):
+                acc = acc + w[k - 1] * m[:, :, top - d + k]
+            m[:, :, top] = acc / (kh * w[d - 1] + 1)
+
+    def _neumann_wall(self, m, order, wall):
+        d, top, w = self.d, self.nph - 1, self.neu[order]
+        if wall == 0:
+            acc = w[d - 1] * m[:, :, 0]
+            for k in range(1, d):
+                acc = acc + w[k - 1] * m[:, :, d - k]
+            m[:, :, 0] = acc
+        else:
+            acc = w[d - 1] * m[:, :, top]
+            for k in range(1, d):
+                acc = acc + w[k - 1] * m[:, :, top - d + k]
+            m[:, :, top] = acc
+
+    def a_imposebc_and_project_walls(self, a, s, e):
+        """bboundary.f90:100-189 for wall kinds s (z = 0) and e (z = Lz): 0 conducting, 1 vacuum."""
+        nz, top = self.nz, self.nph - 1
+        kx, ky, kz = self.kx[:, None, None], self.ky[None, :, None], self.kz[None, None, :]
+        ax, ay, az = [c.astype(CLD).copy() for c in a]
+        az[0, 0, 0] = 0
+        if s == 0 or e == 0:                                               # int_conducting_z on the conducting walls only
+            w = []
+            for c in (ax, ay):
+                m = self.mixed(c)
+                if s == 0:
+                    m[:, :, 0] = 0
+                if e == 0:
+                    m[:, :, top] = 0
+                w.append(self.z_forward_continued(m))
+            ax, ay = w
+        # sol_project(ax, ay, az, ph, 0, 2 s, 2 e)
+        kk2 = kx ** 2 + ky ** 2 + kz ** 2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dd = -1j * (kx * ax + ky * ay + kz * az) / kk2
+        dd[0, 0, 0] = 0
+        ax, ay, az = ax - 1j * kx * dd, ay - 1j * ky * dd, az - 1j * kz * dd
+        C1s = dd / LD(nz)
+        C1 = self.z_backward(C1s)
+        C2 = self.z_backward(1j * kz * C1s)                                # derivk(C1, C2, 3), then to z (:289-292)
+        kh = np.sqrt(self.kx[:, None] ** 2 + self.ky[None, :] ** 2)
+        bc1 = -C1[:, :, 0] if s == 0 else C2[:, :, 0] - kh * C1[:, :, 0]                    # :294-321
+        bc2 = -C1[:, :, top] if e == 0 else -(C2[:, :, top] + kh * C1[:, :, top])           # :323-352
+        Lz = self.Lz
+        phi = np.zeros((self.nxh, self.ny, nz), dtype=CLD)
+        dphi = np.zeros_like(phi)
+        for i in range(self.nxh):
+            for j in range(self.ny):
+                k_h, b1, b2 = kh[i, j], bc1[i, j], bc2[i, j]
+                if (s, e) == (0, 0):                                       # pure Dirichlet :499-528
+                    mean = ((b2 - b1) / Lz, b1)
+                    if k_h > 0:
+                        t = 1 / (1 - np.exp(-2 * k_h * Lz))
+                        c1, c2 = (b2 - b1 * np.exp(-k_h * Lz)) * t, (b1 - b2 * np.exp(-k_h * Lz)) * t
+                elif (s, e) == (1, 1):                                     # pure Robin :563-592
+                    mean = (b1, 0)
+                    if k_h > 0:
+                        c1, c2 = b2 / (2 * k_h), b1 / (2 * k_h)
+                elif (s, e) == (0, 1):                                     # Dirichlet bottom, Robin top :595-624
+                    mean = (b2, b1)
+                    if k_h > 0:
+                        c1 = b2 / (2 * k_h)
+                        c2 = (b1 * 2 * k_h - b2 * np.exp(-k_h * Lz)) / (2 * k_h)
+                else:
+                    raise ValueError("[ERROR] Unsupported BC combination in call to laplace_z. Aborting...")
+                if i == 0 and j == 0:                                      # :635-639
+                    phi[0, 0] = np.real(mean[0]) * self.z + np.real(mean[1])
+                    dphi[0, 0] = np.real(mean[0])
+                else:
+                    ep, em = np.exp(k_h * (self.z - Lz)), np.exp(-k_h * self.z)
+                    phi[i, j] = c1 * ep + c2 * em
+                    dphi[i, j] = k_h * (c1 * ep - c2 * em)
+        ph = C1 + phi
+        ph_hat, dph_hat = self.z_forward_continued(phi), self.z_forward_continued(dphi)
+        ax, ay, az = ax - 1j * kx * ph_hat, ay - 1j * ky * ph_hat, az - dph_hat
+        out = []
+        for c, order in ((ax, 2), (ay, 2), (az, 1)):
+            m = self.mixed(c)
+            for wall, kind in ((0, s), (1, e)):                            # z = 0 first, then z = Lz (:168-181)
+                m[:, :, 0 if wall == 0 else top] = 0
+                if kind == 0:
+                    self._neumann_wall(m, order, wall)                     # conducting_z :239-290
+                else:
+                    self._robin(m, wall)                                   # insulating_z :294-344
+            out.append(self.z_forward_continued(m))
+        return out, ph
+
+    # ---- ROTBOUSS (include/rotbouss/rotbouss_rkstep2.f90:3-56): Coriolis term, no theta filter / round trip ----
+    def rotbouss_rkstep2(self, v, th, v0, th0, f, fs, pr, o, dt, nu, kappa, xmom, xtemp, omega, vwall0=(0, 0), vwallL=(0, 0)):
+        ox, oy, oz = [LD(w) for w in omega]
+        nl = self.gradre(v)
+        adv = self.advect(v, th)
+        nl[0] = nl[0] + 2 * (oy * v[2] - oz * v[1])
+        nl[1] = nl[1] + 2 * (oz * v[0] - ox * v[2])
+        nl[2] = nl[2] + 2 * (ox * v[1] - oy * v[0]) - LD(xmom) * th
+        adv = adv - LD(xtemp) * v[2]
+        nl = [self.fc_filter(c) for c in nl]
+        adv = self.fc_filter(adv)
+        kk2 = self.kx[:, None, None] ** 2 + self.ky[None, :, None] ** 2 + self.kz[None, None, :] ** 2
+        new = [v0[c].astype(CLD) + LD(dt) * (LD(nu) * (-kk2 * v[c]) - nl[c] + f[c]) / LD(o) for c in range(3)]
+        thn = th0.astype(CLD) + LD(dt) * (LD(kappa) * (-kk2 * th) - adv + fs) / LD(o)
+        new, pnew = self.impose_and_project(new, pr.astype(CLD), o, vwall0, vwallL)
+        m = self.mixed(thn)                                                # s_imposebc: zero walls, forward (no filter here)
+        m[:, :, 0] = 0
+        m[:, :, self.nph - 1] = 0
+        thn = self.z_forward_continued(m)
+        return new, thn, pnew
+
+    # ---- MHDBOUSS (include/mhdbouss/mhdbouss_rkstep2.f90:3-106) ----
+    def mhdbouss_rkstep2(self, v, a, th, v0, a0, th0, f, mf, fs, pr, o, dt, nu, mu, kappa, xmom, xtemp, b0, s, e):
+        N = LD(self.nx) * self.ny * self.nz
+        B = self.curl(*a)
+        for c in range(3):
+            B[c][0, 0, 0] = LD(b0[c]) * N
+        J = self.curl(*B)
+        nl = self.cross(self.curl(*v), v)
+        adv = self.advect(v, th)
+        lor = self.cross(J, B)
+        nl = [nl[c] - lor[c] for c in range(3)]
+        nl[2] = nl[2] - LD(xmom) * th
+        adv = adv - LD(xtemp) * v[2]
+        nl = [self.fc_filter(c) for c in nl]
+        adv = self.fc_filter(adv)
+        emf = [self.fc_filter(c) for c in self.cross(v, B)]
+        kk2 = self.kx[:, None, None] ** 2 + self.ky[None, :, None] ** 2 + self.kz[None, None, :] ** 2
+        vn = [v0[c].astype(CLD) + LD(dt) * (LD(nu) * (-kk2 * v[c]) - nl[c] + f[c]) / LD(o) for c in range(3)]
+        an = [a0[c].astype(CLD) + LD(dt) * (-LD(mu) * J[c] + emf[c] + mf[c]) / LD(o) for c in range(3)]
+        thn = th0.astype(CLD) + LD(dt) * (LD(kappa) * (-kk2 * th) - adv + fs) / LD(o)
+        vn, pnew = self.impose_and_project(vn, pr.astype(CLD), o)
+        an, ph = self.a_imposebc_and_project_walls(an, s, e)
+        m = self.mixed(thn)
+        m[:, :, 0] = 0
+        m[:, :, self.nph - 1] = 0
+        thn = self.z_forward_continued(m)
+        thn = self.to_spectral(self.to_real(thn) / N)                      # the round trip without the filter (:103-106)
+        return vn, an, thn, pnew, ph

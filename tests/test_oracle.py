@@ -525,3 +525,65 @@ def test_energy_diagnostic_is_the_physical_space_mean(tables):
     assert float(np.abs(s.vx[n[0] // 2]).max()) == 0.0      # no x-Nyquist content
     mean = sum(float(np.mean((ind.to_real(q)[:nph] / N) ** 2)) for q in (s.vx, s.vy, s.vz))
     assert abs(O.energy(g, s.vx, s.vy, s.vz, 1) / mean - 1) < 1e-12
+
+
+def test_oracle_walls_and_remaining_solvers_match_independent_statement(tables):
+    """SURVEY 8(f) row 2 of the oracle against the independent longdouble dense-DFT statement
+    (tests/independent_hd.py:IndependentWalls) on 8 x 8 x 48, both RK2 substeps: ROTBOUSS with moving walls (Coriolis
+    term, wall velocities in the mean mode), MHDBOUSS with a uniform field for the three wall channels laplace_z accepts
+    (conducting, vacuum, conducting bottom / vacuum top: Robin sol_project boundary values, the Robin and
+    Dirichlet-Robin laplace_z branches, robin_reconstruct with khom), and the fourth combination's error."""
+    from independent_hd import IndependentWalls
+    n, L = (8, 8, 48), (1.0, 0.5, 1.0)
+    dt, nu, kappa, mu = 1e-3, 1e-3, 1e-3, 5e-3
+    g = O.Grid(*n, 25, 5, Lx=L[0], Ly=L[1], Lz=L[2], tdir=tables, ord=2)
+    g.load_neumann()
+    ind = IndependentWalls(*n, 25, 5, *L, tables, 2)
+    nph = g.nz - g.Cz
+    c128 = lambda q: q.astype(np.complex128)
+
+    def err(a, b, scale):
+        return float(np.abs(c128(a) - b).max()) / scale
+
+    def phys_err(a, b):
+        x = np.fft.ifft(c128(a), axis=2)[:, :, :nph]
+        y = np.fft.ifft(b, axis=2)[:, :, :nph]
+        return float(np.abs(x - y).max()) / float(np.abs(y).max())
+
+    # ---- ROTBOUSS, moving walls ----
+    omega, w0, wL = (0.3, -0.2, 1.5), (0.2, -0.1), (-0.3, 0.1)
+    s = O.make_bouss_state(g)
+    v, th = [s.vx.copy(), s.vy.copy(), s.vz.copy()], s.th.copy()
+    v0, th0 = [q.copy() for q in v], th.copy()
+    f, fs, pr = [s.fx.copy(), s.fy.copy(), s.fz.copy()], s.fs.copy(), s.pr.copy()
+    C = [q.copy() for q in v] + [th.copy()]
+    for o in (2, 1):
+        O.rotbouss_rkstep2(g, s, *C, o, dt, nu, kappa, 1.0, 1.0, omega, w0, wL)
+        v, th, pr = ind.rotbouss_rkstep2(v, th, v0, th0, f, fs, pr, o, dt, nu, kappa, 1.0, 1.0, omega, w0, wL)
+        scale = max(float(np.abs(q).max()) for q in (s.vx, s.vy, s.vz))
+        assert max(err(a, b, scale) for a, b in zip(v, (s.vx, s.vy, s.vz))) < 1e-12
+        assert phys_err(th, s.th) < 1e-11
+    # ---- MHDBOUSS, uniform field, every wall channel ----
+    b0 = (0.0, 0.0, 0.1)
+    for bs, be in ((0, 0), (1, 1), (0, 1)):
+        s = O.make_mhdbouss_state(g)
+        v, a, th = [s.vx.copy(), s.vy.copy(), s.vz.copy()], [s.ax.copy(), s.ay.copy(), s.az.copy()], s.th.copy()
+        v0, a0, th0 = [q.copy() for q in v], [q.copy() for q in a], th.copy()
+        f, mf, fs, pr = [s.fx.copy(), s.fy.copy(), s.fz.copy()], [s.mx.copy(), s.my.copy(), s.mz.copy()], s.fs.copy(), s.pr.copy()
+        C = [q.copy() for q in v] + [th.copy()] + [q.copy() for q in a]
+        for o in (2, 1):
+            O.mhdbouss_rkstep2(g, s, *C, o, dt, nu, mu, kappa, 1.0, 1.0, b0, bs, be)
+            v, a, th, pr, ph = ind.mhdbouss_rkstep2(v, a, th, v0, a0, th0, f, mf, fs, pr, o, dt, nu, mu, kappa, 1.0, 1.0, b0, bs, be)
+            vs = max(float(np.abs(q).max()) for q in (s.vx, s.vy, s.vz))
+            as_ = max(float(np.abs(q).max()) for q in (s.ax, s.ay, s.az))
+            assert max(err(x, y, vs) for x, y in zip(v, (s.vx, s.vy, s.vz))) < 1e-12, (bs, be, o)
+            assert max(err(x, y, as_) for x, y in zip(a, (s.ax, s.ay, s.az))) < 1e-11, (bs, be, o)
+            assert phys_err(th, s.th) < 1e-11, (bs, be, o)
+            dph = float(np.abs(c128(ph) - s.ph)[:, :, :nph].max())
+            assert dph < 1e-9 * max(float(np.abs(s.ph[:, :, :nph]).max()), 1e-30) or dph < 1e-11 * as_, (bs, be, o)
+    # vacuum bottom / conducting top is not a channel of laplace_z: both statements refuse it like the reference
+    s = O.make_mhdbouss_state(g)
+    with pytest.raises(ValueError, match="Unsupported BC combination"):
+        O.a_imposebc_and_project_bc(g, s.ax, s.ay, s.az, 1, 0)
+    with pytest.raises(ValueError, match="Unsupported BC combination"):
+        ind.a_imposebc_and_project_walls([s.ax, s.ay, s.az], 1, 0)
