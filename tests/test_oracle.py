@@ -587,3 +587,45 @@ def test_oracle_walls_and_remaining_solvers_match_independent_statement(tables):
         O.a_imposebc_and_project_bc(g, s.ax, s.ay, s.az, 1, 0)
     with pytest.raises(ValueError, match="Unsupported BC combination"):
         ind.a_imposebc_and_project_walls([s.ax, s.ay, s.az], 1, 0)
+
+
+def test_global_quantities_are_the_physical_space_means(tables):
+    """The Parseval-type sums of the diagnostics (pseudospec_hd.f90:638-940, 1118-1235, pseudospec_phd.f90:116-272,
+    boundary_mod.fpp:681-801) against the quantities they stand for, evaluated in REAL space with the independent
+    dense-DFT transform: <v.curl v>, <v.f>, <(div v)^2>, <theta^2>, <theta f_s> as means over the physical grid points and
+    the wall checks as means over the wall planes.  Valid for fields without x-Nyquist content (every kx > 0 plane is
+    weighted by 2), which the initial conditions on nx = 16 satisfy.  energy(kin=0) is the reference's
+    <w_x^2 + 2 w_y^2> (:527, :540: the y component of the curl twice, the z component never) and is checked as such."""
+    from independent_hd import IndependentSolvers, LD
+    n, L = (16, 8, 48), (1.0, 0.5, 1.0)
+    g = O.Grid(*n, 25, 5, Lx=L[0], Ly=L[1], Lz=L[2], tdir=tables, ord=2)
+    ind = IndependentSolvers(*n, 25, 5, *L, tables, 2)
+    s = O.make_bouss_state(g)
+    O.bouss_step(g, s, 1e-3, 1e-3, 1e-3)          # a generic divergence-free state with walls applied
+    fs = s.th * (0.3 + 0.1j) + np.roll(s.th, 1, axis=1) * 0.2        # some other scalar to pair theta with
+    N = LD(n[0]) * n[1] * n[2]
+    nph = g.nz - g.Cz
+    real = lambda q: ind.to_real(q)[:nph] / N
+    v = [real(q) for q in (s.vx, s.vy, s.vz)]
+    f = [real(q) for q in (s.fx, s.fy, s.fz)]
+    w = [real(q) for q in ind.curl(s.vx, s.vy, s.vz)]
+    mean = lambda r: float(np.mean(r))
+    e = mean(v[0] ** 2 + v[1] ** 2 + v[2] ** 2)
+    assert abs(O.energy(g, s.vx, s.vy, s.vz, 1) / e - 1) < 1e-12
+    # derivative-based quantities: i k a at the one-sided Nyquist wavenumbers (index n/2+1 holds -n/2, specter.fpp:772-789)
+    # is not the transform of a real field, so the real-space mean (which drops that imaginary part) and the Parseval sum
+    # differ by the Nyquist content of the field, ~3e-10 here -- far below any error of weights or normalisation
+    assert abs(O.energy(g, s.vx, s.vy, s.vz, 0) / mean(w[0] ** 2 + 2 * w[1] ** 2) - 1) < 1e-8
+    assert abs(O.helicity(g, s.vx, s.vy, s.vz) - mean(v[0] * w[0] + v[1] * w[1] + v[2] * w[2])) < 1e-8 * np.sqrt(e * mean(w[0] ** 2 + w[1] ** 2 + w[2] ** 2))
+    assert abs(O.cross(g, s.vx, s.vy, s.vz, s.fx, s.fy, s.fz, 1) - mean(v[0] * f[0] + v[1] * f[1] + v[2] * f[2])) < 1e-12 * np.sqrt(e * mean(f[0] ** 2))
+    div = sum(real(ind.deriv(q, d + 1)) for d, q in enumerate((s.vx, s.vy, s.vz)))
+    dref = mean(div ** 2)
+    assert abs(O.divergence(g, s.vx, s.vy, s.vz) / dref - 1) < 1e-4      # a residual of 8e-9 <v^2>: the Nyquist part is 3e-6 of it
+    th, fr = real(s.th), real(fs)
+    assert abs(O.variance(g, s.th, 1) / mean(th ** 2) - 1) < 1e-12
+    assert abs(O.product(g, s.th, fs) - mean(th * fr)) < 1e-12 * np.sqrt(mean(th ** 2) * mean(fr ** 2))
+    # wall planes (rows 0 and nph-1 of the physical box): tangential and normal velocity, scalar
+    for got, want in ((O.bouncheck_z(g, s.vx, s.vy), [float(np.mean(v[0][r] ** 2 + v[1][r] ** 2)) for r in (0, nph - 1)]),
+                      (O.bouncheck_z(g, s.th), [float(np.mean(th[r] ** 2)) for r in (0, nph - 1)])):
+        for a, b in zip(got, want):
+            assert abs(a - b) < 1e-12 * e
