@@ -1007,13 +1007,13 @@ def _oracle_substeps(g, solver, ord, dt, eps=0.0, seed=0):
     return s, init, out
 
 
-def case_substeps_other_table(lib, tables, shape, Cz, oz, solver, ord=2, dt=1e-3, impl=0):
+def case_substeps_other_table(lib, tables, shape, Cz, oz, solver, ord=2, dt=1e-3, impl=0, draws=3):
     """One RK step of a solver on another continuation table of the reference, per substep against the oracle.
 
     The continuation rows are sum_j dir(i,j) f(j): rounding differences of the last bit are amplified by max|dir|
     (29 for A15-3, 3.5e3 for A25-5, 2.6e6 for A34-8, 1.1e7 for A33-9) and carried into every spectral coefficient by
     the transform, in the reference as much as here.  Each field is therefore held to the north-star tolerance 1e-11
-    OR to 30 x the oracle's own response to a 1e-16 relative perturbation of its inputs (the largest of three draws),
+    OR to 30 x the oracle's own response to a 1e-16 relative perturbation of its inputs (the largest of `draws` draws),
     whichever is larger: the result of the reference's arithmetic is not defined more sharply than that."""
     with fc_table(Cz, oz, tables):
         g, p = make(lib, tables, *shape, ord=ord)
@@ -1021,7 +1021,7 @@ def case_substeps_other_table(lib, tables, shape, Cz, oz, solver, ord=2, dt=1e-3
         names = _SOLVER_FIELDS[solver]
         groups = [names[:3]] + ([names[3:]] if len(names) > 3 else [])
         sens = [{n: 0.0 for n in names} for _ in ref]
-        for seed in (1, 2, 3):
+        for seed in range(1, draws + 1):
             _, _, pert = _oracle_substeps(g, solver, ord, dt, eps=1e-16, seed=seed)
             for k, (a, b) in enumerate(zip(ref, pert)):
                 for grp in groups:

@@ -213,10 +213,10 @@ def test_solver_diagnostics_100_steps_cfg1(cuda_lib, tables, solver):
 def test_other_fc_tables(cuda_lib, tables, fc):
     P.case_operators_other_table(cuda_lib, tables, CFG1, *fc)
     for solver, impl in (("hd", 0), ("hd", 1), ("bouss", 0), ("mhd", 0)):
-        P.case_substeps_other_table(cuda_lib, tables, CFG1, *fc, solver, impl=impl)
+        P.case_substeps_other_table(cuda_lib, tables, CFG1, *fc, solver, impl=impl, draws=2)
     if fc == (34, 8):
         return
     # the long-line kernel families (bulk-copy tiles, x-pass ring, paired projections), one axis at a time
     for shape in ((16, 16, 512), (512, 16, 64), (16, 512, 64)):
         for solver in ("hd", "mhd"):
-            P.case_substeps_other_table(cuda_lib, tables, shape, *fc, solver)
+            P.case_substeps_other_table(cuda_lib, tables, shape, *fc, solver, draws=2)
