@@ -932,6 +932,31 @@ def _split_fixed(line, widths):
     return out
 
 
+def compare_global_dirs(ours, ref, solver, nrows, eng):
+    """The same files with the same fixed-width layout (the reference's FORMATs) and the same numbers: 16 / 14 printed
+    digits to 1e-9, six printed digits to 2e-6, residual columns on the scale of the energy."""
+    import os
+    from pathlib import Path
+    ours, ref = Path(str(ours)), Path(str(ref))
+    txt = lambda d: sorted(n for n in os.listdir(d) if n.endswith(".txt") and n != "benchmark.txt")
+    assert txt(ours) == txt(ref), (solver, txt(ours), txt(ref))
+    mag = solver in ("MHD", "MHDBOUSS")
+    for name in txt(ref):
+        widths = GLOBAL_WIDTHS.get(name)
+        if widths is None:       # balance.txt / helicity.txt: the widths depend on the solver family
+            widths = ({"balance.txt": [13, 23, 23, 24], "helicity.txt": [13, 24]} if not mag else
+                      {"balance.txt": [13, 23, 23, 23], "helicity.txt": [13, 24, 24]})[name]
+        la, lb = open(ours / name).read().split("\n"), open(ref / name).read().split("\n")
+        assert len(la) == len(lb) == nrows + 1 and la[-1] == "", (name, len(la), len(lb))
+        for a, b in zip(la[:-1], lb[:-1]):
+            fa, fb = _split_fixed(a, widths), _split_fixed(b, widths)
+            assert fa[0] == fb[0]                                   # the time label, character for character
+            for w, x, y in zip(widths[1:], fa[1:], fb[1:]):
+                xv, yv = _fortran_float(x), _fortran_float(y)
+                tol = TOL_DIAG if w > 13 else 2e-6                  # 16 / 14 digits printed, or 6
+                assert abs(xv - yv) <= tol * abs(yv) + TOL_DIAG * eng, (solver, name, x, y)
+
+
 def case_global_files(lib, tables, shape, tmpdir, dt=1e-3):
     """sx_global for HD, BOUSS and MHDBOUSS (conducting bottom / vacuum top, so that both magnetic files appear): the
     same files, the same fixed-width layout (the reference's FORMATs) and the same numbers as the oracle writes."""
@@ -958,23 +983,7 @@ def case_global_files(lib, tables, shape, tmpdir, dt=1e-3):
             p.global_quantities(solver, ours, t, dt)
             O.solver_global(g, s, solver, ref, t, dt, *(bc or (0, 0)))
         eng = O.energy(g, s.vx, s.vy, s.vz, 1)
-        assert sorted(os.listdir(ours)) == sorted(os.listdir(ref)), (solver, sorted(os.listdir(ours)))
-        for name in sorted(os.listdir(ref)):
-            widths = GLOBAL_WIDTHS.get(name)
-            la, lb = open(ours / name).read().split("\n"), open(ref / name).read().split("\n")
-            assert len(la) == len(lb) == len(steps) + 1 and la[-1] == ""
-            for a, b in zip(la[:-1], lb[:-1]):
-                if widths is None:       # balance.txt / helicity.txt: the widths depend on the solver family
-                    widths_ = ({"balance.txt": [13, 23, 23, 24], "helicity.txt": [13, 24]} if solver != "MHDBOUSS" else
-                               {"balance.txt": [13, 23, 23, 23], "helicity.txt": [13, 24, 24]})[name]
-                else:
-                    widths_ = widths
-                fa, fb = _split_fixed(a, widths_), _split_fixed(b, widths_)
-                assert fa[0] == fb[0]                                   # the time label, character for character
-                for w, x, y in zip(widths_[1:], fa[1:], fb[1:]):
-                    xv, yv = _fortran_float(x), _fortran_float(y)
-                    tol = TOL_DIAG if w > 13 else 2e-6                  # 16 / 14 digits printed, or 6
-                    assert abs(xv - yv) <= tol * abs(yv) + TOL_DIAG * eng, (solver, name, x, y)
+        compare_global_dirs(ours, ref, solver, len(steps), eng)
         runs.append(solver)
         p.close()
     return runs
