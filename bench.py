@@ -73,16 +73,41 @@ KERNEL_SOURCES = ("sx_common.cuh", "sx_fft.cuh", "sx_tma.cuh", "sx_plan.h", "sx_
                   "sx_fused_zfwd.cu", "sx_fused_project.cu", "sx_solvers.cu")
 
 
-def sources_hash():
-    """Content hash of the kernel sources: ties a committed ncu capture (profiles/ncu_traffic.json) to the code it
-    was taken from (the GPU box has no .git).  Host-side orchestration (sx_fused.cu, sx_comm.cu, sx_api.cu ...) is not
-    part of it: it does not change what a launch of a kernel reads and writes."""
+def gpu_view(text):
+    """A source file as nvcc sees it with respect to SX_EMU: the regions that only the CPU-thread emulation of the tests
+    compiles (`#ifdef SX_EMU` ... / the `#else` side of `#ifndef SX_EMU`) are dropped together with the directives that
+    delimit them, so that an edit of the emulation side does not look like a change of the kernels."""
+    out, stack = [], []          # stack entries: None for an unrelated #if, else [keep_this_branch]
+    for line in text.splitlines():
+        t = line.strip()
+        if t.startswith("#if"):
+            toks = t.split()
+            if len(toks) >= 2 and toks[1] == "SX_EMU" and toks[0] in ("#ifdef", "#ifndef"):
+                stack.append([toks[0] == "#ifndef"])
+                continue
+            stack.append(None)
+        elif t.startswith("#else") and stack and stack[-1] is not None:
+            stack[-1][0] = not stack[-1][0]
+            continue
+        elif t.startswith("#endif") and stack:
+            if stack.pop() is not None:
+                continue
+        if all(f is None or f[0] for f in stack):
+            out.append(line)
+    return "\n".join(out) + "\n"
+
+
+def sources_hash(root=None):
+    """Content hash of the kernel sources as the GPU build sees them (gpu_view): ties a committed ncu capture
+    (profiles/ncu_traffic.json) to the code it was taken from (the GPU box has no .git).  Host-side orchestration
+    (sx_fused.cu, sx_comm.cu, sx_api.cu ...) is not part of it: it does not change what a launch of a kernel reads and
+    writes."""
     h = hashlib.sha1()
-    d = os.path.join(ROOT, "specter_b200", "csrc")
+    d = os.path.join(root or ROOT, "specter_b200", "csrc")
     for f in KERNEL_SOURCES:
         h.update(f.encode())
-        with open(os.path.join(d, f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(d, f), "r") as fh:
+            h.update(gpu_view(fh.read()).encode())
     return h.hexdigest()[:12]
 
 

@@ -30,9 +30,15 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 #else
-inline void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+// (tests/emu/cuda_emu.h: with SX_EMU_ADVERSARIAL & 4 the copy lands at the issuing thread's wait_group)
+inline void cp_async16(void* smem_dst, const void* gsrc) {
+  if (emu::t_worker->adv & 4) emu::t_worker->cps[emu::flat_tid()].push_back([=]() { memcpy(smem_dst, gsrc, 16); });
+  else memcpy(smem_dst, gsrc, 16);
+}
 inline void cp_async_commit() {}
-inline void cp_async_wait_all() {}
+inline void cp_async_wait_all() {
+  if (emu::t_worker->adv & 4) emu::flush(emu::t_worker->cps[emu::flat_tid()]);
+}
 #endif
 
 // ---- bulk asynchronous copies (TMA, cp.async.bulk) global -> shared, completion on an mbarrier ------------
@@ -78,12 +84,26 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "}\n" ::"r"(a), "r"(parity) : "memory");
 }
 #else
-inline void mbar_init(unsigned long long*, unsigned) {}
+// default emulation: the elected thread runs first and copies synchronously, waits are no-ops; the adversarial modes of
+// tests/emu/cuda_emu.h track the barrier phase and complete the copies as late as the program allows
+inline void mbar_init(unsigned long long* bar, unsigned) {
+  if (emu::t_worker->adv) emu::bar_init(bar);
+}
 inline void mbar_init_fence() {}
-inline void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long*) { memcpy(smem_dst, gsrc, bytes); }
-inline void mbar_expect(unsigned long long*, unsigned) {}
-inline void bulk_load_piece(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long*) { memcpy(smem_dst, gsrc, bytes); }
-inline void mbar_wait(unsigned long long*, unsigned) {}
+inline void mbar_expect(unsigned long long* bar, unsigned bytes) {
+  if (emu::t_worker->adv) emu::bar_expect(bar, bytes);
+}
+inline void bulk_load_piece(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  if (emu::t_worker->adv) emu::bar_issue(bar, bytes, [=]() { memcpy(smem_dst, gsrc, bytes); });
+  else memcpy(smem_dst, gsrc, bytes);
+}
+inline void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  mbar_expect(bar, bytes);
+  bulk_load_piece(smem_dst, gsrc, bytes, bar);
+}
+inline void mbar_wait(unsigned long long* bar, unsigned parity) {
+  if (emu::t_worker->adv) emu::bar_wait(bar, parity);
+}
 inline void l2_prefetch(const void*, unsigned) {}
 #endif
 

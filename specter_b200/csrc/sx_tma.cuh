@@ -48,7 +48,7 @@ struct TmaMap {
 };
 #define SX_GRID_CONSTANT
 inline void fence_proxy_async() {}
-inline void tma_load_3d(void* smem_dst, const TmaMap* m, int c0, int c1, int c2, unsigned long long*) {
+inline void tma_load_3d_now(void* smem_dst, const TmaMap* m, int c0, int c1, int c2) {
   char* d = (char*)smem_dst;
   for (unsigned k = 0; k < m->box[2]; ++k)
     for (unsigned r = 0; r < m->box[1]; ++r)
@@ -59,7 +59,13 @@ inline void tma_load_3d(void* smem_dst, const TmaMap* m, int c0, int c1, int c2,
         *(double*)(d + (((size_t)k * m->box[1] + r) * m->box[0] + e) * 8) = val;
       }
 }
-inline void tma_store_3d(const TmaMap* m, const void* smem_src, int c0, int c1, int c2) {
+inline void tma_load_3d(void* smem_dst, const TmaMap* m, int c0, int c1, int c2, unsigned long long* bar) {
+  if (!emu::t_worker->adv) return tma_load_3d_now(smem_dst, m, c0, c1, c2);
+  const unsigned bytes = m->box[0] * m->box[1] * m->box[2] * 8u;     // the full box counts, clipped or not
+  const TmaMap mm = *m;                                               // the map may live in the issuing thread's frame
+  emu::bar_issue(bar, bytes, [=]() { tma_load_3d_now(smem_dst, &mm, c0, c1, c2); });
+}
+inline void tma_store_3d_now(const TmaMap* m, const void* smem_src, int c0, int c1, int c2) {
   const char* s = (const char*)smem_src;
   for (unsigned k = 0; k < m->box[2]; ++k)
     for (unsigned r = 0; r < m->box[1]; ++r)
@@ -69,9 +75,20 @@ inline void tma_store_3d(const TmaMap* m, const void* smem_src, int c0, int c1, 
           *(double*)(m->base + x * 8 + y * m->stride[1] + z * m->stride[2]) = *(const double*)(s + (((size_t)k * m->box[1] + r) * m->box[0] + e) * 8);
       }
 }
+// adversarial mode 4: the store reads its shared-memory source when the issuing thread waits for its bulk group
+inline void tma_store_3d(const TmaMap* m, const void* smem_src, int c0, int c1, int c2) {
+  if (emu::t_worker->adv & 4) {
+    const TmaMap mm = *m;
+    emu::t_worker->stores[emu::flat_tid()].push_back([=]() { tma_store_3d_now(&mm, smem_src, c0, c1, c2); });
+  } else {
+    tma_store_3d_now(m, smem_src, c0, c1, c2);
+  }
+}
 inline void tma_store_commit() {}
-inline void tma_store_wait_read() {}
-inline void tma_store_wait_all() {}
+inline void tma_store_wait_read() {
+  if (emu::t_worker->adv & 4) emu::flush(emu::t_worker->stores[emu::flat_tid()]);
+}
+inline void tma_store_wait_all() { tma_store_wait_read(); }
 #endif
 
 // host: tensor of complex128 with extents (n0 elements [fastest, contiguous], n1 rows, n2 planes), row / plane pitch in

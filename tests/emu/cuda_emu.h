@@ -19,6 +19,8 @@
 #include <mutex>
 #include <thread>
 #include <ucontext.h>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #define __global__
@@ -52,9 +54,23 @@ namespace emu {
 // One OS worker per block group; the CUDA threads of a block are user-level fibers (ucontext)
 // scheduled round-robin, so __syncthreads() is a yield: every fiber runs up to its next barrier
 // before any fiber passes it.
+//
+// SX_EMU_ADVERSARIAL (bit mask, default 0) turns the emulation into a race check of the kernel sources:
+//   1  the fibers of a block run in REVERSE order between barriers        } a result that depends on the order in which
+//   2  ... in a pseudo-random order, re-drawn for every barrier phase     } the threads run has a missing __syncthreads
+//   4  asynchronous copies complete as LATE as the program allows: cp.async.bulk / tensor loads land when the first
+//      thread gets through mbarrier.try_wait on their barrier, cp.async 16-byte copies at the issuing thread's
+//      wait_group, tensor-map STORES read their shared-memory source at the issuing thread's wait_group(.read) -- data
+//      consumed before its wait, or a store source overwritten before wait_group.read, changes the result.
+// With any bit set the mbarrier phase is tracked (expect_tx / complete_tx bytes) and mbarrier waits really wait, so the
+// producer thread need not run first.
 struct Fiber {
   ucontext_t ctx;
   bool done;
+  bool spinning = false;
+};
+struct BarState {
+  unsigned completed = 0, expected = 0, issued = 0;
 };
 struct Worker {
   ucontext_t main;
@@ -66,7 +82,17 @@ struct Worker {
   dim3 block;
   char* smem = nullptr;
   std::vector<double> shfl;
+  int adv = 0;
+  unsigned long long rng = 0x9E3779B97F4A7C15ull;
+  std::unordered_map<const void*, BarState> bars;
+  unsigned long long events = 0;                                      // mbarrier issues + completions (deadlock detection)
+  std::vector<std::pair<const void*, std::function<void()>>> loads;   // deferred bulk / tensor loads, keyed by barrier
+  std::vector<std::vector<std::function<void()>>> stores, cps;        // deferred tensor stores / cp.async per thread
 };
+inline int adv_mode() {
+  static const int m = [] { const char* e = std::getenv("SX_EMU_ADVERSARIAL"); return e ? std::atoi(e) : 0; }();
+  return m;
+}
 inline thread_local uint3 t_threadIdx, t_blockIdx;
 inline thread_local dim3 t_blockDim, t_gridDim;
 inline thread_local Worker* t_worker = nullptr;
@@ -87,6 +113,16 @@ inline void yield() {
   Worker* w = t_worker;
   swapcontext(&w->fibers[w->current].ctx, &w->main);
 }
+// a thread that waits for another thread of its block (mbarrier wait): it is resumed again WITHIN the same barrier phase
+inline void spin_yield() {
+  Worker* w = t_worker;
+  w->fibers[w->current].spinning = true;
+  swapcontext(&w->fibers[w->current].ctx, &w->main);
+}
+inline void flush(std::vector<std::function<void()>>& q) {
+  for (auto& fn : q) fn();
+  q.clear();
+}
 inline void run_block(Worker* w, unsigned nthr) {
   for (unsigned t = 0; t < nthr; ++t) {
     Fiber& f = w->fibers[t];
@@ -95,20 +131,108 @@ inline void run_block(Worker* w, unsigned nthr) {
     f.ctx.uc_stack.ss_size = w->stack_bytes;
     f.ctx.uc_link = nullptr;
     f.done = false;
+    f.spinning = false;
     makecontext(&f.ctx, (void (*)())fiber_entry, 0);
   }
   unsigned remaining = nthr;
+  if (!w->adv) {
+    while (remaining) {
+      for (unsigned t = 0; t < nthr; ++t) {
+        Fiber& f = w->fibers[t];
+        if (f.done) continue;
+        w->current = (int)t;
+        set_tid(w, t);
+        swapcontext(&w->main, &f.ctx);
+        if (f.done) --remaining;
+      }
+    }
+    return;
+  }
+  w->bars.clear();
+  w->loads.clear();
+  w->stores.assign(nthr, {});
+  w->cps.assign(nthr, {});
+  std::vector<unsigned> order(nthr), retry, again;
   while (remaining) {
-    for (unsigned t = 0; t < nthr; ++t) {
-      Fiber& f = w->fibers[t];
-      if (f.done) continue;
-      w->current = (int)t;
-      set_tid(w, t);
-      swapcontext(&w->main, &f.ctx);
-      if (f.done) --remaining;
+    for (unsigned t = 0; t < nthr; ++t) order[t] = (w->adv & 1) ? nthr - 1 - t : t;
+    if (w->adv & 2)
+      for (unsigned t = nthr; t > 1; --t) {          // Fisher-Yates with xorshift64
+        w->rng ^= w->rng << 13; w->rng ^= w->rng >> 7; w->rng ^= w->rng << 17;
+        std::swap(order[t - 1], order[(unsigned)(w->rng % t)]);
+      }
+    retry.clear();
+    for (unsigned t : order)
+      if (!w->fibers[t].done) retry.push_back(t);
+    while (!retry.empty()) {                          // one barrier phase: every live fiber up to its next barrier
+      again.clear();
+      const unsigned long long events0 = w->events;
+      for (unsigned t : retry) {
+        Fiber& f = w->fibers[t];
+        f.spinning = false;
+        w->current = (int)t;
+        set_tid(w, t);
+        swapcontext(&w->main, &f.ctx);
+        if (f.done) {
+          --remaining;
+          flush(w->stores[t]);                        // the stores of a finished thread complete before the grid ends
+        } else if (f.spinning) {
+          again.push_back(t);
+        }
+      }
+      // every fiber that is left in this phase waits on an mbarrier, and nothing was issued or completed during the pass:
+      // the copies they wait for are never issued (on the GPU: bar.sync and mbarrier.try_wait waiting for each other)
+      if (!again.empty() && again.size() == retry.size() && w->events == events0) {
+        std::fprintf(stderr, "cuda_emu: deadlock -- %zu threads wait on an mbarrier whose copies are never issued\n", again.size());
+        std::abort();
+      }
+      retry.swap(again);
     }
   }
 }
+
+// ---- mbarrier / asynchronous-copy bookkeeping of the adversarial modes ------------------------------------------------
+inline void bar_init(const void* bar) { t_worker->bars[bar] = BarState(); }
+inline void bar_expect(const void* bar, unsigned bytes) { t_worker->bars[bar].expected += bytes; }
+inline void bar_complete_if_full(Worker* w, const void* bar, BarState& st) {
+  if (st.expected > 0 && st.issued == st.expected) {
+    for (size_t i = 0; i < w->loads.size();) {
+      if (w->loads[i].first == bar) {
+        w->loads[i].second();
+        w->loads.erase(w->loads.begin() + (long)i);
+      } else {
+        ++i;
+      }
+    }
+    st.completed++;
+    st.issued = st.expected = 0;
+    w->events++;
+  }
+}
+inline void bar_issue(const void* bar, unsigned bytes, std::function<void()> copy) {
+  Worker* w = t_worker;
+  BarState& st = w->bars[bar];
+  st.issued += bytes;
+  w->events++;
+  if (w->adv & 4) {
+    w->loads.emplace_back(bar, std::move(copy));      // lands when a waiter gets through
+  } else {
+    copy();
+    bar_complete_if_full(w, bar, st);
+  }
+}
+inline void bar_wait(const void* bar, unsigned parity) {
+  Worker* w = t_worker;
+  for (;;) {
+    BarState& st = w->bars[bar];
+    if ((st.completed & 1u) != (parity & 1u)) return;
+    if (w->adv & 4) {
+      bar_complete_if_full(w, bar, st);
+      if ((st.completed & 1u) != (parity & 1u)) return;
+    }
+    spin_yield();
+  }
+}
+inline unsigned flat_tid() { return (unsigned)t_worker->current; }
 
 template <class F>
 void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body_in) {
@@ -131,6 +255,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body_in) {
       std::vector<char> smem(smem_bytes + 64, 0);
       w.smem = smem.data();
       w.shfl.assign((size_t)nthr * 2, 0.0);
+      w.adv = adv_mode();
+      w.rng ^= 0x100000001B3ull * (g + 1);
       t_worker = &w;
       t_blockDim = block;
       t_gridDim = grid;

@@ -86,3 +86,18 @@ def test_final_state_check_on_the_emulation(emu_lib, tables):
         assert sc["ok"] is True, sc
         p.close()
     assert bench.final_state_check(None, "hd", 0)["ok"] is None
+
+
+def test_traffic_capture_belongs_to_these_kernel_sources():
+    """roofline.traffic comes from the committed ncu capture (profiles/ncu_traffic.json) and is dropped when the kernel
+    sources differ from the captured ones: the committed state must carry a capture of ITS sources.  The hash is taken over
+    the GPU view of the files -- what only the test emulation compiles does not count."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+        tj = json.load(fh)
+    cur = bench.sources_hash()
+    assert {w: e["sources_hash"] for w, e in tj["workloads"].items()} == {w: cur for w in tj["workloads"]}
+    src = "a\n#ifndef SX_EMU\ngpu\n#if X\nnested\n#endif\n#else\nemu\n#endif\n#ifdef SX_EMU\nemu2\n#endif\nb\n"
+    assert bench.gpu_view(src) == "a\ngpu\n#if X\nnested\n#endif\nb\n"

@@ -190,3 +190,28 @@ def test_other_fc_tables_long_pencils(emu_lib, tables):
 def test_solver_diagnostics_several_steps(emu_lib, tables, solver):
     # bouss_global.f90 / mhd_global.f90 columns over a few steps (the GPU suite runs 100 steps at 64^3 against goldens)
     P.case_solver_diagnostics(emu_lib, tables, (16, 16, 64), solver, nsteps=2, every=1)
+
+
+def test_adversarial_schedules_and_late_async_copies(tables):
+    """The race check of the emulation (tests/emu/cuda_emu.h, SX_EMU_ADVERSARIAL): the threads of a block run in a random
+    order between barriers, mbarrier waits really wait, and asynchronous copies complete as late as the program allows
+    (bulk / tensor loads when a thread gets through the mbarrier wait, cp.async at the issuing thread's wait_group,
+    tensor-map stores read their shared-memory source at wait_group.read).  A missing barrier or wait changes the result;
+    the bulk-copy kernels of the three solvers must still agree with the oracle.  (The mode is read once per process: the
+    cases run in a child.  tools/emu_racecheck.sh runs the whole emulation suite this way and shows that injected
+    bugs -- a removed mbarrier wait, a removed wait_group.read -- are caught.)"""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "import parity_cases as P\n"
+            "from specter_b200 import api, build\n"
+            "lib = api.Library(build.build_emu())\n"
+            "P.case_hd_substeps(lib, %r, (16, 128, 128), ord=2, nsteps=1, impl=0)\n"
+            "P.case_hd_substeps(lib, %r, (64, 16, 64), ord=2, nsteps=1, impl=1)\n"
+            "P.case_mhd_substeps(lib, %r, (64, 16, 256), ord=2, nsteps=1, impl=0, b0=(0.1, 0.0, 0.2))\n"
+            "print('ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+                                tables, tables, tables)
+    env = dict(os.environ, SX_EMU_ADVERSARIAL="6", SX_TMA_MIN="16", SX_XP="10", SX_PJ="10")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
