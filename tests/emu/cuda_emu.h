@@ -75,7 +75,7 @@ struct BarState {
 struct Worker {
   ucontext_t main;
   std::vector<Fiber> fibers;
-  std::vector<char> stacks;
+  std::unique_ptr<char[]> stacks;   // not value-initialised: only the pages a fiber touches are ever mapped
   size_t stack_bytes = 0;
   int current = 0;
   const std::function<void()>* body = nullptr;
@@ -127,7 +127,7 @@ inline void run_block(Worker* w, unsigned nthr) {
   for (unsigned t = 0; t < nthr; ++t) {
     Fiber& f = w->fibers[t];
     getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = w->stacks.data() + (size_t)t * w->stack_bytes;
+    f.ctx.uc_stack.ss_sp = w->stacks.get() + (size_t)t * w->stack_bytes;
     f.ctx.uc_stack.ss_size = w->stack_bytes;
     f.ctx.uc_link = nullptr;
     f.done = false;
@@ -250,7 +250,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body_in) {
       w.block = block;
       w.body = &body;
       w.stack_bytes = 64 * 1024;
-      w.stacks.resize((size_t)nthr * w.stack_bytes);
+      w.stacks.reset(new char[(size_t)nthr * w.stack_bytes]);
       w.fibers.resize(nthr);
       std::vector<char> smem(smem_bytes + 64, 0);
       w.smem = smem.data();
