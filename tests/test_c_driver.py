@@ -150,10 +150,3 @@ def test_solver_driver_on_emulated_kernels(tables, tmp_path, solver, bc):
     # the two that cover every branch of the driver between them (BOUSS and MHD run in the GPU suite); one step: the cost
     # here is the emulated diagnostics
     run_solver_driver(build.build_emu(), tables, tmp_path, solver, nsteps=1, bc=bc)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("solver,bc", [("HD", (0, 0)), ("BOUSS", (0, 0)), ("ROTBOUSS", (0, 0)), ("MHD", (0, 0)), ("MHDBOUSS", (1, 1))])
-def test_solver_driver_on_gpu(cuda_lib, tables, tmp_path, solver, bc):
-    log = run_solver_driver(api.LIB_PATH, tables, tmp_path, solver, shape=(32, 32, 64), nsteps=2, bc=bc)
-    assert "kernel launches" in log

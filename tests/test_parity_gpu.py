@@ -220,3 +220,12 @@ def test_other_fc_tables(cuda_lib, tables, fc):
     for shape in ((16, 16, 512), (512, 16, 64), (16, 512, 64)):
         for solver in ("hd", "mhd"):
             P.case_substeps_other_table(cuda_lib, tables, shape, *fc, solver, draws=2)
+
+
+# ---- examples/solver_driver.c on the B200 (kept in this file, after the cases above: the suite runs with -x) ---------
+@pytest.mark.parametrize("solver,bc", [("HD", (0, 0)), ("BOUSS", (0, 0)), ("ROTBOUSS", (0, 0)), ("MHD", (0, 0)), ("MHDBOUSS", (1, 1))])
+def test_solver_driver_on_gpu(cuda_lib, tables, tmp_path, solver, bc):
+    from specter_b200 import api
+    from test_c_driver import run_solver_driver
+    log = run_solver_driver(api.LIB_PATH, tables, tmp_path, solver, shape=(32, 32, 64), nsteps=2, bc=bc)
+    assert "kernel launches" in log
