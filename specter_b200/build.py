@@ -75,8 +75,9 @@ def build_emu(force: bool = False) -> str:
     for src in _sources():
         obj = os.path.join(EMU_DIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = ["g++", "-O2", "-std=c++20", "-fPIC", "-DSX_EMU", "-include", shim, "-x", "c++", "-c", src, "-o", obj,
-               "-Wno-unknown-pragmas"]
+        # _FORTIFY_SOURCE off: the fibers switch stacks with _longjmp, which the fortified longjmp check refuses
+        cmd = ["g++", "-O2", "-std=c++20", "-fPIC", "-DSX_EMU", "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0", "-include", shim,
+               "-x", "c++", "-c", src, "-o", obj, "-Wno-unknown-pragmas"]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, pr in procs:
         out, _ = pr.communicate()

@@ -18,6 +18,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <setjmp.h>
 #include <ucontext.h>
 #include <unordered_map>
 #include <utility>
@@ -64,8 +65,13 @@ namespace emu {
 //      consumed before its wait, or a store source overwritten before wait_group.read, changes the result.
 // With any bit set the mbarrier phase is tracked (expect_tx / complete_tx bytes) and mbarrier waits really wait, so the
 // producer thread need not run first.
+// Context switches: a fiber is ENTERED through makecontext / swapcontext (which sets up its stack) and from then on
+// switched with _setjmp / _longjmp, which do not save and restore the signal mask (two system calls per swapcontext: the
+// bulk of the emulation's run time).  SX_EMU_UCONTEXT_ONLY keeps swapcontext throughout (sanitizer builds).
 struct Fiber {
   ucontext_t ctx;
+  jmp_buf jb;
+  bool started = false;
   bool done;
   bool spinning = false;
 };
@@ -74,6 +80,7 @@ struct BarState {
 };
 struct Worker {
   ucontext_t main;
+  jmp_buf main_jb;
   std::vector<Fiber> fibers;
   std::unique_ptr<char[]> stacks;   // not value-initialised: only the pages a fiber touches are ever mapped
   size_t stack_bytes = 0;
@@ -102,22 +109,43 @@ inline void set_tid(Worker* w, unsigned t) {
   t_threadIdx.y = (t / w->block.x) % w->block.y;
   t_threadIdx.z = t / (w->block.x * w->block.y);
 }
+inline void to_main(Worker* w, Fiber& f) {       // from a fiber back to the scheduler
+#ifdef SX_EMU_UCONTEXT_ONLY
+  swapcontext(&f.ctx, &w->main);
+#else
+  if (_setjmp(f.jb) == 0) _longjmp(w->main_jb, 1);
+#endif
+}
+inline void to_fiber(Worker* w, Fiber& f) {      // from the scheduler into a fiber, until it comes back
+#ifdef SX_EMU_UCONTEXT_ONLY
+  swapcontext(&w->main, &f.ctx);
+#else
+  if (_setjmp(w->main_jb) == 0) {
+    if (!f.started) {
+      f.started = true;
+      swapcontext(&w->main, &f.ctx);             // first entry: onto the fiber's own stack
+    } else {
+      _longjmp(f.jb, 1);
+    }
+  }
+#endif
+}
 inline void fiber_entry() {
   Worker* w = t_worker;
   (*w->body)();
   Fiber& f = w->fibers[w->current];
   f.done = true;
-  swapcontext(&f.ctx, &w->main);
+  to_main(w, f);
 }
 inline void yield() {
   Worker* w = t_worker;
-  swapcontext(&w->fibers[w->current].ctx, &w->main);
+  to_main(w, w->fibers[w->current]);
 }
 // a thread that waits for another thread of its block (mbarrier wait): it is resumed again WITHIN the same barrier phase
 inline void spin_yield() {
   Worker* w = t_worker;
   w->fibers[w->current].spinning = true;
-  swapcontext(&w->fibers[w->current].ctx, &w->main);
+  to_main(w, w->fibers[w->current]);
 }
 inline void flush(std::vector<std::function<void()>>& q) {
   for (auto& fn : q) fn();
@@ -131,6 +159,7 @@ inline void run_block(Worker* w, unsigned nthr) {
     f.ctx.uc_stack.ss_size = w->stack_bytes;
     f.ctx.uc_link = nullptr;
     f.done = false;
+    f.started = false;
     f.spinning = false;
     makecontext(&f.ctx, (void (*)())fiber_entry, 0);
   }
@@ -142,7 +171,7 @@ inline void run_block(Worker* w, unsigned nthr) {
         if (f.done) continue;
         w->current = (int)t;
         set_tid(w, t);
-        swapcontext(&w->main, &f.ctx);
+        to_fiber(w, f);
         if (f.done) --remaining;
       }
     }
@@ -171,7 +200,7 @@ inline void run_block(Worker* w, unsigned nthr) {
         f.spinning = false;
         w->current = (int)t;
         set_tid(w, t);
-        swapcontext(&w->main, &f.ctx);
+        to_fiber(w, f);
         if (f.done) {
           --remaining;
           flush(w->stores[t]);                        // the stores of a finished thread complete before the grid ends

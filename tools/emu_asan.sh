@@ -11,7 +11,7 @@ mkdir -p "$OUT"
 objs=""
 for src in "$ROOT"/specter_b200/csrc/*.cu; do
   o="$OUT/$(basename "${src%.cu}").o"
-  g++ -O1 -g -fsanitize=address -fno-omit-frame-pointer -std=c++20 -fPIC -DSX_EMU -include "$ROOT/tests/emu/cuda_emu.h" \
+  g++ -O1 -g -fsanitize=address -fno-omit-frame-pointer -std=c++20 -fPIC -DSX_EMU -DSX_EMU_UCONTEXT_ONLY -include "$ROOT/tests/emu/cuda_emu.h" \
       -x c++ -c "$src" -o "$o" -Wno-unknown-pragmas &
   objs="$objs $o"
 done

@@ -28,7 +28,7 @@ mutant() {   # name, sed expression on sx_fused_tiles.cu
   objs=""
   for src in "$W/$1"/specter_b200/csrc/*.cu; do
     o="$W/$1/$(basename "${src%.cu}").o"
-    g++ -O2 -std=c++20 -fPIC -DSX_EMU -include "$W/$1/tests/emu/cuda_emu.h" -x c++ -c "$src" -o "$o" -Wno-unknown-pragmas &
+    g++ -O2 -std=c++20 -fPIC -DSX_EMU -U_FORTIFY_SOURCE -D_FORTIFY_SOURCE=0 -include "$W/$1/tests/emu/cuda_emu.h" -x c++ -c "$src" -o "$o" -Wno-unknown-pragmas &
     objs="$objs $o"
   done
   wait
