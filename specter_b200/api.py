@@ -375,7 +375,9 @@ class Plan:
         import torch
         buf = (C.c_char * 64)()
         self._call("sx_plan_p2p_export", n_inverse, n_forward, buf)
-        mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8).cuda()
+        mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda()
         allh = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
         dist.all_gather(allh, mine)
         raw = b"".join(bytes(h.cpu().tolist()) for h in allh)

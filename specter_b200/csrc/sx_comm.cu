@@ -240,8 +240,23 @@ int exchange_begin_p2p(Plan& p, int ev, const cplx* send, const size_t* sdispl, 
   p.launches++;
   return 0;
 #else
-  (void)p; (void)ev; (void)send; (void)sdispl; (void)scount; (void)peer_dst;
-  SX_REQUIRE(false, "the emulated build has no peer-to-peer exchange");
+  // emulation: the copies are done in program order into the peers' shared-memory arenas, the completion barrier is a
+  // one-word all-reduce through the caller's callback
+  SX_REQUIRE(p.nprocs > 1 && p.comm && p.comm->allred, "the emulated peer-to-peer exchange needs sx_plan_set_comm_callbacks (barrier)");
+  SX_REQUIRE(ev >= 0 && ev < 32, "exchange: bad event slot");
+  Comm& c = *p.comm;
+  if (stage_mark(p, ST_EXCHANGE)) return 1;
+  for (int q = 1; q <= p.nprocs; ++q) {
+    const int r = (p.myrank + q) % p.nprocs;
+    if (!scount[r]) continue;
+    if (r != p.myrank) c.bytes_sent += (double)scount[r] * sizeof(cplx);
+    memmove(peer_dst[r], send + sdispl[r], scount[r] * sizeof(cplx));
+  }
+  c.exchanges++;
+  double one = 0.0;
+  SX_REQUIRE(c.allred(c.user, &one, 1) == 0, "the all-reduce callback (barrier) reported an error");
+  p.launches++;
+  return 0;
 #endif
 }
 
@@ -292,8 +307,24 @@ int p2p_round(Plan& p, const int* wait_slots, int nwait, const P2PCopy* cp, int 
   p.launches++;
   return 0;
 #else
-  (void)p; (void)wait_slots; (void)nwait; (void)cp; (void)n; (void)barrier; (void)done_slot;
-  SX_REQUIRE(false, "the emulated build has no peer-to-peer exchange");
+  (void)wait_slots; (void)nwait; (void)done_slot;
+  SX_REQUIRE(p.nprocs > 1 && p.comm && p.comm->allred, "the emulated peer-to-peer exchange needs sx_plan_set_comm_callbacks (barrier)");
+  Comm& c = *p.comm;
+  if (stage_mark(p, ST_EXCHANGE)) return 1;
+  for (int i = 0; i < n; ++i) {
+    const P2PCopy& q = cp[i];
+    if (q.width == 0 || q.height == 0) continue;
+    if (q.remote) c.bytes_sent += (double)q.width * q.height * sizeof(cplx);
+    SX_CUDA_CHECK(cudaMemcpy2DAsync(q.dst, q.dpitch * sizeof(cplx), q.src, q.spitch * sizeof(cplx), q.width * sizeof(cplx),
+                                    q.height, cudaMemcpyDeviceToDevice, nullptr));
+  }
+  if (barrier) {
+    double one = 0.0;
+    SX_REQUIRE(c.allred(c.user, &one, 1) == 0, "the all-reduce callback (barrier) reported an error");
+    c.exchanges++;
+  }
+  p.launches++;
+  return 0;
 #endif
 }
 

@@ -24,6 +24,29 @@
 #include <cstdlib>
 #include <cstring>
 #include "sx_fused.h"
+#ifdef SX_EMU
+// CPU-thread emulation (tests only): the peer-to-peer arena is a POSIX shared-memory object, so that the ranks of a
+// multi-process test map each other's receive buffers the way CUDA IPC does on the GPU
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#include <string>
+#include <unordered_map>
+#include <utility>
+namespace {
+struct EmuShm {
+  std::string name;
+  size_t bytes = 0;
+  std::vector<std::pair<void*, size_t>> peers;
+};
+std::unordered_map<const void*, EmuShm> g_emu_shm;   // keyed by the Fused object
+struct EmuHandle {                                     // what travels in the 64 handle bytes
+  unsigned long long bytes;
+  char name[48];
+};
+static_assert(sizeof(EmuHandle) <= 64, "the emulated handle must fit the CUDA IPC handle");
+}  // namespace
+#endif
 
 namespace sx {
 
@@ -45,8 +68,14 @@ int fused_free(Plan& p) {
 #ifndef SX_EMU
     for (size_t r = 0; r < f->peer_arena.size(); ++r)
       if ((int)r != p.myrank && f->peer_arena[r]) cudaIpcCloseMemHandle(f->peer_arena[r]);
-#endif
     cudaFree(f->arena);
+#else
+    EmuShm& sh = g_emu_shm[f];
+    for (auto& pr : sh.peers) munmap(pr.first, pr.second);
+    munmap(f->arena, sh.bytes);
+    shm_unlink(sh.name.c_str());
+    g_emu_shm.erase(f);
+#endif
   }
   release_fields(f->R, &f->W);
   release_fields(f->W);
@@ -331,8 +360,33 @@ int fused_p2p_export(Plan& p, int nw, int nx, void* handle64) {
   memcpy(handle64, &h, sizeof(h));
   return 0;
 #else
-  (void)p; (void)nw; (void)nx; (void)handle64;
-  SX_REQUIRE(false, "the emulated build has no peer-to-peer exchange");
+  SX_REQUIRE(p.nprocs > 1, "sx_plan_p2p_export: single-rank plan");
+  Fused* fp;
+  if (fused_init(p, &fp)) return 1;
+  Fused& f = *fp;
+  SX_REQUIRE(f.arena == nullptr && f.W.empty() && f.X.empty(), "sx_plan_p2p_export: call once, before the first substep");
+  const size_t elems = (size_t)nw * arena_rs(p, p.myrank) + (size_t)nx * arena_ws(p, p.myrank);
+  static int counter = 0;
+  EmuShm sh;
+  sh.name = "/sxemu." + std::to_string((long)getpid()) + "." + std::to_string(counter++);
+  sh.bytes = elems * sizeof(cplx);
+  const int fd = shm_open(sh.name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+  SX_REQUIRE(fd >= 0 && ftruncate(fd, (off_t)sh.bytes) == 0, "emulated arena: shm_open / ftruncate failed");
+  void* ptr = mmap(nullptr, sh.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  SX_REQUIRE(ptr != MAP_FAILED, "emulated arena: mmap failed");
+  f.arena = (cplx*)ptr;
+  f.arena_nw = nw;
+  f.arena_nx = nx;
+  EmuHandle h;
+  memset(&h, 0, sizeof(h));
+  h.bytes = sh.bytes;
+  SX_REQUIRE(sh.name.size() < sizeof(h.name), "emulated arena: name too long");
+  memcpy(h.name, sh.name.c_str(), sh.name.size());
+  memset(handle64, 0, 64);
+  memcpy(handle64, &h, sizeof(h));
+  g_emu_shm[&f] = sh;
+  return 0;
 #endif
 }
 
@@ -360,8 +414,33 @@ int fused_p2p_import(Plan& p, const void* handles) {
   }
   return 0;
 #else
-  (void)p; (void)handles;
-  SX_REQUIRE(false, "the emulated build has no peer-to-peer exchange");
+  Fused* f = p.fused;
+  SX_REQUIRE(f != nullptr && f->arena != nullptr, "sx_plan_p2p_import: call sx_plan_p2p_export first");
+  f->peer_arena.assign(p.nprocs, nullptr);
+  EmuShm& sh = g_emu_shm[f];
+  for (int r = 0; r < p.nprocs; ++r) {
+    if (r == p.myrank) { f->peer_arena[r] = f->arena; continue; }
+    EmuHandle h;
+    memcpy(&h, (const char*)handles + (size_t)r * 64, sizeof(h));
+    h.name[sizeof(h.name) - 1] = 0;
+    const int fd = shm_open(h.name, O_RDWR, 0600);
+    SX_REQUIRE(fd >= 0, "emulated arena: cannot open the arena of a peer rank");
+    void* ptr = mmap(nullptr, (size_t)h.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    SX_REQUIRE(ptr != MAP_FAILED, "emulated arena: mmap of a peer arena failed");
+    sh.peers.emplace_back(ptr, (size_t)h.bytes);
+    f->peer_arena[r] = (cplx*)ptr;
+  }
+  f->p2p = true;
+  if (const char* e = getenv("SX_P2P_DIRECT")) {
+    SX_REQUIRE(e[0] >= '0' && e[0] <= '2' && e[1] == 0, "invalid value of the tuning variable SX_P2P_DIRECT (0, 1 or 2)");
+    f->direct = e[0] - '0';
+  }
+  if (const char* e = getenv("SX_P2P_DIRECT_PEERS")) {
+    SX_REQUIRE(e[0] >= '0' && e[0] <= '7' && e[1] == 0, "invalid value of the tuning variable SX_P2P_DIRECT_PEERS (0..7)");
+    f->direct_peers = e[0] - '0';
+  }
+  return 0;
 #endif
 }
 

@@ -26,6 +26,7 @@ def _worker(rank, world, port, shape, ord_, emu_path, tables, q):
         p = api.Plan(nx, ny, nz, 25, 5, ord=ord_, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, nprocs=world, myrank=rank, lib=lib)
 
         def alltoallv(send, sd, sc, recv, rd, rc):
+            assert os.environ.get("SX_TEST_P2P") != "1", "the fused substep must not use the all-to-all callback with the peer-to-peer transport"
             ins = [torch.from_numpy(np.frombuffer((C.c_char * sc[r]).from_address(send + sd[r]), dtype=np.uint8).copy())
                    if sc[r] else torch.empty(0, dtype=torch.uint8) for r in range(world)]
             outs = [torch.empty(rc[r], dtype=torch.uint8) for r in range(world)]
@@ -41,6 +42,7 @@ def _worker(rank, world, port, shape, ord_, emu_path, tables, q):
                 ptr[i] = float(t[i])
 
         p.set_comm_callbacks(alltoallv, allreduce)
+        _maybe_p2p(p, dist, 6, 3)
         # single-rank oracle state, sliced to this rank's kx-slab
         g = O.Grid(nx, ny, nz, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, ord=ord_)
         s = O.make_hd_state(g)
@@ -59,6 +61,15 @@ def _worker(rank, world, port, shape, ord_, emu_path, tables, q):
         p.close()
     finally:
         dist.destroy_process_group()
+
+
+def _maybe_p2p(p, dist, n_inverse, n_forward):
+    """SX_TEST_P2P=1: the DEFAULT transport of the GPU build on one node -- peer-to-peer copies into the peers' receive
+    arenas (here POSIX shared memory between the rank processes instead of CUDA IPC) with the chunked xy pipeline, the
+    callbacks only carrying the completion barrier."""
+    if os.environ.get("SX_TEST_P2P") == "1":
+        p.init_p2p_torch(dist, n_inverse, n_forward)
+        assert p.p2p
 
 
 def _gloo_a2a(dist, outs, ins, rank, world):
@@ -104,6 +115,7 @@ def _install_gloo_callbacks(p, dist, rank, world):
     import torch
 
     def alltoallv(send, sd, sc, recv, rd, rc):
+        assert os.environ.get("SX_TEST_P2P") != "1", "the fused substep must not use the all-to-all callback with the peer-to-peer transport"
         ins = [torch.from_numpy(np.frombuffer((C.c_char * sc[r]).from_address(send + sd[r]), dtype=np.uint8).copy())
                if sc[r] else torch.empty(0, dtype=torch.uint8) for r in range(world)]
         outs = [torch.empty(rc[r], dtype=torch.uint8) for r in range(world)]
@@ -238,6 +250,7 @@ def _worker_solvers(rank, world, port, solver, shape, emu_path, tables, q):
         nx, ny, nz = shape
         p = api.Plan(nx, ny, nz, 25, 5, ord=2, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, nprocs=world, myrank=rank, lib=lib)
         _install_gloo_callbacks(p, dist, rank, world)
+        _maybe_p2p(p, dist, *{"bouss": (8, 4), "mhd": (12, 6), "mhdbouss": (14, 7)}[solver])
         g = O.Grid(nx, ny, nz, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, ord=2)
         g.load_neumann()
         sl = slice(p.ista - 1, p.iend)
@@ -318,3 +331,87 @@ def test_fused_solvers_multirank(solver, world, shape, emu_lib, tables):
         assert nex > 0
         covered += iend - ista + 1
     assert covered == shape[0] // 2 + 1
+
+
+# ---- the peer-to-peer transport and the chunked xy pipeline (the default of the GPU build on one node) ---------------
+def _worker_p2p(rank, world, port, variants, emu_path, tables, q):
+    """One HD step per variant (shape, tuning environment) through the peer-to-peer transport: the receive arenas of the
+    ranks are mapped into each other (POSIX shared memory here, CUDA IPC on the GPU), the blocks are copied -- or stored by
+    the producing kernels -- straight into them, the xy stage runs as a pipeline over z chunks, and the callbacks carry
+    nothing but the completion barrier (the all-to-all callback must stay unused)."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from oracle import specter_oracle as O
+    from specter_b200 import api
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        lib = api.Library(emu_path)
+        out = []
+        for shape, env in variants:
+            for k in ("SX_ZCHUNKS", "SX_TMA_MIN", "SX_P2P_DIRECT", "SX_P2P_DIRECT_PEERS"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            nx, ny, nz = shape
+            p = api.Plan(nx, ny, nz, 25, 5, ord=2, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, nprocs=world, myrank=rank, lib=lib)
+
+            def alltoallv(*a):
+                raise AssertionError("the all-to-all callback was used with the peer-to-peer transport")
+
+            def allreduce(ptr, n):
+                t = torch.tensor([ptr[i] for i in range(n)], dtype=torch.float64)
+                dist.all_reduce(t)
+                for i in range(n):
+                    ptr[i] = float(t[i])
+
+            p.set_comm_callbacks(alltoallv, allreduce)
+            p.init_p2p_torch(dist, 6, 3)
+            g = O.Grid(nx, ny, nz, 25, 5, Lx=1.0, Ly=0.5, Lz=1.0, tdir=tables, ord=2)
+            s = O.make_hd_state(g)
+            sl = slice(p.ista - 1, p.iend)
+            p.hd_put_state(*[np.ascontiguousarray(a[sl]) for a in (s.vx, s.vy, s.vz, s.pr, s.fx, s.fy, s.fz)])
+            errs = []
+            for _ in range(2):                      # two steps: the receive arenas are reused
+                p.hd_step(1e-3, 1e-3)
+                O.hd_step(g, s, 1e-3, 1e-3)
+                got = p.hd_get_state()
+                scale = max(np.abs(a).max() for a in (s.vx, s.vy, s.vz))
+                errs.append(float(max(np.abs(a - b[sl]).max() for a, b in zip(got[:3], (s.vx, s.vy, s.vz))) / scale))
+            out.append((max(errs), p.comm_stats()["exchanges"], p.iend - p.ista + 1))
+            p.close()
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,variants", [
+    (2, [((32, 16, 64), {}),                                               # 4 z chunks, the local block stored in place
+         ((16, 128, 128), {"SX_TMA_MIN": "16", "SX_P2P_DIRECT": "2"}),     # bulk-copy tile kernels storing EVERY block into the peers
+         ((32, 16, 64), {"SX_P2P_DIRECT": "0", "SX_ZCHUNKS": "8"})]),      # every block copied; more chunks than some ranks have row pairs
+    (3, [((16, 16, 64), {"SX_ZCHUNKS": "2"}),                              # uneven slabs, 2 chunks
+         ((16, 16, 64), {"SX_ZCHUNKS": "1"}),                              # no pipeline: one exchange per field
+         ((32, 16, 64), {"SX_P2P_DIRECT_PEERS": "1"})]),                   # the next peer's blocks stored directly, the other copied
+])
+def test_fused_substep_multirank_p2p(world, variants, emu_lib, tables):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_p2p, args=(r, world, port, variants, emu_lib.path, tables, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(timeout=900)
+    assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
+    res = dict(q.get(timeout=10) for _ in range(world))
+    for v, (shape, env) in enumerate(variants):
+        assert sum(res[r][v][2] for r in range(world)) == shape[0] // 2 + 1
+        for r in range(world):
+            err, nex, _ = res[r][v]
+            assert err < 1e-11, (world, shape, env, r, err)
+            assert nex > 0
+
+
+@pytest.mark.parametrize("solver,world,shape", [("bouss", 2, (32, 16, 64)), ("mhd", 3, (16, 16, 64)), ("mhdbouss", 2, (32, 16, 64))])
+def test_fused_solvers_multirank_p2p(solver, world, shape, emu_lib, tables, monkeypatch):
+    monkeypatch.setenv("SX_TEST_P2P", "1")
+    test_fused_solvers_multirank(solver, world, shape, emu_lib, tables)
