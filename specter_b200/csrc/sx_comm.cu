@@ -240,21 +240,29 @@ int exchange_begin_p2p(Plan& p, int ev, const cplx* send, const size_t* sdispl, 
   p.launches++;
   return 0;
 #else
-  // emulation: the copies are done in program order into the peers' shared-memory arenas, the completion barrier is a
-  // one-word all-reduce through the caller's callback
+  // emulation: the same stream / event structure as above with one copy stream; the copies go into the peers'
+  // shared-memory arenas and the completion barrier is a one-word all-reduce through the caller's callback, run as an
+  // operation of the communication stream (tests/emu/cuda_emu.h: in program order by default, deferred with
+  // SX_EMU_ADVERSARIAL & 8)
   SX_REQUIRE(p.nprocs > 1 && p.comm && p.comm->allred, "the emulated peer-to-peer exchange needs sx_plan_set_comm_callbacks (barrier)");
   SX_REQUIRE(ev >= 0 && ev < 32, "exchange: bad event slot");
   Comm& c = *p.comm;
   if (stage_mark(p, ST_EXCHANGE)) return 1;
+  SX_CUDA_CHECK(cudaEventRecord(c.ready[ev], p.stream));
+  SX_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ready[ev], 0));
   for (int q = 1; q <= p.nprocs; ++q) {
     const int r = (p.myrank + q) % p.nprocs;
     if (!scount[r]) continue;
     if (r != p.myrank) c.bytes_sent += (double)scount[r] * sizeof(cplx);
-    memmove(peer_dst[r], send + sdispl[r], scount[r] * sizeof(cplx));
+    SX_CUDA_CHECK(cudaMemcpyAsync(peer_dst[r], send + sdispl[r], scount[r] * sizeof(cplx), cudaMemcpyDeviceToDevice, c.stream));
   }
   c.exchanges++;
-  double one = 0.0;
-  SX_REQUIRE(c.allred(c.user, &one, 1) == 0, "the all-reduce callback (barrier) reported an error");
+  Comm* cp = &c;
+  emu::enqueue(c.stream, [cp]() {
+    double one = 0.0;
+    if (cp->allred(cp->user, &one, 1) != 0) { std::fprintf(stderr, "emulated barrier: the all-reduce callback failed\n"); std::abort(); }
+  });
+  SX_CUDA_CHECK(cudaEventRecord(c.done[ev], c.stream));
   p.launches++;
   return 0;
 #endif
@@ -307,22 +315,26 @@ int p2p_round(Plan& p, const int* wait_slots, int nwait, const P2PCopy* cp, int 
   p.launches++;
   return 0;
 #else
-  (void)wait_slots; (void)nwait; (void)done_slot;
   SX_REQUIRE(p.nprocs > 1 && p.comm && p.comm->allred, "the emulated peer-to-peer exchange needs sx_plan_set_comm_callbacks (barrier)");
   Comm& c = *p.comm;
   if (stage_mark(p, ST_EXCHANGE)) return 1;
+  for (int i = 0; i < nwait; ++i) SX_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ready[wait_slots[i]], 0));
   for (int i = 0; i < n; ++i) {
     const P2PCopy& q = cp[i];
     if (q.width == 0 || q.height == 0) continue;
     if (q.remote) c.bytes_sent += (double)q.width * q.height * sizeof(cplx);
     SX_CUDA_CHECK(cudaMemcpy2DAsync(q.dst, q.dpitch * sizeof(cplx), q.src, q.spitch * sizeof(cplx), q.width * sizeof(cplx),
-                                    q.height, cudaMemcpyDeviceToDevice, nullptr));
+                                    q.height, cudaMemcpyDeviceToDevice, c.stream));
   }
   if (barrier) {
-    double one = 0.0;
-    SX_REQUIRE(c.allred(c.user, &one, 1) == 0, "the all-reduce callback (barrier) reported an error");
+    Comm* cq = &c;
+    emu::enqueue(c.stream, [cq]() {
+      double one = 0.0;
+      if (cq->allred(cq->user, &one, 1) != 0) { std::fprintf(stderr, "emulated barrier: the all-reduce callback failed\n"); std::abort(); }
+    });
     c.exchanges++;
   }
+  if (done_slot >= 0) SX_CUDA_CHECK(cudaEventRecord(c.done[done_slot], c.stream));
   p.launches++;
   return 0;
 #endif
@@ -330,8 +342,10 @@ int p2p_round(Plan& p, const int* wait_slots, int nwait, const P2PCopy* cp, int 
 
 int exchange_wait(Plan& p, int ev) {
   Comm& c = *p.comm;
+#ifndef SX_EMU
   if (c.a2a) return 0;
-  SX_CUDA_CHECK(cudaStreamWaitEvent(p.stream, c.done[ev], 0));
+#endif
+  SX_CUDA_CHECK(cudaStreamWaitEvent(p.stream, c.done[ev], 0));   // (emulation: a never recorded event is no wait)
   return 0;
 }
 

@@ -14,10 +14,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <tuple>
 #include <setjmp.h>
 #include <ucontext.h>
 #include <unordered_map>
@@ -44,7 +47,10 @@ struct dim3 {
 
 typedef int cudaError_t;
 typedef void* cudaStream_t;
-struct emu_event { std::chrono::steady_clock::time_point t; };
+struct emu_event {
+  std::chrono::steady_clock::time_point t;
+  unsigned long long recorded = 0, done = 0;   // ticket of the last cudaEventRecord enqueued / executed (deferred streams)
+};
 typedef emu_event* cudaEvent_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
@@ -63,6 +69,8 @@ namespace emu {
 //      thread gets through mbarrier.try_wait on their barrier, cp.async 16-byte copies at the issuing thread's
 //      wait_group, tensor-map STORES read their shared-memory source at the issuing thread's wait_group(.read) -- data
 //      consumed before its wait, or a store source overwritten before wait_group.read, changes the result.
+//   8  streams are lazy queues (see "runtime subset" below): work that no event orders before its consumer has not run
+//      when the consumer does.
 // With any bit set the mbarrier phase is tracked (expect_tx / complete_tx bytes) and mbarrier waits really wait, so the
 // producer thread need not run first.
 // Context switches: a fiber is ENTERED through makecontext / swapcontext (which sets up its stack) and from then on
@@ -344,41 +352,208 @@ static inline double __shfl_down_sync(unsigned, double v, int delta) {
 }
 
 // ---- runtime subset -------------------------------------------------------
+// Streams.  Default: every operation runs at the call, in program order.  With SX_EMU_ADVERSARIAL & 8 the streams are
+// queues that run as LATE and as LITTLE as the program allows: an operation executes only when the host waits for it
+// (cudaStreamSynchronize, cudaEventSynchronize, a copy to pageable host memory, cudaFree) or when an operation the host
+// waits for depends on it through cudaStreamWaitEvent.  Work of another stream that no event orders before its consumer
+// has then NOT run when the consumer does: a missing event wait changes the result.  Pageable host memory follows the
+// CUDA rules (sources are staged at the call, copies into it are synchronous); page-locked memory (cudaMallocHost) is
+// read and written when the copy executes, so a host buffer reused too early shows as well.
+namespace emu {
+struct StreamOp {
+  std::function<void()> fn;
+  emu_event* ev = nullptr;
+  unsigned long long ticket = 0;
+  int kind = 0;                      // 0 work, 1 record ev/ticket, 2 wait for ev/ticket
+};
+struct Stream {
+  std::deque<StreamOp> q;
+};
+struct Runtime {
+  std::vector<Stream*> streams;
+  std::map<const char*, size_t> pinned;   // page-locked host allocations: start -> bytes
+  unsigned long long tickets = 0;
+  bool deferred() const { return (adv_mode() & 8) != 0; }
+  bool is_pinned(const void* p) const {
+    auto it = pinned.upper_bound((const char*)p);
+    if (it == pinned.begin()) return false;
+    --it;
+    return (const char*)p < it->first + it->second;
+  }
+  void run_until(emu_event* e, unsigned long long ticket) {   // until record `ticket` of e has executed
+    if (e->done >= ticket) return;
+    for (Stream* s : streams)
+      for (const StreamOp& op : s->q)
+        if (op.kind == 1 && op.ev == e && op.ticket == ticket) {
+          while (e->done < ticket) step(s);
+          return;
+        }
+    e->done = ticket;   // the record is gone with its stream: nothing left to wait for
+  }
+  void step(Stream* s) {                                      // executes the head of s (and what it waits for)
+    StreamOp op = std::move(s->q.front());
+    s->q.pop_front();
+    if (op.kind == 2) {
+      run_until(op.ev, op.ticket);
+    } else if (op.kind == 1) {
+      op.ev->t = std::chrono::steady_clock::now();
+      if (op.ev->done < op.ticket) op.ev->done = op.ticket;
+    } else {
+      op.fn();
+    }
+  }
+  void drain(Stream* s) {
+    while (!s->q.empty()) step(s);
+  }
+  void drain_all() {
+    for (Stream* s : streams) drain(s);
+  }
+};
+inline Runtime& rt() {
+  static Runtime r;
+  return r;
+}
+// run fn on the stream: now (default, or the null stream), or when the stream gets there
+inline void enqueue(cudaStream_t st, std::function<void()> fn) {
+  if (!st || !rt().deferred()) return fn();
+  StreamOp op;
+  op.fn = std::move(fn);
+  static_cast<Stream*>(st)->q.push_back(std::move(op));
+}
+}  // namespace emu
+
 static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(1, n ? n : 1); return *p ? 0 : 2; }
-static inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
-static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
-static inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
+static inline cudaError_t cudaFree(void* p) {
+  emu::rt().drain_all();             // cudaFree waits for the device
+  std::free(p);
+  return 0;
+}
+static inline cudaError_t cudaMallocHost(void** p, size_t n) {
+  *p = std::calloc(1, n ? n : 1);
+  if (!*p) return 2;
+  emu::rt().pinned[(const char*)*p] = n ? n : 1;
+  return 0;
+}
+static inline cudaError_t cudaFreeHost(void* p) {
+  emu::rt().drain_all();
+  emu::rt().pinned.erase((const char*)p);
+  std::free(p);
+  return 0;
+}
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return 0; }
-static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { std::memmove(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind kind, cudaStream_t st = 0) {
+  emu::Runtime& r = emu::rt();
+  if (!st || !r.deferred()) { std::memmove(d, s, n); return 0; }
+  if (kind == cudaMemcpyHostToDevice && !r.is_pinned(s)) {          // pageable source: staged at the call
+    auto stage = std::make_shared<std::vector<char>>((const char*)s, (const char*)s + n);
+    emu::enqueue(st, [=]() { std::memcpy(d, stage->data(), n); });
+  } else if (kind == cudaMemcpyDeviceToHost && !r.is_pinned(d)) {   // pageable destination: the call returns with the data
+    r.drain(static_cast<emu::Stream*>(st));
+    std::memmove(d, s, n);
+  } else {
+    emu::enqueue(st, [=]() { std::memmove(d, s, n); });
+  }
+  return 0;
+}
 static inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return 0; }
-static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = 0) {
-  for (size_t r = 0; r < h; ++r) std::memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind kind,
+                                            cudaStream_t st = 0) {
+  emu::Runtime& r = emu::rt();
+  auto copy = [=]() { for (size_t row = 0; row < h; ++row) std::memmove((char*)d + row * dp, (const char*)s + row * sp, w); };
+  if (!st || !r.deferred()) { copy(); return 0; }
+  if (kind == cudaMemcpyHostToDevice && !r.is_pinned(s)) {
+    auto stage = std::make_shared<std::vector<char>>((const char*)s, (const char*)s + (h ? (h - 1) * sp + w : 0));
+    emu::enqueue(st, [=]() { for (size_t row = 0; row < h; ++row) std::memcpy((char*)d + row * dp, stage->data() + row * sp, w); });
+  } else if (kind == cudaMemcpyDeviceToHost && !r.is_pinned(d)) {
+    r.drain(static_cast<emu::Stream*>(st));
+    copy();
+  } else {
+    emu::enqueue(st, copy);
+  }
   return 0;
 }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return 0; }
-static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { std::memset(d, v, n); return 0; }
-static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
-static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
-static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
-static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
-static inline cudaError_t cudaDeviceSynchronize() { return 0; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st = 0) {
+  emu::enqueue(st, [=]() { std::memset(d, v, n); });
+  return 0;
+}
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
+  emu::Stream* st = new emu::Stream();
+  emu::rt().streams.push_back(st);
+  *s = st;
+  return 0;
+}
+static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { return cudaStreamCreateWithFlags(s, 0); }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t s) {
+  if (s) emu::rt().drain(static_cast<emu::Stream*>(s));
+  return 0;
+}
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) {
+  if (!s) return 0;
+  emu::Runtime& r = emu::rt();
+  r.drain(static_cast<emu::Stream*>(s));
+  for (size_t i = 0; i < r.streams.size(); ++i)
+    if (r.streams[i] == s) { r.streams.erase(r.streams.begin() + (long)i); break; }
+  delete static_cast<emu::Stream*>(s);
+  return 0;
+}
+static inline cudaError_t cudaDeviceSynchronize() { emu::rt().drain_all(); return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event(); return 0; }
 enum { cudaEventDisableTiming = 2 };
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new emu_event(); return 0; }
-static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
-static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0) { e->t = std::chrono::steady_clock::now(); return 0; }
-static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
-static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = 0) {
+  emu::Runtime& r = emu::rt();
+  const unsigned long long ticket = ++r.tickets;
+  e->recorded = ticket;
+  if (!st || !r.deferred()) {
+    e->t = std::chrono::steady_clock::now();
+    e->done = ticket;
+    return 0;
+  }
+  emu::StreamOp op;
+  op.kind = 1; op.ev = e; op.ticket = ticket;
+  static_cast<emu::Stream*>(st)->q.push_back(std::move(op));
+  return 0;
+}
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t e) {
+  emu::rt().run_until(e, e->recorded);
+  return 0;
+}
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
+  emu::rt().run_until(e, e->recorded);   // queued operations may still name it
+  delete e;
+  return 0;
+}
+// the stream waits for the record of e that is the latest one AT THIS CALL (a never recorded event: no wait)
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned = 0) {
+  emu::Runtime& r = emu::rt();
+  if (!r.deferred() || e->recorded == 0 || e->done >= e->recorded) return 0;
+  if (!st) { r.run_until(e, e->recorded); return 0; }
+  emu::StreamOp op;
+  op.kind = 2; op.ev = e; op.ticket = e->recorded;
+  static_cast<emu::Stream*>(st)->q.push_back(std::move(op));
+  return 0;
+}
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  emu::rt().run_until(a, a->recorded);
+  emu::rt().run_until(b, b->recorded);
   *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
   return 0;
 }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 
-#define SX_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+// the arguments are EVALUATED at the call, like the parameter buffer of a real launch (a deferred launch must not read
+// host variables later)
+#define SX_LAUNCH(kernel, grid, block, smem, stream, ...)                                                    \
+  do {                                                                                                       \
+    const dim3 sx_g_ = (grid), sx_b_ = (block);                                                              \
+    const size_t sx_s_ = (smem);                                                                             \
+    auto sx_k_ = (kernel);                                                                                   \
+    auto sx_a_ = std::make_tuple(__VA_ARGS__);                                                               \
+    emu::enqueue((stream), [=]() { emu::launch(sx_g_, sx_b_, sx_s_, [&]() { std::apply(sx_k_, sx_a_); }); }); \
+  } while (0)

@@ -392,7 +392,12 @@ def _worker_p2p(rank, world, port, variants, emu_path, tables, q):
          ((16, 16, 64), {"SX_ZCHUNKS": "1"}),                              # no pipeline: one exchange per field
          ((32, 16, 64), {"SX_P2P_DIRECT_PEERS": "1"})]),                   # the next peer's blocks stored directly, the other copied
 ])
-def test_fused_substep_multirank_p2p(world, variants, emu_lib, tables):
+def test_fused_substep_multirank_p2p(world, variants, emu_lib, tables, monkeypatch):
+    if world == 3:
+        # the adversarial emulation for one of the two: random thread order, late asynchronous copies and LAZY STREAMS -- the
+        # copies and the barrier of an exchange run on the communication stream only when the compute stream's wait for its
+        # completion event pulls them, a kernel without that wait would read a buffer nothing has landed in
+        monkeypatch.setenv("SX_EMU_ADVERSARIAL", "14")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 35500 + (os.getpid() % 2000) + world

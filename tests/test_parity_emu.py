@@ -196,8 +196,9 @@ def test_adversarial_schedules_and_late_async_copies(tables):
     """The race check of the emulation (tests/emu/cuda_emu.h, SX_EMU_ADVERSARIAL): the threads of a block run in a random
     order between barriers, mbarrier waits really wait, and asynchronous copies complete as late as the program allows
     (bulk / tensor loads when a thread gets through the mbarrier wait, cp.async at the issuing thread's wait_group,
-    tensor-map stores read their shared-memory source at wait_group.read).  A missing barrier or wait changes the result;
-    the bulk-copy kernels of the three solvers must still agree with the oracle.  (The mode is read once per process: the
+    tensor-map stores read their shared-memory source at wait_group.read), and the streams are lazy queues (the copy stream
+    of sx_hd_step_host runs only through the events the compute stream waits for).  A missing barrier or wait changes the
+    result; the bulk-copy kernels and the host-buffer step must still agree with the oracle.  (The mode is read once per process: the
     cases run in a child.  tools/emu_racecheck.sh runs the whole emulation suite this way and shows that injected
     bugs -- a removed mbarrier wait, a removed wait_group.read -- are caught.)"""
     import os
@@ -210,8 +211,11 @@ def test_adversarial_schedules_and_late_async_copies(tables):
             "P.case_hd_substeps(lib, %r, (16, 128, 128), ord=2, nsteps=1, impl=0)\n"
             "P.case_hd_substeps(lib, %r, (64, 16, 64), ord=2, nsteps=1, impl=1)\n"
             "P.case_mhd_substeps(lib, %r, (64, 16, 256), ord=2, nsteps=1, impl=0, b0=(0.1, 0.0, 0.2))\n"
+            "P.case_hd_step_host(lib, %r, (32, 16, 64))\n"
             "print('ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
-                                tables, tables, tables)
-    env = dict(os.environ, SX_EMU_ADVERSARIAL="6", SX_TMA_MIN="16", SX_XP="10", SX_PJ="10")
+                                tables, tables, tables, tables)
+    # 14 = random order + late asynchronous copies + lazy streams (operations of a stream run only when the host, or an
+    # event another stream waits for, needs them: work that no event orders before its consumer has not run by then)
+    env = dict(os.environ, SX_EMU_ADVERSARIAL="14", SX_TMA_MIN="16", SX_XP="10", SX_PJ="10")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
