@@ -302,14 +302,22 @@ def case_hd_substeps(lib, tables, shape, ord=2, nsteps=1, impl=0, dt=1e-3, nu=1e
     p.close()
 
 
-def case_hd_step_host(lib, tables, shape, ord=2):
-    """The host-buffer entry (H2D, ord substeps, D2H) used for the end-to-end number."""
+def case_hd_step_host(lib, tables, shape, ord=2, pinned=False, nsteps=1):
+    """The host-buffer entry (H2D, ord substeps, D2H) used for the end-to-end number.  pinned: page-locked host arrays as in
+    bench.py's e2e leg (copies from / into them are truly asynchronous), the forcing uploaded by the first call only and
+    kept resident (NULL afterwards)."""
     g, p = make(lib, tables, *shape, ord=ord)
     s = O.make_hd_state(g)
     h = [q.copy() for q in (s.vx, s.vy, s.vz, s.pr, s.fx, s.fy, s.fz)]
-    p.hd_step_host(*h, 1e-3, 1e-3)
-    O.hd_step(g, s, 1e-3, 1e-3)
-    hd_fields_close(h[:4], s, g)
+    if pinned:
+        h = [p.pinned_like(q) for q in h]
+    for k in range(nsteps):
+        if k == 0:
+            p.hd_step_host(*h, 1e-3, 1e-3)
+        else:
+            p.hd_step_host(*h[:4], None, None, None, 1e-3, 1e-3)
+        O.hd_step(g, s, 1e-3, 1e-3)
+        hd_fields_close(h[:4], s, g)
     p.close()
 
 

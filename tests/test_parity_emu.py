@@ -59,6 +59,7 @@ def test_hd_substeps_rk4_moving_walls(emu_lib, tables):
 
 def test_hd_step_host(emu_lib, tables):
     P.case_hd_step_host(emu_lib, tables, SMALL)
+    P.case_hd_step_host(emu_lib, tables, (16, 16, 64), pinned=True, nsteps=2)
 
 
 def test_advect_vector(emu_lib, tables):
@@ -211,7 +212,7 @@ def test_adversarial_schedules_and_late_async_copies(tables):
             "P.case_hd_substeps(lib, %r, (16, 128, 128), ord=2, nsteps=1, impl=0)\n"
             "P.case_hd_substeps(lib, %r, (64, 16, 64), ord=2, nsteps=1, impl=1)\n"
             "P.case_mhd_substeps(lib, %r, (64, 16, 256), ord=2, nsteps=1, impl=0, b0=(0.1, 0.0, 0.2))\n"
-            "P.case_hd_step_host(lib, %r, (32, 16, 64))\n"
+            "P.case_hd_step_host(lib, %r, (32, 16, 64), pinned=True, nsteps=2)\n"
             "print('ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
                                 tables, tables, tables, tables)
     # 14 = random order + late asynchronous copies + lazy streams (operations of a stream run only when the host, or an
