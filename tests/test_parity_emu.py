@@ -199,7 +199,8 @@ def test_adversarial_schedules_and_late_async_copies(tables):
     (bulk / tensor loads when a thread gets through the mbarrier wait, cp.async at the issuing thread's wait_group,
     tensor-map stores read their shared-memory source at wait_group.read), and the streams are lazy queues (the copy stream
     of sx_hd_step_host runs only through the events the compute stream waits for).  A missing barrier or wait changes the
-    result; the bulk-copy kernels and the host-buffer step must still agree with the oracle.  (The mode is read once per process: the
+    result; the bulk-copy kernels (forced on small grids, then the length-512 instantiations of the 512^3 bench under the
+    default selection) and the host-buffer step must still agree with the oracle.  (The mode is read once per process: the
     cases run in a child.  tools/emu_racecheck.sh runs the whole emulation suite this way and shows that injected
     bugs -- a removed mbarrier wait, a removed wait_group.read -- are caught.)"""
     import os
@@ -213,8 +214,13 @@ def test_adversarial_schedules_and_late_async_copies(tables):
             "P.case_hd_substeps(lib, %r, (64, 16, 64), ord=2, nsteps=1, impl=1)\n"
             "P.case_mhd_substeps(lib, %r, (64, 16, 256), ord=2, nsteps=1, impl=0, b0=(0.1, 0.0, 0.2))\n"
             "P.case_hd_step_host(lib, %r, (32, 16, 64), pinned=True, nsteps=2)\n"
+            "import os\n"
+            "for k in ('SX_TMA_MIN', 'SX_XP', 'SX_PJ'): del os.environ[k]\n"
+            "# default kernel selection: the template instantiations the 512^3 bench runs, one axis at a time\n"
+            "for shape in ((512, 16, 64), (16, 512, 64), (16, 16, 512)):\n"
+            "    P.case_hd_substeps(lib, %r, shape, ord=2, nsteps=1, impl=0)\n"
             "print('ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
-                                tables, tables, tables, tables)
+                                tables, tables, tables, tables, tables)
     # 14 = random order + late asynchronous copies + lazy streams (operations of a stream run only when the host, or an
     # event another stream waits for, needs them: work that no event orders before its consumer has not run by then)
     env = dict(os.environ, SX_EMU_ADVERSARIAL="14", SX_TMA_MIN="16", SX_XP="10", SX_PJ="10")
