@@ -16,10 +16,13 @@ and ships no golden vectors: its own tests (src/tests/*.f90) only *print*
 error norms of analytic identities.  The oracle is therefore pinned against
 (i) those analytic known-answer identities re-stated as assertions
 (tests/test_oracle.py), (ii) the reference's FC-Gram table fixtures, and
-(iii) INDEPENDENT second statements of the HD, BOUSS and MHD substeps
+(iii) INDEPENDENT second statements of the HD, BOUSS, MHD, ROTBOUSS (moving
+walls) and MHDBOUSS (conducting, vacuum and mixed walls) substeps
 (tests/independent_hd.py: dense DFT matrices, full Hermitian x spectrum,
 longdouble; no shared code), which it matches to better than 1e-12 of the field
-maxima over two substeps each.  FFTW is a third-party
+maxima over two substeps each, and (iv) real-space evaluations of every global
+quantity (energy, enstrophy-like column, helicity, cross, divergence, variance,
+product, wall checks) with the same independent transform.  FFTW is a third-party
 dependency absent from /root/reference (only hint of a version: 3.3.8,
 src/Makefile.in:59); the DFT is mathematically fixed (forward sign -1, backward
 +1, both unnormalised), so bitwise parity with an FFTW build is unpinned only
