@@ -79,6 +79,9 @@ static int comm_get(Plan& p, Comm** out) {
     Comm* c = new Comm();
     p.comm = c;
     SX_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+#ifdef SX_EMU
+    emu::mark_eager(c->stream);   // tests/emu/cuda_emu.h, SX_EMU_ADVERSARIAL & 16
+#endif
     for (int i = 0; i < 32; ++i) {
       SX_CUDA_CHECK(cudaEventCreate(&c->ready[i]));
       SX_CUDA_CHECK(cudaEventCreate(&c->done[i]));

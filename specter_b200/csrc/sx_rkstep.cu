@@ -124,6 +124,9 @@ int sx_hd_step_host(sx_plan* plan, double* vx, double* vy, double* vz, double* p
   if (hd_state(p, &s)) return 1;
   if (!p.copy_stream) {
     SX_CUDA_CHECK(cudaStreamCreateWithFlags(&p.copy_stream, cudaStreamNonBlocking));
+#ifdef SX_EMU
+    emu::mark_eager(p.copy_stream);   // tests/emu/cuda_emu.h, SX_EMU_ADVERSARIAL & 16
+#endif
     for (int i = 0; i < 4; ++i) SX_CUDA_CHECK(cudaEventCreateWithFlags(&p.h2d_ev[i], cudaEventDisableTiming));
   }
   const size_t bytes = p.csize() * sizeof(cplx);

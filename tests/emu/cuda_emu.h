@@ -70,7 +70,9 @@ namespace emu {
 //      wait_group, tensor-map STORES read their shared-memory source at the issuing thread's wait_group(.read) -- data
 //      consumed before its wait, or a store source overwritten before wait_group.read, changes the result.
 //   8  streams are lazy queues (see "runtime subset" below): work that no event orders before its consumer has not run
-//      when the consumer does.
+//      when the consumer does;
+//  16  (with 8) the streams the library marks as communication / copy streams run as EARLY as their event waits allow
+//      while the compute stream stays lazy: a buffer overwritten before its readers are done changes the result.
 // With any bit set the mbarrier phase is tracked (expect_tx / complete_tx bytes) and mbarrier waits really wait, so the
 // producer thread need not run first.
 // Context switches: a fiber is ENTERED through makecontext / swapcontext (which sets up its stack) and from then on
@@ -368,6 +370,7 @@ struct StreamOp {
 };
 struct Stream {
   std::deque<StreamOp> q;
+  bool eager = false;                // SX_EMU_ADVERSARIAL & 16: runs as EARLY as its event waits allow (mark_eager)
 };
 struct Runtime {
   std::vector<Stream*> streams;
@@ -401,6 +404,34 @@ struct Runtime {
     } else {
       op.fn();
     }
+    pump();
+  }
+  // eager streams: everything at their heads whose event waits are already satisfied runs NOW -- the earliest moment the
+  // program allows, e.g. a copy that overwrites a buffer as soon as the events it waits for have fired
+  bool pumping = false;
+  void pump() {
+    if (pumping || !(adv_mode() & 16)) return;
+    pumping = true;
+    for (bool progress = true; progress;) {
+      progress = false;
+      for (size_t i = 0; i < streams.size(); ++i) {
+        Stream* s = streams[i];
+        while (s->eager && !s->q.empty()) {
+          StreamOp& head = s->q.front();
+          if (head.kind == 2 && head.ev->done < head.ticket) break;   // blocked: the awaited record has not executed
+          StreamOp op = std::move(head);
+          s->q.pop_front();
+          if (op.kind == 1) {
+            op.ev->t = std::chrono::steady_clock::now();
+            if (op.ev->done < op.ticket) op.ev->done = op.ticket;
+          } else if (op.kind == 0) {
+            op.fn();
+          }
+          progress = true;
+        }
+      }
+    }
+    pumping = false;
   }
   void drain(Stream* s) {
     while (!s->q.empty()) step(s);
@@ -419,6 +450,12 @@ inline void enqueue(cudaStream_t st, std::function<void()> fn) {
   StreamOp op;
   op.fn = std::move(fn);
   static_cast<Stream*>(st)->q.push_back(std::move(op));
+  rt().pump();
+}
+// the library marks its communication / copy streams: with SX_EMU_ADVERSARIAL & 16 they run as early as their event waits
+// allow while the compute stream stays lazy -- the adversary of a buffer that is overwritten before its readers are done
+inline void mark_eager(cudaStream_t st) {
+  if (st) static_cast<Stream*>(st)->eager = true;
 }
 }  // namespace emu
 
@@ -518,6 +555,7 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = 0) {
   emu::StreamOp op;
   op.kind = 1; op.ev = e; op.ticket = ticket;
   static_cast<emu::Stream*>(st)->q.push_back(std::move(op));
+  r.pump();
   return 0;
 }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t e) {
@@ -537,6 +575,7 @@ static inline cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, un
   emu::StreamOp op;
   op.kind = 2; op.ev = e; op.ticket = e->recorded;
   static_cast<emu::Stream*>(st)->q.push_back(std::move(op));
+  r.pump();
   return 0;
 }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {

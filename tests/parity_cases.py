@@ -302,7 +302,7 @@ def case_hd_substeps(lib, tables, shape, ord=2, nsteps=1, impl=0, dt=1e-3, nu=1e
     p.close()
 
 
-def case_hd_step_host(lib, tables, shape, ord=2, pinned=False, nsteps=1):
+def case_hd_step_host(lib, tables, shape, ord=2, pinned=False, nsteps=1, inflight=False):
     """The host-buffer entry (H2D, ord substeps, D2H) used for the end-to-end number.  pinned: page-locked host arrays as in
     bench.py's e2e leg (copies from / into them are truly asynchronous), the forcing uploaded by the first call only and
     kept resident (NULL afterwards)."""
@@ -311,6 +311,13 @@ def case_hd_step_host(lib, tables, shape, ord=2, pinned=False, nsteps=1):
     h = [q.copy() for q in (s.vx, s.vy, s.vz, s.pr, s.fx, s.fy, s.fz)]
     if pinned:
         h = [p.pinned_like(q) for q in h]
+    if inflight:
+        # a substep of some OTHER state is still in flight (nothing waited for it) when the host-buffer step overwrites the
+        # plan-owned state: the entry has to wait for it first (sx_hd_step_host: "nothing in flight still reads the state
+        # that is overwritten")
+        p.hd_put_state(*[0.5 * q[::-1].copy() for q in (s.vx, s.vy, s.vz)], s.pr, s.fx, s.fy, s.fz)
+        p.hd_rkstep1()
+        p.hd_rkstep2(ord, 1e-3, 1e-3)
     for k in range(nsteps):
         if k == 0:
             p.hd_step_host(*h, 1e-3, 1e-3)

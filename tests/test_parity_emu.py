@@ -59,7 +59,7 @@ def test_hd_substeps_rk4_moving_walls(emu_lib, tables):
 
 def test_hd_step_host(emu_lib, tables):
     P.case_hd_step_host(emu_lib, tables, SMALL)
-    P.case_hd_step_host(emu_lib, tables, (16, 16, 64), pinned=True, nsteps=2)
+    P.case_hd_step_host(emu_lib, tables, (16, 16, 64), pinned=True, nsteps=2, inflight=True)
 
 
 def test_advect_vector(emu_lib, tables):
@@ -213,7 +213,7 @@ def test_adversarial_schedules_and_late_async_copies(tables):
             "P.case_hd_substeps(lib, %r, (16, 128, 128), ord=2, nsteps=1, impl=0)\n"
             "P.case_hd_substeps(lib, %r, (64, 16, 64), ord=2, nsteps=1, impl=1)\n"
             "P.case_mhd_substeps(lib, %r, (64, 16, 256), ord=2, nsteps=1, impl=0, b0=(0.1, 0.0, 0.2))\n"
-            "P.case_hd_step_host(lib, %r, (32, 16, 64), pinned=True, nsteps=2)\n"
+            "P.case_hd_step_host(lib, %r, (32, 16, 64), pinned=True, nsteps=2, inflight=True)\n"
             "import os\n"
             "for k in ('SX_TMA_MIN', 'SX_XP', 'SX_PJ'): del os.environ[k]\n"
             "# default kernel selection: the template instantiations the 512^3 bench runs, one axis at a time\n"
@@ -221,8 +221,9 @@ def test_adversarial_schedules_and_late_async_copies(tables):
             "    P.case_hd_substeps(lib, %r, shape, ord=2, nsteps=1, impl=0)\n"
             "print('ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
                                 tables, tables, tables, tables, tables)
-    # 14 = random order + late asynchronous copies + lazy streams (operations of a stream run only when the host, or an
+    # 30 = random order + late asynchronous copies + lazy streams + eager copy stream: 14 = (operations of a stream run only when the host, or an
     # event another stream waits for, needs them: work that no event orders before its consumer has not run by then)
-    env = dict(os.environ, SX_EMU_ADVERSARIAL="14", SX_TMA_MIN="16", SX_XP="10", SX_PJ="10")
+    # + 16: the copy stream of the host-buffer step runs as EARLY as its event waits allow while the compute stream is lazy
+    env = dict(os.environ, SX_EMU_ADVERSARIAL="30", SX_TMA_MIN="16", SX_XP="10", SX_PJ="10")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
