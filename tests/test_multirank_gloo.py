@@ -388,6 +388,8 @@ def _worker_p2p(rank, world, port, variants, emu_path, tables, q):
     (2, [((32, 16, 64), {}),                                               # 4 z chunks, the local block stored in place
          ((16, 128, 128), {"SX_TMA_MIN": "16", "SX_P2P_DIRECT": "2"}),     # bulk-copy tile kernels storing EVERY block into the peers
          ((32, 16, 64), {"SX_P2P_DIRECT": "0", "SX_ZCHUNKS": "8"})]),      # every block copied; more chunks than some ranks have row pairs
+    (8, [((64, 16, 64), {}),                                               # the rank count of BASELINE configs[2..4]: 33 kx planes and 20 row pairs over 8 ranks
+         ((32, 128, 128), {"SX_TMA_MIN": "16", "SX_P2P_DIRECT": "2"})]),   # eight tensor-map blocks per tile, every block stored into its peer
     (3, [((16, 16, 64), {"SX_ZCHUNKS": "2"}),                              # uneven slabs, 2 chunks
          ((16, 16, 64), {"SX_ZCHUNKS": "1"}),                              # no pipeline: one exchange per field
          ((32, 16, 64), {"SX_P2P_DIRECT_PEERS": "1"})]),                   # the next peer's blocks stored directly, the other copied
