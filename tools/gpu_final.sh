@@ -9,5 +9,5 @@ timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 
 python - <<PY
 import json
 d=json.load(open("gpurun_out/${tag}_bench.json"))
-print("hd512 ms/substep", round(d["ms_per_substep"],3), "whole", round(d["roofline"]["whole_substep"]["frac"],3), "dominant", d["roofline"]["kernel"], round(d["roofline"]["frac"],3), "traffic", d["roofline"]["traffic"], d["roofline"]["traffic_from_profile"], "e2e", d["e2e"]["ms_per_step"], "clocks", d["clocks"], "cpu", d["cpu_baseline"]["value"])
+print("hd512 ms/substep", round(d["ms_per_substep"],3), "whole", round(d["roofline"]["whole_substep"]["frac"],3), "dominant", d["roofline"]["kernel"], round(d["roofline"]["frac"],3), "traffic", d["roofline"]["traffic"], d["roofline"]["traffic_from_profile"], "e2e", d["e2e"]["ms_per_step"], "clocks", d["clocks"], "cpu", d["cpu_baseline"]["value"], "state_check", d.get("state_check"))
 PY
